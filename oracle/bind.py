@@ -1,0 +1,398 @@
+"""oracle/bind.py -- TEST INFRASTRUCTURE ONLY.
+
+ctypes bindings for the two CPU checkers:
+
+* ``RefOracle``  -> oracle/_ref/libimr_ref.so : the UNMODIFIED reference sources compiled
+  in place from /root/reference (oracle/Makefile ``ref``) behind oracle/ref_shim.cpp.
+* ``PortOracle`` -> oracle/liboracle_port.so  : the plain-C restatement (oracle/imr_oracle.c).
+
+Both expose the same Python surface so tests can run either against the CUDA path.
+Only tests/, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference``
+legs may import this module; the product package never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_SO = os.path.join(HERE, "_ref", "libimr_ref.so")
+PORT_SO = os.path.join(HERE, "liboracle_port.so")
+
+_f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+_u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+_u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+_u64p = np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS")
+_f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+
+
+def build(which: str = "all") -> None:
+    """Compile the checkers (``port``, ``ref`` or ``all``).  ``ref`` is a no-op when
+    /root/reference is absent (the GPU box): the prebuilt _ref/ library travels with the repo."""
+    subprocess.run(["make", "-s", "-C", HERE, which], check=True)
+
+
+def _c(a, dt):
+    return np.ascontiguousarray(a, dtype=dt)
+
+
+def _opt(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+@dataclass
+class FlatTree:
+    """Flat interchange form of an OBB tree (see imr_oracle.h)."""
+    boxes: np.ndarray      # (nv,12) f32
+    left: np.ndarray       # (nv,) i32
+    right: np.ndarray      # (nv,) i32
+    tri_off: np.ndarray    # (nv,) u32
+    tri_cnt: np.ndarray    # (nv,) u32
+    tri_pos: np.ndarray    # (n,9) f32, leaf order
+    tri_nrm: np.ndarray    # (n,9) f32
+    tri_vid: np.ndarray    # (n,3) u32
+    tri_orig: np.ndarray   # (n,) u32
+
+    @property
+    def nv(self):
+        return self.boxes.shape[0]
+
+    @property
+    def n_tri(self):
+        return self.tri_pos.shape[0]
+
+
+@dataclass
+class PairResult:
+    hit_ids: np.ndarray    # (h,2) u32 original triangle indices (first tree, second tree)
+    hit_seg: np.ndarray    # (h,7) f32 source(3) target(3) weight
+    n_combos: int
+    n_tri_tests: int
+    n_hits: int
+    n_coplanar: int
+    rays_first: int
+    rays_second: int
+    colliding: bool
+    avg: np.ndarray        # (6,) f32
+    seconds: tuple = (0.0, 0.0)
+
+
+class _Base:
+    prefix = ""
+
+    def __init__(self, path):
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.lib = C.CDLL(path)
+        self._sig()
+
+    def _fn(self, name):
+        return getattr(self.lib, self.prefix + name)
+
+    # ---- common predicate surface -------------------------------------
+    def sat(self, a12, b12, m16=None) -> int:
+        a12 = _c(a12, np.float32); b12 = _c(b12, np.float32)
+        m = None if m16 is None else _c(m16, np.float32)
+        f = self._fn("sat"); f.restype = C.c_int
+        f.argtypes = [C.c_void_p] * 3
+        return f(a12.ctypes.data, b12.ctypes.data, _opt(m))
+
+    def surface(self, a12, m16=None) -> np.float32:
+        a12 = _c(a12, np.float32)
+        m = None if m16 is None else _c(m16, np.float32)
+        f = self._fn("surface"); f.restype = C.c_float
+        f.argtypes = [C.c_void_p] * 2
+        return np.float32(f(a12.ctypes.data, _opt(m)))
+
+    def box_transform(self, a12, m16):
+        a12 = _c(a12, np.float32); m16 = _c(m16, np.float32)
+        out = np.empty(12, np.float32)
+        f = self._fn("box_transform"); f.restype = None
+        f.argtypes = [C.c_void_p] * 3
+        f(a12.ctypes.data, m16.ctypes.data, out.ctypes.data)
+        return out
+
+    def tri_tri(self, a, b, m16=None):
+        a = _c(a, np.float32).reshape(-1, 9); b = _c(b, np.float32).reshape(-1, 9)
+        n = a.shape[0]
+        m = None if m16 is None else _c(m16, np.float32)
+        flags = np.zeros(n, np.uint8)
+        seg = np.zeros((n, 6), np.float32)
+        f = self._fn("tri_tri"); f.restype = None
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+        f(a.ctypes.data, b.ctypes.data, _opt(m), n, flags.ctypes.data, seg.ctypes.data)
+        return flags, seg
+
+    def pair_matrix(self, a16, b16):
+        a16 = _c(a16, np.float32); b16 = _c(b16, np.float32)
+        out = np.empty(16, np.float32)
+        f = self._fn("pair_matrix"); f.restype = None
+        f.argtypes = [C.c_void_p] * 3
+        f(a16.ctypes.data, b16.ctypes.data, out.ctypes.data)
+        return out
+
+    def obb_from_points(self, pts):
+        pts = _c(pts, np.float32).reshape(-1, 3)
+        out = np.empty(12, np.float32)
+        f = self._fn("obb_from_points"); f.restype = None
+        f.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+        f(pts.ctypes.data, pts.shape[0], out.ctypes.data)
+        return out
+
+    def sweep_axes(self):
+        out = np.empty(9, np.float32)
+        f = self._fn("sweep_axes"); f.restype = None
+        f.argtypes = [C.c_void_p]
+        f(out.ctypes.data)
+        return out.reshape(3, 3)
+
+    # ---- trees ---------------------------------------------------------
+    def tree_build(self, pos, nrm=None, vid=None):
+        pos = _c(pos, np.float32).reshape(-1, 9)
+        nrm = None if nrm is None else _c(nrm, np.float32).reshape(-1, 9)
+        vid = None if vid is None else _c(vid, np.uint32).reshape(-1, 3)
+        f = self._fn("tree_create" if self.prefix == "imr_ref_" else "tree_build")
+        f.restype = C.c_void_p
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+        h = f(pos.ctypes.data, _opt(nrm), _opt(vid), pos.shape[0])
+        return Tree(self, h)
+
+    def _tree_free(self, h):
+        f = self._fn("tree_destroy" if self.prefix == "imr_ref_" else "tree_free")
+        f.restype = None; f.argtypes = [C.c_void_p]
+        f(h)
+
+    def _tree_counts(self, h):
+        fv = self._fn("tree_vertex_count"); fv.restype = C.c_uint64; fv.argtypes = [C.c_void_p]
+        ft = self._fn("tree_tri_count"); ft.restype = C.c_uint64; ft.argtypes = [C.c_void_p]
+        return int(fv(h)), int(ft(h))
+
+    def _tree_flatten(self, h) -> FlatTree:
+        nv, n = self._tree_counts(h)
+        ft = FlatTree(np.empty((nv, 12), np.float32), np.empty(nv, np.int32), np.empty(nv, np.int32),
+                      np.empty(nv, np.uint32), np.empty(nv, np.uint32), np.empty((n, 9), np.float32),
+                      np.empty((n, 9), np.float32), np.empty((n, 3), np.uint32), np.empty(n, np.uint32))
+        f = self._fn("tree_flatten"); f.restype = None
+        f.argtypes = [C.c_void_p] * 10
+        f(h, ft.boxes.ctypes.data, ft.left.ctypes.data, ft.right.ctypes.data, ft.tri_off.ctypes.data,
+          ft.tri_cnt.ctypes.data, ft.tri_pos.ctypes.data, ft.tri_nrm.ctypes.data, ft.tri_vid.ctypes.data,
+          ft.tri_orig.ctypes.data)
+        return ft
+
+
+class Tree:
+    def __init__(self, owner: _Base, handle):
+        self.owner = owner
+        self.h = handle
+        self._flat = None
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.owner._tree_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    @property
+    def flat(self) -> FlatTree:
+        if self._flat is None:
+            self._flat = self.owner._tree_flatten(self.h)
+        return self._flat
+
+    @property
+    def root_box(self):
+        return self.flat.boxes[0]
+
+
+class RefOracle(_Base):
+    """The unmodified reference (kind = "reference")."""
+    prefix = "imr_ref_"
+    kind = "reference"
+
+    def __init__(self, path=REF_SO):
+        super().__init__(path)
+
+    def _sig(self):
+        pass
+
+    def broad(self, mats, trees, should_cb):
+        """SweepAndPrune::ExecuteSweepAndPrune on <= 65534 entries.  Returns (pairs (k,2) u32, seconds)."""
+        mats = _c(mats, np.float32).reshape(-1, 16)
+        n = mats.shape[0]
+        cb = _c(should_cb, np.uint8)
+        handles = (C.c_void_p * n)(*[t.h for t in trees])
+        secs = C.c_double(0)
+        cap = max(1024, 64 * n)
+        f = self.lib.imr_ref_broad; f.restype = C.c_uint64
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p]
+        while True:
+            pairs = np.empty((cap, 2), np.uint32)
+            k = f(mats.ctypes.data, handles, cb.ctypes.data, n, pairs.ctypes.data, cap, C.byref(secs))
+            if k == 2 ** 64 - 1:
+                raise ValueError("reference broad phase is limited to 65534 entries (Entity is uint16_t)")
+            if k <= cap:
+                return pairs[:k].copy(), secs.value
+            cap = int(k)
+
+    def mid(self, ta: Tree, ma, tb: Tree, mb):
+        ma = _c(ma, np.float32); mb = _c(mb, np.float32)
+        f = self.lib.imr_ref_mid; f.restype = C.c_uint64
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+        cap = 1 << 16
+        secs = C.c_double(0)
+        while True:
+            combos = np.empty((cap, 4), np.uint32)
+            k = f(ta.h, ma.ctypes.data, tb.h, mb.ctypes.data, combos.ctypes.data, cap, C.byref(secs))
+            if k <= cap:
+                return combos[:k].copy(), secs.value
+            cap = int(k)
+
+    def mid_stats(self, ta, ma, tb, mb):
+        ma = _c(ma, np.float32); mb = _c(mb, np.float32)
+        out = np.zeros(5, np.uint64)
+        f = self.lib.imr_ref_mid_stats; f.restype = None
+        f.argtypes = [C.c_void_p] * 5
+        f(ta.h, ma.ctypes.data, tb.h, mb.ctypes.data, out.ctypes.data)
+        return dict(visits=int(out[0]), passes=int(out[1]), combos=int(out[2]), tri_tests=int(out[3]), max_depth=int(out[4]))
+
+    def pair(self, ta, ma, tb, mb) -> PairResult:
+        ma = _c(ma, np.float32); mb = _c(mb, np.float32)
+        f = self.lib.imr_ref_pair; f.restype = None
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
+                      C.c_void_p, C.c_void_p, C.c_void_p]
+        cap = 1 << 12
+        while True:
+            ids = np.empty((cap, 2), np.uint32); seg = np.empty((cap, 7), np.float32)
+            summ = np.zeros(7, np.uint64); avg = np.zeros(6, np.float32); secs = np.zeros(2, np.float64)
+            f(ta.h, ma.ctypes.data, tb.h, mb.ctypes.data, ids.ctypes.data, seg.ctypes.data, cap,
+              summ.ctypes.data, avg.ctypes.data, secs.ctypes.data)
+            h = int(summ[2])
+            if h <= cap:
+                return PairResult(ids[:h].copy(), seg[:h].copy(), int(summ[0]), int(summ[1]), h, int(summ[3]),
+                                  int(summ[4]), int(summ[5]), bool(summ[6]), avg, (float(secs[0]), float(secs[1])))
+            cap = h
+
+
+class PortOracle(_Base):
+    """The plain-C restatement (kind = "port")."""
+    prefix = "imro_"
+    kind = "port"
+
+    def __init__(self, path=PORT_SO):
+        super().__init__(path)
+
+    def _sig(self):
+        pass
+
+    def eig3(self, A):
+        A = _c(A, np.float64).reshape(9)
+        V = np.empty(9, np.float64); d = np.empty(3, np.float64)
+        f = self.lib.imro_eig3; f.restype = None; f.argtypes = [C.c_void_p] * 3
+        f(A.ctypes.data, V.ctypes.data, d.ctypes.data)
+        return V.reshape(3, 3), d
+
+    def tree_import(self, ft: FlatTree) -> Tree:
+        f = self.lib.imro_tree_import; f.restype = C.c_void_p
+        f.argtypes = [C.c_uint64] + [C.c_void_p] * 5 + [C.c_uint64] + [C.c_void_p] * 4
+        keep = [_c(ft.boxes, np.float32), _c(ft.left, np.int32), _c(ft.right, np.int32), _c(ft.tri_off, np.uint32),
+                _c(ft.tri_cnt, np.uint32), _c(ft.tri_pos, np.float32), _c(ft.tri_nrm, np.float32),
+                _c(ft.tri_vid, np.uint32), _c(ft.tri_orig, np.uint32)]
+        h = f(ft.nv, keep[0].ctypes.data, keep[1].ctypes.data, keep[2].ctypes.data, keep[3].ctypes.data,
+              keep[4].ctypes.data, ft.n_tri, keep[5].ctypes.data, keep[6].ctypes.data, keep[7].ctypes.data,
+              keep[8].ctypes.data)
+        return Tree(self, h)
+
+    def extents(self, mats, root_boxes):
+        mats = _c(mats, np.float32).reshape(-1, 16); rb = _c(root_boxes, np.float32).reshape(-1, 12)
+        out = np.empty((mats.shape[0], 6), np.float32)
+        f = self.lib.imro_extents; f.restype = None
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+        f(mats.ctypes.data, rb.ctypes.data, mats.shape[0], out.ctypes.data)
+        return out
+
+    def broad(self, mats, trees, should_cb):
+        """32-bit restatement of the sweep; `trees` may be Tree objects or an (n,12) array of root boxes."""
+        import time
+        mats = _c(mats, np.float32).reshape(-1, 16)
+        n = mats.shape[0]
+        if isinstance(trees, np.ndarray):
+            rb = _c(trees, np.float32).reshape(-1, 12)
+        else:
+            rb = np.stack([t.root_box for t in trees]).astype(np.float32) if n else np.zeros((0, 12), np.float32)
+        cb = _c(should_cb, np.uint8)
+        f = self.lib.imro_broad; f.restype = C.c_uint64
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
+        cap = max(1024, 64 * n)
+        while True:
+            pairs = np.empty((cap, 2), np.uint32)
+            t0 = time.perf_counter()
+            k = f(mats.ctypes.data, rb.ctypes.data, cb.ctypes.data, n, pairs.ctypes.data, cap)
+            dt = time.perf_counter() - t0
+            if k <= cap:
+                return pairs[:k].copy(), dt
+            cap = int(k)
+
+    def mid(self, ta, ma, tb, mb):
+        import time
+        ma = _c(ma, np.float32); mb = _c(mb, np.float32)
+        f = self.lib.imro_mid; f.restype = C.c_uint64
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+        cap = 1 << 16
+        while True:
+            combos = np.empty((cap, 4), np.uint32)
+            t0 = time.perf_counter()
+            k = f(ta.h, ma.ctypes.data, tb.h, mb.ctypes.data, combos.ctypes.data, cap, None)
+            dt = time.perf_counter() - t0
+            if k <= cap:
+                return combos[:k].copy(), dt
+            cap = int(k)
+
+    def mid_stats(self, ta, ma, tb, mb):
+        ma = _c(ma, np.float32); mb = _c(mb, np.float32)
+        out = np.zeros(5, np.uint64)
+        f = self.lib.imro_mid; f.restype = C.c_uint64
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+        f(ta.h, ma.ctypes.data, tb.h, mb.ctypes.data, None, 0, out.ctypes.data)
+        return dict(visits=int(out[0]), passes=int(out[1]), combos=int(out[2]), tri_tests=int(out[3]), max_depth=int(out[4]))
+
+    def pair(self, ta, ma, tb, mb, want_rays=False):
+        import time
+        ma = _c(ma, np.float32); mb = _c(mb, np.float32)
+        f = self.lib.imro_pair; f.restype = None
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
+                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+        cap = 1 << 12
+        ray_cap = 1 << 12
+        while True:
+            ids = np.empty((cap, 2), np.uint32); seg = np.empty((cap, 7), np.float32)
+            summ = np.zeros(7, np.uint64); avg = np.zeros(6, np.float32)
+            r1 = np.zeros((ray_cap, 6), np.float32) if want_rays else None
+            r2 = np.zeros((ray_cap, 6), np.float32) if want_rays else None
+            t0 = time.perf_counter()
+            f(ta.h, ma.ctypes.data, tb.h, mb.ctypes.data, ids.ctypes.data, seg.ctypes.data, cap,
+              summ.ctypes.data, avg.ctypes.data, _opt(r1), _opt(r2), ray_cap)
+            dt = time.perf_counter() - t0
+            h = int(summ[2])
+            if h <= cap and (not want_rays or max(int(summ[4]), int(summ[5])) <= ray_cap):
+                res = PairResult(ids[:h].copy(), seg[:h].copy(), int(summ[0]), int(summ[1]), h, int(summ[3]),
+                                 int(summ[4]), int(summ[5]), bool(summ[6]), avg, (0.0, dt))
+                if want_rays:
+                    res.rays = (r1[:int(summ[4])].copy(), r2[:int(summ[5])].copy())
+                return res
+            cap = max(cap, h)
+            ray_cap = max(ray_cap, int(summ[4]), int(summ[5]))
+
+
+def load(prefer: str = "reference"):
+    """Return the strongest available checker: the real reference if its .so exists, else the port."""
+    if prefer == "reference" and os.path.exists(REF_SO):
+        return RefOracle()
+    if not os.path.exists(PORT_SO):
+        build("port")
+    return PortOracle()
