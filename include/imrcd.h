@@ -1,0 +1,140 @@
+/* imrcd.h -- C ABI of libimrcd.so: B200-native (sm_100a CUDA) replacement for the CPU
+ * collision-detection path of thesmallcreeper/inMyRoom_vulkan.
+ *
+ * The boundary it replaces ("IMR/" = inMyRoom_vulkan/ in the reference checkout):
+ *   class CollisionDetection            IMR/include/CollisionDetection/CollisionDetection.h:11-35
+ *     Reset()                           IMR/src/CollisionDetection/CollisionDetection.cpp:28
+ *     AddCollisionDetectionEntry(e)     IMR/src/CollisionDetection/CollisionDetection.cpp:33
+ *     ExecuteCollisionDetection()       IMR/src/CollisionDetection/CollisionDetection.cpp:38-129
+ *   OBBtree::OBBtree(vector<Triangle>&&) IMR/include/Geometry/OBBtree.h:105, src/Geometry/OBBtree.cpp:321
+ *   struct CollisionDetectionEntry      IMR/include/ECS/ECStypes.h:149-156
+ *
+ * Conventions: plain pointers and sizes only; every call returns 0 on success or a negative
+ * IMRCD_E_* code, with text in imrcd_last_error(); no exceptions cross the ABI; a context is
+ * single-threaded like the reference (it runs under ECSwrapper::controlMutex, ECSwrapper.cpp:316).
+ * Matrices are glm::mat4 layout: 16 contiguous floats, column-major.  There is no CPU fallback:
+ * imrcd_create fails when no CUDA device of compute capability 10.x is usable.
+ */
+#ifndef IMRCD_H
+#define IMRCD_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IMRCD_OK            0
+#define IMRCD_E_CUDA       -1   /* CUDA runtime / launch failure */
+#define IMRCD_E_ARG        -2   /* bad argument */
+#define IMRCD_E_NODEVICE   -3   /* no usable sm_100 device: the library has no CPU path */
+#define IMRCD_E_CAPACITY   -4   /* an internal queue could not be grown */
+#define IMRCD_E_STATE      -5   /* call sequence error */
+
+typedef struct imrcd_ctx imrcd_ctx;
+
+/* build modes for imrcd_mesh_create */
+#define IMRCD_BUILD_MORTON     0u  /* bottom-up Morton-ordered GPU build (default, fast) */
+#define IMRCD_BUILD_REFERENCE  1u  /* top-down build with the reference's split rule and summation order:
+                                      bit-identical tree to OBBtree.cpp:321 (parity mode, slower) */
+
+/* One colliding entity pair (CollisionDetection.cpp:60-78).  `first` is the entity earlier on the
+ * sweep's U axis (SweepAndPrune.cpp:63); contact data live in first's model space. */
+typedef struct {
+    uint32_t entry_first, entry_second;    /* indices into this frame's entry list */
+    uint32_t entity_first, entity_second;  /* ids given to imrcd_frame_add_entry */
+    uint32_t n_hits;                       /* non-coplanar intersecting triangle pairs */
+    uint32_t n_rays_first, n_rays_second;  /* "uncollide" rays per side (CreateUncollideRays.cpp:131-178) */
+    uint32_t flags;                        /* bit0: colliding (>= 1 ray, CollisionDetection.cpp:63) */
+    float    avg_first[3];                 /* average_point_first_modelspace  (CreateUncollideRays.cpp:185-189) */
+    float    avg_second[3];                /* average_point_second_modelspace (CreateUncollideRays.cpp:191-198) */
+    float    delta_first[3];               /* CollisionCallbackData.deltaVector for first  (CollisionDetection.cpp:80-103) */
+    float    delta_second[3];              /* ... for second */
+} imrcd_entity_pair;                       /* 80 bytes */
+
+/* One intersecting, non-coplanar triangle pair (CreateUncollideRays.cpp:86-100). */
+typedef struct {
+    uint32_t pair;          /* index into the broad-phase pair list of this frame (imrcd_frame_pairs) */
+    uint32_t tri_first;     /* ORIGINAL input triangle index in first's mesh (not leaf order) */
+    uint32_t tri_second;    /* ORIGINAL input triangle index in second's mesh */
+    float    source[3];     /* TrianglesIntersectionInfo.source (Triangle.h:13-19), first's model space */
+    float    target[3];     /* TrianglesIntersectionInfo.target */
+    float    weight;        /* |source - target| (CreateUncollideRays.cpp:93) */
+} imrcd_tri_hit;            /* 40 bytes */
+
+typedef struct {
+    uint64_t n_entries;
+    uint64_t n_pairs;           /* broad-phase pairs owned by this shard */
+    uint64_t n_sat_tests;       /* OBB-OBB SAT evaluations (IntersectOBBtreesRecursive visits) */
+    uint64_t n_combos;          /* leaf x leaf candidate range combinations */
+    uint64_t n_tri_tests;       /* sum over combos of cntA*cntB == triangle-pair tests */
+    uint64_t n_hits;            /* non-coplanar intersecting triangle pairs */
+    uint64_t n_coplanar_hits;   /* intersecting but coplanar (dropped, CreateUncollideRays.cpp:88) */
+    uint64_t n_colliding;       /* colliding entity pairs */
+    uint64_t traverse_launches; /* kernel launches of the traversal stage */
+    uint64_t total_launches;    /* all kernel launches of the frame */
+    float    ms_total;          /* device time of imrcd_frame_run (CUDA events) */
+    float    ms_broad, ms_pair_setup, ms_traverse, ms_narrow, ms_reduce;
+} imrcd_frame_stats;
+
+/* ---- context ---------------------------------------------------------------------------- */
+/* `cuda_stream` is a cudaStream_t to launch on (e.g. torch.cuda.current_stream().cuda_stream) or NULL
+ * for a stream owned by the context. */
+int  imrcd_create(int device, void* cuda_stream, imrcd_ctx** out);
+void imrcd_destroy(imrcd_ctx* ctx);
+const char* imrcd_last_error(const imrcd_ctx* ctx);
+const char* imrcd_version(void);
+
+/* ---- meshes: replaces OBBtree::OBBtree(std::vector<Triangle>&&) (OBBtree.cpp:321) --------- */
+/* positions/normals: n_tri*9 floats (p0,p1,p2 per triangle; normals may be NULL -> face normals,
+ * Triangle.cpp:214-234); vertex_ids: n_tri*3 u32 (TriangleIndices, Triangle.cpp:242-250) or NULL. */
+int imrcd_mesh_create(imrcd_ctx* ctx, const float* positions, const float* normals, const uint32_t* vertex_ids,
+                      uint64_t n_tri, uint32_t build_mode, uint32_t* mesh_id);
+/* Test-only: upload a tree built elsewhere (flat pre-order form, see oracle/imr_oracle.h). */
+int imrcd_mesh_import_tree(imrcd_ctx* ctx, uint64_t n_vertices, const float* boxes, const int32_t* left, const int32_t* right,
+                           const uint32_t* tri_off, const uint32_t* tri_cnt, uint64_t n_tri, const float* tri_pos,
+                           const float* tri_nrm, const uint32_t* tri_vid, const uint32_t* tri_orig, uint32_t* mesh_id);
+int imrcd_mesh_info(imrcd_ctx* ctx, uint32_t mesh_id, uint64_t* n_tri, uint64_t* n_vertices);
+/* Read a tree back in the flat pre-order form (any pointer may be NULL). */
+int imrcd_mesh_export_tree(imrcd_ctx* ctx, uint32_t mesh_id, float* boxes, int32_t* left, int32_t* right,
+                           uint32_t* tri_off, uint32_t* tri_cnt, float* tri_pos, float* tri_nrm, uint32_t* tri_vid,
+                           uint32_t* tri_orig);
+/* device time of the last imrcd_mesh_create in ms */
+int imrcd_mesh_last_build_ms(imrcd_ctx* ctx, float* ms);
+
+/* ---- frame: Reset / AddCollisionDetectionEntry / ExecuteCollisionDetection -------------- */
+int imrcd_frame_reset(imrcd_ctx* ctx);
+int imrcd_frame_add_entry(imrcd_ctx* ctx, const float current[16], const float previous[16], uint32_t mesh_id,
+                          uint8_t should_callback, uint32_t entity);
+int imrcd_frame_add_entries(imrcd_ctx* ctx, uint64_t n, const float* current, const float* previous,
+                            const uint32_t* mesh_ids, const uint8_t* should_callback, const uint32_t* entities);
+/* Multi-GPU: this context keeps only the broad-phase pairs whose owner entry (the larger entry index)
+ * satisfies owner % n_ranks == rank.  Default (0,1) = everything. */
+int imrcd_frame_set_shard(imrcd_ctx* ctx, uint32_t rank, uint32_t n_ranks);
+/* ExecuteCollisionDetection() = upload + run + fetch.  The three steps are exposed so that a caller
+ * can time the device part with inputs already resident. */
+int imrcd_frame_execute(imrcd_ctx* ctx);
+int imrcd_frame_upload(imrcd_ctx* ctx);   /* host entries -> HBM (async on the stream) */
+int imrcd_frame_run(imrcd_ctx* ctx);      /* all kernels; returns after the stream has drained */
+int imrcd_frame_fetch(imrcd_ctx* ctx);    /* results -> pinned host memory */
+/* Results stay valid until the next imrcd_frame_reset / imrcd_frame_run. */
+int imrcd_frame_results(imrcd_ctx* ctx, const imrcd_entity_pair** pairs, uint64_t* n_pairs,
+                        const imrcd_tri_hit** hits, uint64_t* n_hits);
+/* Broad-phase pair list of this shard as (first,second) entry indices; host copy made on demand. */
+int imrcd_frame_pairs(imrcd_ctx* ctx, const uint32_t** pairs, uint64_t* n_pairs);
+/* Leaf combos (pair, offA, offB, cntA | cntB<<16) in leaf order; test/diagnostic, host copy on demand. */
+int imrcd_frame_combos(imrcd_ctx* ctx, const uint32_t** combos, uint64_t* n_combos);
+int imrcd_frame_get_stats(imrcd_ctx* ctx, imrcd_frame_stats* out);
+/* Device pointers of the result arrays (for an NCCL gather by the caller): hits, entity pairs. */
+int imrcd_frame_results_device(imrcd_ctx* ctx, void** d_pairs, uint64_t* n_pairs, void** d_hits, uint64_t* n_hits);
+
+/* ---- unit-level entry points used by the parity tests (device kernels on flat arrays) ---- */
+int imrcd_test_sat(imrcd_ctx* ctx, uint64_t n, const float* boxes_a, const float* boxes_b, const float* mats /* n*16 or NULL */,
+                   uint8_t* verdict, float* surface_a, float* surface_b);
+int imrcd_test_tri_tri(imrcd_ctx* ctx, uint64_t n, const float* tris_a, const float* tris_b, const float* mat16 /* or NULL */,
+                       uint8_t* flags, float* seg /* n*6 */);
+int imrcd_test_pair_matrix(imrcd_ctx* ctx, uint64_t n, const float* a, const float* b, float* out /* n*16 */);
+int imrcd_test_obb_fit(imrcd_ctx* ctx, uint64_t n_points, const float* points, float* out12);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IMRCD_H */

@@ -1,0 +1,496 @@
+// imrcd_api.cu -- the extern "C" surface of libimrcd.so (declared in include/imrcd.h): context,
+// mesh arena (import / export), frame entry list, upload / run / fetch, and the unit-level test hooks.
+#include "imrcd_internal.cuh"
+#include <algorithm>
+#include <cstring>
+#include <deque>
+
+static_assert(sizeof(imrcd_entity_pair) == 80, "imrcd_entity_pair layout");
+static_assert(sizeof(imrcd_tri_hit) == 40, "imrcd_tri_hit layout");
+static_assert(sizeof(TreeRec) == 64 && sizeof(TriRec) == 48 && sizeof(PairRec) == 64 && sizeof(SweepRec) == 32, "HBM layouts");
+
+#define CHECK_CTX(ctx) do { if (!(ctx)) return IMRCD_E_ARG; } while (0)
+
+extern "C" const char* imrcd_version(void) { return "imrcd 0.1 (sm_100a, fmad=false)"; }
+
+extern "C" const char* imrcd_last_error(const imrcd_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+extern "C" int imrcd_create(int device, void* cuda_stream, imrcd_ctx** out) {
+    if (!out) return IMRCD_E_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) return IMRCD_E_NODEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return IMRCD_E_NODEVICE;
+    if (prop.major != 10) return IMRCD_E_NODEVICE;       // the only code in this library is sm_100a SASS
+    if (cudaSetDevice(device) != cudaSuccess) return IMRCD_E_CUDA;
+    imrcd_ctx* ctx = new imrcd_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cuda_stream) { ctx->stream = static_cast<cudaStream_t>(cuda_stream); ctx->own_stream = false; }
+    else { if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return IMRCD_E_CUDA; } ctx->own_stream = true; }
+    for (auto& e : ctx->ev) if (cudaEventCreate(&e) != cudaSuccess) { delete ctx; return IMRCD_E_CUDA; }
+    *out = ctx;
+    return IMRCD_OK;
+}
+
+extern "C" void imrcd_destroy(imrcd_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf* bufs[] = { &ctx->d_recs, &ctx->d_tris, &ctx->d_tri_nrm, &ctx->d_tri_vid, &ctx->d_meshes, &ctx->d_cur, &ctx->d_prev, &ctx->d_mesh,
+                       &ctx->d_cb, &ctx->d_entity, &ctx->d_inv, &ctx->d_ext, &ctx->d_keys, &ctx->d_keys2, &ctx->d_idx, &ctx->d_idx2,
+                       &ctx->d_sorted, &ctx->d_cubtmp, &ctx->d_pairs, &ctx->d_pairrec, &ctx->d_pairacc, &ctx->d_queue, &ctx->d_combos,
+                       &ctx->d_hits, &ctx->d_epairs, &ctx->d_ctl };
+    for (DevBuf* b : bufs) b->release();
+    PinBuf* pins[] = { &ctx->p_stage, &ctx->p_ctl, &ctx->p_epairs, &ctx->p_hits, &ctx->p_pairs, &ctx->p_combos };
+    for (PinBuf* b : pins) b->release();
+    for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+// ------------------------------------------------------------------------------------------
+// meshes
+// ------------------------------------------------------------------------------------------
+__global__ void k_rec_surface(TreeRec* recs, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    TreeRec r = recs[i];
+    Box b;
+    b.c = mk3(r.q0.x, r.q0.y, r.q0.z); b.u = mk3(r.q0.w, r.q1.x, r.q1.y); b.v = mk3(r.q1.z, r.q1.w, r.q2.x); b.w = mk3(r.q2.y, r.q2.z, r.q2.w);
+    recs[i].q3.x = box_surface(b);
+}
+
+int imr_mesh_finalize_records(imrcd_ctx* ctx, uint32_t rec_base, uint32_t n_rec) {
+    if (n_rec == 0) return IMRCD_OK;
+    k_rec_surface<<<(n_rec + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_recs.as<TreeRec>() + rec_base, n_rec);
+    IMR_CUDA(ctx, cudaGetLastError());
+    return IMRCD_OK;
+}
+
+// reserve arena space for a mesh and register it; returns its id
+static int mesh_alloc(imrcd_ctx* ctx, uint64_t n_rec, uint64_t n_tri, MeshHost* mh) {
+    if (ctx->n_rec_total + n_rec >= (1ull << 32) || ctx->n_tri_total + n_tri >= (1ull << 32)) { ctx->err = "mesh arena exceeds 2^32 records"; return IMRCD_E_CAPACITY; }
+    cudaStream_t s = ctx->stream;
+    IMR_CUDA(ctx, ctx->d_recs.reserve(sizeof(TreeRec) * (ctx->n_rec_total + n_rec), sizeof(TreeRec) * ctx->n_rec_total, s));
+    IMR_CUDA(ctx, ctx->d_tris.reserve(sizeof(TriRec) * (ctx->n_tri_total + n_tri), sizeof(TriRec) * ctx->n_tri_total, s));
+    IMR_CUDA(ctx, ctx->d_tri_nrm.reserve(36ull * (ctx->n_tri_total + n_tri), 36ull * ctx->n_tri_total, s));
+    IMR_CUDA(ctx, ctx->d_tri_vid.reserve(12ull * (ctx->n_tri_total + n_tri), 12ull * ctx->n_tri_total, s));
+    mh->dev.rec_base = (uint32_t)ctx->n_rec_total; mh->dev.tri_base = (uint32_t)ctx->n_tri_total;
+    mh->dev.n_rec = (uint32_t)n_rec; mh->dev.n_tri = (uint32_t)n_tri;
+    ctx->n_rec_total += n_rec; ctx->n_tri_total += n_tri;
+    return IMRCD_OK;
+}
+
+static int mesh_register(imrcd_ctx* ctx, const MeshHost& mh, uint32_t* mesh_id) {
+    ctx->meshes.push_back(mh);
+    ctx->meshes_dirty = true;
+    *mesh_id = (uint32_t)(ctx->meshes.size() - 1);
+    return IMRCD_OK;
+}
+
+static int meshes_sync(imrcd_ctx* ctx) {
+    if (!ctx->meshes_dirty) return IMRCD_OK;
+    std::vector<MeshDev> tab(ctx->meshes.size());
+    for (size_t i = 0; i < tab.size(); ++i) tab[i] = ctx->meshes[i].dev;
+    IMR_CUDA(ctx, ctx->d_meshes.reserve(sizeof(MeshDev) * tab.size(), 0, ctx->stream));
+    IMR_CUDA(ctx, cudaMemcpyAsync(ctx->d_meshes.p, tab.data(), sizeof(MeshDev) * tab.size(), cudaMemcpyHostToDevice, ctx->stream));
+    IMR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->meshes_dirty = false;
+    return IMRCD_OK;
+}
+
+static inline float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+static inline uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+
+extern "C" int imrcd_mesh_import_tree(imrcd_ctx* ctx, uint64_t nv, const float* boxes, const int32_t* left, const int32_t* right,
+                                      const uint32_t* tri_off, const uint32_t* tri_cnt, uint64_t n_tri, const float* tri_pos,
+                                      const float* tri_nrm, const uint32_t* tri_vid, const uint32_t* tri_orig, uint32_t* mesh_id) {
+    CHECK_CTX(ctx);
+    if (!boxes || !left || !right || !tri_off || !tri_cnt || !mesh_id || nv == 0 || (n_tri && !tri_pos)) { ctx->err = "imrcd_mesh_import_tree: bad argument"; return IMRCD_E_ARG; }
+    cudaSetDevice(ctx->device);
+    // flat pre-order -> sibling-adjacent records: root at 0, slot 1 padding, children pairs from 2 on (BFS order)
+    std::vector<uint32_t> rec_of(nv, 0xffffffffu);
+    std::deque<uint32_t> bfs;
+    uint64_t next = 2;
+    rec_of[0] = 0; bfs.push_back(0);
+    while (!bfs.empty()) {
+        uint32_t v = bfs.front(); bfs.pop_front();
+        if (left[v] >= 0) {
+            if ((uint64_t)left[v] >= nv || (uint64_t)right[v] >= nv || right[v] < 0) { ctx->err = "imrcd_mesh_import_tree: child index out of range"; return IMRCD_E_ARG; }
+            rec_of[left[v]] = (uint32_t)next; rec_of[right[v]] = (uint32_t)(next + 1); next += 2;
+            bfs.push_back((uint32_t)left[v]); bfs.push_back((uint32_t)right[v]);
+        }
+    }
+    const uint64_t n_rec = next;
+    std::vector<TreeRec> recs(n_rec);
+    memset(recs.data(), 0, sizeof(TreeRec) * n_rec);
+    for (uint64_t v = 0; v < nv; ++v) {
+        if (rec_of[v] == 0xffffffffu) continue;    // unreachable vertex
+        const float* b = boxes + 12 * v;
+        TreeRec& r = recs[rec_of[v]];
+        r.q0 = make_float4(b[0], b[1], b[2], b[3]); r.q1 = make_float4(b[4], b[5], b[6], b[7]); r.q2 = make_float4(b[8], b[9], b[10], b[11]);
+        if (left[v] >= 0) r.q3 = make_float4(0.f, u2f(rec_of[left[v]]), u2f(0u), u2f(0u));
+        else {
+            if ((uint64_t)tri_off[v] + tri_cnt[v] > n_tri || tri_cnt[v] > 4) { ctx->err = "imrcd_mesh_import_tree: bad leaf range (leaves hold <= 4 triangles, OBBtree.h:49)"; return IMRCD_E_ARG; }
+            r.q3 = make_float4(0.f, u2f(tri_off[v]), u2f(tri_cnt[v]), u2f(1u));
+        }
+    }
+    std::vector<TriRec> tris(n_tri ? n_tri : 1);
+    std::vector<float> nrm(9 * (n_tri ? n_tri : 1), 0.f);
+    std::vector<uint32_t> vid(3 * (n_tri ? n_tri : 1), 0u);
+    for (uint64_t i = 0; i < n_tri; ++i) {
+        const float* p = tri_pos + 9 * i;
+        tris[i].t0 = make_float4(p[0], p[1], p[2], u2f(tri_orig ? tri_orig[i] : (uint32_t)i));
+        tris[i].t1 = make_float4(p[3], p[4], p[5], 0.f);
+        tris[i].t2 = make_float4(p[6], p[7], p[8], 0.f);
+        if (tri_nrm) memcpy(&nrm[9 * i], tri_nrm + 9 * i, 36);
+        for (int k = 0; k < 3; ++k) vid[3 * i + k] = tri_vid ? tri_vid[3 * i + k] : (uint32_t)(3 * i + k);
+    }
+    MeshHost mh;
+    int rc = mesh_alloc(ctx, n_rec, n_tri, &mh);
+    if (rc) return rc;
+    memcpy(mh.root_box, boxes, 48);
+    cudaStream_t s = ctx->stream;
+    IMR_CUDA(ctx, cudaMemcpyAsync(ctx->d_recs.as<TreeRec>() + mh.dev.rec_base, recs.data(), sizeof(TreeRec) * n_rec, cudaMemcpyHostToDevice, s));
+    if (n_tri) {
+        IMR_CUDA(ctx, cudaMemcpyAsync(ctx->d_tris.as<TriRec>() + mh.dev.tri_base, tris.data(), sizeof(TriRec) * n_tri, cudaMemcpyHostToDevice, s));
+        IMR_CUDA(ctx, cudaMemcpyAsync(ctx->d_tri_nrm.as<float>() + 9ull * mh.dev.tri_base, nrm.data(), 36ull * n_tri, cudaMemcpyHostToDevice, s));
+        IMR_CUDA(ctx, cudaMemcpyAsync(ctx->d_tri_vid.as<uint32_t>() + 3ull * mh.dev.tri_base, vid.data(), 12ull * n_tri, cudaMemcpyHostToDevice, s));
+    }
+    rc = imr_mesh_finalize_records(ctx, mh.dev.rec_base, mh.dev.n_rec);
+    if (rc) return rc;
+    IMR_CUDA(ctx, cudaStreamSynchronize(s));
+    return mesh_register(ctx, mh, mesh_id);
+}
+
+extern "C" int imrcd_mesh_create(imrcd_ctx* ctx, const float* positions, const float* normals, const uint32_t* vertex_ids,
+                                 uint64_t n_tri, uint32_t build_mode, uint32_t* mesh_id) {
+    CHECK_CTX(ctx);
+    if (!mesh_id || (n_tri && !positions)) { ctx->err = "imrcd_mesh_create: bad argument"; return IMRCD_E_ARG; }
+    cudaSetDevice(ctx->device);
+    MeshHost mh;
+    int rc = imr_build_mesh_device(ctx, positions, normals, vertex_ids, n_tri, build_mode, &mh);
+    if (rc) return rc;
+    ctx->last_build_ms = mh.build_ms;
+    return mesh_register(ctx, mh, mesh_id);
+}
+
+extern "C" int imrcd_mesh_last_build_ms(imrcd_ctx* ctx, float* ms) { CHECK_CTX(ctx); if (ms) *ms = ctx->last_build_ms; return IMRCD_OK; }
+
+// used by imr_build_mesh_device
+int imr_mesh_arena_alloc(imrcd_ctx* ctx, uint64_t n_rec, uint64_t n_tri, MeshHost* mh) { return mesh_alloc(ctx, n_rec, n_tri, mh); }
+
+extern "C" int imrcd_mesh_info(imrcd_ctx* ctx, uint32_t mesh_id, uint64_t* n_tri, uint64_t* n_vertices) {
+    CHECK_CTX(ctx);
+    if (mesh_id >= ctx->meshes.size()) { ctx->err = "bad mesh id"; return IMRCD_E_ARG; }
+    const MeshDev& m = ctx->meshes[mesh_id].dev;
+    if (n_tri) *n_tri = m.n_tri;
+    if (n_vertices) *n_vertices = m.n_rec >= 2 ? m.n_rec - 1 : 1;   // slot 1 is padding
+    return IMRCD_OK;
+}
+
+extern "C" int imrcd_mesh_export_tree(imrcd_ctx* ctx, uint32_t mesh_id, float* boxes, int32_t* left, int32_t* right,
+                                      uint32_t* tri_off, uint32_t* tri_cnt, float* tri_pos, float* tri_nrm, uint32_t* tri_vid,
+                                      uint32_t* tri_orig) {
+    CHECK_CTX(ctx);
+    if (mesh_id >= ctx->meshes.size()) { ctx->err = "bad mesh id"; return IMRCD_E_ARG; }
+    cudaSetDevice(ctx->device);
+    const MeshDev m = ctx->meshes[mesh_id].dev;
+    std::vector<TreeRec> recs(m.n_rec);
+    std::vector<TriRec> tris(m.n_tri ? m.n_tri : 1);
+    cudaStream_t s = ctx->stream;
+    IMR_CUDA(ctx, cudaMemcpyAsync(recs.data(), ctx->d_recs.as<TreeRec>() + m.rec_base, sizeof(TreeRec) * m.n_rec, cudaMemcpyDeviceToHost, s));
+    if (m.n_tri) IMR_CUDA(ctx, cudaMemcpyAsync(tris.data(), ctx->d_tris.as<TriRec>() + m.tri_base, sizeof(TriRec) * m.n_tri, cudaMemcpyDeviceToHost, s));
+    if (tri_nrm && m.n_tri) IMR_CUDA(ctx, cudaMemcpyAsync(tri_nrm, ctx->d_tri_nrm.as<float>() + 9ull * m.tri_base, 36ull * m.n_tri, cudaMemcpyDeviceToHost, s));
+    if (tri_vid && m.n_tri) IMR_CUDA(ctx, cudaMemcpyAsync(tri_vid, ctx->d_tri_vid.as<uint32_t>() + 3ull * m.tri_base, 12ull * m.n_tri, cudaMemcpyDeviceToHost, s));
+    IMR_CUDA(ctx, cudaStreamSynchronize(s));
+    // iterative pre-order walk (left first) over the sibling-adjacent layout
+    struct Fr { uint32_t rec; int32_t parent; bool is_right; };
+    std::vector<Fr> stack; stack.push_back({0u, -1, false});
+    uint64_t nvx = 0;
+    while (!stack.empty()) {
+        Fr f = stack.back(); stack.pop_back();
+        const TreeRec& r = recs[f.rec];
+        uint64_t me = nvx++;
+        if (boxes) { float* b = boxes + 12 * me; b[0] = r.q0.x; b[1] = r.q0.y; b[2] = r.q0.z; b[3] = r.q0.w; b[4] = r.q1.x; b[5] = r.q1.y; b[6] = r.q1.z; b[7] = r.q1.w; b[8] = r.q2.x; b[9] = r.q2.y; b[10] = r.q2.z; b[11] = r.q2.w; }
+        if (f.parent >= 0) { if (f.is_right) { if (right) right[f.parent] = (int32_t)me; } else { if (left) left[f.parent] = (int32_t)me; } }
+        const bool leaf = f2u(r.q3.w) != 0u;
+        if (leaf) {
+            if (left) left[me] = -1; if (right) right[me] = -1;
+            if (tri_off) tri_off[me] = f2u(r.q3.y); if (tri_cnt) tri_cnt[me] = f2u(r.q3.z);
+        } else {
+            if (tri_off) tri_off[me] = 0; if (tri_cnt) tri_cnt[me] = 0;
+            uint32_t c = f2u(r.q3.y);
+            stack.push_back({c + 1u, (int32_t)me, true});
+            stack.push_back({c, (int32_t)me, false});
+        }
+    }
+    for (uint64_t i = 0; i < m.n_tri; ++i) {
+        if (tri_pos) { float* p = tri_pos + 9 * i; p[0] = tris[i].t0.x; p[1] = tris[i].t0.y; p[2] = tris[i].t0.z; p[3] = tris[i].t1.x; p[4] = tris[i].t1.y; p[5] = tris[i].t1.z; p[6] = tris[i].t2.x; p[7] = tris[i].t2.y; p[8] = tris[i].t2.z; }
+        if (tri_orig) tri_orig[i] = f2u(tris[i].t0.w);
+    }
+    return IMRCD_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// frame
+// ------------------------------------------------------------------------------------------
+extern "C" int imrcd_frame_reset(imrcd_ctx* ctx) {
+    CHECK_CTX(ctx);
+    ctx->h_cur.clear(); ctx->h_prev.clear(); ctx->h_mesh.clear(); ctx->h_cb.clear(); ctx->h_entity.clear();
+    ctx->uploaded = ctx->ran = ctx->fetched = false;
+    return IMRCD_OK;
+}
+
+extern "C" int imrcd_frame_add_entries(imrcd_ctx* ctx, uint64_t n, const float* current, const float* previous,
+                                       const uint32_t* mesh_ids, const uint8_t* should_callback, const uint32_t* entities) {
+    CHECK_CTX(ctx);
+    if (n && (!current || !mesh_ids)) { ctx->err = "imrcd_frame_add_entries: bad argument"; return IMRCD_E_ARG; }
+    for (uint64_t i = 0; i < n; ++i) if (mesh_ids[i] >= ctx->meshes.size()) { ctx->err = "imrcd_frame_add_entries: unknown mesh id"; return IMRCD_E_ARG; }
+    if (ctx->h_mesh.size() + n >= (1ull << 32) - 1) { ctx->err = "too many entries"; return IMRCD_E_ARG; }
+    ctx->h_cur.insert(ctx->h_cur.end(), current, current + 16 * n);
+    const float* prev = previous ? previous : current;
+    ctx->h_prev.insert(ctx->h_prev.end(), prev, prev + 16 * n);
+    ctx->h_mesh.insert(ctx->h_mesh.end(), mesh_ids, mesh_ids + n);
+    for (uint64_t i = 0; i < n; ++i) {
+        ctx->h_cb.push_back(should_callback ? (should_callback[i] ? 1 : 0) : 1);
+        ctx->h_entity.push_back(entities ? entities[i] : (uint32_t)(ctx->h_entity.size()));
+    }
+    ctx->uploaded = ctx->ran = ctx->fetched = false;
+    return IMRCD_OK;
+}
+
+extern "C" int imrcd_frame_add_entry(imrcd_ctx* ctx, const float current[16], const float previous[16], uint32_t mesh_id,
+                                     uint8_t should_callback, uint32_t entity) {
+    return imrcd_frame_add_entries(ctx, 1, current, previous, &mesh_id, &should_callback, &entity);
+}
+
+extern "C" int imrcd_frame_set_shard(imrcd_ctx* ctx, uint32_t rank, uint32_t n_ranks) {
+    CHECK_CTX(ctx);
+    if (n_ranks == 0 || rank >= n_ranks) { ctx->err = "imrcd_frame_set_shard: bad rank"; return IMRCD_E_ARG; }
+    ctx->shard_rank = rank; ctx->shard_n = n_ranks;
+    return IMRCD_OK;
+}
+
+extern "C" int imrcd_frame_upload(imrcd_ctx* ctx) {
+    CHECK_CTX(ctx);
+    cudaSetDevice(ctx->device);
+    int rc = meshes_sync(ctx);
+    if (rc) return rc;
+    const size_t n = ctx->h_mesh.size();
+    cudaStream_t s = ctx->stream;
+    if (n) {
+        // one pinned staging block: cur | prev | mesh | entity | cb
+        const size_t b_cur = 64 * n, b_mesh = 4 * n, b_cb = n;
+        IMR_CUDA(ctx, ctx->p_stage.reserve(2 * b_cur + 2 * b_mesh + b_cb));
+        char* st = ctx->p_stage.as<char>();
+        memcpy(st, ctx->h_cur.data(), b_cur);
+        memcpy(st + b_cur, ctx->h_prev.data(), b_cur);
+        memcpy(st + 2 * b_cur, ctx->h_mesh.data(), b_mesh);
+        memcpy(st + 2 * b_cur + b_mesh, ctx->h_entity.data(), b_mesh);
+        memcpy(st + 2 * b_cur + 2 * b_mesh, ctx->h_cb.data(), b_cb);
+        IMR_CUDA(ctx, ctx->d_cur.reserve(b_cur, 0, s));
+        IMR_CUDA(ctx, ctx->d_prev.reserve(b_cur, 0, s));
+        IMR_CUDA(ctx, ctx->d_mesh.reserve(b_mesh, 0, s));
+        IMR_CUDA(ctx, ctx->d_entity.reserve(b_mesh, 0, s));
+        IMR_CUDA(ctx, ctx->d_cb.reserve(b_cb, 0, s));
+        IMR_CUDA(ctx, cudaMemcpyAsync(ctx->d_cur.p, st, b_cur, cudaMemcpyHostToDevice, s));
+        IMR_CUDA(ctx, cudaMemcpyAsync(ctx->d_prev.p, st + b_cur, b_cur, cudaMemcpyHostToDevice, s));
+        IMR_CUDA(ctx, cudaMemcpyAsync(ctx->d_mesh.p, st + 2 * b_cur, b_mesh, cudaMemcpyHostToDevice, s));
+        IMR_CUDA(ctx, cudaMemcpyAsync(ctx->d_entity.p, st + 2 * b_cur + b_mesh, b_mesh, cudaMemcpyHostToDevice, s));
+        IMR_CUDA(ctx, cudaMemcpyAsync(ctx->d_cb.p, st + 2 * b_cur + 2 * b_mesh, b_cb, cudaMemcpyHostToDevice, s));
+    }
+    ctx->uploaded = true; ctx->ran = ctx->fetched = false;
+    return IMRCD_OK;
+}
+
+extern "C" int imrcd_frame_run(imrcd_ctx* ctx) {
+    CHECK_CTX(ctx);
+    if (!ctx->uploaded) { ctx->err = "imrcd_frame_run before imrcd_frame_upload"; return IMRCD_E_STATE; }
+    cudaSetDevice(ctx->device);
+    int rc = imr_frame_run_device(ctx);
+    if (rc) return rc;
+    ctx->ran = true; ctx->fetched = false;
+    return IMRCD_OK;
+}
+
+extern "C" int imrcd_frame_fetch(imrcd_ctx* ctx) {
+    CHECK_CTX(ctx);
+    if (!ctx->ran) { ctx->err = "imrcd_frame_fetch before imrcd_frame_run"; return IMRCD_E_STATE; }
+    cudaSetDevice(ctx->device);
+    const uint64_t nc = ctx->ctl_host.n_colliding;
+    if (nc) {
+        IMR_CUDA(ctx, ctx->p_epairs.reserve(sizeof(imrcd_entity_pair) * nc));
+        IMR_CUDA(ctx, cudaMemcpyAsync(ctx->p_epairs.p, ctx->d_epairs.p, sizeof(imrcd_entity_pair) * nc, cudaMemcpyDeviceToHost, ctx->stream));
+        IMR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->fetched = true;
+    return IMRCD_OK;
+}
+
+extern "C" int imrcd_frame_execute(imrcd_ctx* ctx) {
+    int rc = imrcd_frame_upload(ctx); if (rc) return rc;
+    rc = imrcd_frame_run(ctx); if (rc) return rc;
+    return imrcd_frame_fetch(ctx);
+}
+
+extern "C" int imrcd_frame_results(imrcd_ctx* ctx, const imrcd_entity_pair** pairs, uint64_t* n_pairs,
+                                   const imrcd_tri_hit** hits, uint64_t* n_hits) {
+    CHECK_CTX(ctx);
+    if (!ctx->fetched) { ctx->err = "imrcd_frame_results before imrcd_frame_fetch/execute"; return IMRCD_E_STATE; }
+    if (pairs) *pairs = ctx->p_epairs.as<imrcd_entity_pair>();
+    if (n_pairs) *n_pairs = ctx->ctl_host.n_colliding;
+    if (hits) {   // the hit list is an intermediate of the contact reduction; copied to the host only on demand
+        const uint64_t nh = ctx->ctl_host.n_hits;
+        if (!ctx->hits_fetched && nh) {
+            cudaSetDevice(ctx->device);
+            IMR_CUDA(ctx, ctx->p_hits.reserve(sizeof(imrcd_tri_hit) * nh));
+            IMR_CUDA(ctx, cudaMemcpyAsync(ctx->p_hits.p, ctx->d_hits.p, sizeof(imrcd_tri_hit) * nh, cudaMemcpyDeviceToHost, ctx->stream));
+            IMR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            ctx->hits_fetched = true;
+        }
+        *hits = ctx->p_hits.as<imrcd_tri_hit>();
+    }
+    if (n_hits) *n_hits = ctx->ctl_host.n_hits;
+    return IMRCD_OK;
+}
+
+extern "C" int imrcd_frame_pairs(imrcd_ctx* ctx, const uint32_t** pairs, uint64_t* n_pairs) {
+    CHECK_CTX(ctx);
+    if (!ctx->ran) { ctx->err = "imrcd_frame_pairs before imrcd_frame_run"; return IMRCD_E_STATE; }
+    const uint64_t n = ctx->ctl_host.n_pairs;
+    if (n) {
+        cudaSetDevice(ctx->device);
+        IMR_CUDA(ctx, ctx->p_pairs.reserve(8 * n));
+        IMR_CUDA(ctx, cudaMemcpyAsync(ctx->p_pairs.p, ctx->d_pairs.p, 8 * n, cudaMemcpyDeviceToHost, ctx->stream));
+        IMR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    if (pairs) *pairs = ctx->p_pairs.as<uint32_t>();
+    if (n_pairs) *n_pairs = n;
+    return IMRCD_OK;
+}
+
+extern "C" int imrcd_frame_combos(imrcd_ctx* ctx, const uint32_t** combos, uint64_t* n_combos) {
+    CHECK_CTX(ctx);
+    if (!ctx->ran) { ctx->err = "imrcd_frame_combos before imrcd_frame_run"; return IMRCD_E_STATE; }
+    const uint64_t n = ctx->ctl_host.n_combos;
+    if (n) {
+        cudaSetDevice(ctx->device);
+        IMR_CUDA(ctx, ctx->p_combos.reserve(16 * n));
+        IMR_CUDA(ctx, cudaMemcpyAsync(ctx->p_combos.p, ctx->d_combos.p, 16 * n, cudaMemcpyDeviceToHost, ctx->stream));
+        IMR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    if (combos) *combos = ctx->p_combos.as<uint32_t>();
+    if (n_combos) *n_combos = n;
+    return IMRCD_OK;
+}
+
+extern "C" int imrcd_frame_get_stats(imrcd_ctx* ctx, imrcd_frame_stats* out) {
+    CHECK_CTX(ctx);
+    if (!out) return IMRCD_E_ARG;
+    *out = ctx->stats;
+    return IMRCD_OK;
+}
+
+extern "C" int imrcd_frame_results_device(imrcd_ctx* ctx, void** d_pairs, uint64_t* n_pairs, void** d_hits, uint64_t* n_hits) {
+    CHECK_CTX(ctx);
+    if (!ctx->ran) { ctx->err = "imrcd_frame_results_device before imrcd_frame_run"; return IMRCD_E_STATE; }
+    if (d_pairs) *d_pairs = ctx->d_epairs.p;
+    if (n_pairs) *n_pairs = ctx->ctl_host.n_colliding;
+    if (d_hits) *d_hits = ctx->d_hits.p;
+    if (n_hits) *n_hits = ctx->ctl_host.n_hits;
+    return IMRCD_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// unit-level test hooks: the same device functions the pipeline uses, on flat arrays
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ Box load_box12(const float* f) {
+    Box b; b.c = mk3(f[0], f[1], f[2]); b.u = mk3(f[3], f[4], f[5]); b.v = mk3(f[6], f[7], f[8]); b.w = mk3(f[9], f[10], f[11]); return b;
+}
+__device__ __forceinline__ Rel load_rel16(const float* m) {
+    Rel r; r.r0 = make_float4(m[0], m[4], m[8], m[12]); r.r1 = make_float4(m[1], m[5], m[9], m[13]); r.r2 = make_float4(m[2], m[6], m[10], m[14]); return r;
+}
+__global__ void k_test_sat(uint64_t n, const float* a, const float* b, const float* mats, uint8_t* verdict, float* sa, float* sb) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Box A = load_box12(a + 12 * i), B = load_box12(b + 12 * i);
+    if (mats) B = box_transform(load_rel16(mats + 16 * i), B);
+    verdict[i] = box_sat(A, B) ? 1 : 0;
+    if (sa) sa[i] = box_surface(A);
+    if (sb) sb[i] = box_surface(B);
+}
+__global__ void k_test_tri(uint64_t n, const float* a, const float* b, const float* mat, uint8_t* flags, float* seg) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* p = a + 9 * i; const float* q = b + 9 * i;
+    V3 V0 = mk3(p[0], p[1], p[2]), V1 = mk3(p[3], p[4], p[5]), V2 = mk3(p[6], p[7], p[8]);
+    V3 U0 = mk3(q[0], q[1], q[2]), U1 = mk3(q[3], q[4], q[5]), U2 = mk3(q[6], q[7], q[8]);
+    if (mat) { Rel r = load_rel16(mat); U0 = rel_mul(r, U0, 1.f); U1 = rel_mul(r, U1, 1.f); U2 = rel_mul(r, U2, 1.f); }
+    V3 s = mk3(0, 0, 0), t = mk3(0, 0, 0);
+    int f = tri_tri_isectline(V0, V1, V2, U0, U1, U2, s, t);
+    flags[i] = (uint8_t)f;    // bit0 doIntersept, bit1 areCoplanar
+    if (f == 1) { float* o = seg + 6 * i; o[0] = s.x; o[1] = s.y; o[2] = s.z; o[3] = t.x; o[4] = t.y; o[5] = t.z; }
+}
+__global__ void k_test_pair_matrix(uint64_t n, const float* a, const float* b, float* out) {
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float inv[16];
+    mat4_inverse(a + 16 * i, inv);
+    mat4_mul(inv, b + 16 * i, out + 16 * i);
+}
+
+template <class F>
+static int with_device_arrays(imrcd_ctx* ctx, std::vector<std::pair<const void*, size_t>> ins, std::vector<std::pair<void*, size_t>> outs, F launch) {
+    cudaSetDevice(ctx->device);
+    std::vector<void*> din(ins.size(), nullptr), dout(outs.size(), nullptr);
+    int rc = IMRCD_OK;
+    auto cleanup = [&]() { for (void* p : din) if (p) cudaFree(p); for (void* p : dout) if (p) cudaFree(p); };
+    for (size_t i = 0; i < ins.size(); ++i) {
+        if (!ins[i].first || !ins[i].second) continue;
+        if (cudaMalloc(&din[i], ins[i].second) != cudaSuccess || cudaMemcpyAsync(din[i], ins[i].first, ins[i].second, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { ctx->err = "test hook: alloc/copy failed"; cleanup(); return IMRCD_E_CUDA; }
+    }
+    for (size_t i = 0; i < outs.size(); ++i) {
+        if (!outs[i].first || !outs[i].second) continue;
+        if (cudaMalloc(&dout[i], outs[i].second) != cudaSuccess || cudaMemsetAsync(dout[i], 0, outs[i].second, ctx->stream) != cudaSuccess) { ctx->err = "test hook: alloc failed"; cleanup(); return IMRCD_E_CUDA; }
+    }
+    launch(din, dout);
+    if (cudaGetLastError() != cudaSuccess) { ctx->err = "test hook: launch failed"; rc = IMRCD_E_CUDA; }
+    for (size_t i = 0; i < outs.size() && rc == IMRCD_OK; ++i)
+        if (dout[i] && cudaMemcpyAsync(outs[i].first, dout[i], outs[i].second, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) { ctx->err = "test hook: copy back failed"; rc = IMRCD_E_CUDA; }
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { ctx->err = std::string("test hook: ") + cudaGetErrorString(cudaGetLastError()); rc = IMRCD_E_CUDA; }
+    cleanup();
+    return rc;
+}
+
+extern "C" int imrcd_test_sat(imrcd_ctx* ctx, uint64_t n, const float* boxes_a, const float* boxes_b, const float* mats,
+                              uint8_t* verdict, float* surface_a, float* surface_b) {
+    CHECK_CTX(ctx);
+    if (!n) return IMRCD_OK;
+    return with_device_arrays(ctx, { {boxes_a, 48 * n}, {boxes_b, 48 * n}, {mats, mats ? 64 * n : 0} },
+                              { {verdict, n}, {surface_a, surface_a ? 4 * n : 0}, {surface_b, surface_b ? 4 * n : 0} },
+                              [&](std::vector<void*>& i, std::vector<void*>& o) {
+                                  k_test_sat<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(n, (const float*)i[0], (const float*)i[1], (const float*)i[2],
+                                                                                                   (uint8_t*)o[0], (float*)o[1], (float*)o[2]);
+                              });
+}
+extern "C" int imrcd_test_tri_tri(imrcd_ctx* ctx, uint64_t n, const float* tris_a, const float* tris_b, const float* mat16,
+                                  uint8_t* flags, float* seg) {
+    CHECK_CTX(ctx);
+    if (!n) return IMRCD_OK;
+    return with_device_arrays(ctx, { {tris_a, 36 * n}, {tris_b, 36 * n}, {mat16, mat16 ? 64 : 0} }, { {flags, n}, {seg, 24 * n} },
+                              [&](std::vector<void*>& i, std::vector<void*>& o) {
+                                  k_test_tri<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(n, (const float*)i[0], (const float*)i[1], (const float*)i[2],
+                                                                                                   (uint8_t*)o[0], (float*)o[1]);
+                              });
+}
+extern "C" int imrcd_test_pair_matrix(imrcd_ctx* ctx, uint64_t n, const float* a, const float* b, float* out) {
+    CHECK_CTX(ctx);
+    if (!n) return IMRCD_OK;
+    return with_device_arrays(ctx, { {a, 64 * n}, {b, 64 * n} }, { {out, 64 * n} },
+                              [&](std::vector<void*>& i, std::vector<void*>& o) {
+                                  k_test_pair_matrix<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(n, (const float*)i[0], (const float*)i[1], (float*)o[0]);
+                              });
+}

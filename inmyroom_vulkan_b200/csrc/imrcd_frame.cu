@@ -1,0 +1,572 @@
+// imrcd_frame.cu -- the per-frame collision pipeline on the device:
+//   broad  : k_entry_prep -> radix sort on U-min -> k_sweep           (SweepAndPrune.cpp:15-88)
+//   setup  : k_pair_setup  rel = inverse(first.M) * second.M           (OBBtreesCollision.cpp:15)
+//   mid    : k_traverse    persistent work-queue dual-tree descent     (OBBtree.cpp:396-477, Paralgram.cpp:17-173)
+//   narrow : k_tritri      leaf x leaf triangle tests                  (CreateUncollideRays.cpp:74-115, Triangle.cpp:866-1002)
+//   reduce : k_finalize    colliding entity pairs                      (CollisionDetection.cpp:60-67)
+#include "imrcd_internal.cuh"
+#include <cub/device/device_radix_sort.cuh>
+#include <algorithm>
+#include <cstring>
+
+#define FULL_MASK 0xffffffffu
+
+// ------------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) { return *((const volatile unsigned long long*)p); }
+__device__ __forceinline__ long long ld_volatile_s64(const long long* p) { return *((const volatile long long*)p); }
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+
+__device__ __forceinline__ Box unpack_box(const float4& q0, const float4& q1, const float4& q2) {
+    Box b;
+    b.c = mk3(q0.x, q0.y, q0.z); b.u = mk3(q0.w, q1.x, q1.y); b.v = mk3(q1.z, q1.w, q2.x); b.w = mk3(q2.y, q2.z, q2.w);
+    return b;
+}
+__device__ __forceinline__ Rel rel_from_mat(const float* m) {   // rows of a column-major mat4
+    Rel r;
+    r.r0 = make_float4(m[0], m[4], m[8], m[12]);
+    r.r1 = make_float4(m[1], m[5], m[9], m[13]);
+    r.r2 = make_float4(m[2], m[6], m[10], m[14]);
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------
+// broad phase
+// ------------------------------------------------------------------------------------------
+// One thread per entry: world-space root box (SweepAndPrune.cpp:23), its extents on the three fixed
+// sweep axes (Paralgram.cpp:175-190), the sort key, and inverse(M) for the pair stage.
+__global__ void k_entry_prep(uint32_t n, const float* __restrict__ cur, const uint32_t* __restrict__ mesh_id,
+                             const MeshDev* __restrict__ meshes, const TreeRec* __restrict__ recs,
+                             float* __restrict__ inv_out, float* __restrict__ ext_out,
+                             uint32_t* __restrict__ keys, uint32_t* __restrict__ idx) {
+    uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    float m[16];
+    const float4* mp = reinterpret_cast<const float4*>(cur + 16 * (size_t)e);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { float4 v = mp[k]; m[4 * k] = v.x; m[4 * k + 1] = v.y; m[4 * k + 2] = v.z; m[4 * k + 3] = v.w; }
+    const TreeRec& root = recs[meshes[mesh_id[e]].rec_base];
+    Box b = box_transform(rel_from_mat(m), unpack_box(root.q0, root.q1, root.q2));
+    V3 U, V, W; sweep_axes(U, V, W);
+    float mn, mx;
+    float* eo = ext_out + 6 * (size_t)e;
+    box_minmax(b, U, mn, mx); eo[0] = mn; eo[1] = mx;
+    keys[e] = float_orderable(mn + 0.0f);   // -0 -> +0 so equal floats get equal keys; ties then keep entry order (stable sort)
+    idx[e] = e;
+    box_minmax(b, V, mn, mx); eo[2] = mn; eo[3] = mx;
+    box_minmax(b, W, mn, mx); eo[4] = mn; eo[5] = mx;
+    float inv[16];
+    mat4_inverse(m, inv);
+    float4* ip = reinterpret_cast<float4*>(inv_out + 16 * (size_t)e);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) ip[k] = make_float4(inv[4 * k], inv[4 * k + 1], inv[4 * k + 2], inv[4 * k + 3]);
+}
+
+__global__ void k_gather_sorted(uint32_t n, const uint32_t* __restrict__ sorted_idx, const float* __restrict__ ext,
+                                const uint8_t* __restrict__ cb, SweepRec* __restrict__ out) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    uint32_t e = sorted_idx[p];
+    const float* eo = ext + 6 * (size_t)e;
+    SweepRec r;
+    r.umin = eo[0]; r.umax = eo[1]; r.vmin = eo[2]; r.vmax = eo[3]; r.wmin = eo[4]; r.wmax = eo[5];
+    r.idx = e; r.cb = cb[e];
+    out[p] = r;
+}
+
+// One warp per sorted position p ("active" element a); lanes stride the forward window of entries whose
+// U interval starts no later than a's ends.  The reference's active-list sweep reports (a,e) on an axis
+// iff a precedes e in min-order and NOT (a.max < e.min) (SweepAndPrune.cpp:58); a pair survives iff that
+// holds on U, V and W and either side has shouldCallback (:60,84).  Orientation = U order (:63).
+__global__ void k_sweep(uint32_t n, const SweepRec* __restrict__ sorted, uint2* __restrict__ pairs, unsigned long long cap,
+                        FrameCtl* ctl, uint32_t rank, uint32_t n_ranks) {
+    const uint32_t lane = lane_id();
+    const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; p < n; p += warps_total) {
+        const SweepRec a = sorted[p];
+        for (uint32_t q0 = p + 1; q0 < n; q0 += 32) {
+            uint32_t q = q0 + lane;
+            bool in_window = false, emit = false;
+            SweepRec e;
+            if (q < n) {
+                e = sorted[q];
+                in_window = !(a.umax < e.umin);
+                if (in_window && (a.cb | e.cb)) {
+                    bool v_ok = (a.vmin <= e.vmin) ? !(a.vmax < e.vmin) : !(e.vmax < a.vmin);
+                    bool w_ok = (a.wmin <= e.wmin) ? !(a.wmax < e.wmin) : !(e.wmax < a.wmin);
+                    uint32_t owner = a.idx > e.idx ? a.idx : e.idx;
+                    emit = v_ok && w_ok && (owner % n_ranks == rank);
+                }
+            }
+            uint32_t m = __ballot_sync(FULL_MASK, emit);
+            if (m) {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(&ctl->n_pairs, (unsigned long long)__popc(m));
+                base = __shfl_sync(FULL_MASK, base, 0);
+                if (emit) {
+                    unsigned long long slot = base + __popc(m & ((1u << lane) - 1));
+                    if (slot < cap) pairs[slot] = make_uint2(a.idx, e.idx);
+                    else atomicOr(&ctl->overflow, (unsigned)OVF_PAIRS);
+                }
+            }
+            if (!__all_sync(FULL_MASK, in_window)) break;   // window is contiguous in U-min order
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// pair setup
+// ------------------------------------------------------------------------------------------
+struct PairAcc { uint32_t n_hits; uint32_t flags; };
+
+__global__ void k_queue_init(FrameCtl* ctl, unsigned long long cap_pairs, unsigned long long cap_queue) {
+    unsigned long long n = ctl->n_pairs < cap_pairs ? ctl->n_pairs : cap_pairs;
+    if (n > cap_queue) { n = cap_queue; atomicOr(&ctl->overflow, (unsigned)OVF_QUEUE); }
+    ctl->q_head = 0; ctl->q_tail = n; ctl->pending = (long long)n;
+}
+
+// One thread per pair: rel = glm::inverse(first.M) * second.M (OBBtreesCollision.cpp:15), the bases of the
+// two meshes, the pair's accumulators, and the root work item (root_obb vs root_obb, OBBtree.cpp:396-411).
+__global__ void k_pair_setup(const FrameCtl* ctl, unsigned long long cap_pairs, const uint2* __restrict__ pairs,
+                             const float* __restrict__ cur, const float* __restrict__ inv, const uint32_t* __restrict__ mesh_id,
+                             const MeshDev* __restrict__ meshes, PairRec* __restrict__ pairrec, PairAcc* __restrict__ acc,
+                             WorkItem* __restrict__ queue, unsigned long long cap_queue) {
+    unsigned long long n = ctl->n_pairs < cap_pairs ? ctl->n_pairs : cap_pairs;
+    for (unsigned long long p = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; p < n; p += (unsigned long long)gridDim.x * blockDim.x) {
+        uint2 pr = pairs[p];
+        float a[16], b[16], r[16];
+        const float4* ap = reinterpret_cast<const float4*>(inv + 16 * (size_t)pr.x);
+        const float4* bp = reinterpret_cast<const float4*>(cur + 16 * (size_t)pr.y);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float4 v = ap[k]; a[4 * k] = v.x; a[4 * k + 1] = v.y; a[4 * k + 2] = v.z; a[4 * k + 3] = v.w;
+            float4 w = bp[k]; b[4 * k] = w.x; b[4 * k + 1] = w.y; b[4 * k + 2] = w.z; b[4 * k + 3] = w.w;
+        }
+        mat4_mul(a, b, r);
+        MeshDev ma = meshes[mesh_id[pr.x]], mb = meshes[mesh_id[pr.y]];
+        PairRec o;
+        o.r0 = make_float4(r[0], r[4], r[8], r[12]);
+        o.r1 = make_float4(r[1], r[5], r[9], r[13]);
+        o.r2 = make_float4(r[2], r[6], r[10], r[14]);
+        o.recA = ma.rec_base; o.recB = mb.rec_base; o.triA = ma.tri_base; o.triB = mb.tri_base;
+        pairrec[p] = o;
+        PairAcc z; z.n_hits = 0; z.flags = 0;
+        acc[p] = z;
+        if (p < cap_queue) queue[p] = make_uint4((uint32_t)p, 0u, 0u, 1u);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// mid phase: persistent work-queue dual-tree traversal
+// ------------------------------------------------------------------------------------------
+#define TRAV_WARPS 4
+#define STK_CAP 256u          // per-warp deque capacity (power of two)
+#define STK_MASK (STK_CAP - 1u)
+
+struct TravStack { uint32_t pair[TRAV_WARPS][STK_CAP]; uint32_t a[TRAV_WARPS][STK_CAP]; uint32_t b[TRAV_WARPS][STK_CAP]; };
+
+// Move k (<= 32) oldest items of this warp's deque to the global queue.  The caller has flushed `delta`
+// so that `pending` already counts them.
+__device__ __forceinline__ void trav_donate(TravStack& st, uint32_t warp, uint32_t lane, uint32_t& bot, uint32_t k,
+                                            FrameCtl* ctl, WorkItem* queue, unsigned long long cap_queue) {
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(&ctl->q_tail, (unsigned long long)k);
+    base = __shfl_sync(FULL_MASK, base, 0);
+    bool dropped = false;
+    if (lane < k) {
+        uint32_t s = (bot + lane) & STK_MASK;
+        unsigned long long slot = base + lane;
+        if (slot < cap_queue) {
+            uint4 it = make_uint4(st.pair[warp][s], st.a[warp][s], st.b[warp][s], 0u);
+            __stcg(&queue[slot], it);
+            __threadfence();
+            *((volatile uint32_t*)&queue[slot].w) = 1u;       // publish
+        } else dropped = true;
+    }
+    uint32_t dm = __ballot_sync(FULL_MASK, dropped);
+    if (dm && lane == 0) {                                     // queue full: the frame will be re-run with a larger queue
+        atomicOr(&ctl->overflow, (unsigned)OVF_QUEUE);
+        atomicAdd((unsigned long long*)&ctl->pending, (unsigned long long)(-(long long)__popc(dm)));
+    }
+    if (lane == 0) atomicAdd(&ctl->n_donated, (unsigned long long)k);
+    bot += k;
+}
+
+__global__ void __launch_bounds__(TRAV_WARPS * 32)
+k_traverse(FrameCtl* ctl, const PairRec* __restrict__ pairrec, const TreeRec* __restrict__ recs,
+           WorkItem* queue, unsigned long long cap_queue, Combo* __restrict__ combos, unsigned long long cap_combos,
+           uint32_t n_warps_total, uint32_t hungry) {
+    __shared__ TravStack st;
+    const uint32_t lane = lane_id();
+    const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    uint32_t top = 0, bot = 0;      // deque: items live in [bot, top)
+    int delta = 0;                  // alive-item change not yet added to ctl->pending
+    unsigned long long my_sat = 0, my_tri = 0;
+
+    for (;;) {
+        uint32_t cnt = top - bot;
+        bool have = false;
+        uint32_t ip = 0, ia = 0, ib = 0;
+        // queue length sample for the donation decision (issued early, used late)
+        unsigned long long qh = 0, qt = 0;
+        if (lane == 0) { qh = ld_volatile_u64(&ctl->q_head); qt = ld_volatile_u64(&ctl->q_tail); }
+
+        if (cnt == 0) {
+            // ---- refill from the global queue ----
+            unsigned long long h = 0; uint32_t n = 0; int done = 0;
+            if (lane == 0) {
+                if (delta != 0) { atomicAdd((unsigned long long*)&ctl->pending, (unsigned long long)(long long)delta); }
+                unsigned long long t = qt < cap_queue ? qt : cap_queue;
+                h = qh;
+                while (h < t) {
+                    unsigned long long avail = t - h;
+                    unsigned long long take = avail / n_warps_total;
+                    take = take < 1 ? 1 : (take > 32 ? 32 : take);
+                    unsigned long long old = atomicCAS(&ctl->q_head, h, h + take);
+                    if (old == h) { n = (uint32_t)take; break; }
+                    h = old;
+                    t = ld_volatile_u64(&ctl->q_tail); if (t > cap_queue) t = cap_queue;
+                }
+                if (n == 0) done = (ld_volatile_s64(&ctl->pending) == 0) ? 1 : 0;
+            }
+            delta = 0;
+            h = __shfl_sync(FULL_MASK, h, 0);
+            n = __shfl_sync(FULL_MASK, n, 0);
+            done = __shfl_sync(FULL_MASK, done, 0);
+            if (n == 0) {
+                if (done) break;
+                __nanosleep(200);
+                continue;
+            }
+            if (lane < n) {
+                volatile uint32_t* flag = &queue[h + lane].w;
+                while (*flag == 0u) { }
+                __threadfence();
+                uint4 it = __ldcg(&queue[h + lane]);
+                ip = it.x; ia = it.y; ib = it.z; have = true;
+            }
+            __syncwarp();
+        } else {
+            uint32_t take = cnt < 32u ? cnt : 32u;
+            if (lane < take) {
+                uint32_t s = (top - 1u - lane) & STK_MASK;
+                ip = st.pair[warp][s]; ia = st.a[warp][s]; ib = st.b[warp][s]; have = true;
+            }
+            top -= take;
+            __syncwarp();
+        }
+
+        // ---- one SAT visit per lane (IntersectOBBtreesRecursive, OBBtree.cpp:414-477) ----
+        bool push = false, emit = false;
+        uint32_t c0a = 0, c0b = 0, c1a = 0, c1b = 0;
+        Combo cmb = make_uint4(0, 0, 0, 0);
+        if (have) {
+            const float4* pp = reinterpret_cast<const float4*>(pairrec + ip);
+            Rel rel; rel.r0 = __ldg(pp); rel.r1 = __ldg(pp + 1); rel.r2 = __ldg(pp + 2);
+            const uint4 bases = __ldg(reinterpret_cast<const uint4*>(pp + 3));
+            const float4* ra = reinterpret_cast<const float4*>(recs + bases.x + ia);
+            const float4* rb = reinterpret_cast<const float4*>(recs + bases.y + ib);
+            float4 a0 = __ldg(ra), a1 = __ldg(ra + 1), a2 = __ldg(ra + 2), a3 = __ldg(ra + 3);
+            float4 b0 = __ldg(rb), b1 = __ldg(rb + 1), b2 = __ldg(rb + 2), b3 = __ldg(rb + 3);
+            Box first = unpack_box(a0, a1, a2);
+            Box second = box_transform(rel, unpack_box(b0, b1, b2));        // :420
+            ++my_sat;
+            if (box_sat(first, second)) {                                    // :422
+                const bool leafA = __float_as_uint(a3.w) != 0u, leafB = __float_as_uint(b3.w) != 0u;
+                const uint32_t childA = __float_as_uint(a3.y), childB = __float_as_uint(b3.y);
+                if (leafA && leafB) {
+                    const uint32_t cntA = __float_as_uint(a3.z), cntB = __float_as_uint(b3.z);
+                    emit = true;
+                    cmb = make_uint4(ip, childA, childB, cntA | (cntB << 16));   // :473
+                    my_tri += (unsigned long long)cntA * cntB;
+                } else {
+                    bool descend_first;
+                    if (!leafA && !leafB) descend_first = a3.x >= box_surface(second);   // :426 (a3.x caches first.GetSurface())
+                    else descend_first = !leafA;
+                    push = true;
+                    if (descend_first) { c0a = childA; c1a = childA + 1u; c0b = ib; c1b = ib; }
+                    else { c0a = ia; c1a = ia; c0b = childB; c1b = childB + 1u; }
+                }
+            }
+        }
+        const uint32_t have_m = __ballot_sync(FULL_MASK, have);
+        const uint32_t push_m = __ballot_sync(FULL_MASK, push);
+        const uint32_t emit_m = __ballot_sync(FULL_MASK, emit);
+        const uint32_t total = 2u * (uint32_t)__popc(push_m);
+        delta += (int)total - (int)__popc(have_m);
+
+        // ---- leaf combos: warp-aggregated append ----
+        if (emit_m) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(&ctl->n_combos, (unsigned long long)__popc(emit_m));
+            base = __shfl_sync(FULL_MASK, base, 0);
+            if (emit) {
+                unsigned long long slot = base + __popc(emit_m & lt_mask);
+                if (slot < cap_combos) combos[slot] = cmb;
+                else atomicOr(&ctl->overflow, (unsigned)OVF_COMBOS);
+            }
+        }
+
+        // ---- make room, then push the children on the warp's deque ----
+        cnt = top - bot;
+        if (cnt + total > STK_CAP) {
+            if (lane == 0 && delta != 0) atomicAdd((unsigned long long*)&ctl->pending, (unsigned long long)(long long)delta);
+            delta = 0;
+            trav_donate(st, warp, lane, bot, 32u, ctl, queue, cap_queue);
+            trav_donate(st, warp, lane, bot, 32u, ctl, queue, cap_queue);
+        }
+        if (push) {
+            uint32_t s0 = (top + 2u * (uint32_t)__popc(push_m & lt_mask)) & STK_MASK, s1 = (s0 + 1u) & STK_MASK;
+            st.pair[warp][s0] = ip; st.a[warp][s0] = c0a; st.b[warp][s0] = c0b;
+            st.pair[warp][s1] = ip; st.a[warp][s1] = c1a; st.b[warp][s1] = c1b;
+        }
+        top += total;
+        __syncwarp();
+
+        // ---- feed idle warps: donate the oldest (closest to the roots) items when the queue runs low ----
+        cnt = top - bot;
+        int hungry_now = 0;
+        if (lane == 0) hungry_now = (qt < qh + hungry) ? 1 : 0;
+        hungry_now = __shfl_sync(FULL_MASK, hungry_now, 0);
+        if (hungry_now && cnt >= 64u) {
+            if (lane == 0 && delta != 0) atomicAdd((unsigned long long*)&ctl->pending, (unsigned long long)(long long)delta);
+            delta = 0;
+            trav_donate(st, warp, lane, bot, 32u, ctl, queue, cap_queue);
+            __syncwarp();
+        }
+    }
+
+    // ---- statistics ----
+    for (int o = 16; o > 0; o >>= 1) {
+        my_sat += __shfl_down_sync(FULL_MASK, my_sat, o);
+        my_tri += __shfl_down_sync(FULL_MASK, my_tri, o);
+    }
+    if (lane == 0) {
+        if (my_sat) atomicAdd(&ctl->n_sat, my_sat);
+        if (my_tri) atomicAdd(&ctl->n_tri_tests, my_tri);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// narrow phase: 16 lanes per leaf combo, lane (i,j) tests triangle i of first's leaf against
+// triangle j of second's leaf (loops of CreateUncollideRays.cpp:74-115).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_tritri(FrameCtl* ctl, const Combo* __restrict__ combos, unsigned long long cap_combos, const PairRec* __restrict__ pairrec,
+         const TriRec* __restrict__ tris, imrcd_tri_hit* __restrict__ hits, unsigned long long cap_hits, PairAcc* acc) {
+    const uint32_t lane = lane_id();
+    const uint32_t sub = lane & 15u, half = lane >> 4;
+    const uint32_t i = sub >> 2, j = sub & 3u;
+    unsigned long long n = ctl->n_combos < cap_combos ? ctl->n_combos : cap_combos;
+    const unsigned long long warps_total = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+    unsigned long long my_cop = 0;
+    for (unsigned long long w = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; 2ull * w < n; w += warps_total) {
+        const unsigned long long c = 2ull * w + half;
+        bool active = false, hit = false;
+        V3 src = mk3(0, 0, 0), tgt = mk3(0, 0, 0);
+        uint32_t pair = 0, origA = 0, origB = 0;
+        if (c < n) {
+            const Combo cb = __ldg(combos + c);
+            const uint32_t cntA = cb.w & 0xffffu, cntB = cb.w >> 16;
+            active = (i < cntA) && (j < cntB);
+            if (active) {
+                pair = cb.x;
+                const float4* pp = reinterpret_cast<const float4*>(pairrec + pair);
+                Rel rel; rel.r0 = __ldg(pp); rel.r1 = __ldg(pp + 1); rel.r2 = __ldg(pp + 2);
+                const uint4 bases = __ldg(reinterpret_cast<const uint4*>(pp + 3));
+                const float4* ta = reinterpret_cast<const float4*>(tris + bases.z + cb.y + i);
+                const float4* tb = reinterpret_cast<const float4*>(tris + bases.w + cb.z + j);
+                const float4 a0 = __ldg(ta), a1 = __ldg(ta + 1), a2 = __ldg(ta + 2);
+                const float4 b0 = __ldg(tb), b1 = __ldg(tb + 1), b2 = __ldg(tb + 2);
+                origA = __float_as_uint(a0.w); origB = __float_as_uint(b0.w);
+                const V3 V0 = mk3(a0.x, a0.y, a0.z), V1 = mk3(a1.x, a1.y, a1.z), V2 = mk3(a2.x, a2.y, a2.z);
+                // seconds_triangle = second_to_first_space_matrix * tri (CreateUncollideRays.cpp:84, Triangle.cpp:69-78)
+                const V3 U0 = rel_mul(rel, mk3(b0.x, b0.y, b0.z), 1.f);
+                const V3 U1 = rel_mul(rel, mk3(b1.x, b1.y, b1.z), 1.f);
+                const V3 U2 = rel_mul(rel, mk3(b2.x, b2.y, b2.z), 1.f);
+                const int f = tri_tri_isectline(V0, V1, V2, U0, U1, U2, src, tgt);     // :86
+                hit = (f == 1);                                                        // doIntersept && !areCoplanar (:88)
+                if (f == 3) ++my_cop;
+            }
+        }
+        const uint32_t hm = __ballot_sync(FULL_MASK, hit);
+        if (hm) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(&ctl->n_hits, (unsigned long long)__popc(hm));
+            base = __shfl_sync(FULL_MASK, base, 0);
+            if (hit) {
+                const float weight = length3(sub3(src, tgt));                          // :93
+                unsigned long long slot = base + __popc(hm & ((1u << lane) - 1u));
+                if (slot < cap_hits) {
+                    imrcd_tri_hit h;
+                    h.pair = pair; h.tri_first = origA; h.tri_second = origB;
+                    h.source[0] = src.x; h.source[1] = src.y; h.source[2] = src.z;
+                    h.target[0] = tgt.x; h.target[1] = tgt.y; h.target[2] = tgt.z;
+                    h.weight = weight;
+                    hits[slot] = h;
+                } else atomicOr(&ctl->overflow, (unsigned)OVF_HITS);
+                atomicAdd(&acc[pair].n_hits, 1u);
+                // a candidate survives IsNull() iff its accumulated weight != 0 (CreateUncollideRays.cpp:22-25,117-127);
+                // weights are >= 0 (or NaN), so that is "some hit of the triangle has weight != 0".
+                if (!(weight == 0.0f)) atomicOr(&acc[pair].flags, 1u);
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) my_cop += __shfl_down_sync(FULL_MASK, my_cop, o);
+    if (lane == 0 && my_cop) atomicAdd(&ctl->n_coplanar, my_cop);
+}
+
+// ------------------------------------------------------------------------------------------
+// reduce: colliding entity pairs (CollisionDetection.cpp:60-78)
+// ------------------------------------------------------------------------------------------
+__global__ void k_finalize(FrameCtl* ctl, unsigned long long cap_pairs, const uint2* __restrict__ pairs, const PairAcc* __restrict__ acc,
+                           const uint32_t* __restrict__ entity, imrcd_entity_pair* __restrict__ out) {
+    unsigned long long n = ctl->n_pairs < cap_pairs ? ctl->n_pairs : cap_pairs;
+    for (unsigned long long p = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; p < n; p += (unsigned long long)gridDim.x * blockDim.x) {
+        PairAcc a = acc[p];
+        if (a.flags & 1u) {
+            unsigned long long slot = atomicAdd(&ctl->n_colliding, 1ull);
+            uint2 pr = pairs[p];
+            imrcd_entity_pair o;
+            memset(&o, 0, sizeof(o));
+            o.entry_first = pr.x; o.entry_second = pr.y;
+            o.entity_first = entity[pr.x]; o.entity_second = entity[pr.y];
+            o.n_hits = a.n_hits; o.flags = 1u;
+            out[slot] = o;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host orchestration
+// ------------------------------------------------------------------------------------------
+static inline unsigned blocks_for(unsigned long long n, unsigned bs) { return (unsigned)((n + bs - 1) / bs); }
+
+int imr_frame_run_device(imrcd_ctx* ctx) {
+    cudaStream_t s = ctx->stream;
+    const uint32_t n = (uint32_t)ctx->h_mesh.size();
+    memset(&ctx->stats, 0, sizeof(ctx->stats));
+    memset(&ctx->ctl_host, 0, sizeof(ctx->ctl_host));
+    ctx->stats.n_entries = n;
+    ctx->hits_fetched = false;
+    if (n < 2) return IMRCD_OK;                                   // CollisionDetection.cpp:40
+
+    // capacities (persist across frames; grown on overflow)
+    if (ctx->cap_pairs == 0) ctx->cap_pairs = std::max<uint64_t>(1u << 16, 32ull * n);
+    if (ctx->cap_queue == 0) ctx->cap_queue = ctx->cap_pairs + (1ull << 22);
+    if (ctx->cap_combos == 0) ctx->cap_combos = 1ull << 22;
+    if (ctx->cap_hits == 0) ctx->cap_hits = 1ull << 20;
+
+    IMR_CUDA(ctx, ctx->d_inv.reserve(64ull * n, 0, s));
+    IMR_CUDA(ctx, ctx->d_ext.reserve(24ull * n, 0, s));
+    IMR_CUDA(ctx, ctx->d_keys.reserve(4ull * n, 0, s));
+    IMR_CUDA(ctx, ctx->d_keys2.reserve(4ull * n, 0, s));
+    IMR_CUDA(ctx, ctx->d_idx.reserve(4ull * n, 0, s));
+    IMR_CUDA(ctx, ctx->d_idx2.reserve(4ull * n, 0, s));
+    IMR_CUDA(ctx, ctx->d_sorted.reserve(sizeof(SweepRec) * (size_t)n, 0, s));
+    IMR_CUDA(ctx, ctx->d_ctl.reserve(sizeof(FrameCtl), 0, s));
+    IMR_CUDA(ctx, ctx->p_ctl.reserve(sizeof(FrameCtl)));
+    size_t cub_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, ctx->d_keys.as<uint32_t>(), ctx->d_keys2.as<uint32_t>(),
+                                    ctx->d_idx.as<uint32_t>(), ctx->d_idx2.as<uint32_t>(), (int)n, 0, 32, s);
+    IMR_CUDA(ctx, ctx->d_cubtmp.reserve(cub_bytes, 0, s));
+
+    if (ctx->trav_blocks == 0) {
+        int per_sm = 0;
+        IMR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_traverse, TRAV_WARPS * 32, 0));
+        if (per_sm < 1) per_sm = 1;
+        ctx->trav_blocks = per_sm * ctx->sm_count;
+    }
+
+    for (int attempt = 0; attempt < 8; ++attempt) {
+        IMR_CUDA(ctx, ctx->d_pairs.reserve(8ull * ctx->cap_pairs, 0, s));
+        IMR_CUDA(ctx, ctx->d_pairrec.reserve(sizeof(PairRec) * ctx->cap_pairs, 0, s));
+        IMR_CUDA(ctx, ctx->d_pairacc.reserve(sizeof(PairAcc) * ctx->cap_pairs, 0, s));
+        IMR_CUDA(ctx, ctx->d_epairs.reserve(sizeof(imrcd_entity_pair) * ctx->cap_pairs, 0, s));
+        if (16ull * ctx->cap_queue > ctx->d_queue.cap) { IMR_CUDA(ctx, ctx->d_queue.reserve(16ull * ctx->cap_queue, 0, s)); ctx->queue_dirty = ctx->cap_queue; }
+        IMR_CUDA(ctx, ctx->d_combos.reserve(16ull * ctx->cap_combos, 0, s));
+        IMR_CUDA(ctx, ctx->d_hits.reserve(sizeof(imrcd_tri_hit) * ctx->cap_hits, 0, s));
+
+        FrameCtl* ctl = ctx->d_ctl.as<FrameCtl>();
+        uint64_t launches = 0;
+        IMR_CUDA(ctx, cudaEventRecord(ctx->ev[0], s));
+        IMR_CUDA(ctx, cudaMemsetAsync(ctl, 0, sizeof(FrameCtl), s));
+        if (ctx->queue_dirty) {                       // clear publication flags left by the previous frame
+            uint64_t nclr = std::min<uint64_t>(ctx->queue_dirty, ctx->cap_queue);
+            IMR_CUDA(ctx, cudaMemsetAsync(ctx->d_queue.p, 0, 16ull * nclr, s));
+        }
+        // ---- broad ----
+        k_entry_prep<<<blocks_for(n, 128), 128, 0, s>>>(n, ctx->d_cur.as<float>(), ctx->d_mesh.as<uint32_t>(), ctx->d_meshes.as<MeshDev>(),
+                                                         ctx->d_recs.as<TreeRec>(), ctx->d_inv.as<float>(), ctx->d_ext.as<float>(),
+                                                         ctx->d_keys.as<uint32_t>(), ctx->d_idx.as<uint32_t>());
+        cub::DeviceRadixSort::SortPairs(ctx->d_cubtmp.p, cub_bytes, ctx->d_keys.as<uint32_t>(), ctx->d_keys2.as<uint32_t>(),
+                                        ctx->d_idx.as<uint32_t>(), ctx->d_idx2.as<uint32_t>(), (int)n, 0, 32, s);
+        k_gather_sorted<<<blocks_for(n, 256), 256, 0, s>>>(n, ctx->d_idx2.as<uint32_t>(), ctx->d_ext.as<float>(), ctx->d_cb.as<uint8_t>(),
+                                                            ctx->d_sorted.as<SweepRec>());
+        {
+            unsigned warps = std::min<unsigned long long>(n, (unsigned long long)ctx->sm_count * 64ull);
+            k_sweep<<<blocks_for(32ull * warps, 256), 256, 0, s>>>(n, ctx->d_sorted.as<SweepRec>(), ctx->d_pairs.as<uint2>(), ctx->cap_pairs,
+                                                                     ctl, ctx->shard_rank, ctx->shard_n);
+        }
+        launches += 3 + 4;   // radix sort of <= a few 100k keys: histogram + onesweep passes (counted as 4)
+        IMR_CUDA(ctx, cudaEventRecord(ctx->ev[1], s));
+        // ---- pair setup ----
+        k_queue_init<<<1, 1, 0, s>>>(ctl, ctx->cap_pairs, ctx->cap_queue);
+        k_pair_setup<<<ctx->sm_count * 8, 128, 0, s>>>(ctl, ctx->cap_pairs, ctx->d_pairs.as<uint2>(), ctx->d_cur.as<float>(), ctx->d_inv.as<float>(),
+                                                        ctx->d_mesh.as<uint32_t>(), ctx->d_meshes.as<MeshDev>(), ctx->d_pairrec.as<PairRec>(),
+                                                        ctx->d_pairacc.as<PairAcc>(), ctx->d_queue.as<WorkItem>(), ctx->cap_queue);
+        launches += 2;
+        IMR_CUDA(ctx, cudaEventRecord(ctx->ev[2], s));
+        // ---- mid ----
+        {
+            uint32_t n_warps = (uint32_t)ctx->trav_blocks * TRAV_WARPS;
+            k_traverse<<<ctx->trav_blocks, TRAV_WARPS * 32, 0, s>>>(ctl, ctx->d_pairrec.as<PairRec>(), ctx->d_recs.as<TreeRec>(),
+                                                                     ctx->d_queue.as<WorkItem>(), ctx->cap_queue, ctx->d_combos.as<Combo>(),
+                                                                     ctx->cap_combos, n_warps, n_warps * 4u);
+            launches += 1;
+        }
+        IMR_CUDA(ctx, cudaEventRecord(ctx->ev[3], s));
+        // ---- narrow ----
+        k_tritri<<<ctx->sm_count * 8, 256, 0, s>>>(ctl, ctx->d_combos.as<Combo>(), ctx->cap_combos, ctx->d_pairrec.as<PairRec>(),
+                                                    ctx->d_tris.as<TriRec>(), ctx->d_hits.as<imrcd_tri_hit>(), ctx->cap_hits,
+                                                    ctx->d_pairacc.as<PairAcc>());
+        launches += 1;
+        IMR_CUDA(ctx, cudaEventRecord(ctx->ev[4], s));
+        // ---- reduce ----
+        k_finalize<<<ctx->sm_count * 4, 256, 0, s>>>(ctl, ctx->cap_pairs, ctx->d_pairs.as<uint2>(), ctx->d_pairacc.as<PairAcc>(),
+                                                      ctx->d_entity.as<uint32_t>(), ctx->d_epairs.as<imrcd_entity_pair>());
+        launches += 1;
+        IMR_CUDA(ctx, cudaEventRecord(ctx->ev[5], s));
+        IMR_CUDA(ctx, cudaMemcpyAsync(ctx->p_ctl.p, ctl, sizeof(FrameCtl), cudaMemcpyDeviceToHost, s));
+        IMR_CUDA(ctx, cudaStreamSynchronize(s));
+        IMR_CUDA(ctx, cudaGetLastError());
+        ctx->ctl_host = *ctx->p_ctl.as<FrameCtl>();
+        const FrameCtl& c = ctx->ctl_host;
+        ctx->queue_dirty = std::min<uint64_t>(c.q_tail, ctx->cap_queue);
+
+        if (c.overflow) {
+            if (c.overflow & OVF_PAIRS) ctx->cap_pairs = std::max<uint64_t>(c.n_pairs + c.n_pairs / 8, ctx->cap_pairs * 2);
+            if (c.overflow & OVF_QUEUE) ctx->cap_queue = std::max<uint64_t>(ctx->cap_queue * 2, ctx->cap_pairs + (1ull << 22));
+            if (ctx->cap_queue < ctx->cap_pairs) ctx->cap_queue = ctx->cap_pairs + (1ull << 22);
+            if (c.overflow & OVF_COMBOS) ctx->cap_combos = std::max<uint64_t>(c.n_combos + c.n_combos / 8, ctx->cap_combos * 2);
+            if (c.overflow & OVF_HITS) ctx->cap_hits = std::max<uint64_t>(c.n_hits + c.n_hits / 8, ctx->cap_hits * 2);
+            continue;   // re-run the frame with the larger buffers
+        }
+
+        imrcd_frame_stats& st = ctx->stats;
+        st.n_pairs = c.n_pairs; st.n_sat_tests = c.n_sat; st.n_combos = c.n_combos; st.n_tri_tests = c.n_tri_tests;
+        st.n_hits = c.n_hits; st.n_coplanar_hits = c.n_coplanar; st.n_colliding = c.n_colliding;
+        st.traverse_launches = 1; st.total_launches = launches;
+        cudaEventElapsedTime(&st.ms_total, ctx->ev[0], ctx->ev[5]);
+        cudaEventElapsedTime(&st.ms_broad, ctx->ev[0], ctx->ev[1]);
+        cudaEventElapsedTime(&st.ms_pair_setup, ctx->ev[1], ctx->ev[2]);
+        cudaEventElapsedTime(&st.ms_traverse, ctx->ev[2], ctx->ev[3]);
+        cudaEventElapsedTime(&st.ms_narrow, ctx->ev[3], ctx->ev[4]);
+        cudaEventElapsedTime(&st.ms_reduce, ctx->ev[4], ctx->ev[5]);
+        return IMRCD_OK;
+    }
+    ctx->err = "frame buffers could not be grown enough (8 attempts)";
+    return IMRCD_E_CAPACITY;
+}

@@ -1,0 +1,143 @@
+// imrcd_internal.cuh -- shared declarations of libimrcd.so (context, HBM layouts, helpers).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/imrcd.h"
+#include "imrcd_math.cuh"
+
+// ------------------------------------------------------------------------------------------
+// HBM layouts
+// ------------------------------------------------------------------------------------------
+// Tree vertex record, 64 B = 4 x float4, siblings adjacent (children of one node share a 128-B line):
+//   q0 = (c.x c.y c.z u.x)  q1 = (u.y u.z v.x v.y)  q2 = (v.z w.x w.y w.z)
+//   q3 = (surface, child_or_tri_off [u32 bits], tri_cnt [u32 bits], kind [u32 bits: 0 inner, 1 leaf])
+// Record 0 of a mesh is its root (OBBtree::root_obb, OBBtree.h:129); record 1 is padding;
+// an inner record's children are records `child` (left) and `child+1` (right).
+// `surface` caches Paralgram::GetSurface() of the untransformed box (Paralgram.cpp:203-210).
+struct __align__(16) TreeRec { float4 q0, q1, q2, q3; };
+
+// Triangle, 48 B = 3 x float4 in LEAF order (OBBtree.cpp:207-214):
+//   t0 = (p0.xyz, orig_index bits)  t1 = (p1.xyz, 0)  t2 = (p2.xyz, 0)
+struct __align__(16) TriRec { float4 t0, t1, t2; };
+
+struct MeshDev { uint32_t rec_base, tri_base, n_rec, n_tri; };
+
+// Per broad-phase pair, 64 B: rel = inverse(first.M) * second.M stored by rows (imrcd_math.cuh Rel)
+// plus the two meshes' bases so the hot kernels do not chase entry -> mesh -> base.
+struct __align__(16) PairRec { float4 r0, r1, r2; uint32_t recA, recB, triA, triB; };
+
+// Work item of the traversal queue: test record a of first's tree against record b of second's tree.
+// .w is the publication flag of a global-queue slot (0 = not yet written).
+typedef uint4 WorkItem;   // (pair, a, b, ready)
+
+// Leaf x leaf candidate (OBBtreesIntersectInfo::CandidateTriangleRangeCombination, OBBtree.h:9-18)
+typedef uint4 Combo;      // (pair, offA, offB, cntA | cntB << 16), offsets relative to the mesh
+
+// sorted sweep record, 32 B
+struct __align__(16) SweepRec { float umin, umax, vmin, vmax, wmin, wmax; uint32_t idx, cb; };
+
+// Device control block of one frame (one 256-B allocation, read back once per frame).
+struct FrameCtl {
+    unsigned long long q_head, q_tail;     // global traversal queue
+    long long pending;                     // alive work items (queue + stacks), termination detector
+    unsigned long long n_pairs;            // broad-phase pairs emitted (may exceed capacity -> overflow)
+    unsigned long long n_combos;
+    unsigned long long n_hits;
+    unsigned long long n_coplanar;
+    unsigned long long n_sat;
+    unsigned long long n_tri_tests;
+    unsigned long long n_colliding;
+    unsigned long long n_donated;          // items that went through the global queue after the roots
+    unsigned int overflow;                 // bit0 pairs, bit1 queue, bit2 combos, bit3 hits
+    unsigned int pad;
+};
+enum { OVF_PAIRS = 1, OVF_QUEUE = 2, OVF_COMBOS = 4, OVF_HITS = 8 };
+
+// ------------------------------------------------------------------------------------------
+// host-side helpers
+// ------------------------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr; size_t cap = 0;
+    // grow to at least `bytes`; keep the first `keep` bytes
+    cudaError_t reserve(size_t bytes, size_t keep, cudaStream_t s) {
+        if (bytes <= cap) return cudaSuccess;
+        size_t ncap = cap ? cap : 4096;
+        while (ncap < bytes) ncap += ncap / 2 + 4096;
+        void* np = nullptr;
+        cudaError_t e = cudaMalloc(&np, ncap);
+        if (e != cudaSuccess) return e;
+        if (keep && p) { e = cudaMemcpyAsync(np, p, keep, cudaMemcpyDeviceToDevice, s); if (e != cudaSuccess) return e; e = cudaStreamSynchronize(s); if (e != cudaSuccess) return e; }
+        if (p) cudaFree(p);
+        p = np; cap = ncap;
+        return cudaSuccess;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+struct PinBuf {
+    void* p = nullptr; size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        size_t ncap = cap ? cap : 4096;
+        while (ncap < bytes) ncap += ncap / 2 + 4096;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMallocHost(&p, ncap);
+        if (e == cudaSuccess) cap = ncap;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+struct MeshHost {
+    MeshDev dev;
+    float root_box[12];
+    float build_ms = 0.f;
+};
+
+struct imrcd_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+
+    // mesh arena
+    std::vector<MeshHost> meshes;
+    DevBuf d_recs, d_tris, d_tri_nrm, d_tri_vid, d_meshes;
+    uint64_t n_rec_total = 0, n_tri_total = 0;
+    bool meshes_dirty = false;
+    float last_build_ms = 0.f;
+
+    // frame, host side
+    std::vector<float> h_cur, h_prev;
+    std::vector<uint32_t> h_mesh, h_entity;
+    std::vector<uint8_t> h_cb;
+    uint32_t shard_rank = 0, shard_n = 1;
+    bool uploaded = false, ran = false, fetched = false;
+    PinBuf p_stage;                      // pinned staging for entry upload
+    // frame, device side
+    DevBuf d_cur, d_prev, d_mesh, d_cb, d_entity, d_inv, d_ext, d_keys, d_keys2, d_idx, d_idx2, d_sorted, d_cubtmp;
+    DevBuf d_pairs, d_pairrec, d_pairacc, d_queue, d_combos, d_hits, d_epairs, d_ctl;
+    uint64_t cap_pairs = 0, cap_queue = 0, cap_combos = 0, cap_hits = 0;
+    uint64_t queue_dirty = 0;            // slots whose ready flag may still be set
+    // results
+    PinBuf p_ctl, p_epairs, p_hits, p_pairs, p_combos;
+    FrameCtl ctl_host;
+    imrcd_frame_stats stats;
+    bool hits_fetched = false;
+    cudaEvent_t ev[8] = {};
+    int trav_blocks = 0;
+};
+
+#define IMR_CUDA(ctx, call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(_e); return IMRCD_E_CUDA; } } while (0)
+
+// ---- kernels / stages implemented in the .cu files ----------------------------------------
+int imr_mesh_finalize_records(imrcd_ctx* ctx, uint32_t rec_base, uint32_t n_rec);            // surfaces
+int imr_build_mesh_device(imrcd_ctx* ctx, const float* pos, const float* nrm, const uint32_t* vid, uint64_t n_tri,
+                          uint32_t mode, MeshHost* out);
+int imr_frame_run_device(imrcd_ctx* ctx);
