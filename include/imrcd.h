@@ -71,6 +71,10 @@ typedef struct {
     uint64_t n_colliding;       /* colliding entity pairs */
     uint64_t traverse_launches; /* kernel launches of the traversal stage */
     uint64_t total_launches;    /* all kernel launches of the frame */
+    uint64_t n_queue_items;     /* work items that went through the global queue after the roots (load balancing) */
+    uint64_t n_warp_iterations; /* traversal warp-iterations (<= 32 SAT visits each) */
+    uint64_t trav_busy_cycles;  /* sum over traversal warps of SM cycles spent inside iterations (diagnostic) */
+    uint64_t trav_idle_polls;   /* failed refill attempts of starving traversal warps (diagnostic) */
     float    ms_total;          /* device time of imrcd_frame_run (CUDA events) */
     float    ms_broad, ms_pair_setup, ms_traverse, ms_narrow, ms_reduce;
 } imrcd_frame_stats;

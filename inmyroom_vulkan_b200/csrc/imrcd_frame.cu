@@ -159,6 +159,19 @@ __global__ void k_pair_setup(const FrameCtl* ctl, unsigned long long cap_pairs, 
 
 // ------------------------------------------------------------------------------------------
 // mid phase: persistent work-queue dual-tree traversal
+//
+// One persistent grid (as many CTAs as are co-resident).  Every warp owns a deque of work items in shared
+// memory and runs the descent depth-first on it, 32 SAT visits per iteration (one per lane).  Load balancing
+// goes through ONE global linear queue used as a ticket rendezvous:
+//   * a warp whose deque is empty takes a ticket for 32 consecutive slots (one atomicAdd on q_head, no CAS
+//     retry loop) and then polls only the publication flags of ITS OWN slots - no shared hot word;
+//   * a warp with more than 32 items (more than it can start on next iteration) looks at q_head > q_tail
+//     ("somebody is waiting on unfilled slots") and, if so, moves its oldest items - the ones closest to the
+//     roots, i.e. the largest subtrees - to the slots at q_tail (one atomicAdd, then payload, fence, flag);
+//   * `pending` counts alive items (queue + deques); warps add their net production lazily (when they go idle
+//     or publish), and everybody leaves when it reads 0.
+// Producers never wait, consumers wait only on slots that a producer has already reserved or will never
+// fill once pending == 0, so the scheme cannot deadlock.
 // ------------------------------------------------------------------------------------------
 #define TRAV_WARPS 4
 #define STK_CAP 256u          // per-warp deque capacity (power of two)
@@ -185,78 +198,81 @@ __device__ __forceinline__ void trav_donate(TravStack& st, uint32_t warp, uint32
         } else dropped = true;
     }
     uint32_t dm = __ballot_sync(FULL_MASK, dropped);
-    if (dm && lane == 0) {                                     // queue full: the frame will be re-run with a larger queue
-        atomicOr(&ctl->overflow, (unsigned)OVF_QUEUE);
-        atomicAdd((unsigned long long*)&ctl->pending, (unsigned long long)(-(long long)__popc(dm)));
+    if (lane == 0) {
+        if (dm) {                                              // queue full: the frame will be re-run with a larger queue
+            atomicOr(&ctl->overflow, (unsigned)OVF_QUEUE);
+            atomicAdd((unsigned long long*)&ctl->pending, (unsigned long long)(-(long long)__popc(dm)));
+        }
+        atomicAdd(&ctl->n_donated, (unsigned long long)k);
     }
-    if (lane == 0) atomicAdd(&ctl->n_donated, (unsigned long long)k);
     bot += k;
+    __syncwarp();
 }
 
 __global__ void __launch_bounds__(TRAV_WARPS * 32)
 k_traverse(FrameCtl* ctl, const PairRec* __restrict__ pairrec, const TreeRec* __restrict__ recs,
-           WorkItem* queue, unsigned long long cap_queue, Combo* __restrict__ combos, unsigned long long cap_combos,
-           uint32_t n_warps_total, uint32_t hungry) {
+           WorkItem* queue, unsigned long long cap_queue, Combo* __restrict__ combos, unsigned long long cap_combos) {
     __shared__ TravStack st;
     const uint32_t lane = lane_id();
     const uint32_t warp = threadIdx.x >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    uint32_t top = 0, bot = 0;      // deque: items live in [bot, top)
-    int delta = 0;                  // alive-item change not yet added to ctl->pending
-    unsigned long long my_sat = 0, my_tri = 0;
+    uint32_t top = 0, bot = 0;          // deque: items live in [bot, top)
+    int delta = 0;                      // alive-item change not yet added to ctl->pending
+    unsigned long long own_base = 0;    // ticket: this warp consumes global slots own_base + lane for set bits of own_mask
+    uint32_t own_mask = 0;
+    unsigned long long my_sat = 0, my_tri = 0, my_iter = 0, my_busy = 0, my_polls = 0;
+    bool finished = false;
 
-    for (;;) {
+    while (!finished) {
         uint32_t cnt = top - bot;
         bool have = false;
         uint32_t ip = 0, ia = 0, ib = 0;
-        // queue length sample for the donation decision (issued early, used late)
-        unsigned long long qh = 0, qt = 0;
-        if (lane == 0) { qh = ld_volatile_u64(&ctl->q_head); qt = ld_volatile_u64(&ctl->q_tail); }
 
         if (cnt == 0) {
-            // ---- refill from the global queue ----
-            unsigned long long h = 0; uint32_t n = 0; int done = 0;
-            if (lane == 0) {
-                if (delta != 0) { atomicAdd((unsigned long long*)&ctl->pending, (unsigned long long)(long long)delta); }
-                unsigned long long t = qt < cap_queue ? qt : cap_queue;
-                h = qh;
-                while (h < t) {
-                    unsigned long long avail = t - h;
-                    unsigned long long take = avail / n_warps_total;
-                    take = take < 1 ? 1 : (take > 32 ? 32 : take);
-                    unsigned long long old = atomicCAS(&ctl->q_head, h, h + take);
-                    if (old == h) { n = (uint32_t)take; break; }
-                    h = old;
-                    t = ld_volatile_u64(&ctl->q_tail); if (t > cap_queue) t = cap_queue;
-                }
-                if (n == 0) done = (ld_volatile_s64(&ctl->pending) == 0) ? 1 : 0;
-            }
+            // ---- refill: wait on this warp's own global slots ----
+            if (lane == 0 && delta != 0) atomicAdd((unsigned long long*)&ctl->pending, (unsigned long long)(long long)delta);
             delta = 0;
-            h = __shfl_sync(FULL_MASK, h, 0);
-            n = __shfl_sync(FULL_MASK, n, 0);
-            done = __shfl_sync(FULL_MASK, done, 0);
-            if (n == 0) {
-                if (done) break;
-                __nanosleep(200);
-                continue;
+            uint32_t backoff = 32;
+            for (;;) {
+                if (own_mask == 0u) {
+                    unsigned long long base = 0;
+                    if (lane == 0) base = atomicAdd(&ctl->q_head, 32ull);
+                    own_base = __shfl_sync(FULL_MASK, base, 0);
+                    own_mask = FULL_MASK;
+                }
+                const unsigned long long slot = own_base + lane;
+                uint32_t f = 0;
+                if (((own_mask >> lane) & 1u) && slot < cap_queue) f = *((volatile uint32_t*)&queue[slot].w);
+                const uint32_t ready = __ballot_sync(FULL_MASK, f != 0u);
+                if (ready) {
+                    if (f) {
+                        __threadfence();
+                        const uint4 it = __ldcg(&queue[slot]);
+                        ip = it.x; ia = it.y; ib = it.z; have = true;
+                    }
+                    own_mask &= ~ready;
+                    break;
+                }
+                int done = 0;
+                if (lane == 0) done = (ld_volatile_s64(&ctl->pending) == 0) ? 1 : 0;
+                done = __shfl_sync(FULL_MASK, done, 0);
+                if (done) { finished = true; break; }
+                ++my_polls;
+                __nanosleep(backoff);
+                if (backoff < 1024) backoff <<= 1;
             }
-            if (lane < n) {
-                volatile uint32_t* flag = &queue[h + lane].w;
-                while (*flag == 0u) { }
-                __threadfence();
-                uint4 it = __ldcg(&queue[h + lane]);
-                ip = it.x; ia = it.y; ib = it.z; have = true;
-            }
-            __syncwarp();
+            if (finished) break;
         } else {
-            uint32_t take = cnt < 32u ? cnt : 32u;
+            const uint32_t take = cnt < 32u ? cnt : 32u;
             if (lane < take) {
-                uint32_t s = (top - 1u - lane) & STK_MASK;
+                const uint32_t s = (top - 1u - lane) & STK_MASK;
                 ip = st.pair[warp][s]; ia = st.a[warp][s]; ib = st.b[warp][s]; have = true;
             }
             top -= take;
             __syncwarp();
         }
+        ++my_iter;
+        const long long t_begin = clock64();
 
         // ---- one SAT visit per lane (IntersectOBBtreesRecursive, OBBtree.cpp:414-477) ----
         bool push = false, emit = false;
@@ -268,18 +284,18 @@ k_traverse(FrameCtl* ctl, const PairRec* __restrict__ pairrec, const TreeRec* __
             const uint4 bases = __ldg(reinterpret_cast<const uint4*>(pp + 3));
             const float4* ra = reinterpret_cast<const float4*>(recs + bases.x + ia);
             const float4* rb = reinterpret_cast<const float4*>(recs + bases.y + ib);
-            float4 a0 = __ldg(ra), a1 = __ldg(ra + 1), a2 = __ldg(ra + 2), a3 = __ldg(ra + 3);
-            float4 b0 = __ldg(rb), b1 = __ldg(rb + 1), b2 = __ldg(rb + 2), b3 = __ldg(rb + 3);
-            Box first = unpack_box(a0, a1, a2);
-            Box second = box_transform(rel, unpack_box(b0, b1, b2));        // :420
+            const float4 a0 = __ldg(ra), a1 = __ldg(ra + 1), a2 = __ldg(ra + 2), a3 = __ldg(ra + 3);
+            const float4 b0 = __ldg(rb), b1 = __ldg(rb + 1), b2 = __ldg(rb + 2), b3 = __ldg(rb + 3);
+            const Box first = unpack_box(a0, a1, a2);
+            const Box second = box_transform(rel, unpack_box(b0, b1, b2));        // :420
             ++my_sat;
-            if (box_sat(first, second)) {                                    // :422
+            if (box_sat(first, second)) {                                          // :422
                 const bool leafA = __float_as_uint(a3.w) != 0u, leafB = __float_as_uint(b3.w) != 0u;
                 const uint32_t childA = __float_as_uint(a3.y), childB = __float_as_uint(b3.y);
                 if (leafA && leafB) {
                     const uint32_t cntA = __float_as_uint(a3.z), cntB = __float_as_uint(b3.z);
                     emit = true;
-                    cmb = make_uint4(ip, childA, childB, cntA | (cntB << 16));   // :473
+                    cmb = make_uint4(ip, childA, childB, cntA | (cntB << 16));     // :473
                     my_tri += (unsigned long long)cntA * cntB;
                 } else {
                     bool descend_first;
@@ -303,7 +319,7 @@ k_traverse(FrameCtl* ctl, const PairRec* __restrict__ pairrec, const TreeRec* __
             if (lane == 0) base = atomicAdd(&ctl->n_combos, (unsigned long long)__popc(emit_m));
             base = __shfl_sync(FULL_MASK, base, 0);
             if (emit) {
-                unsigned long long slot = base + __popc(emit_m & lt_mask);
+                const unsigned long long slot = base + __popc(emit_m & lt_mask);
                 if (slot < cap_combos) combos[slot] = cmb;
                 else atomicOr(&ctl->overflow, (unsigned)OVF_COMBOS);
             }
@@ -318,23 +334,35 @@ k_traverse(FrameCtl* ctl, const PairRec* __restrict__ pairrec, const TreeRec* __
             trav_donate(st, warp, lane, bot, 32u, ctl, queue, cap_queue);
         }
         if (push) {
-            uint32_t s0 = (top + 2u * (uint32_t)__popc(push_m & lt_mask)) & STK_MASK, s1 = (s0 + 1u) & STK_MASK;
+            const uint32_t s0 = (top + 2u * (uint32_t)__popc(push_m & lt_mask)) & STK_MASK, s1 = (s0 + 1u) & STK_MASK;
             st.pair[warp][s0] = ip; st.a[warp][s0] = c0a; st.b[warp][s0] = c0b;
             st.pair[warp][s1] = ip; st.a[warp][s1] = c1a; st.b[warp][s1] = c1b;
         }
         top += total;
         __syncwarp();
 
-        // ---- feed idle warps: donate the oldest (closest to the roots) items when the queue runs low ----
+        // ---- feed waiting warps with what this warp cannot start on in its next iteration ----
         cnt = top - bot;
-        int hungry_now = 0;
-        if (lane == 0) hungry_now = (qt < qh + hungry) ? 1 : 0;
-        hungry_now = __shfl_sync(FULL_MASK, hungry_now, 0);
-        if (hungry_now && cnt >= 64u) {
+        uint32_t give = 0;
+        if (cnt > 32u && lane == 0) {           // only a warp with a surplus looks at the shared control words
+            const unsigned long long qh = ld_volatile_u64(&ctl->q_head), qt = ld_volatile_u64(&ctl->q_tail);
+            if (qh > qt) {
+                const unsigned long long want = qh - qt;
+                give = cnt - 32u;
+                if (give > 64u) give = 64u;
+                if ((unsigned long long)give > want) give = (uint32_t)want;
+            }
+        }
+        give = __shfl_sync(FULL_MASK, give, 0);
+        my_busy += (unsigned long long)(clock64() - t_begin);
+        if (give) {
             if (lane == 0 && delta != 0) atomicAdd((unsigned long long*)&ctl->pending, (unsigned long long)(long long)delta);
             delta = 0;
-            trav_donate(st, warp, lane, bot, 32u, ctl, queue, cap_queue);
-            __syncwarp();
+            while (give) {
+                const uint32_t k = give < 32u ? give : 32u;
+                trav_donate(st, warp, lane, bot, k, ctl, queue, cap_queue);
+                give -= k;
+            }
         }
     }
 
@@ -344,6 +372,7 @@ k_traverse(FrameCtl* ctl, const PairRec* __restrict__ pairrec, const TreeRec* __
         my_tri += __shfl_down_sync(FULL_MASK, my_tri, o);
     }
     if (lane == 0) {
+        atomicAdd(&ctl->n_iterations, my_iter); atomicAdd(&ctl->busy_cycles, my_busy); atomicAdd(&ctl->idle_polls, my_polls);
         if (my_sat) atomicAdd(&ctl->n_sat, my_sat);
         if (my_tri) atomicAdd(&ctl->n_tri_tests, my_tri);
     }
@@ -521,10 +550,9 @@ int imr_frame_run_device(imrcd_ctx* ctx) {
         IMR_CUDA(ctx, cudaEventRecord(ctx->ev[2], s));
         // ---- mid ----
         {
-            uint32_t n_warps = (uint32_t)ctx->trav_blocks * TRAV_WARPS;
             k_traverse<<<ctx->trav_blocks, TRAV_WARPS * 32, 0, s>>>(ctl, ctx->d_pairrec.as<PairRec>(), ctx->d_recs.as<TreeRec>(),
                                                                      ctx->d_queue.as<WorkItem>(), ctx->cap_queue, ctx->d_combos.as<Combo>(),
-                                                                     ctx->cap_combos, n_warps, n_warps * 4u);
+                                                                     ctx->cap_combos);
             launches += 1;
         }
         IMR_CUDA(ctx, cudaEventRecord(ctx->ev[3], s));
@@ -544,7 +572,7 @@ int imr_frame_run_device(imrcd_ctx* ctx) {
         IMR_CUDA(ctx, cudaGetLastError());
         ctx->ctl_host = *ctx->p_ctl.as<FrameCtl>();
         const FrameCtl& c = ctx->ctl_host;
-        ctx->queue_dirty = std::min<uint64_t>(c.q_tail, ctx->cap_queue);
+        ctx->queue_dirty = std::min<uint64_t>(std::max(c.q_tail, c.q_head), ctx->cap_queue);
 
         if (c.overflow) {
             if (c.overflow & OVF_PAIRS) ctx->cap_pairs = std::max<uint64_t>(c.n_pairs + c.n_pairs / 8, ctx->cap_pairs * 2);
@@ -558,7 +586,7 @@ int imr_frame_run_device(imrcd_ctx* ctx) {
         imrcd_frame_stats& st = ctx->stats;
         st.n_pairs = c.n_pairs; st.n_sat_tests = c.n_sat; st.n_combos = c.n_combos; st.n_tri_tests = c.n_tri_tests;
         st.n_hits = c.n_hits; st.n_coplanar_hits = c.n_coplanar; st.n_colliding = c.n_colliding;
-        st.traverse_launches = 1; st.total_launches = launches;
+        st.traverse_launches = 1; st.total_launches = launches; st.n_queue_items = c.n_donated; st.n_warp_iterations = c.n_iterations; st.trav_busy_cycles = c.busy_cycles; st.trav_idle_polls = c.idle_polls;
         cudaEventElapsedTime(&st.ms_total, ctx->ev[0], ctx->ev[5]);
         cudaEventElapsedTime(&st.ms_broad, ctx->ev[0], ctx->ev[1]);
         cudaEventElapsedTime(&st.ms_pair_setup, ctx->ev[1], ctx->ev[2]);

@@ -38,18 +38,23 @@ typedef uint4 Combo;      // (pair, offA, offB, cntA | cntB << 16), offsets rela
 // sorted sweep record, 32 B
 struct __align__(16) SweepRec { float umin, umax, vmin, vmax, wmin, wmax; uint32_t idx, cb; };
 
-// Device control block of one frame (one 256-B allocation, read back once per frame).
-struct FrameCtl {
-    unsigned long long q_head, q_tail;     // global traversal queue
-    long long pending;                     // alive work items (queue + stacks), termination detector
-    unsigned long long n_pairs;            // broad-phase pairs emitted (may exceed capacity -> overflow)
-    unsigned long long n_combos;
-    unsigned long long n_hits;
+// Device control block of one frame (read back once per frame).  Every hot word sits on its own 128-B line so
+// that polling warps and the atomics of different kernels do not serialise on one L2 line.
+struct __align__(128) FrameCtl {
+    unsigned long long q_head;      unsigned long long _p0[15];   // global traversal queue: next slot to pop
+    unsigned long long q_tail;      unsigned long long _p1[15];   //                          next slot to reserve
+    long long pending;              unsigned long long _p2[15];   // alive work items (queue + stacks): termination detector
+    unsigned int idle_warps;        unsigned int _p3[31];         // traversal warps currently starving (drives donation)
+    unsigned long long n_pairs;     unsigned long long _p4[15];   // broad-phase pairs emitted (may exceed capacity -> overflow)
+    unsigned long long n_combos;    unsigned long long _p5[15];
+    unsigned long long n_hits;      unsigned long long _p6[15];
+    unsigned long long n_colliding; unsigned long long _p7[15];
     unsigned long long n_coplanar;
     unsigned long long n_sat;
     unsigned long long n_tri_tests;
-    unsigned long long n_colliding;
     unsigned long long n_donated;          // items that went through the global queue after the roots
+    unsigned long long n_iterations;       // traversal warp-iterations (diagnostic)
+    unsigned long long busy_cycles, idle_polls;
     unsigned int overflow;                 // bit0 pairs, bit1 queue, bit2 combos, bit3 hits
     unsigned int pad;
 };

@@ -274,7 +274,9 @@ __host__ __device__ inline int tri_tri_isectline(V3 V0, V3 V1, V3 V2, V3 U0, V3 
     float vp0 = tt_pick(V0, index), vp1 = tt_pick(V1, index), vp2 = tt_pick(V2, index);
     float up0 = tt_pick(U0, index), up1 = tt_pick(U1, index), up2 = tt_pick(U2, index);
 
-    float i1a, i1b, i2a, i2b; V3 A1, A2, B1, B2;
+    // If the second interval computation finds U coplanar (all du == 0) while the first did not, the reference reads
+    // isect2[] / isectpointB* uninitialised (Triangle.cpp:959-960): undefined behaviour.  Defined here as zeros.
+    float i1a, i1b, i2a = 0.f, i2b = 0.f; V3 A1, A2, B1 = mk3(0.f, 0.f, 0.f), B2 = mk3(0.f, 0.f, 0.f);
     bool cop = tt_intervals(V0, V1, V2, vp0, vp1, vp2, dv0, dv1, dv2, dv0dv1, dv0dv2, i1a, i1b, A1, A2);
     if (cop) {
         // rare path: only here do the vertices go to indexable (local-memory) arrays

@@ -685,8 +685,11 @@ static int tri_tri_isectline(const float* V0, const float* V1, const float* V2,
                              int* coplanar, float* isectpt1, float* isectpt2) {
     float E1[3], E2[3], N1[3], N2[3], d1, d2;
     float du0, du1, du2, dv0, dv1, dv2, D[3];
-    float isect1[2], isect2v[2];
-    float ipA1[3], ipA2[3], ipB1[3], ipB2[3];
+    /* isect2v / ipB*: the reference leaves these uninitialised when the second compute_intervals_isectline call
+     * reports coplanar (Triangle.cpp:959-960, return value ignored) -- undefined behaviour there; zeros here and
+     * in the CUDA path so that both are deterministic. */
+    float isect1[2], isect2v[2] = { 0.f, 0.f };
+    float ipA1[3], ipA2[3], ipB1[3] = { 0.f, 0.f, 0.f }, ipB2[3] = { 0.f, 0.f, 0.f };
     float du0du1, du0du2, dv0dv1, dv0dv2;
     int index; float vp0, vp1, vp2, up0, up1, up2, b, c, max;
     int smallest1, smallest2;
