@@ -389,6 +389,45 @@ class PortOracle(_Base):
             ray_cap = max(ray_cap, int(summ[4]), int(summ[5]))
 
 
+def frame_pairs(orc, mats, trees, pairs, threads: int = 1):
+    """Mid + narrow over a pair list with the checker `orc` (the loop of CollisionDetection.cpp:44-69), split over
+    `threads` host threads (ctypes releases the GIL; both libraries' batch entry points are re-entrant).
+    Returns dict(combos, tri_tests, colliding, with_combos, wall_s, mid_s, narrow_s)."""
+    import time
+    from concurrent.futures import ThreadPoolExecutor
+    mats = _c(mats, np.float32).reshape(-1, 16)
+    pairs = _c(pairs, np.uint32).reshape(-1, 2)
+    n = mats.shape[0]
+    handles = (C.c_void_p * n)(*[t.h for t in trees])
+    ref = orc.kind == "reference"
+    f = orc.lib.imr_ref_frame_pairs if ref else orc.lib.imro_frame_pairs
+    f.restype = None
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p] + ([C.c_void_p] if ref else [])
+
+    def run(chunk):
+        tot = np.zeros(4, np.uint64); secs = np.zeros(2, np.float64)
+        if len(chunk):
+            if ref:
+                f(mats.ctypes.data, handles, chunk.ctypes.data, len(chunk), tot.ctypes.data, secs.ctypes.data)
+            else:
+                f(mats.ctypes.data, handles, chunk.ctypes.data, len(chunk), tot.ctypes.data)
+        return tot, secs
+
+    threads = max(1, int(threads))
+    # interleaved slices balance the load (neighbouring pairs have similar cost)
+    chunks = [np.ascontiguousarray(pairs[i::threads]) for i in range(threads)]
+    t0 = time.perf_counter()
+    if threads == 1:
+        res = [run(chunks[0])]
+    else:
+        with ThreadPoolExecutor(threads) as ex:
+            res = list(ex.map(run, chunks))
+    wall = time.perf_counter() - t0
+    tot = sum(r[0] for r in res); secs = sum(r[1] for r in res)
+    return dict(combos=int(tot[0]), tri_tests=int(tot[1]), colliding=int(tot[2]), with_combos=int(tot[3]), wall_s=wall,
+                mid_s=float(secs[0]), narrow_s=float(secs[1]))
+
+
 def load(prefer: str = "reference"):
     """Return the strongest available checker: the real reference if its .so exists, else the port."""
     if prefer == "reference" and os.path.exists(REF_SO):

@@ -1043,3 +1043,17 @@ void imro_pair(const imro_tree* a, const float* mat_a, const imro_tree* b, const
     free(combos);
     free(ma.map); free(ma.present); free(ma.order); free(mb.map); free(mb.present); free(mb.order);
 }
+
+/* Batch mid + narrow over a pair list: the loop of IMR/src/CollisionDetection/CollisionDetection.cpp:44-69 on
+ * (first,second) entry-index pairs.  Re-entrant.  totals: [0] combos [1] tri-pair tests [2] colliding pairs
+ * [3] pairs with >= 1 combo. */
+void imro_frame_pairs(const float* mats, const imro_tree* const* trees, const uint32_t* pairs, uint64_t n_pairs, uint64_t* totals) {
+    uint64_t combos = 0, tests = 0, colliding = 0, with_combos = 0;
+    for (uint64_t k = 0; k < n_pairs; ++k) {
+        const uint32_t ia = pairs[2 * k], ib = pairs[2 * k + 1];
+        uint64_t summ[7]; float avg[6];
+        imro_pair(trees[ia], mats + 16 * (uint64_t)ia, trees[ib], mats + 16 * (uint64_t)ib, NULL, NULL, 0, summ, avg, NULL, NULL, 0);
+        combos += summ[0]; tests += summ[1]; colliding += summ[6]; with_combos += summ[0] ? 1 : 0;
+    }
+    totals[0] = combos; totals[1] = tests; totals[2] = colliding; totals[3] = with_combos;
+}

@@ -384,6 +384,41 @@ void imr_ref_pair(void* tree_a, const float* mat_a, void* tree_b, const float* m
     }
 }
 
+// ---- batch mid + narrow over a pair list (bench.py's --impl reference / cpu_baseline legs) ----------
+// For each (first,second) entry pair: OBBtreesCollision::ExecuteOBBtreesCollision, then -- when there is at least
+// one leaf combo (CollisionDetection.cpp:51) -- CreateUncollideRays::ExecuteCreateUncollideRays, exactly the loop of
+// CollisionDetection.cpp:44-69.  Re-entrant (no shared state), so the caller may run several pair slices on
+// several threads.  totals: [0] combos [1] tri-pair tests [2] colliding pairs [3] pairs with >= 1 combo.
+// seconds: [0] mid [1] narrow.
+void imr_ref_frame_pairs(const float* mats, void* const* trees, const uint32_t* pairs, uint64_t n_pairs,
+                         uint64_t* totals, double* seconds) {
+    OBBtreesCollision mid;
+    CreateUncollideRays narrow;
+    uint64_t combos = 0, tests = 0, colliding = 0, with_combos = 0;
+    double s_mid = 0.0, s_narrow = 0.0;
+    for (uint64_t k = 0; k < n_pairs; ++k) {
+        const uint32_t ia = pairs[2 * k], ib = pairs[2 * k + 1];
+        auto pr = std::make_pair(make_entry(mats + 16 * uint64_t(ia), nullptr, static_cast<RefTree*>(trees[ia]), true, 1),
+                                 make_entry(mats + 16 * uint64_t(ib), nullptr, static_cast<RefTree*>(trees[ib]), true, 2));
+        auto t0 = std::chrono::steady_clock::now();
+        CDentriesPairTrianglesPairs m = mid.ExecuteOBBtreesCollision(pr);
+        auto t1 = std::chrono::steady_clock::now();
+        s_mid += std::chrono::duration<double>(t1 - t0).count();
+        const auto& cc = m.OBBtreesIntersectInfoObj.candidateTriangleRangeCombinations;
+        if (cc.empty()) continue;
+        ++with_combos;
+        combos += cc.size();
+        for (auto& c : cc) tests += uint64_t(c.first_obbtree_count) * uint64_t(c.second_obbtree_count);
+        auto t2 = std::chrono::steady_clock::now();
+        CDentriesUncollideRays rays = narrow.ExecuteCreateUncollideRays(m);
+        auto t3 = std::chrono::steady_clock::now();
+        s_narrow += std::chrono::duration<double>(t3 - t2).count();
+        if (rays.rays_from_first_to_second.size() || rays.rays_from_second_to_first.size()) ++colliding;   // CollisionDetection.cpp:63
+    }
+    totals[0] = combos; totals[1] = tests; totals[2] = colliding; totals[3] = with_combos;
+    if (seconds) { seconds[0] = s_mid; seconds[1] = s_narrow; }
+}
+
 const char* imr_ref_build_info() { return "reference sources compiled in place: g++ -std=c++20 -O2 -ffp-contract=off"; }
 
 }  // extern "C"

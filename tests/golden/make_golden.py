@@ -1,0 +1,159 @@
+"""Generate tests/golden/*.npz from the UNMODIFIED reference (oracle/_ref/libimr_ref.so, compiled in place from
+/root/reference by oracle/Makefile).  Run here, in the build container; the fixtures are committed and travel to the
+GPU box, where /root/reference does not exist.
+
+    python tests/golden/make_golden.py
+
+Every array below is an output of the reference's own translation units (IEEE build: -O2 -ffp-contract=off) on the
+stored inputs.  Floats are compared by bit pattern in the tests.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from inmyroom_vulkan_b200 import scenes  # noqa: E402
+from oracle import bind  # noqa: E402
+
+
+def rand_mats(rng, n, tscale=1.0):
+    s = rng.random((n, 3)) * 1.5 + 0.25
+    return scenes.trs_matrices(rng.normal(size=(n, 3)) * tscale, scenes.random_quaternions(rng, n), s)
+
+
+def degenerate_tris(rng, count=800):
+    A, B = [], []
+    base = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32)
+    for k in range(count):
+        t = base * np.float32(0.5 + rng.random()) + rng.normal(size=3).astype(np.float32) * np.float32(k % 3 == 0)
+        kind = k % 8
+        if kind == 0:
+            u = t + np.array([0.2, 0.1, 0], np.float32)
+        elif kind == 1:
+            u = t + np.array([5, 5, 0], np.float32)
+        elif kind == 2:
+            u = t.copy(); u[2] = t[2] + np.array([0, 0, 1], np.float32)
+        elif kind == 3:
+            u = t.copy(); u[1] += np.array([0, 0.3, 1], np.float32); u[2] += np.array([0.4, 0, -1], np.float32)
+        elif kind == 4:
+            u = np.stack([t[0], t[0], t[1]])
+        elif kind == 5:
+            u = t + np.array([0.1, 0.1, 5e-7], np.float32); u[2] += np.array([0, 0, 1], np.float32)
+        elif kind == 6:
+            u = t.copy()
+        else:
+            u = np.array([[0.2, 0.2, -1], [0.3, 0.2, 1], [0.2, 0.3, 1]], np.float32) * np.float32(0.5 + rng.random())
+        A.append(t.reshape(9)); B.append(u.reshape(9))
+    return np.array(A, np.float32), np.array(B, np.float32)
+
+
+def main():
+    bind.build("ref")
+    ref = bind.RefOracle()
+    rng = np.random.default_rng(20261017)
+
+    # ---- predicates ----
+    n = 1500
+    a = rng.normal(size=(n, 12)).astype(np.float32); b = rng.normal(size=(n, 12)).astype(np.float32)
+    b[:, :3] *= 2.5
+    b[:100, 3:] = a[:100, 3:]              # parallel axes: zero cross products
+    a[100:140, 3:6] = 0                    # degenerate (flat) boxes
+    mats = rand_mats(rng, n)
+    verdict = np.array([ref.sat(a[i], b[i], mats[i]) for i in range(n)], np.uint8)
+    surf_a = np.array([ref.surface(a[i]) for i in range(n)], np.float32)
+    surf_b = np.array([ref.surface(b[i], mats[i]) for i in range(n)], np.float32)
+    xform = np.stack([ref.box_transform(b[i], mats[i]) for i in range(n)])
+    np.savez_compressed(os.path.join(HERE, "sat.npz"), a=a, b=b, mats=mats, verdict=verdict, surf_a=surf_a, surf_b=surf_b, xform=xform)
+
+    n = 4000
+    ta = rng.normal(size=(n, 9)).astype(np.float32); tb = (rng.normal(size=(n, 9)) * 0.8).astype(np.float32)
+    m = rand_mats(rng, 1, 0.2)[0]
+    f, s = ref.tri_tri(ta, tb, m)
+    da, db = degenerate_tris(rng)
+    df, ds = ref.tri_tri(da, db, None)
+    np.savez_compressed(os.path.join(HERE, "tri_tri.npz"), a=ta, b=tb, m=m, flags=f, seg=s, da=da, db=db, dflags=df, dseg=ds)
+
+    n = 400
+    ma = rand_mats(rng, n, 20.0); mb = rand_mats(rng, n, 20.0)
+    ma[:20] = scenes.trs_matrices(np.zeros((20, 3)), np.tile([[0.70710678, 0, 0, 0.70710678]], (20, 1)),
+                                  np.tile([[0.0399999991, 0.0400000028, 0.0400000028]], (20, 1)))
+    rel = np.stack([ref.pair_matrix(ma[i], mb[i]) for i in range(n)])
+    np.savez_compressed(os.path.join(HERE, "pair_matrix.npz"), a=ma, b=mb, rel=rel, axes=ref.sweep_axes())
+
+    # ---- OBB fit (OBB.cpp:33-166 incl. the rows-of-V quirk, SURVEY finding 3) ----
+    clouds, boxes, sizes = [], [], []
+    for k in range(40):
+        cnt = int(rng.integers(3, 60))
+        p = (rng.normal(size=(cnt, 3)) * (rng.random(3) * 3 + 0.1) + rng.normal(size=3) * 5).astype(np.float32)
+        if k % 10 == 0:
+            p[:] = p[0]                   # a single unique point
+        if k % 10 == 1:
+            p[:, 2] = p[0, 2]             # planar cloud
+        clouds.append(p); sizes.append(cnt); boxes.append(ref.obb_from_points(p))
+    np.savez_compressed(os.path.join(HERE, "obb_fit.npz"), points=np.concatenate(clouds), sizes=np.array(sizes, np.int64), boxes=np.stack(boxes))
+
+    # ---- trees (OBBtree.cpp:321) ----
+    tree_meshes = {"torus20x10": scenes.torus(20, 10), "box3": scenes.box_mesh(1, 2, 3, sub=3), "sphere12x9": scenes.uv_sphere(12, 9),
+                   "tiny4": None, "one": None}
+    bm = scenes.box_mesh(1, 1, 1, sub=1)
+    tree_meshes["tiny4"] = scenes.Mesh(bm.positions[:4].copy(), bm.normals[:4].copy(), bm.vertex_ids[:4].copy(), "tiny4")
+    tree_meshes["one"] = scenes.Mesh(bm.positions[:1].copy(), bm.normals[:1].copy(), bm.vertex_ids[:1].copy(), "one")
+    out = {}
+    for name, msh in tree_meshes.items():
+        ft = ref.tree_build(msh.positions, msh.normals, msh.vertex_ids).flat
+        for fld in ("boxes", "left", "right", "tri_off", "tri_cnt", "tri_pos", "tri_nrm", "tri_vid", "tri_orig"):
+            out[f"{name}.{fld}"] = getattr(ft, fld)
+        out[f"{name}.in_pos"] = msh.positions; out[f"{name}.in_nrm"] = msh.normals; out[f"{name}.in_vid"] = msh.vertex_ids
+    np.savez_compressed(os.path.join(HERE, "trees.npz"), **out)
+
+    # ---- whole frames: broad + mid + narrow with the reference's own trees ----
+    from helpers import oracle_frame
+    port = None
+    try:
+        bind.build("port"); port = bind.PortOracle()
+    except Exception:
+        pass
+    frames = {}
+    static = scenes.atrium_static(detail=1)
+    keep = [0, 3, 7, 8, 64, 120, 125, 130]
+    small_static = ([scenes.Mesh(static[0][i].positions[::7].copy(), static[0][i].normals[::7].copy(), static[0][i].vertex_ids[::7].copy(), static[0][i].name)
+                     for i in keep], static[1][keep])
+    cases = {
+        "torus_instances": scenes.scene_instances(scenes.torus(20, 10), 40, seed=77, neighbours=6.0),
+        "static_vs_bodies": scenes.scene_static_vs_bodies(scenes.uv_sphere(12, 9), 240, seed=5, body_scale=(1.0, 3.0), static=small_static),
+    }
+    for name, sc in cases.items():
+        trees = [ref.tree_build(msh.positions, msh.normals, msh.vertex_ids) for msh in sc.meshes]
+        res = oracle_frame(ref, sc, trees, port=port)
+        pairs = res["pairs"]
+        hit_pair, hit_ids, hit_seg, summ, avg = [], [], [], [], []
+        for k, (pa, pb) in enumerate(pairs.tolist()):
+            r = res["per_pair"][(pa, pb)]
+            hit_pair.append(np.full(r.n_hits, k, np.uint32)); hit_ids.append(r.hit_ids.reshape(-1, 2)); hit_seg.append(r.hit_seg.reshape(-1, 7))
+            summ.append([r.n_combos, r.n_tri_tests, r.n_hits, r.n_coplanar, r.rays_first, r.rays_second, int(r.colliding)])
+            avg.append(r.avg)
+        frames[f"{name}.matrices"] = sc.matrices; frames[f"{name}.mesh_index"] = sc.mesh_index
+        frames[f"{name}.should_callback"] = sc.should_callback; frames[f"{name}.entities"] = sc.entities
+        frames[f"{name}.n_meshes"] = np.array([len(sc.meshes)])
+        for mi, msh in enumerate(sc.meshes):
+            frames[f"{name}.mesh{mi}.pos"] = msh.positions; frames[f"{name}.mesh{mi}.nrm"] = msh.normals; frames[f"{name}.mesh{mi}.vid"] = msh.vertex_ids
+        frames[f"{name}.pairs"] = pairs
+        frames[f"{name}.hit_pair"] = np.concatenate(hit_pair) if hit_pair else np.zeros(0, np.uint32)
+        frames[f"{name}.hit_ids"] = np.concatenate(hit_ids) if hit_ids else np.zeros((0, 2), np.uint32)
+        frames[f"{name}.hit_seg"] = np.concatenate(hit_seg) if hit_seg else np.zeros((0, 7), np.float32)
+        frames[f"{name}.summary"] = np.array(summ, np.uint64).reshape(-1, 7)
+        frames[f"{name}.avg"] = np.array(avg, np.float32).reshape(-1, 6)
+        print(name, "entries", sc.n_entries, "pairs", len(pairs), "totals", res["totals"])
+    np.savez_compressed(os.path.join(HERE, "frames.npz"), **frames)
+    for fn in sorted(os.listdir(HERE)):
+        if fn.endswith(".npz"):
+            print(fn, os.path.getsize(os.path.join(HERE, fn)))
+
+
+if __name__ == "__main__":
+    main()

@@ -8,6 +8,20 @@ def f32_bits(a):
     return np.ascontiguousarray(a, np.float32).view(np.uint32)
 
 
+def contacts_close(avg, gold, rel, rtol=1e-5):
+    """Contact points agree within `rtol` relative (north star): average_point_first lives in first's model space;
+    average_point_second is inverse(rel) * (a first-space point) (CreateUncollideRays.cpp:191-198), so its rounding noise
+    scales with the FIRST-space magnitude -- compare it after mapping back with rel, relative to the vector norms."""
+    avg = np.asarray(avg, np.float64); gold = np.asarray(gold, np.float64)
+    M = np.asarray(rel, np.float64).reshape(4, 4).T           # column-major -> math layout
+    def fwd(p):
+        return M[:3, :3] @ p + M[:3, 3]
+    a_ok = np.linalg.norm(avg[:3] - gold[:3]) <= rtol * max(np.linalg.norm(gold[:3]), 1e-30)
+    b1, b2 = fwd(avg[3:]), fwd(gold[3:])
+    b_ok = np.linalg.norm(b1 - b2) <= 4 * rtol * max(np.linalg.norm(b2), np.linalg.norm(M[:3, 3]), 1e-30)
+    return bool(a_ok and b_ok)
+
+
 def oracle_frame(orc, scene, trees, port=None, max_pairs=None):
     """Broad + mid + narrow through an oracle.  `trees` = one oracle Tree per scene mesh.
     Returns dict(pairs=(k,2) ordered entry pairs, per_pair={(a,b): PairResult}, totals)."""

@@ -1,0 +1,56 @@
+"""CPU: the C-ABI library loads without a GPU and exports every symbol include/imrcd.h declares; the Python binding's
+struct layouts match the header; creating a context without a GPU fails loudly (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "imrcd.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(imrcd_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__ as g
+    g.build()
+    from inmyroom_vulkan_b200 import _lib
+    lib = _lib.load()
+    declared = _declared_symbols()
+    assert len(declared) >= 25
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/imrcd.h but not exported by libimrcd.so"
+    assert sorted(_lib.EXPORTED_SYMBOLS) == declared, "the ctypes binding and the header disagree"
+    assert b"sm_100a" in lib.imrcd_version()
+
+
+def test_struct_layouts_match_header():
+    from inmyroom_vulkan_b200 import _lib
+    from inmyroom_vulkan_b200.collision import HIT_DTYPE, PAIR_DTYPE
+    assert C.sizeof(_lib.EntityPair) == 80 == PAIR_DTYPE.itemsize
+    assert C.sizeof(_lib.TriHit) == 40 == HIT_DTYPE.itemsize
+    for (name, _), f in zip(_lib.EntityPair._fields_, PAIR_DTYPE.names):
+        assert name == f and getattr(_lib.EntityPair, name).offset == PAIR_DTYPE.fields[f][1]
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from inmyroom_vulkan_b200.collision import Context, ImrcdError
+    with pytest.raises(ImrcdError, match="no sm_100 device"):
+        Context(0)
+
+
+def test_product_never_imports_the_oracle():
+    """Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may touch oracle/."""
+    pkg = os.path.join(ROOT, "inmyroom_vulkan_b200")
+    for dp, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".h", "Makefile")):
+                txt = open(os.path.join(dp, fn)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt and "liboracle" not in txt and "libimr_ref" not in txt, fn

@@ -1,0 +1,51 @@
+"""GPU parity against the COMMITTED golden vectors (outputs of the unmodified reference, tests/golden/make_golden.py):
+the device predicates and whole frames through the C ABI.  Bit-exact."""
+import numpy as np
+import pytest
+
+import golden_io
+from inmyroom_vulkan_b200.collision import CollisionDetection, OBBtree
+from helpers import f32_bits, gpu_frame
+
+pytestmark = pytest.mark.gpu
+
+
+def test_sat_golden(gpu_ctx):
+    z = golden_io.load("sat")
+    v, sa, sb = gpu_ctx.test_sat(z["a"], z["b"], z["mats"])
+    assert np.array_equal(v, z["verdict"])
+    assert np.array_equal(f32_bits(sa), f32_bits(z["surf_a"])) and np.array_equal(f32_bits(sb), f32_bits(z["surf_b"]))
+
+
+def test_tri_tri_golden(gpu_ctx):
+    z = golden_io.load("tri_tri")
+    f, s = gpu_ctx.test_tri_tri(z["a"], z["b"], z["m"])
+    assert np.array_equal(f, z["flags"]) and np.array_equal(f32_bits(s), f32_bits(z["seg"]))
+    f, s = gpu_ctx.test_tri_tri(z["da"], z["db"], None)
+    assert np.array_equal(f, z["dflags"]) and np.array_equal(f32_bits(s), f32_bits(z["dseg"]))
+
+
+def test_pair_matrix_golden(gpu_ctx):
+    z = golden_io.load("pair_matrix")
+    assert np.array_equal(f32_bits(gpu_ctx.test_pair_matrix(z["a"], z["b"])), f32_bits(z["rel"]))
+
+
+@pytest.mark.parametrize("name", golden_io.frame_names())
+def test_frame_golden(gpu_ctx, port, name):
+    """Reference-identical trees (the port's build is pinned bit-exact to the reference's by test_oracle_golden.py)
+    imported into the GPU; the frame must reproduce the reference's pairs, hits and segments."""
+    sc, gold = golden_io.golden_frame(golden_io.load("frames"), name)
+    trees = [OBBtree.from_flat(gpu_ctx, port.tree_build(m.positions, m.normals, m.vertex_ids).flat) for m in sc.meshes]
+    cd = CollisionDetection(ctx=gpu_ctx)
+    st, bp, ep, hits = gpu_frame(cd, sc, trees)
+    assert set(map(tuple, bp.tolist())) == set(map(tuple, gold["pairs"].tolist()))
+    summ = gold["summary"]
+    assert st["n_combos"] == summ[:, 0].sum() and st["n_tri_tests"] == summ[:, 1].sum()
+    assert st["n_hits"] == summ[:, 2].sum() and st["n_coplanar_hits"] == summ[:, 3].sum() and st["n_colliding"] == summ[:, 6].sum()
+    gp = gold["pairs"][gold["hit_pair"]]
+    g = {(int(a), int(b), int(i), int(j)): f32_bits(seg).tobytes() for (a, b), (i, j), seg in zip(gp.tolist(), gold["hit_ids"].tolist(), gold["hit_seg"])}
+    o = {(int(bp[h["pair"]][0]), int(bp[h["pair"]][1]), int(h["tri_first"]), int(h["tri_second"])):
+         f32_bits(np.concatenate([h["source"], h["target"], [h["weight"]]])).tobytes() for h in hits}
+    assert o == g
+    coll = {tuple(p) for p, s in zip(gold["pairs"].tolist(), summ) if s[6]}
+    assert {(int(p["entry_first"]), int(p["entry_second"])) for p in ep} == coll
