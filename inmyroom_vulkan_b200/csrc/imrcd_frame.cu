@@ -6,6 +6,7 @@
 //   reduce : k_finalize    colliding entity pairs                      (CollisionDetection.cpp:60-67)
 #include "imrcd_internal.cuh"
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 #include <algorithm>
 #include <cstring>
 
@@ -64,8 +65,9 @@ __global__ void k_entry_prep(uint32_t n, const float* __restrict__ cur, const ui
 }
 
 __global__ void k_gather_sorted(uint32_t n, const uint32_t* __restrict__ sorted_idx, const float* __restrict__ ext,
-                                const uint8_t* __restrict__ cb, SweepRec* __restrict__ out) {
+                                const uint8_t* __restrict__ cb, SweepRec* __restrict__ out, uint32_t* __restrict__ cb_flag) {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p == 0) cb_flag[n] = 0u;          // the scans run over n + 1 elements so that element n of the output is the total
     if (p >= n) return;
     uint32_t e = sorted_idx[p];
     const float* eo = ext + 6 * (size_t)e;
@@ -73,44 +75,102 @@ __global__ void k_gather_sorted(uint32_t n, const uint32_t* __restrict__ sorted_
     r.umin = eo[0]; r.umax = eo[1]; r.vmin = eo[2]; r.vmax = eo[3]; r.wmin = eo[4]; r.wmax = eo[5];
     r.idx = e; r.cb = cb[e];
     out[p] = r;
+    cb_flag[p] = r.cb ? 1u : 0u;
 }
 
-// One warp per sorted position p ("active" element a); lanes stride the forward window of entries whose
-// U interval starts no later than a's ends.  The reference's active-list sweep reports (a,e) on an axis
-// iff a precedes e in min-order and NOT (a.max < e.min) (SweepAndPrune.cpp:58); a pair survives iff that
-// holds on U, V and W and either side has shouldCallback (:60,84).  Orientation = U order (:63).
-__global__ void k_sweep(uint32_t n, const SweepRec* __restrict__ sorted, uint2* __restrict__ pairs, unsigned long long cap,
-                        FrameCtl* ctl, uint32_t rank, uint32_t n_ranks) {
+// The sweep (SweepAndPrune.cpp:50-85) reports (a,e), a before e in U-min order, iff e.umin <= a.umax on U (:58), the same
+// on V and W, and a.shouldCallback || e.shouldCallback (:60).  So an entry WITH the flag must look at every later entry
+// of its U window, an entry WITHOUT it only at the later entries that have it.  Two sorted lists make both windows
+// contiguous: S_all (everything) and S_C (the flagged entries, same order; cpos[p] = flagged entries before position p).
+__global__ void k_compact_flagged(uint32_t n, const SweepRec* __restrict__ sorted, const uint32_t* __restrict__ cpos, SweepRec* __restrict__ sorted_c) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const SweepRec r = sorted[p];
+    if (r.cb) sorted_c[cpos[p]] = r;
+}
+
+#define SWEEP_CHUNK 512u     // candidates per work item of k_sweep
+
+// Window of every entry by binary search (the lists are sorted by umin): candidates [start, start + len) of its list.
+__global__ void k_window(uint32_t n, const SweepRec* __restrict__ sorted, const SweepRec* __restrict__ sorted_c, const uint32_t* __restrict__ cpos,
+                         uint32_t* __restrict__ wlen, uint32_t* __restrict__ chunks) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p == 0) chunks[n] = 0u;
+    if (p >= n) return;
+    const SweepRec a = sorted[p];
+    const SweepRec* list = a.cb ? sorted : sorted_c;
+    const uint32_t start = a.cb ? p + 1u : cpos[p];
+    uint32_t lo = start, hi = a.cb ? n : cpos[n];
+    while (lo < hi) {                                   // first index whose umin > a.umax  (expiry is strict, :58)
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if (!(a.umax < list[mid].umin)) lo = mid + 1u; else hi = mid;
+    }
+    const uint32_t len = lo - start;
+    wlen[p] = len;
+    chunks[p] = (len + SWEEP_CHUNK - 1u) / SWEEP_CHUNK;
+}
+
+// Largest p in [0, n) with arr[p] <= c, found by the whole warp 32 probes at a time (arr is non-decreasing, arr[0] = 0).
+__device__ __forceinline__ uint32_t warp_find_owner(const uint32_t* __restrict__ arr, uint32_t n, uint32_t c, uint32_t lane) {
+    uint32_t lo = 0, hi = n;                            // arr[lo] <= c ; hi == n or arr[hi] > c
+    while (hi - lo > 1u) {
+        const uint32_t span = hi - lo - 1u;             // candidates lo+1 .. hi-1
+        uint32_t idx;
+        if (span <= 32u) idx = lo + 1u + lane;
+        else idx = lo + 1u + (uint32_t)(((unsigned long long)span * lane) >> 5);
+        const bool ok = (idx < hi) && (__ldg(arr + idx) <= c);
+        const uint32_t m = __ballot_sync(FULL_MASK, ok);        // monotone: a prefix of ones
+        const uint32_t cnt = (uint32_t)__popc(m);
+        const uint32_t new_lo = cnt ? __shfl_sync(FULL_MASK, idx, cnt - 1u) : lo;
+        const uint32_t nxt = __shfl_sync(FULL_MASK, idx, cnt < 32u ? cnt : 31u);
+        const uint32_t new_hi = (cnt < 32u && nxt < hi) ? nxt : hi;
+        if (span <= 32u) { lo = new_lo; break; }
+        lo = new_lo; hi = new_hi;
+    }
+    return lo;
+}
+
+// Load-balanced sweep: one warp per chunk of SWEEP_CHUNK candidates, so that the few entries with very long windows
+// (a floor spanning the whole scene) are spread over the machine.  Orientation = U order (:63).
+__global__ void __launch_bounds__(256)
+k_sweep(uint32_t n, const SweepRec* __restrict__ sorted, const SweepRec* __restrict__ sorted_c, const uint32_t* __restrict__ cpos,
+        const uint32_t* __restrict__ wlen, const uint32_t* __restrict__ chunk_off, uint2* __restrict__ pairs, unsigned long long cap,
+        FrameCtl* ctl, uint32_t rank, uint32_t n_ranks) {
     const uint32_t lane = lane_id();
     const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; p < n; p += warps_total) {
+    const uint32_t total = chunk_off[n];
+    for (uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; c < total; c += warps_total) {
+        const uint32_t p = warp_find_owner(chunk_off, n, c, lane);
         const SweepRec a = sorted[p];
-        for (uint32_t q0 = p + 1; q0 < n; q0 += 32) {
-            uint32_t q = q0 + lane;
-            bool in_window = false, emit = false;
+        const SweepRec* list = a.cb ? sorted : sorted_c;
+        const uint32_t start = a.cb ? p + 1u : cpos[p];
+        const uint32_t k0 = (c - chunk_off[p]) * SWEEP_CHUNK;
+        const uint32_t len = wlen[p];
+        const uint32_t k1 = (k0 + SWEEP_CHUNK < len) ? k0 + SWEEP_CHUNK : len;
+        for (uint32_t kb = k0; kb < k1; kb += 32u) {
+            const uint32_t k = kb + lane;
+            bool emit = false;
             SweepRec e;
-            if (q < n) {
-                e = sorted[q];
-                in_window = !(a.umax < e.umin);
-                if (in_window && (a.cb | e.cb)) {
-                    bool v_ok = (a.vmin <= e.vmin) ? !(a.vmax < e.vmin) : !(e.vmax < a.vmin);
-                    bool w_ok = (a.wmin <= e.wmin) ? !(a.wmax < e.wmin) : !(e.wmax < a.wmin);
-                    uint32_t owner = a.idx > e.idx ? a.idx : e.idx;
+            if (k < k1) {
+                e = list[start + k];
+                if (a.cb | e.cb) {
+                    const bool v_ok = (a.vmin <= e.vmin) ? !(a.vmax < e.vmin) : !(e.vmax < a.vmin);
+                    const bool w_ok = (a.wmin <= e.wmin) ? !(a.wmax < e.wmin) : !(e.wmax < a.wmin);
+                    const uint32_t owner = a.idx > e.idx ? a.idx : e.idx;
                     emit = v_ok && w_ok && (owner % n_ranks == rank);
                 }
             }
-            uint32_t m = __ballot_sync(FULL_MASK, emit);
+            const uint32_t m = __ballot_sync(FULL_MASK, emit);
             if (m) {
                 unsigned long long base = 0;
                 if (lane == 0) base = atomicAdd(&ctl->n_pairs, (unsigned long long)__popc(m));
                 base = __shfl_sync(FULL_MASK, base, 0);
                 if (emit) {
-                    unsigned long long slot = base + __popc(m & ((1u << lane) - 1));
+                    const unsigned long long slot = base + __popc(m & ((1u << lane) - 1));
                     if (slot < cap) pairs[slot] = make_uint2(a.idx, e.idx);
                     else atomicOr(&ctl->overflow, (unsigned)OVF_PAIRS);
                 }
             }
-            if (!__all_sync(FULL_MASK, in_window)) break;   // window is contiguous in U-min order
         }
     }
 }
@@ -495,11 +555,22 @@ int imr_frame_run_device(imrcd_ctx* ctx) {
     IMR_CUDA(ctx, ctx->d_idx.reserve(4ull * n, 0, s));
     IMR_CUDA(ctx, ctx->d_idx2.reserve(4ull * n, 0, s));
     IMR_CUDA(ctx, ctx->d_sorted.reserve(sizeof(SweepRec) * (size_t)n, 0, s));
+    IMR_CUDA(ctx, ctx->d_sorted_c.reserve(sizeof(SweepRec) * (size_t)n, 0, s));
+    IMR_CUDA(ctx, ctx->d_flag.reserve(4ull * (n + 1), 0, s));
+    IMR_CUDA(ctx, ctx->d_cpos.reserve(4ull * (n + 1), 0, s));
+    IMR_CUDA(ctx, ctx->d_wlen.reserve(4ull * (n + 1), 0, s));
+    IMR_CUDA(ctx, ctx->d_chunks.reserve(4ull * (n + 1), 0, s));
+    IMR_CUDA(ctx, ctx->d_chunkoff.reserve(4ull * (n + 1), 0, s));
     IMR_CUDA(ctx, ctx->d_ctl.reserve(sizeof(FrameCtl), 0, s));
     IMR_CUDA(ctx, ctx->p_ctl.reserve(sizeof(FrameCtl)));
     size_t cub_bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, ctx->d_keys.as<uint32_t>(), ctx->d_keys2.as<uint32_t>(),
                                     ctx->d_idx.as<uint32_t>(), ctx->d_idx2.as<uint32_t>(), (int)n, 0, 32, s);
+    {
+        size_t scan_bytes = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, ctx->d_flag.as<uint32_t>(), ctx->d_cpos.as<uint32_t>(), (int)(n + 1), s);
+        cub_bytes = std::max(cub_bytes, scan_bytes);
+    }
     IMR_CUDA(ctx, ctx->d_cubtmp.reserve(cub_bytes, 0, s));
 
     if (ctx->trav_blocks == 0) {
@@ -533,13 +604,16 @@ int imr_frame_run_device(imrcd_ctx* ctx) {
         cub::DeviceRadixSort::SortPairs(ctx->d_cubtmp.p, cub_bytes, ctx->d_keys.as<uint32_t>(), ctx->d_keys2.as<uint32_t>(),
                                         ctx->d_idx.as<uint32_t>(), ctx->d_idx2.as<uint32_t>(), (int)n, 0, 32, s);
         k_gather_sorted<<<blocks_for(n, 256), 256, 0, s>>>(n, ctx->d_idx2.as<uint32_t>(), ctx->d_ext.as<float>(), ctx->d_cb.as<uint8_t>(),
-                                                            ctx->d_sorted.as<SweepRec>());
-        {
-            unsigned warps = std::min<unsigned long long>(n, (unsigned long long)ctx->sm_count * 64ull);
-            k_sweep<<<blocks_for(32ull * warps, 256), 256, 0, s>>>(n, ctx->d_sorted.as<SweepRec>(), ctx->d_pairs.as<uint2>(), ctx->cap_pairs,
-                                                                     ctl, ctx->shard_rank, ctx->shard_n);
-        }
-        launches += 3 + 4;   // radix sort of <= a few 100k keys: histogram + onesweep passes (counted as 4)
+                                                            ctx->d_sorted.as<SweepRec>(), ctx->d_flag.as<uint32_t>());
+        cub::DeviceScan::ExclusiveSum(ctx->d_cubtmp.p, cub_bytes, ctx->d_flag.as<uint32_t>(), ctx->d_cpos.as<uint32_t>(), (int)(n + 1), s);
+        k_compact_flagged<<<blocks_for(n, 256), 256, 0, s>>>(n, ctx->d_sorted.as<SweepRec>(), ctx->d_cpos.as<uint32_t>(), ctx->d_sorted_c.as<SweepRec>());
+        k_window<<<blocks_for(n, 256), 256, 0, s>>>(n, ctx->d_sorted.as<SweepRec>(), ctx->d_sorted_c.as<SweepRec>(), ctx->d_cpos.as<uint32_t>(),
+                                                     ctx->d_wlen.as<uint32_t>(), ctx->d_chunks.as<uint32_t>());
+        cub::DeviceScan::ExclusiveSum(ctx->d_cubtmp.p, cub_bytes, ctx->d_chunks.as<uint32_t>(), ctx->d_chunkoff.as<uint32_t>(), (int)(n + 1), s);
+        k_sweep<<<ctx->sm_count * 8, 256, 0, s>>>(n, ctx->d_sorted.as<SweepRec>(), ctx->d_sorted_c.as<SweepRec>(), ctx->d_cpos.as<uint32_t>(),
+                                                   ctx->d_wlen.as<uint32_t>(), ctx->d_chunkoff.as<uint32_t>(), ctx->d_pairs.as<uint2>(), ctx->cap_pairs,
+                                                   ctl, ctx->shard_rank, ctx->shard_n);
+        launches += 6 + 4 + 2 * 2;   // + radix sort (histogram + onesweep passes, counted as 4) + two decoupled-look-back scans (init + scan)
         IMR_CUDA(ctx, cudaEventRecord(ctx->ev[1], s));
         // ---- pair setup ----
         k_queue_init<<<1, 1, 0, s>>>(ctl, ctx->cap_pairs, ctx->cap_queue);

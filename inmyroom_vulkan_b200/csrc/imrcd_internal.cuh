@@ -126,7 +126,7 @@ struct imrcd_ctx {
     bool uploaded = false, ran = false, fetched = false;
     PinBuf p_stage;                      // pinned staging for entry upload
     // frame, device side
-    DevBuf d_cur, d_prev, d_mesh, d_cb, d_entity, d_inv, d_ext, d_keys, d_keys2, d_idx, d_idx2, d_sorted, d_cubtmp;
+    DevBuf d_cur, d_prev, d_mesh, d_cb, d_entity, d_inv, d_ext, d_keys, d_keys2, d_idx, d_idx2, d_sorted, d_sorted_c, d_flag, d_cpos, d_wlen, d_chunks, d_chunkoff, d_cubtmp;
     DevBuf d_pairs, d_pairrec, d_pairacc, d_queue, d_combos, d_hits, d_epairs, d_ctl;
     uint64_t cap_pairs = 0, cap_queue = 0, cap_combos = 0, cap_hits = 0;
     uint64_t queue_dirty = 0;            // slots whose ready flag may still be set
