@@ -330,7 +330,7 @@ def run_gpu_arm(args):
     e2e_s_max = global_max(e2e_s)
     e2e_value = tests_total * args.steps / e2e_s_max
     n_entries = scene.n_entries
-    h2d = n_entries * (64 + 64 + 4 + 4 + 1)
+    h2d = n_entries * (64 + 4 + 4 + 1 + (64 if scene.previous is not None else 0))   # previous == current is not re-sent
     d2h = int(len(res)) * 80 + 1280
 
     # ---- roofline of the dominant kernel (stage times from CUDA events on the launching stream, this rank) ----

@@ -7,7 +7,7 @@
 
 static_assert(sizeof(imrcd_entity_pair) == 80, "imrcd_entity_pair layout");
 static_assert(sizeof(imrcd_tri_hit) == 40, "imrcd_tri_hit layout");
-static_assert(sizeof(TreeRec) == 64 && sizeof(TriRec) == 48 && sizeof(PairRec) == 64 && sizeof(SweepRec) == 32, "HBM layouts");
+static_assert(sizeof(TreeRec) == 64 && sizeof(TriRec) == 64 && sizeof(PairRec) == 64 && sizeof(SweepRec) == 32, "HBM layouts");
 
 #define CHECK_CTX(ctx) do { if (!(ctx)) return IMRCD_E_ARG; } while (0)
 
@@ -43,7 +43,7 @@ extern "C" void imrcd_destroy(imrcd_ctx* ctx) {
                        &ctx->d_sorted, &ctx->d_sorted_c, &ctx->d_flag, &ctx->d_cpos, &ctx->d_wlen, &ctx->d_chunks, &ctx->d_chunkoff, &ctx->d_cubtmp, &ctx->d_pairs, &ctx->d_pairrec, &ctx->d_pairacc, &ctx->d_queue, &ctx->d_combos,
                        &ctx->d_hits, &ctx->d_epairs, &ctx->d_ctl };
     for (DevBuf* b : bufs) b->release();
-    PinBuf* pins[] = { &ctx->p_stage, &ctx->p_ctl, &ctx->p_epairs, &ctx->p_hits, &ctx->p_pairs, &ctx->p_combos };
+    PinBuf* pins[] = { &ctx->p_cur, &ctx->p_prev, &ctx->p_mesh, &ctx->p_entity, &ctx->p_cb, &ctx->p_ctl, &ctx->p_epairs, &ctx->p_hits, &ctx->p_pairs, &ctx->p_combos };
     for (PinBuf* b : pins) b->release();
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -65,6 +65,22 @@ __global__ void k_rec_surface(TreeRec* recs, uint32_t n) {
 int imr_mesh_finalize_records(imrcd_ctx* ctx, uint32_t rec_base, uint32_t n_rec) {
     if (n_rec == 0) return IMRCD_OK;
     k_rec_surface<<<(n_rec + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_recs.as<TreeRec>() + rec_base, n_rec);
+    IMR_CUDA(ctx, cudaGetLastError());
+    return IMRCD_OK;
+}
+
+__global__ void k_tri_planes(TriRec* tris, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 a = tris[i].t0, b = tris[i].t1, c = tris[i].t2;
+    V3 N; float d;
+    tt_plane(mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c.x, c.y, c.z), N, d);
+    tris[i].t3 = make_float4(N.x, N.y, N.z, d);
+}
+
+int imr_mesh_finalize_tris(imrcd_ctx* ctx, uint32_t tri_base, uint32_t n_tri) {
+    if (n_tri == 0) return IMRCD_OK;
+    k_tri_planes<<<(n_tri + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_tris.as<TriRec>() + tri_base, n_tri);
     IMR_CUDA(ctx, cudaGetLastError());
     return IMRCD_OK;
 }
@@ -145,6 +161,7 @@ extern "C" int imrcd_mesh_import_tree(imrcd_ctx* ctx, uint64_t nv, const float* 
         tris[i].t0 = make_float4(p[0], p[1], p[2], u2f(tri_orig ? tri_orig[i] : (uint32_t)i));
         tris[i].t1 = make_float4(p[3], p[4], p[5], 0.f);
         tris[i].t2 = make_float4(p[6], p[7], p[8], 0.f);
+        tris[i].t3 = make_float4(0.f, 0.f, 0.f, 0.f);        // filled on the device (imr_mesh_finalize_tris)
         if (tri_nrm) memcpy(&nrm[9 * i], tri_nrm + 9 * i, 36);
         for (int k = 0; k < 3; ++k) vid[3 * i + k] = tri_vid ? tri_vid[3 * i + k] : (uint32_t)(3 * i + k);
     }
@@ -160,6 +177,8 @@ extern "C" int imrcd_mesh_import_tree(imrcd_ctx* ctx, uint64_t nv, const float* 
         IMR_CUDA(ctx, cudaMemcpyAsync(ctx->d_tri_vid.as<uint32_t>() + 3ull * mh.dev.tri_base, vid.data(), 12ull * n_tri, cudaMemcpyHostToDevice, s));
     }
     rc = imr_mesh_finalize_records(ctx, mh.dev.rec_base, mh.dev.n_rec);
+    if (rc) return rc;
+    rc = imr_mesh_finalize_tris(ctx, mh.dev.tri_base, mh.dev.n_tri);
     if (rc) return rc;
     IMR_CUDA(ctx, cudaStreamSynchronize(s));
     return mesh_register(ctx, mh, mesh_id);
@@ -239,8 +258,24 @@ extern "C" int imrcd_mesh_export_tree(imrcd_ctx* ctx, uint32_t mesh_id, float* b
 // ------------------------------------------------------------------------------------------
 extern "C" int imrcd_frame_reset(imrcd_ctx* ctx) {
     CHECK_CTX(ctx);
-    ctx->h_cur.clear(); ctx->h_prev.clear(); ctx->h_mesh.clear(); ctx->h_cb.clear(); ctx->h_entity.clear();
+    ctx->n_entries = 0; ctx->n_sent = 0; ctx->prev_distinct = false;
     ctx->uploaded = ctx->ran = ctx->fetched = false;
+    return IMRCD_OK;
+}
+
+#define ENTRY_CHUNK 16384u     // entries per H2D chunk of the pipelined upload (1 MiB of matrices)
+
+// enqueue the H2D copies of entries [n_sent, upto)
+static int entries_send(imrcd_ctx* ctx, uint64_t upto) {
+    const uint64_t a = ctx->n_sent;
+    if (upto <= a) return IMRCD_OK;
+    cudaStream_t s = ctx->stream;
+    const uint64_t k = upto - a;
+    IMR_CUDA(ctx, cudaMemcpyAsync(ctx->d_cur.as<char>() + 64 * a, ctx->p_cur.as<char>() + 64 * a, 64 * k, cudaMemcpyHostToDevice, s));
+    IMR_CUDA(ctx, cudaMemcpyAsync(ctx->d_mesh.as<char>() + 4 * a, ctx->p_mesh.as<char>() + 4 * a, 4 * k, cudaMemcpyHostToDevice, s));
+    IMR_CUDA(ctx, cudaMemcpyAsync(ctx->d_entity.as<char>() + 4 * a, ctx->p_entity.as<char>() + 4 * a, 4 * k, cudaMemcpyHostToDevice, s));
+    IMR_CUDA(ctx, cudaMemcpyAsync(ctx->d_cb.as<char>() + a, ctx->p_cb.as<char>() + a, k, cudaMemcpyHostToDevice, s));
+    ctx->n_sent = upto;
     return IMRCD_OK;
 }
 
@@ -248,15 +283,40 @@ extern "C" int imrcd_frame_add_entries(imrcd_ctx* ctx, uint64_t n, const float* 
                                        const uint32_t* mesh_ids, const uint8_t* should_callback, const uint32_t* entities) {
     CHECK_CTX(ctx);
     if (n && (!current || !mesh_ids)) { ctx->err = "imrcd_frame_add_entries: bad argument"; return IMRCD_E_ARG; }
-    for (uint64_t i = 0; i < n; ++i) if (mesh_ids[i] >= ctx->meshes.size()) { ctx->err = "imrcd_frame_add_entries: unknown mesh id"; return IMRCD_E_ARG; }
-    if (ctx->h_mesh.size() + n >= (1ull << 32) - 1) { ctx->err = "too many entries"; return IMRCD_E_ARG; }
-    ctx->h_cur.insert(ctx->h_cur.end(), current, current + 16 * n);
-    const float* prev = previous ? previous : current;
-    ctx->h_prev.insert(ctx->h_prev.end(), prev, prev + 16 * n);
-    ctx->h_mesh.insert(ctx->h_mesh.end(), mesh_ids, mesh_ids + n);
-    for (uint64_t i = 0; i < n; ++i) {
-        ctx->h_cb.push_back(should_callback ? (should_callback[i] ? 1 : 0) : 1);
-        ctx->h_entity.push_back(entities ? entities[i] : (uint32_t)(ctx->h_entity.size()));
+    const uint32_t n_meshes = (uint32_t)ctx->meshes.size();
+    const uint64_t base = ctx->n_entries, total = base + n;
+    if (total >= (1ull << 32) - 1) { ctx->err = "too many entries"; return IMRCD_E_ARG; }
+    if (n == 0) return IMRCD_OK;
+    cudaSetDevice(ctx->device);
+    cudaStream_t s = ctx->stream;
+    IMR_CUDA(ctx, ctx->p_cur.reserve(64 * total, 64 * base, s));
+    IMR_CUDA(ctx, ctx->p_prev.reserve(64 * total, 64 * base, s));
+    IMR_CUDA(ctx, ctx->p_mesh.reserve(4 * total, 4 * base, s));
+    IMR_CUDA(ctx, ctx->p_entity.reserve(4 * total, 4 * base, s));
+    IMR_CUDA(ctx, ctx->p_cb.reserve(total, base, s));
+    const bool bulk = n >= ENTRY_CHUNK / 4;      // single entries (the reference's call pattern) are sent by imrcd_frame_upload
+    if (bulk) {
+        IMR_CUDA(ctx, ctx->d_cur.reserve(64 * total, 64 * ctx->n_sent, s));
+        IMR_CUDA(ctx, ctx->d_mesh.reserve(4 * total, 4 * ctx->n_sent, s));
+        IMR_CUDA(ctx, ctx->d_entity.reserve(4 * total, 4 * ctx->n_sent, s));
+        IMR_CUDA(ctx, ctx->d_cb.reserve(total, ctx->n_sent, s));
+    }
+    float* pc = ctx->p_cur.as<float>(); float* pp = ctx->p_prev.as<float>();
+    uint32_t* pm = ctx->p_mesh.as<uint32_t>(); uint32_t* pe = ctx->p_entity.as<uint32_t>(); uint8_t* pb = ctx->p_cb.as<uint8_t>();
+    for (uint64_t c0 = 0; c0 < n; c0 += ENTRY_CHUNK) {
+        const uint64_t c1 = std::min<uint64_t>(n, c0 + ENTRY_CHUNK), k = c1 - c0, at = base + c0;
+        for (uint64_t i = c0; i < c1; ++i) if (mesh_ids[i] >= n_meshes) { ctx->err = "imrcd_frame_add_entries: unknown mesh id"; return IMRCD_E_ARG; }
+        memcpy(pc + 16 * at, current + 16 * c0, 64 * k);
+        if (previous && previous != current) {
+            if (!ctx->prev_distinct && at) memcpy(pp, pc, 64 * at);      // earlier entries of this frame had previous == current
+            memcpy(pp + 16 * at, previous + 16 * c0, 64 * k); ctx->prev_distinct = true;
+        }
+        else if (ctx->prev_distinct) memcpy(pp + 16 * at, current + 16 * c0, 64 * k);
+        memcpy(pm + at, mesh_ids + c0, 4 * k);
+        if (entities) memcpy(pe + at, entities + c0, 4 * k); else for (uint64_t i = 0; i < k; ++i) pe[at + i] = (uint32_t)(at + i);
+        if (should_callback) for (uint64_t i = 0; i < k; ++i) pb[at + i] = should_callback[c0 + i] ? 1 : 0; else memset(pb + at, 1, k);
+        ctx->n_entries = at + k;
+        if (bulk) { int rc = entries_send(ctx, ctx->n_entries); if (rc) return rc; }
     }
     ctx->uploaded = ctx->ran = ctx->fetched = false;
     return IMRCD_OK;
@@ -279,28 +339,21 @@ extern "C" int imrcd_frame_upload(imrcd_ctx* ctx) {
     cudaSetDevice(ctx->device);
     int rc = meshes_sync(ctx);
     if (rc) return rc;
-    const size_t n = ctx->h_mesh.size();
+    const uint64_t n = ctx->n_entries;
     cudaStream_t s = ctx->stream;
     if (n) {
-        // one pinned staging block: cur | prev | mesh | entity | cb
-        const size_t b_cur = 64 * n, b_mesh = 4 * n, b_cb = n;
-        IMR_CUDA(ctx, ctx->p_stage.reserve(2 * b_cur + 2 * b_mesh + b_cb));
-        char* st = ctx->p_stage.as<char>();
-        memcpy(st, ctx->h_cur.data(), b_cur);
-        memcpy(st + b_cur, ctx->h_prev.data(), b_cur);
-        memcpy(st + 2 * b_cur, ctx->h_mesh.data(), b_mesh);
-        memcpy(st + 2 * b_cur + b_mesh, ctx->h_entity.data(), b_mesh);
-        memcpy(st + 2 * b_cur + 2 * b_mesh, ctx->h_cb.data(), b_cb);
-        IMR_CUDA(ctx, ctx->d_cur.reserve(b_cur, 0, s));
-        IMR_CUDA(ctx, ctx->d_prev.reserve(b_cur, 0, s));
-        IMR_CUDA(ctx, ctx->d_mesh.reserve(b_mesh, 0, s));
-        IMR_CUDA(ctx, ctx->d_entity.reserve(b_mesh, 0, s));
-        IMR_CUDA(ctx, ctx->d_cb.reserve(b_cb, 0, s));
-        IMR_CUDA(ctx, cudaMemcpyAsync(ctx->d_cur.p, st, b_cur, cudaMemcpyHostToDevice, s));
-        IMR_CUDA(ctx, cudaMemcpyAsync(ctx->d_prev.p, st + b_cur, b_cur, cudaMemcpyHostToDevice, s));
-        IMR_CUDA(ctx, cudaMemcpyAsync(ctx->d_mesh.p, st + 2 * b_cur, b_mesh, cudaMemcpyHostToDevice, s));
-        IMR_CUDA(ctx, cudaMemcpyAsync(ctx->d_entity.p, st + 2 * b_cur + b_mesh, b_mesh, cudaMemcpyHostToDevice, s));
-        IMR_CUDA(ctx, cudaMemcpyAsync(ctx->d_cb.p, st + 2 * b_cur + 2 * b_mesh, b_cb, cudaMemcpyHostToDevice, s));
+        IMR_CUDA(ctx, ctx->d_cur.reserve(64 * n, 64 * ctx->n_sent, s));
+        IMR_CUDA(ctx, ctx->d_mesh.reserve(4 * n, 4 * ctx->n_sent, s));
+        IMR_CUDA(ctx, ctx->d_entity.reserve(4 * n, 4 * ctx->n_sent, s));
+        IMR_CUDA(ctx, ctx->d_cb.reserve(n, ctx->n_sent, s));
+        rc = entries_send(ctx, n);
+        if (rc) return rc;
+        // previous matrices feed only the response stage (CollisionDetection.cpp:80-98); an entry added with previous == NULL
+        // or == current has not moved, and a frame where that holds for every entry uploads nothing for them
+        if (ctx->prev_distinct) {
+            IMR_CUDA(ctx, ctx->d_prev.reserve(64 * n, 0, s));
+            IMR_CUDA(ctx, cudaMemcpyAsync(ctx->d_prev.p, ctx->p_prev.p, 64 * n, cudaMemcpyHostToDevice, s));
+        }
     }
     ctx->uploaded = true; ctx->ran = ctx->fetched = false;
     return IMRCD_OK;

@@ -99,6 +99,7 @@ __global__ void k_gather_tris(uint32_t n, const uint32_t* __restrict__ sorted_id
     r.t0 = make_float4(p[0], p[1], p[2], __uint_as_float(src));
     r.t1 = make_float4(p[3], p[4], p[5], 0.f);
     r.t2 = make_float4(p[6], p[7], p[8], 0.f);
+    { V3 N; float d; tt_plane(mk3(p[0], p[1], p[2]), mk3(p[3], p[4], p[5]), mk3(p[6], p[7], p[8]), N, d); r.t3 = make_float4(N.x, N.y, N.z, d); }
     tris[t] = r;
     float* no = nrm_out + 9ull * t;
     if (nrm) { const float* q = nrm + 9ull * src;

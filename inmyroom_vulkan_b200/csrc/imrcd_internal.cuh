@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
+#include <cstring>
 #include <vector>
 #include "../../include/imrcd.h"
 #include "imrcd_math.cuh"
@@ -18,9 +19,12 @@
 // `surface` caches Paralgram::GetSurface() of the untransformed box (Paralgram.cpp:203-210).
 struct __align__(16) TreeRec { float4 q0, q1, q2, q3; };
 
-// Triangle, 48 B = 3 x float4 in LEAF order (OBBtree.cpp:207-214):
+// Triangle, 64 B = 4 x float4 in LEAF order (OBBtree.cpp:207-214):
 //   t0 = (p0.xyz, orig_index bits)  t1 = (p1.xyz, 0)  t2 = (p2.xyz, 0)
-struct __align__(16) TriRec { float4 t0, t1, t2; };
+//   t3 = (N.xyz, d): the triangle's plane exactly as tri_tri_intersect_with_isectline computes it for its FIRST argument
+//        (N = (p1-p0) x (p2-p0), d = -N.p0, Triangle.cpp:877-882) -- a pure function of the model-space triangle, hoisted
+//        out of the per-pair test (the first entity's triangles are never transformed, CreateUncollideRays.cpp:82-86).
+struct __align__(16) TriRec { float4 t0, t1, t2, t3; };
 
 struct MeshDev { uint32_t rec_base, tri_base, n_rec, n_tri; };
 
@@ -84,15 +88,22 @@ struct DevBuf {
 
 struct PinBuf {
     void* p = nullptr; size_t cap = 0;
-    cudaError_t reserve(size_t bytes) {
+    // grow to at least `bytes`, keeping the first `keep` bytes; `s` is drained before the old block is freed
+    // (asynchronous copies may still be reading it)
+    cudaError_t reserve(size_t bytes, size_t keep = 0, cudaStream_t s = nullptr) {
         if (bytes <= cap) return cudaSuccess;
         size_t ncap = cap ? cap : 4096;
         while (ncap < bytes) ncap += ncap / 2 + 4096;
-        if (p) cudaFreeHost(p);
-        p = nullptr; cap = 0;
-        cudaError_t e = cudaMallocHost(&p, ncap);
-        if (e == cudaSuccess) cap = ncap;
-        return e;
+        void* np = nullptr;
+        cudaError_t e = cudaMallocHost(&np, ncap);
+        if (e != cudaSuccess) return e;
+        if (p) {
+            if (keep) memcpy(np, p, keep);
+            if (s) cudaStreamSynchronize(s);
+            cudaFreeHost(p);
+        }
+        p = np; cap = ncap;
+        return cudaSuccess;
     }
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
     template <class T> T* as() const { return static_cast<T*>(p); }
@@ -118,13 +129,14 @@ struct imrcd_ctx {
     bool meshes_dirty = false;
     float last_build_ms = 0.f;
 
-    // frame, host side
-    std::vector<float> h_cur, h_prev;
-    std::vector<uint32_t> h_mesh, h_entity;
-    std::vector<uint8_t> h_cb;
+    // frame, host side: the entry table is written straight into pinned memory (one host copy per entry) and goes to
+    // HBM in chunks while the caller is still adding entries
+    PinBuf p_cur, p_prev, p_mesh, p_entity, p_cb;
+    uint64_t n_entries = 0;              // entries added this frame
+    uint64_t n_sent = 0;                 // entries whose H2D copy has been enqueued
+    bool prev_distinct = false;          // some entry of this frame carries a previous matrix different from its current one
     uint32_t shard_rank = 0, shard_n = 1;
     bool uploaded = false, ran = false, fetched = false;
-    PinBuf p_stage;                      // pinned staging for entry upload
     // frame, device side
     DevBuf d_cur, d_prev, d_mesh, d_cb, d_entity, d_inv, d_ext, d_keys, d_keys2, d_idx, d_idx2, d_sorted, d_sorted_c, d_flag, d_cpos, d_wlen, d_chunks, d_chunkoff, d_cubtmp;
     DevBuf d_pairs, d_pairrec, d_pairacc, d_queue, d_combos, d_hits, d_epairs, d_ctl;
@@ -136,13 +148,14 @@ struct imrcd_ctx {
     imrcd_frame_stats stats;
     bool hits_fetched = false;
     cudaEvent_t ev[8] = {};
-    int trav_blocks = 0;
+    int trav_blocks = 0, narrow_blocks = 0;
 };
 
 #define IMR_CUDA(ctx, call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(_e); return IMRCD_E_CUDA; } } while (0)
 
 // ---- kernels / stages implemented in the .cu files ----------------------------------------
 int imr_mesh_finalize_records(imrcd_ctx* ctx, uint32_t rec_base, uint32_t n_rec);            // surfaces
+int imr_mesh_finalize_tris(imrcd_ctx* ctx, uint32_t tri_base, uint32_t n_tri);               // triangle planes (TriRec.t3)
 int imr_build_mesh_device(imrcd_ctx* ctx, const float* pos, const float* nrm, const uint32_t* vid, uint64_t n_tri,
                           uint32_t mode, MeshHost* out);
 int imr_frame_run_device(imrcd_ctx* ctx);

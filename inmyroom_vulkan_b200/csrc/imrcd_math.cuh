@@ -241,31 +241,32 @@ IMR_HD bool tt_intervals(V3 X0, V3 X1, V3 X2, float VV0, float VV1, float VV2, f
 }
 IMR_HD float tt_pick(V3 a, int index) { return index == 0 ? a.x : (index == 1 ? a.y : a.z); }
 
-// Triangle.cpp:866-1002.  Returns bit0 = intersect, bit1 = coplanar; src/tgt valid iff flags == 1.
-__host__ __device__ inline int tri_tri_isectline(V3 V0, V3 V1, V3 V2, V3 U0, V3 U1, V3 U2, V3& src, V3& tgt) {
-    // CROSS macro (Triangle.cpp:336-339): dest = v1 x v2 with (v1[1]*v2[2]-v1[2]*v2[1], ...)
-    #define TT_CROSS(a, b) mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x)
-    #define TT_DOT(a, b) ((a.x * b.x + a.y * b.y) + a.z * b.z)
-    V3 E1 = sub3(V1, V0), E2 = sub3(V2, V0);
-    V3 N1 = TT_CROSS(E1, E2);
-    float d1 = -TT_DOT(N1, V0);
-    float du0 = TT_DOT(N1, U0) + d1, du1 = TT_DOT(N1, U1) + d1, du2 = TT_DOT(N1, U2) + d1;
-    if (fabsf(du0) <= IMR_TT_EPS_F) du0 = 0.0f;
-    if (fabsf(du1) <= IMR_TT_EPS_F) du1 = 0.0f;
-    if (fabsf(du2) <= IMR_TT_EPS_F) du2 = 0.0f;
-    float du0du1 = du0 * du1, du0du2 = du0 * du2;
-    if (du0du1 > 0.0f && du0du2 > 0.0f) return 0;
+// ---- tri_tri_intersect_with_isectline (Triangle.cpp:866-1002) in three pure pieces, so that the narrow-phase kernel can
+// hoist the plane of each triangle out of the pair loop and run the cheap rejection and the expensive segment
+// computation as two dense passes.  Every piece is a pure function of its inputs, evaluated in the reference's order,
+// so any composition gives the reference's bits.
+#define TT_CROSS(a, b) mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x)   /* CROSS macro, Triangle.cpp:336-339 */
+#define TT_DOT(a, b) ((a.x * b.x + a.y * b.y) + a.z * b.z)
 
-    E1 = sub3(U1, U0); E2 = sub3(U2, U0);
-    V3 N2 = TT_CROSS(E1, E2);
-    float d2 = -TT_DOT(N2, U0);
-    float dv0 = TT_DOT(N2, V0) + d2, dv1 = TT_DOT(N2, V1) + d2, dv2 = TT_DOT(N2, V2) + d2;
-    if (fabsf(dv0) <= IMR_TT_EPS_F) dv0 = 0.0f;
-    if (fabsf(dv1) <= IMR_TT_EPS_F) dv1 = 0.0f;
-    if (fabsf(dv2) <= IMR_TT_EPS_F) dv2 = 0.0f;
-    float dv0dv1 = dv0 * dv1, dv0dv2 = dv0 * dv2;
-    if (dv0dv1 > 0.0f && dv0dv2 > 0.0f) return 0;
-
+// plane equation of a triangle: N = E1 x E2, d = -N.P0   (Triangle.cpp:877-882 and :905-910)
+IMR_HD void tt_plane(V3 P0, V3 P1, V3 P2, V3& N, float& d) {
+    V3 E1 = sub3(P1, P0), E2 = sub3(P2, P0);
+    N = TT_CROSS(E1, E2);
+    d = -TT_DOT(N, P0);
+}
+// signed distances of X0..X2 to the plane with the coplanarity clamp (:884-903 / :912-926); true = all on one side (reject)
+IMR_HD bool tt_side(V3 N, float d, V3 X0, V3 X1, V3 X2, float& s0, float& s1, float& s2, float& s0s1, float& s0s2) {
+    s0 = TT_DOT(N, X0) + d; s1 = TT_DOT(N, X1) + d; s2 = TT_DOT(N, X2) + d;
+    if (fabsf(s0) <= IMR_TT_EPS_F) s0 = 0.0f;
+    if (fabsf(s1) <= IMR_TT_EPS_F) s1 = 0.0f;
+    if (fabsf(s2) <= IMR_TT_EPS_F) s2 = 0.0f;
+    s0s1 = s0 * s1; s0s2 = s0 * s2;
+    return s0s1 > 0.0f && s0s2 > 0.0f;
+}
+// everything after the two rejection tests (:928-1001).  Returns bit0 = intersect, bit1 = coplanar; src/tgt valid iff 1.
+__host__ __device__ inline int tt_segment(V3 V0, V3 V1, V3 V2, V3 U0, V3 U1, V3 U2, V3 N1, V3 N2,
+                                          float du0, float du1, float du2, float du0du1, float du0du2,
+                                          float dv0, float dv1, float dv2, float dv0dv1, float dv0dv2, V3& src, V3& tgt) {
     V3 D = TT_CROSS(N1, N2);
     float mx = fabsf(D.x); int index = 0;
     float b = fabsf(D.y), c = fabsf(D.z);
@@ -303,8 +304,16 @@ __host__ __device__ inline int tri_tri_isectline(V3 V0, V3 V1, V3 V2, V3 U0, V3 
         else           tgt = (smallest2 == 0) ? B2 : B1;
     }
     return 1;
-    #undef TT_CROSS
-    #undef TT_DOT
+}
+// Triangle.cpp:866-1002 as one call (unit-test hook).
+__host__ __device__ inline int tri_tri_isectline(V3 V0, V3 V1, V3 V2, V3 U0, V3 U1, V3 U2, V3& src, V3& tgt) {
+    V3 N1, N2; float d1, d2;
+    float du0, du1, du2, du0du1, du0du2, dv0, dv1, dv2, dv0dv1, dv0dv2;
+    tt_plane(V0, V1, V2, N1, d1);
+    if (tt_side(N1, d1, U0, U1, U2, du0, du1, du2, du0du1, du0du2)) return 0;
+    tt_plane(U0, U1, U2, N2, d2);
+    if (tt_side(N2, d2, V0, V1, V2, dv0, dv1, dv2, dv0dv1, dv0dv2)) return 0;
+    return tt_segment(V0, V1, V2, U0, U1, U2, N1, N2, du0, du1, du2, du0du1, du0du2, dv0, dv1, dv2, dv0dv1, dv0dv2, src, tgt);
 }
 
 // IMR/src/CollisionDetection/CollisionDetection.cpp:9-13
