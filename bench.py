@@ -278,10 +278,10 @@ def run_gpu_arm(args):
             e1.record(stream)
         return e0, e1
 
+    clocks = ClockSampler(local); clocks.start()          # sampled from the warm-up to the end of the e2e loop
     for _ in range(args.warmup):
         l2_flush(); device_step()
     barrier()
-    clocks = ClockSampler(local); clocks.start()
     ev = []; st_acc = {}; launches = 0
     for _ in range(args.steps):
         l2_flush()

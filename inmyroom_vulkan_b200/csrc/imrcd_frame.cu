@@ -9,6 +9,7 @@
 #include <cub/device/device_scan.cuh>
 #include <algorithm>
 #include <cstring>
+#include <cstdlib>
 
 #define FULL_MASK 0xffffffffu
 
@@ -269,7 +270,8 @@ __device__ __forceinline__ void trav_donate(TravStack& st, uint32_t warp, uint32
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(TRAV_WARPS * 32)
+template <bool STRAIGHT, int MIN_BLOCKS>
+__global__ void __launch_bounds__(TRAV_WARPS * 32, MIN_BLOCKS)
 k_traverse(FrameCtl* ctl, const PairRec* __restrict__ pairrec, const TreeRec* __restrict__ recs,
            WorkItem* queue, unsigned long long cap_queue, Combo* __restrict__ combos, unsigned long long cap_combos) {
     __shared__ TravStack st;
@@ -349,7 +351,7 @@ k_traverse(FrameCtl* ctl, const PairRec* __restrict__ pairrec, const TreeRec* __
             const Box first = unpack_box(a0, a1, a2);
             const Box second = box_transform(rel, unpack_box(b0, b1, b2));        // :420
             ++my_sat;
-            if (box_sat(first, second)) {                                          // :422
+            if (box_sat_t<STRAIGHT>(first, second)) {                              // :422
                 const bool leafA = __float_as_uint(a3.w) != 0u, leafB = __float_as_uint(b3.w) != 0u;
                 const uint32_t childA = __float_as_uint(a3.y), childB = __float_as_uint(b3.y);
                 if (leafA && leafB) {
@@ -688,7 +690,16 @@ int imr_frame_run_device(imrcd_ctx* ctx) {
     }
     if (ctx->trav_blocks == 0) {
         int per_sm = 0;
-        IMR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_traverse, TRAV_WARPS * 32, 0));
+        const char* ev = getenv("IMRCD_TRAV_VARIANT");
+        ctx->trav_variant = ev ? atoi(ev) : 0;
+        switch (ctx->trav_variant) {
+            case 1: ctx->trav_fn = (const void*)k_traverse<true, 6>; break;
+            case 2: ctx->trav_fn = (const void*)k_traverse<true, 8>; break;
+            case 3: ctx->trav_fn = (const void*)k_traverse<false, 8>; break;
+            case 4: ctx->trav_fn = (const void*)k_traverse<true, 4>; break;
+            default: ctx->trav_fn = (const void*)k_traverse<false, 6>; break;
+        }
+        IMR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ctx->trav_fn, TRAV_WARPS * 32, 0));
         if (per_sm < 1) per_sm = 1;
         ctx->trav_blocks = per_sm * ctx->sm_count;
     }
@@ -737,9 +748,10 @@ int imr_frame_run_device(imrcd_ctx* ctx) {
         IMR_CUDA(ctx, cudaEventRecord(ctx->ev[2], s));
         // ---- mid ----
         {
-            k_traverse<<<ctx->trav_blocks, TRAV_WARPS * 32, 0, s>>>(ctl, ctx->d_pairrec.as<PairRec>(), ctx->d_recs.as<TreeRec>(),
-                                                                     ctx->d_queue.as<WorkItem>(), ctx->cap_queue, ctx->d_combos.as<Combo>(),
-                                                                     ctx->cap_combos);
+            const PairRec* a_pairrec = ctx->d_pairrec.as<PairRec>(); const TreeRec* a_recs = ctx->d_recs.as<TreeRec>();
+            WorkItem* a_queue = ctx->d_queue.as<WorkItem>(); Combo* a_combos = ctx->d_combos.as<Combo>();
+            void* targs[] = { &ctl, &a_pairrec, &a_recs, &a_queue, &ctx->cap_queue, &a_combos, &ctx->cap_combos };
+            IMR_CUDA(ctx, cudaLaunchKernel(ctx->trav_fn, dim3(ctx->trav_blocks), dim3(TRAV_WARPS * 32), targs, 0, s));
             launches += 1;
         }
         IMR_CUDA(ctx, cudaEventRecord(ctx->ev[3], s));

@@ -148,7 +148,8 @@ struct imrcd_ctx {
     imrcd_frame_stats stats;
     bool hits_fetched = false;
     cudaEvent_t ev[8] = {};
-    int trav_blocks = 0, narrow_blocks = 0;
+    int trav_blocks = 0, narrow_blocks = 0, trav_variant = 0;
+    const void* trav_fn = nullptr;
 };
 
 #define IMR_CUDA(ctx, call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(_e); return IMRCD_E_CUDA; } } while (0)

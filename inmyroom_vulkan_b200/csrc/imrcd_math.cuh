@@ -123,7 +123,7 @@ IMR_HD bool axis_overlap(const Box& l, const Box& r, V3 axis) {
     float lmn, lmx, rmn, rmx;
     box_minmax(l, axis, lmn, lmx);
     box_minmax(r, axis, rmn, rmx);
-    return (lmx >= rmn) && (rmx >= lmn);
+    return (lmx >= rmn) & (rmx >= lmn);
 }
 // The k-th separating axis in the reference's fixed order (Paralgram.cpp:21,31,41,52,62,72,83-163).
 IMR_HD V3 sat_axis(const Box& l, const Box& r, int k) {
@@ -147,12 +147,17 @@ IMR_HD V3 sat_axis(const Box& l, const Box& r, int k) {
 }
 // Paralgram.cpp:17-173.  The verdict does not depend on evaluation order or early exit
 // (each axis test is a pure function of the two boxes), so the device evaluates all 15 and ANDs.
-IMR_HD bool box_sat(const Box& l, const Box& r) {
+template <bool STRAIGHT>
+IMR_HD bool box_sat_t(const Box& l, const Box& r) {
     bool ok = true;
 #pragma unroll
-    for (int k = 0; k < 15; ++k) ok = ok && axis_overlap(l, r, sat_axis(l, r, k));
+    for (int k = 0; k < 15; ++k) {
+        if (STRAIGHT) ok = ok & axis_overlap(l, r, sat_axis(l, r, k));     // straight-line: no per-axis branches
+        else ok = ok && axis_overlap(l, r, sat_axis(l, r, k));             // lane-level early exit (branches)
+    }
     return ok;
 }
+IMR_HD bool box_sat(const Box& l, const Box& r) { return box_sat_t<false>(l, r); }
 // Paralgram.cpp:203-210
 IMR_HD float box_surface(const Box& b) {
     float uv = length3(cross3(b.u, b.v));
