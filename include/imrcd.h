@@ -77,6 +77,8 @@ typedef struct {
     uint64_t trav_idle_polls;   /* failed refill attempts of starving traversal warps (diagnostic) */
     float    ms_total;          /* device time of imrcd_frame_run (CUDA events) */
     float    ms_broad, ms_pair_setup, ms_traverse, ms_narrow, ms_reduce;
+    uint64_t n_contact_pairs;   /* pairs with at least one hit that went through the contact reduction (CreateUncollideRays.cpp:117-198) */
+    uint64_t n_rays;            /* "uncollide" rays of the colliding pairs, both sides (CreateUncollideRays.cpp:131-178) */
 } imrcd_frame_stats;
 
 /* ---- context ---------------------------------------------------------------------------- */

@@ -34,7 +34,8 @@ class FrameStats(C.Structure):
     _fields_ = [("n_entries", C.c_uint64), ("n_pairs", C.c_uint64), ("n_sat_tests", C.c_uint64), ("n_combos", C.c_uint64),
                 ("n_tri_tests", C.c_uint64), ("n_hits", C.c_uint64), ("n_coplanar_hits", C.c_uint64), ("n_colliding", C.c_uint64),
                 ("traverse_launches", C.c_uint64), ("total_launches", C.c_uint64), ("n_queue_items", C.c_uint64), ("n_warp_iterations", C.c_uint64), ("trav_busy_cycles", C.c_uint64), ("trav_idle_polls", C.c_uint64), ("ms_total", C.c_float), ("ms_broad", C.c_float),
-                ("ms_pair_setup", C.c_float), ("ms_traverse", C.c_float), ("ms_narrow", C.c_float), ("ms_reduce", C.c_float)]
+                ("ms_pair_setup", C.c_float), ("ms_traverse", C.c_float), ("ms_narrow", C.c_float), ("ms_reduce", C.c_float),
+                ("n_contact_pairs", C.c_uint64), ("n_rays", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -179,7 +179,28 @@ k_sweep(uint32_t n, const SweepRec* __restrict__ sorted, const SweepRec* __restr
 // ------------------------------------------------------------------------------------------
 // pair setup
 // ------------------------------------------------------------------------------------------
-struct PairAcc { uint32_t n_hits; uint32_t flags; };
+// Per broad-phase pair accumulators, 64 B.  sum_* / rays_* are the ray origins of CreateUncollideRays.cpp:131-178 summed per side
+// (first's model space), in FP64 so that the order of the atomic adds does not show in the FP32 result.
+struct __align__(16) PairAcc { uint32_t n_hits, flags, rays_a, rays_b, cursor, off, pad0, pad1; double sum_a[3], sum_b[3]; };   // 80 B
+
+// Side record of one hit for the contact reduction (the 40-B imrcd_tri_hit keeps source, target and weight), 12 B:
+// arena indices of the two triangles and flags = bitsA | bitsB << 3 | i << 6 | j << 8, where bitsX has bit k set iff vertex k of
+// that triangle is NOT outside the other triangle's plane (CreateUncollideRays.cpp:102-112) and (i, j) are the positions of the
+// triangles inside their leaves (so tri - i / tri - j name the leaf, i.e. the combo the hit came from).
+struct HitAux { uint32_t triA, triB, flags; };
+
+// Plane.cpp:5-21 through TrianglePosition::GetTrianglePlane: normal = normalize(cross(p1-p0, p2-p0)), d = -dot(p0, normal),
+// then the Plane ctor divides both by length(normal).
+struct PlaneN { V3 n; float d; };
+IMR_D PlaneN plane_from_tri(V3 p0, V3 p1, V3 p2) {
+    const V3 nrm = normalize3(cross3(sub3(p1, p0), sub3(p2, p0)));
+    const float d = -dot3(p0, nrm);
+    const float len = length3(nrm);
+    PlaneN pl; pl.n = mk3(nrm.x / len, nrm.y / len, nrm.z / len); pl.d = d / len;
+    return pl;
+}
+IMR_D bool plane_outside(const PlaneN& pl, V3 p) { return dot3(p, pl.n) + pl.d > 0.f; }     // Plane.cpp:23-29
+
 
 __global__ void k_queue_init(FrameCtl* ctl, unsigned long long cap_pairs, unsigned long long cap_queue) {
     unsigned long long n = ctl->n_pairs < cap_pairs ? ctl->n_pairs : cap_pairs;
@@ -212,7 +233,7 @@ __global__ void k_pair_setup(const FrameCtl* ctl, unsigned long long cap_pairs, 
         o.r2 = make_float4(r[2], r[6], r[10], r[14]);
         o.recA = ma.rec_base; o.recB = mb.rec_base; o.triA = ma.tri_base; o.triB = mb.tri_base;
         pairrec[p] = o;
-        PairAcc z; z.n_hits = 0; z.flags = 0;
+        PairAcc z; z.n_hits = 0; z.flags = 0; z.rays_a = z.rays_b = 0; z.cursor = z.off = z.pad0 = z.pad1 = 0; z.sum_a[0] = z.sum_a[1] = z.sum_a[2] = 0.0; z.sum_b[0] = z.sum_b[1] = z.sum_b[2] = 0.0;
         acc[p] = z;
         if (p < cap_queue) queue[p] = make_uint4((uint32_t)p, 0u, 0u, 1u);
     }
@@ -462,7 +483,7 @@ k_traverse(FrameCtl* ctl, const PairRec* __restrict__ pairrec, const TreeRec* __
 struct NarrowWarp {
     float ux[3][NT_SLOTS], uy[3][NT_SLOTS], uz[3][NT_SLOTS];   // [vertex][slot], slot = 4 * combo_in_tile + j
     float nx[NT_SLOTS], ny[NT_SLOTS], nz[NT_SLOTS], nd[NT_SLOTS];   // plane of the transformed triangle
-    uint32_t origB[NT_SLOTS];
+    uint32_t absB[NT_SLOTS];              // arena index of the second entity's triangle
     uint4 cmb[NT_TILE];                   // (pair, absolute index of first's leaf triangle 0, cntA | cntB << 16, unused)
     uint16_t test[NT_TESTS];              // dense list of the tile's pairs: combo | i << 5 | j << 7; pass 1 compacts the
                                           // survivors of the rejection tests into its front (in place: writes trail reads)
@@ -470,7 +491,7 @@ struct NarrowWarp {
 
 __global__ void __launch_bounds__(NT_WARPS * 32)
 k_tritri(FrameCtl* ctl, const Combo* __restrict__ combos, unsigned long long cap_combos, const PairRec* __restrict__ pairrec,
-         const TriRec* __restrict__ tris, imrcd_tri_hit* __restrict__ hits, unsigned long long cap_hits, PairAcc* acc) {
+         const TriRec* __restrict__ tris, imrcd_tri_hit* __restrict__ hits, unsigned long long cap_hits, PairAcc* acc, HitAux* __restrict__ aux) {
     extern __shared__ __align__(16) unsigned char nt_smem[];
     NarrowWarp& sm = reinterpret_cast<NarrowWarp*>(nt_smem)[threadIdx.x >> 5];
     const uint32_t lane = lane_id();
@@ -519,7 +540,7 @@ k_tritri(FrameCtl* ctl, const Combo* __restrict__ combos, unsigned long long cap
                 sm.ux[1][slot] = U1.x; sm.uy[1][slot] = U1.y; sm.uz[1][slot] = U1.z;
                 sm.ux[2][slot] = U2.x; sm.uy[2][slot] = U2.y; sm.uz[2][slot] = U2.z;
                 sm.nx[slot] = N2.x; sm.ny[slot] = N2.y; sm.nz[slot] = N2.z; sm.nd[slot] = d2;
-                sm.origB[slot] = __float_as_uint(b0.w);
+                sm.absB[slot] = c_triB0 + j;
             }
         }
         __syncwarp();
@@ -552,14 +573,14 @@ k_tritri(FrameCtl* ctl, const Combo* __restrict__ combos, unsigned long long cap
         }
         __syncwarp();
 
-        // ---- pass 2: segment computation for the survivors ----
+        // ---- pass 2: segment computation for the survivors, hit records, contact candidates ----
         for (uint32_t t0 = 0; t0 < n_surv; t0 += 32u) {
             const uint32_t t = t0 + lane;
             bool hit = false;
             V3 src = mk3(0, 0, 0), tgt = mk3(0, 0, 0);
-            uint32_t hpair = 0xffffffffu, origA = 0, origB = 0;
+            uint32_t hpair = 0xffffffffu, triA = 0, triB = 0, origA = 0, bits_a = 7u, bits_b = 7u, code = 0;
             if (t < n_surv) {
-                const uint32_t code = sm.test[t];
+                code = sm.test[t];
                 const uint32_t c = code & 31u, i = (code >> 5) & 3u, slot = 4u * c + (code >> 7);
                 const uint4 cm = sm.cmb[c];
                 const float4* ta = reinterpret_cast<const float4*>(tris + cm.y + i);
@@ -575,36 +596,45 @@ k_tritri(FrameCtl* ctl, const Combo* __restrict__ combos, unsigned long long cap
                 const int f = tt_segment(V0, V1, V2, U0, U1, U2, N1, N2, du0, du1, du2, du0du1, du0du2, dv0, dv1, dv2, dv0dv1, dv0dv2, src, tgt);   // :86
                 hit = (f == 1);                                                        // doIntersept && !areCoplanar (:88)
                 if (f == 3) ++my_cop;
-                if (hit) { hpair = cm.x; origA = __float_as_uint(a0.w); origB = sm.origB[slot]; }
+                if (hit) {
+                    hpair = cm.x; triA = cm.y + i; triB = sm.absB[slot]; origA = __float_as_uint(a0.w);
+                    // each vertex against the other triangle's plane (:102-112)
+                    const PlaneN pa = plane_from_tri(V0, V1, V2), pb = plane_from_tri(U0, U1, U2);
+                    if (plane_outside(pb, V0)) bits_a &= ~1u; if (plane_outside(pb, V1)) bits_a &= ~2u; if (plane_outside(pb, V2)) bits_a &= ~4u;
+                    if (plane_outside(pa, U0)) bits_b &= ~1u; if (plane_outside(pa, U1)) bits_b &= ~2u; if (plane_outside(pa, U2)) bits_b &= ~4u;
+                }
             }
             const uint32_t hm = __ballot_sync(FULL_MASK, hit);
-            if (hm) {
-                unsigned long long base = 0;
-                if (lane == 0) base = atomicAdd(&ctl->n_hits, (unsigned long long)__popc(hm));
-                base = __shfl_sync(FULL_MASK, base, 0);
-                float weight = 0.f;
-                if (hit) {
-                    weight = length3(sub3(src, tgt));                                  // :93
-                    const unsigned long long slot = base + __popc(hm & lt_mask);
-                    if (slot < cap_hits) {
-                        imrcd_tri_hit h;
-                        h.pair = hpair; h.tri_first = origA; h.tri_second = origB;
-                        h.source[0] = src.x; h.source[1] = src.y; h.source[2] = src.z;
-                        h.target[0] = tgt.x; h.target[1] = tgt.y; h.target[2] = tgt.z;
-                        h.weight = weight;
-                        hits[slot] = h;
-                    } else atomicOr(&ctl->overflow, (unsigned)OVF_HITS);
-                }
-                // per-pair accumulators: one atomic per distinct pair among the hitting lanes.
-                // A candidate survives IsNull() iff its accumulated weight != 0 (CreateUncollideRays.cpp:22-25,117-127);
-                // weights are >= 0 (or NaN), so that is "some hit of the triangle has weight != 0".
-                const uint32_t peers = __match_any_sync(FULL_MASK, hpair);
-                if (hit) {
-                    const uint32_t nz = __ballot_sync(peers, !(weight == 0.0f)) & peers;
-                    if (lane == (uint32_t)(__ffs(peers) - 1)) {
-                        atomicAdd(&acc[hpair].n_hits, (uint32_t)__popc(peers));
-                        if (nz) atomicOr(&acc[hpair].flags, 1u);
-                    }
+            if (hm == 0u) continue;
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(&ctl->n_hits, (unsigned long long)__popc(hm));
+            base = __shfl_sync(FULL_MASK, base, 0);
+            float weight = 0.f;
+            bool zero_w = false;
+            if (hit) {
+                weight = length3(sub3(src, tgt));                                      // :93
+                const unsigned long long slot = base + __popc(hm & lt_mask);
+                if (slot < cap_hits) {
+                    imrcd_tri_hit h;
+                    h.pair = hpair; h.tri_first = origA; h.tri_second = __float_as_uint(__ldg(reinterpret_cast<const float4*>(tris + triB)).w);
+                    h.source[0] = src.x; h.source[1] = src.y; h.source[2] = src.z;
+                    h.target[0] = tgt.x; h.target[1] = tgt.y; h.target[2] = tgt.z;
+                    h.weight = weight;
+                    hits[slot] = h;
+                    HitAux x; x.triA = triA; x.triB = triB; x.flags = bits_a | (bits_b << 3) | (((code >> 5) & 3u) << 6) | ((code >> 7) << 8);
+                    aux[slot] = x;
+                } else atomicOr(&ctl->overflow, (unsigned)OVF_HITS);
+                zero_w = (weight == 0.0f);
+            }
+            // per-pair accumulators: one atomic per distinct pair among the hitting lanes.
+            // A candidate survives IsNull() iff its accumulated weight != 0 (CreateUncollideRays.cpp:22-25,117-127);
+            // weights are >= 0 (or NaN), so that is "some hit of the triangle has weight != 0".
+            const uint32_t peers = __match_any_sync(FULL_MASK, hpair);
+            if (hit) {
+                const uint32_t nz = __ballot_sync(peers, !zero_w) & peers;
+                if (lane == (uint32_t)(__ffs(peers) - 1)) {
+                    atomicAdd(&acc[hpair].n_hits, (uint32_t)__popc(peers));
+                    if (nz) atomicOr(&acc[hpair].flags, 1u);
                 }
             }
         }
@@ -615,23 +645,299 @@ k_tritri(FrameCtl* ctl, const Combo* __restrict__ combos, unsigned long long cap
 }
 
 // ------------------------------------------------------------------------------------------
-// reduce: colliding entity pairs (CollisionDetection.cpp:60-78)
+// reduce: ray origins per pair and side (find_rays_lambda, CreateUncollideRays.cpp:131-178), then the colliding entity
+// pairs with their contact points (CreateUncollideRays.cpp:185-198, CollisionDetection.cpp:60-78)
 // ------------------------------------------------------------------------------------------
+// The hits of a frame come out in no particular order; the reduction of CreateUncollideRays.cpp:117-178 is per entity pair.
+// So: (1) k_hit_layout gives every pair with hits a slice of the scratch arrays (power-of-two sized, offsets by one scan) and
+// puts it on the list of small or large pairs; (2) k_group_hits drops each hit index into its pair's slice; (3) one warp
+// 128-thread block (small pairs) or one 512-thread block (large pairs) per pair sorts the slice and walks it:
+//     sort by (first's triangle, second's triangle)  ->  runs of equal first's triangle are its TriangleCandidateRays
+//     merged over combos (a run of equal second's LEAF inside it is one combo: dropped when its weight is 0, :117-121);
+//     bits != 0: every still-flagged vertex is a ray candidate (deduplicated by vertex id with a second sort = the
+//     `emplaced` set, :139-141); bits == 0: one ray at the weighted average point (:34-37, :160-163).
+//   The same again with the roles swapped for the second entity, whose triangles live in first's space (:84, :134).
+// Everything a pair needs sits in its own slice (L1-resident for the typical 200-hit pair); no global atomics, and the
+// result does not depend on the order in which the hits were produced.
+// three size classes: S (<= 256 hits: 64 threads, everything in shared memory), M (<= 1024 hits: 256 threads, shared memory),
+// L (more: 512 threads, scratch slices in global memory)
+#define PC_S_MAX 256u
+#define PC_M_MAX 1024u
+
+__global__ void k_hit_layout(const FrameCtl* ctl, unsigned long long cap_pairs, const PairAcc* __restrict__ acc, uint32_t* __restrict__ padded) {
+    const unsigned long long n = ctl->n_pairs < cap_pairs ? ctl->n_pairs : cap_pairs;
+    for (unsigned long long p = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; p <= cap_pairs; p += (unsigned long long)gridDim.x * blockDim.x) {
+        uint32_t m = 0;
+        if (p < n) { const uint32_t h = acc[p].n_hits; if (h) { m = 1u; while (m < h) m <<= 1; } }
+        padded[p] = m;                                     // zeros from n on; the scan runs over cap_pairs + 1 elements
+    }
+}
+
+__global__ void k_hit_lists(FrameCtl* ctl, unsigned long long cap_pairs, PairAcc* acc, const uint32_t* __restrict__ padded_off,
+                            uint32_t* __restrict__ list_s, uint32_t* __restrict__ list_m, uint32_t* __restrict__ list_l) {
+    const unsigned long long n = ctl->n_pairs < cap_pairs ? ctl->n_pairs : cap_pairs;
+    const uint32_t lane = lane_id();
+    for (unsigned long long p0 = (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x) & ~31ull; p0 < n; p0 += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long p = p0 + lane;
+        uint32_t h = 0;
+        if (p < n) { h = acc[p].n_hits; acc[p].off = padded_off[p]; }
+        const int cls = h == 0 ? -1 : (h <= PC_S_MAX ? 0 : (h <= PC_M_MAX ? 1 : 2));
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const uint32_t mm = __ballot_sync(FULL_MASK, cls == c);
+            if (mm) {
+                unsigned long long b = 0;
+                if (lane == 0) b = atomicAdd(&ctl->n_class[c * 16], (unsigned long long)__popc(mm));
+                b = __shfl_sync(FULL_MASK, b, 0);
+                uint32_t* list = c == 0 ? list_s : (c == 1 ? list_m : list_l);
+                if (cls == c) list[b + __popc(mm & ((1u << lane) - 1u))] = (uint32_t)p;
+            }
+        }
+    }
+}
+
+__global__ void k_group_hits(const FrameCtl* ctl, unsigned long long cap_hits, const imrcd_tri_hit* __restrict__ hits, PairAcc* acc,
+                             uint32_t* __restrict__ grouped) {
+    if (ctl->overflow & (OVF_PAIRS | OVF_QUEUE | OVF_COMBOS | OVF_HITS)) return;      // slices would not fit: the frame is re-run
+    const unsigned long long n = ctl->n_hits < cap_hits ? ctl->n_hits : cap_hits;
+    const uint32_t lane = lane_id();
+    for (unsigned long long h0 = (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x) & ~31ull; h0 < n; h0 += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long h = h0 + lane;
+        const uint32_t pair = h < n ? hits[h].pair : 0xffffffffu;
+        const uint32_t peers = __match_any_sync(FULL_MASK, pair);             // neighbouring hits mostly share the pair
+        uint32_t base = 0;
+        const uint32_t leader = (uint32_t)__ffs(peers) - 1u;
+        if (h < n && lane == leader) base = atomicAdd(&acc[pair].cursor, (uint32_t)__popc(peers));
+        base = __shfl_sync(FULL_MASK, base, leader);
+        if (h < n) grouped[acc[pair].off + base + __popc(peers & ((1u << lane) - 1u))] = (uint32_t)h;
+    }
+}
+
+template <int T> __device__ __forceinline__ void pc_sync() { if (T == 32) __syncwarp(); else __syncthreads(); }
+
+// in-place bitonic sort of m (power of two) 64-bit keys by T cooperating threads
+template <int T>
+__device__ __forceinline__ void pc_sort(unsigned long long* k, uint32_t m, uint32_t tid) {
+    for (uint32_t size = 2; size <= m; size <<= 1) {
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            for (uint32_t t = tid; t < (m >> 1); t += T) {
+                const uint32_t lo = 2u * t - (t & (stride - 1u)), hi = lo + stride;
+                const bool up = ((lo & size) == 0u);
+                const unsigned long long a = k[lo], b = k[hi];
+                if ((a > b) == up) { k[lo] = b; k[hi] = a; }
+            }
+            pc_sync<T>();
+        }
+    }
+}
+
+struct SideSum { double x, y, z; uint32_t rays; };
+
+// open-addressing vertex set in shared memory: entry = vid << 32 | smallest reference to a (sorted position, corner) that has it
+template <uint32_t VSET>
+__device__ __forceinline__ void vset_insert(unsigned long long* vset, unsigned long long ent) {
+    const uint32_t vid = (uint32_t)(ent >> 32);
+    uint32_t slot = (vid * 2654435761u) & (VSET - 1u);
+    for (;;) {
+        const unsigned long long old = atomicCAS(&vset[slot], ~0ull, ent);
+        if (old == ~0ull) return;
+        if ((uint32_t)(old >> 32) == vid) { atomicMin(&vset[slot], ent); return; }
+        slot = (slot + 1u) & (VSET - 1u);
+    }
+}
+
+// One side of one pair.  side 0: runs of first's triangle, combos = second's leaves;  side 1: the mirror image.
+// SMEM: key[] / hit_at[] / vset[] live in shared memory and ray vertices go straight into the set; otherwise key[] (m slots) and
+// vkey[] (8m slots: [0,4m) vertex list, [4m,5m) hit index per sorted position) are the pair's slices of the global scratch.
+template <int T, bool SMEM, uint32_t VSET>
+__device__ __forceinline__ SideSum pc_side(uint32_t side, uint32_t n, uint32_t m, const uint32_t* __restrict__ grp, unsigned long long* key, unsigned long long* vkey,
+                                           uint32_t* hit_at32, uint32_t* d_fl, float* d_w, float* d_cx, float* d_cy, float* d_cz,
+                                           uint32_t* s_count, unsigned long long* vset,
+                                           const imrcd_tri_hit* __restrict__ hits, const HitAux* __restrict__ aux,
+                                           const TriRec* __restrict__ tris, const uint32_t* __restrict__ tri_vid, const Rel& rel, uint32_t tid) {
+    // ---- sort the hits by (own triangle, other triangle) ----
+    // two hits of a pair never share (triA, triB): a leaf pair is visited once and tests each (i, j) once
+    for (uint32_t k = tid; k < m; k += T) {
+        unsigned long long v = ~0ull;
+        if (k < n) { const HitAux x = aux[grp[k]]; v = side ? (((unsigned long long)x.triB << 32) | x.triA) : (((unsigned long long)x.triA << 32) | x.triB); }
+        key[k] = v;
+    }
+    if (tid == 0) *s_count = 0u;
+    if (SMEM) for (uint32_t k = tid; k < VSET; k += T) vset[k] = ~0ull;
+    pc_sync<T>();
+    pc_sort<T>(key, m, tid);
+    // every hit finds its sorted position by binary search and leaves its index there
+    for (uint32_t k = tid; k < n; k += T) {
+        const uint32_t h = grp[k];
+        const HitAux x = aux[h];
+        const unsigned long long v = side ? (((unsigned long long)x.triB << 32) | x.triA) : (((unsigned long long)x.triA << 32) | x.triB);
+        uint32_t lo = 0, hi = n;
+        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (key[mid] < v) lo = mid + 1; else hi = mid; }
+        if (SMEM) hit_at32[lo] = h; else vkey[4u * m + lo] = (unsigned long long)h;
+    }
+    pc_sync<T>();
+    // what the run walk needs of every hit, in sorted order (one parallel gather instead of dependent loads inside the runs)
+    for (uint32_t e = tid; e < n; e += T) {
+        const uint32_t h = SMEM ? hit_at32[e] : (uint32_t)vkey[4u * m + e];
+        const HitAux x = aux[h];
+        const imrcd_tri_hit hh = hits[h];
+        const V3 sum = add3(mk3(hh.source[0], hh.source[1], hh.source[2]), mk3(hh.target[0], hh.target[1], hh.target[2]));
+        d_fl[e] = x.flags; d_w[e] = hh.weight;
+        d_cx[e] = (hh.weight * sum.x) / 2.f; d_cy[e] = (hh.weight * sum.y) / 2.f; d_cz[e] = (hh.weight * sum.z) / 2.f;       // :94-100
+    }
+    pc_sync<T>();
+    SideSum acc; acc.x = acc.y = acc.z = 0.0; acc.rays = 0u;
+    // ---- runs of equal own triangle: merge the combos' candidates (TriangleCandidateRays, :13-58,117-127) ----
+    for (uint32_t k = tid; k < n; k += T) {
+        const uint32_t tri = (uint32_t)(key[k] >> 32);
+        if (k > 0 && (uint32_t)(key[k - 1] >> 32) == tri) continue;              // not the head of a run
+        uint32_t bits = 7u; V3 wavg = mk3(0.f, 0.f, 0.f); float weight = 0.f; bool present = false;
+        uint32_t e = k;
+        while (e < n && (uint32_t)(key[e] >> 32) == tri) {
+            // one combo: hits whose other triangle lies in the same leaf
+            uint32_t cbits = 7u; V3 cw = mk3(0.f, 0.f, 0.f); float cwt = 0.f;
+            uint32_t leaf = 0xffffffffu;
+            while (e < n && (uint32_t)(key[e] >> 32) == tri) {
+                const uint32_t fl = d_fl[e];
+                const uint32_t other_pos = side ? ((fl >> 6) & 3u) : ((fl >> 8) & 3u);
+                const uint32_t this_leaf = (uint32_t)key[e] - other_pos;
+                if (leaf != 0xffffffffu && this_leaf != leaf) break;
+                leaf = this_leaf;
+                cw = add3(cw, mk3(d_cx[e], d_cy[e], d_cz[e]));
+                cwt += d_w[e];
+                cbits &= side ? ((fl >> 3) & 7u) : (fl & 7u);
+                ++e;
+            }
+            if (!(cwt == 0.f)) {                                                  // IsNull() (:22-25), MergeWithMap (:39-49)
+                if (!present) { present = true; bits = cbits; wavg = cw; weight = cwt; }
+                else { bits &= cbits; wavg = add3(wavg, cw); weight += cwt; }
+            }
+        }
+        if (!present) continue;
+        if (bits == 0u) {                                                         // ray at the weighted average point (:34-37,160-163)
+            acc.x += (double)(wavg.x / weight); acc.y += (double)(wavg.y / weight); acc.z += (double)(wavg.z / weight); acc.rays += 1u;
+        } else {
+#pragma unroll
+            for (uint32_t pi = 0; pi < 3; ++pi) {
+                if (!((bits >> pi) & 1u)) continue;
+                const unsigned long long ent = ((unsigned long long)tri_vid[3ull * tri + pi] << 32) | (unsigned long long)(k * 4u + pi);
+                if (SMEM) vset_insert<VSET>(vset, ent);
+                else vkey[atomicAdd(s_count, 1u)] = ent;
+            }
+        }
+    }
+    pc_sync<T>();
+    // ---- vertex rays: one per distinct vertex id (the `emplaced` set, :139-141) ----
+    if (SMEM) {
+        for (uint32_t k = tid; k < VSET; k += T) {
+            const unsigned long long ent = vset[k];
+            if (ent == ~0ull) continue;
+            const uint32_t ref = (uint32_t)ent, pi = ref & 3u;
+            const float4 q = __ldg(reinterpret_cast<const float4*>(tris + (uint32_t)(key[ref >> 2] >> 32)) + pi);
+            V3 pos = mk3(q.x, q.y, q.z);
+            if (side) pos = rel_mul(rel, pos, 1.f);                                // second's triangles live in first's space (:84,:134)
+            acc.x += (double)pos.x; acc.y += (double)pos.y; acc.z += (double)pos.z; acc.rays += 1u;
+        }
+    } else {
+        const uint32_t nv = *s_count;
+        if (nv) {
+            uint32_t mv = 1u; while (mv < nv) mv <<= 1;                           // nv <= 3n, so mv <= 4m: the vertex list owns vkey[0 .. 4m)
+            for (uint32_t k = nv + tid; k < mv; k += T) vkey[k] = ~0ull;
+            pc_sync<T>();
+            pc_sort<T>(vkey, mv, tid);
+            for (uint32_t k = tid; k < nv; k += T) {
+                const uint32_t vid = (uint32_t)(vkey[k] >> 32);
+                if (k > 0 && (uint32_t)(vkey[k - 1] >> 32) == vid) continue;
+                const uint32_t ref = (uint32_t)vkey[k], pi = ref & 3u;
+                const float4 q = __ldg(reinterpret_cast<const float4*>(tris + (uint32_t)(key[ref >> 2] >> 32)) + pi);
+                V3 pos = mk3(q.x, q.y, q.z);
+                if (side) pos = rel_mul(rel, pos, 1.f);
+                acc.x += (double)pos.x; acc.y += (double)pos.y; acc.z += (double)pos.z; acc.rays += 1u;
+            }
+        }
+    }
+    pc_sync<T>();
+    return acc;
+}
+
+template <int T, uint32_t M_MAX, uint32_t VSET>        // M_MAX == 0: scratch in global memory
+__global__ void __launch_bounds__(T)
+k_pair_contacts(const FrameCtl* ctl, const uint32_t* __restrict__ list, int cls, PairAcc* acc, const uint32_t* __restrict__ grouped,
+                unsigned long long* scratch_key, unsigned long long* scratch_vkey, const imrcd_tri_hit* __restrict__ hits,
+                const HitAux* __restrict__ aux, const PairRec* __restrict__ pairrec, const TriRec* __restrict__ tris, const uint32_t* __restrict__ tri_vid) {
+    constexpr bool SMEM = M_MAX != 0;
+    extern __shared__ __align__(16) unsigned char pc_smem[];
+    unsigned long long* s_key = reinterpret_cast<unsigned long long*>(pc_smem);                  // M_MAX
+    unsigned long long* s_vset = s_key + M_MAX;                                                  // VSET
+    uint32_t* s_hit = reinterpret_cast<uint32_t*>(s_vset + (SMEM ? VSET : 0));                   // M_MAX, then 5 x M_MAX words of per-hit data
+    __shared__ uint32_t s_count;
+    __shared__ double s_red[3][T / 32];
+    __shared__ uint32_t s_redc[T / 32];
+    const uint32_t tid = threadIdx.x;
+    if (ctl->overflow & (OVF_PAIRS | OVF_QUEUE | OVF_COMBOS | OVF_HITS)) return;      // the frame is re-run with larger buffers
+    const unsigned long long n_list = ctl->n_class[cls * 16];
+    for (unsigned long long b = blockIdx.x; b < n_list; b += gridDim.x) {
+        const uint32_t p = list[b];
+        const uint32_t n = acc[p].n_hits, off = acc[p].off;
+        uint32_t m = 1u; while (m < n) m <<= 1;
+        const uint32_t* grp = grouped + off;
+        unsigned long long* key = SMEM ? s_key : scratch_key + off;
+        unsigned long long* vkey = scratch_vkey + 8ull * off;         // [0,4m) vertex list, [4m,5m) hit per sorted position, [5m,8m) per-hit data
+        uint32_t* d_fl = SMEM ? s_hit + M_MAX : reinterpret_cast<uint32_t*>(vkey + 5ull * m);
+        float* d_w = reinterpret_cast<float*>(d_fl + (SMEM ? M_MAX : m));
+        float* d_cx = d_w + (SMEM ? M_MAX : m); float* d_cy = d_cx + (SMEM ? M_MAX : m); float* d_cz = d_cy + (SMEM ? M_MAX : m);
+        const float4* pp = reinterpret_cast<const float4*>(pairrec + p);
+        Rel rel; rel.r0 = __ldg(pp); rel.r1 = __ldg(pp + 1); rel.r2 = __ldg(pp + 2);
+        for (uint32_t side = 0; side < 2; ++side) {
+            SideSum r = pc_side<T, SMEM, (SMEM ? VSET : 2u)>(side, n, m, grp, key, vkey, s_hit, d_fl, d_w, d_cx, d_cy, d_cz, &s_count, s_vset, hits, aux, tris, tri_vid, rel, tid);
+            // fixed-order reduction over the threads (deterministic)
+            for (int o = 16; o > 0; o >>= 1) {
+                r.x += __shfl_down_sync(FULL_MASK, r.x, o); r.y += __shfl_down_sync(FULL_MASK, r.y, o); r.z += __shfl_down_sync(FULL_MASK, r.z, o);
+                r.rays += __shfl_down_sync(FULL_MASK, r.rays, o);
+            }
+            if (T > 32) {
+                if ((tid & 31u) == 0u) { s_red[0][tid >> 5] = r.x; s_red[1][tid >> 5] = r.y; s_red[2][tid >> 5] = r.z; s_redc[tid >> 5] = r.rays; }
+                __syncthreads();
+                if (tid == 0) { for (int w = 1; w < T / 32; ++w) { r.x += s_red[0][w]; r.y += s_red[1][w]; r.z += s_red[2][w]; r.rays += s_redc[w]; } }
+                __syncthreads();
+            }
+            if (tid == 0) {
+                PairAcc* pa = acc + p;
+                double* sum = side ? pa->sum_b : pa->sum_a;
+                sum[0] = r.x; sum[1] = r.y; sum[2] = r.z;
+                if (side) pa->rays_b = r.rays; else pa->rays_a = r.rays;
+            }
+        }
+    }
+}
+
 __global__ void k_finalize(FrameCtl* ctl, unsigned long long cap_pairs, const uint2* __restrict__ pairs, const PairAcc* __restrict__ acc,
-                           const uint32_t* __restrict__ entity, imrcd_entity_pair* __restrict__ out) {
+                           const uint32_t* __restrict__ entity, const float* __restrict__ cur, const float* __restrict__ inv,
+                           imrcd_entity_pair* __restrict__ out) {
     unsigned long long n = ctl->n_pairs < cap_pairs ? ctl->n_pairs : cap_pairs;
     for (unsigned long long p = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; p < n; p += (unsigned long long)gridDim.x * blockDim.x) {
-        PairAcc a = acc[p];
-        if (a.flags & 1u) {
-            unsigned long long slot = atomicAdd(&ctl->n_colliding, 1ull);
-            uint2 pr = pairs[p];
-            imrcd_entity_pair o;
-            memset(&o, 0, sizeof(o));
-            o.entry_first = pr.x; o.entry_second = pr.y;
-            o.entity_first = entity[pr.x]; o.entity_second = entity[pr.y];
-            o.n_hits = a.n_hits; o.flags = 1u;
-            out[slot] = o;
-        }
+        if (!(acc[p].flags & 1u)) continue;
+        const PairAcc a = acc[p];
+        unsigned long long slot = atomicAdd(&ctl->n_colliding, 1ull);
+        uint2 pr = pairs[p];
+        imrcd_entity_pair o;
+        memset(&o, 0, sizeof(o));
+        o.entry_first = pr.x; o.entry_second = pr.y;
+        o.entity_first = entity[pr.x]; o.entity_second = entity[pr.y];
+        o.n_hits = a.n_hits; o.flags = 1u;
+        o.n_rays_first = a.rays_a; o.n_rays_second = a.rays_b;
+        atomicAdd(&ctl->n_rays, (unsigned long long)(a.rays_a + a.rays_b));
+        // average_point_first_modelspace = sum / count (:185-189); second: back to its own model space through
+        // inverse(second_to_first_space_matrix) (:191-198).  0 rays on a side gives NaN exactly like the reference.
+        const float fa = (float)a.rays_a, fb = (float)a.rays_b;
+        o.avg_first[0] = (float)a.sum_a[0] / fa; o.avg_first[1] = (float)a.sum_a[1] / fa; o.avg_first[2] = (float)a.sum_a[2] / fa;
+        const V3 sb = mk3((float)a.sum_b[0] / fb, (float)a.sum_b[1] / fb, (float)a.sum_b[2] / fb);
+        float rel[16], rinv[16];
+        mat4_mul(inv + 16 * (size_t)pr.x, cur + 16 * (size_t)pr.y, rel);            // the same rel as k_pair_setup (OBBtreesCollision.cpp:15)
+        mat4_inverse(rel, rinv);
+        const V3 back = rel_mul(rel_from_mat(rinv), sb, 1.f);
+        o.avg_second[0] = back.x; o.avg_second[1] = back.y; o.avg_second[2] = back.z;
+        out[slot] = o;
     }
 }
 
@@ -712,7 +1018,21 @@ int imr_frame_run_device(imrcd_ctx* ctx) {
         if (16ull * ctx->cap_queue > ctx->d_queue.cap) { IMR_CUDA(ctx, ctx->d_queue.reserve(16ull * ctx->cap_queue, 0, s)); ctx->queue_dirty = ctx->cap_queue; }
         IMR_CUDA(ctx, ctx->d_combos.reserve(16ull * ctx->cap_combos, 0, s));
         IMR_CUDA(ctx, ctx->d_hits.reserve(sizeof(imrcd_tri_hit) * ctx->cap_hits, 0, s));
-
+        // contact reduction scratch: per-pair slices are power-of-two padded, so at most 2 x hits slots in total
+        IMR_CUDA(ctx, ctx->d_aux.reserve(sizeof(HitAux) * ctx->cap_hits, 0, s));
+        IMR_CUDA(ctx, ctx->d_grouped.reserve(4ull * 2 * ctx->cap_hits, 0, s));
+        IMR_CUDA(ctx, ctx->d_skey.reserve(8ull * 2 * ctx->cap_hits, 0, s));
+        IMR_CUDA(ctx, ctx->d_svkey.reserve(64ull * 2 * ctx->cap_hits, 0, s));
+        IMR_CUDA(ctx, ctx->d_padded.reserve(4ull * (ctx->cap_pairs + 1), 0, s));
+        IMR_CUDA(ctx, ctx->d_padoff.reserve(4ull * (ctx->cap_pairs + 1), 0, s));
+        IMR_CUDA(ctx, ctx->d_lsmall.reserve(4ull * ctx->cap_pairs, 0, s));
+        IMR_CUDA(ctx, ctx->d_llarge.reserve(4ull * ctx->cap_pairs, 0, s));
+        IMR_CUDA(ctx, ctx->d_lmid.reserve(4ull * ctx->cap_pairs, 0, s));
+        {
+            size_t scan_bytes = 0;
+            cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, ctx->d_padded.as<uint32_t>(), ctx->d_padoff.as<uint32_t>(), (int)(ctx->cap_pairs + 1), s);
+            if (scan_bytes > cub_bytes) { cub_bytes = scan_bytes; IMR_CUDA(ctx, ctx->d_cubtmp.reserve(cub_bytes, 0, s)); }
+        }
         FrameCtl* ctl = ctx->d_ctl.as<FrameCtl>();
         uint64_t launches = 0;
         IMR_CUDA(ctx, cudaEventRecord(ctx->ev[0], s));
@@ -758,12 +1078,33 @@ int imr_frame_run_device(imrcd_ctx* ctx) {
         // ---- narrow ----
         k_tritri<<<ctx->narrow_blocks, NT_WARPS * 32, NT_WARPS * sizeof(NarrowWarp), s>>>(ctl, ctx->d_combos.as<Combo>(), ctx->cap_combos, ctx->d_pairrec.as<PairRec>(),
                                                     ctx->d_tris.as<TriRec>(), ctx->d_hits.as<imrcd_tri_hit>(), ctx->cap_hits,
-                                                    ctx->d_pairacc.as<PairAcc>());
+                                                    ctx->d_pairacc.as<PairAcc>(), ctx->d_aux.as<HitAux>());
         launches += 1;
         IMR_CUDA(ctx, cudaEventRecord(ctx->ev[4], s));
         // ---- reduce ----
+        k_hit_layout<<<ctx->sm_count * 8, 256, 0, s>>>(ctl, ctx->cap_pairs, ctx->d_pairacc.as<PairAcc>(), ctx->d_padded.as<uint32_t>());
+        cub::DeviceScan::ExclusiveSum(ctx->d_cubtmp.p, cub_bytes, ctx->d_padded.as<uint32_t>(), ctx->d_padoff.as<uint32_t>(), (int)(ctx->cap_pairs + 1), s);
+        k_hit_lists<<<ctx->sm_count * 4, 256, 0, s>>>(ctl, ctx->cap_pairs, ctx->d_pairacc.as<PairAcc>(), ctx->d_padoff.as<uint32_t>(),
+                                                       ctx->d_lsmall.as<uint32_t>(), ctx->d_lmid.as<uint32_t>(), ctx->d_llarge.as<uint32_t>());
+        k_group_hits<<<ctx->sm_count * 8, 256, 0, s>>>(ctl, ctx->cap_hits, ctx->d_hits.as<imrcd_tri_hit>(), ctx->d_pairacc.as<PairAcc>(), ctx->d_grouped.as<uint32_t>());
+        {
+            const size_t smem_s = PC_S_MAX * 8 + 1024 * 8 + PC_S_MAX * 24, smem_m = PC_M_MAX * 8 + 4096 * 8 + PC_M_MAX * 24;
+            if (!ctx->pc_attr_set) {
+                IMR_CUDA(ctx, cudaFuncSetAttribute(k_pair_contacts<256, PC_M_MAX, 4096>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m));
+                ctx->pc_attr_set = true;
+            }
+            PairAcc* a_acc = ctx->d_pairacc.as<PairAcc>(); const uint32_t* a_grp = ctx->d_grouped.as<uint32_t>();
+            unsigned long long* a_key = ctx->d_skey.as<unsigned long long>(); unsigned long long* a_vkey = ctx->d_svkey.as<unsigned long long>();
+            const imrcd_tri_hit* a_hits = ctx->d_hits.as<imrcd_tri_hit>(); const HitAux* a_aux = ctx->d_aux.as<HitAux>();
+            const PairRec* a_pr = ctx->d_pairrec.as<PairRec>(); const TriRec* a_tris = ctx->d_tris.as<TriRec>(); const uint32_t* a_vid = ctx->d_tri_vid.as<uint32_t>();
+            k_pair_contacts<64, PC_S_MAX, 1024><<<ctx->sm_count * 16, 64, smem_s, s>>>(ctl, ctx->d_lsmall.as<uint32_t>(), 0, a_acc, a_grp, a_key, a_vkey, a_hits, a_aux, a_pr, a_tris, a_vid);
+            k_pair_contacts<256, PC_M_MAX, 4096><<<ctx->sm_count * 3, 256, smem_m, s>>>(ctl, ctx->d_lmid.as<uint32_t>(), 1, a_acc, a_grp, a_key, a_vkey, a_hits, a_aux, a_pr, a_tris, a_vid);
+            k_pair_contacts<512, 0, 2><<<ctx->sm_count * 2, 512, 0, s>>>(ctl, ctx->d_llarge.as<uint32_t>(), 2, a_acc, a_grp, a_key, a_vkey, a_hits, a_aux, a_pr, a_tris, a_vid);
+        }
+        launches += 8;      // layout, scan (2), lists, group, three size classes
         k_finalize<<<ctx->sm_count * 4, 256, 0, s>>>(ctl, ctx->cap_pairs, ctx->d_pairs.as<uint2>(), ctx->d_pairacc.as<PairAcc>(),
-                                                      ctx->d_entity.as<uint32_t>(), ctx->d_epairs.as<imrcd_entity_pair>());
+                                                      ctx->d_entity.as<uint32_t>(), ctx->d_cur.as<float>(), ctx->d_inv.as<float>(),
+                                                      ctx->d_epairs.as<imrcd_entity_pair>());
         launches += 1;
         IMR_CUDA(ctx, cudaEventRecord(ctx->ev[5], s));
         IMR_CUDA(ctx, cudaMemcpyAsync(ctx->p_ctl.p, ctl, sizeof(FrameCtl), cudaMemcpyDeviceToHost, s));
@@ -779,12 +1120,14 @@ int imr_frame_run_device(imrcd_ctx* ctx) {
             if (ctx->cap_queue < ctx->cap_pairs) ctx->cap_queue = ctx->cap_pairs + (1ull << 22);
             if (c.overflow & OVF_COMBOS) ctx->cap_combos = std::max<uint64_t>(c.n_combos + c.n_combos / 8, ctx->cap_combos * 2);
             if (c.overflow & OVF_HITS) ctx->cap_hits = std::max<uint64_t>(c.n_hits + c.n_hits / 8, ctx->cap_hits * 2);
+
             continue;   // re-run the frame with the larger buffers
         }
 
         imrcd_frame_stats& st = ctx->stats;
         st.n_pairs = c.n_pairs; st.n_sat_tests = c.n_sat; st.n_combos = c.n_combos; st.n_tri_tests = c.n_tri_tests;
         st.n_hits = c.n_hits; st.n_coplanar_hits = c.n_coplanar; st.n_colliding = c.n_colliding;
+        st.n_contact_pairs = c.n_class[0] + c.n_class[16] + c.n_class[32]; st.n_rays = c.n_rays;
         st.traverse_launches = 1; st.total_launches = launches; st.n_queue_items = c.n_donated; st.n_warp_iterations = c.n_iterations; st.trav_busy_cycles = c.busy_cycles; st.trav_idle_polls = c.idle_polls;
         cudaEventElapsedTime(&st.ms_total, ctx->ev[0], ctx->ev[5]);
         cudaEventElapsedTime(&st.ms_broad, ctx->ev[0], ctx->ev[1]);

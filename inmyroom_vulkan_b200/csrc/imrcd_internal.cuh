@@ -53,12 +53,14 @@ struct __align__(128) FrameCtl {
     unsigned long long n_combos;    unsigned long long _p5[15];
     unsigned long long n_hits;      unsigned long long _p6[15];
     unsigned long long n_colliding; unsigned long long _p7[15];
+    unsigned long long n_class[48];                               // pairs with hits per size class of the contact reduction ([0], [16], [32])
     unsigned long long n_coplanar;
     unsigned long long n_sat;
     unsigned long long n_tri_tests;
     unsigned long long n_donated;          // items that went through the global queue after the roots
     unsigned long long n_iterations;       // traversal warp-iterations (diagnostic)
     unsigned long long busy_cycles, idle_polls;
+    unsigned long long n_rays;             // rays of all colliding pairs, both sides
     unsigned int overflow;                 // bit0 pairs, bit1 queue, bit2 combos, bit3 hits
     unsigned int pad;
 };
@@ -140,6 +142,7 @@ struct imrcd_ctx {
     // frame, device side
     DevBuf d_cur, d_prev, d_mesh, d_cb, d_entity, d_inv, d_ext, d_keys, d_keys2, d_idx, d_idx2, d_sorted, d_sorted_c, d_flag, d_cpos, d_wlen, d_chunks, d_chunkoff, d_cubtmp;
     DevBuf d_pairs, d_pairrec, d_pairacc, d_queue, d_combos, d_hits, d_epairs, d_ctl;
+    DevBuf d_aux, d_grouped, d_skey, d_svkey, d_padded, d_padoff, d_lsmall, d_lmid, d_llarge;      // contact reduction scratch (imrcd_frame.cu)
     uint64_t cap_pairs = 0, cap_queue = 0, cap_combos = 0, cap_hits = 0;
     uint64_t queue_dirty = 0;            // slots whose ready flag may still be set
     // results
@@ -149,6 +152,7 @@ struct imrcd_ctx {
     bool hits_fetched = false;
     cudaEvent_t ev[8] = {};
     int trav_blocks = 0, narrow_blocks = 0, trav_variant = 0;
+    bool pc_attr_set = false;
     const void* trav_fn = nullptr;
 };
 

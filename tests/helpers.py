@@ -65,7 +65,7 @@ def gpu_frame(cd, scene, gpu_trees):
     return st, bp, ep, hits
 
 
-def compare_frame(orc_res, st, bp, ep, hits, check_hits_bits=True):
+def compare_frame(orc_res, st, bp, ep, hits, check_hits_bits=True, check_contacts=True, rel_of=None):
     """Assert the GPU frame equals the oracle frame: ordered pair set, per-pair hit sets (bit-exact segments),
     colliding-entity set, counters."""
     o_pairs = set(map(tuple, orc_res["pairs"].tolist()))
@@ -97,6 +97,17 @@ def compare_frame(orc_res, st, bp, ep, hits, check_hits_bits=True):
             assert not bad, f"pair {key}: {len(bad)} hit segments differ in bits, e.g. {bad[:3]}"
     o_coll = {k for k, r in orc_res["per_pair"].items() if r.colliding}
     g_coll = {(int(p["entry_first"]), int(p["entry_second"])) for p in ep}
+    # contact reduction (CreateUncollideRays.cpp:117-198): ray counts exact, contact points within 1e-5 relative
+    if check_contacts:
+        for p in ep:
+            key = (int(p["entry_first"]), int(p["entry_second"]))
+            r = orc_res["per_pair"].get(key)
+            if r is None:
+                continue
+            assert (int(p["n_rays_first"]), int(p["n_rays_second"])) == (r.rays_first, r.rays_second), f"pair {key}: ray counts {p['n_rays_first']},{p['n_rays_second']} vs {r.rays_first},{r.rays_second}"
+            assert int(p["n_hits"]) == r.n_hits
+            if rel_of is not None and r.rays_first and r.rays_second:
+                assert contacts_close(np.concatenate([p["avg_first"], p["avg_second"]]), r.avg, rel_of(key)), f"pair {key}: contact points {p['avg_first']} {p['avg_second']} vs {r.avg}"
     if len(orc_res["per_pair"]) == len(o_pairs):
         assert g_coll == o_coll, "colliding-entity sets differ"
     else:

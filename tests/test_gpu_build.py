@@ -88,7 +88,7 @@ def _frame_with_gpu_trees(gpu_ctx, port, oracle, scene, strict_sets=True):
     # (a) the port oracle on the exported GPU trees: everything bit-exact
     p_trees = [port.tree_import(t.export()) for t in g_trees]
     pres = oracle_frame(port, scene, p_trees, port=port)
-    compare_frame(pres, st, bp, ep, hits)
+    compare_frame(pres, st, bp, ep, hits, rel_of=lambda k: port.pair_matrix(scene.matrices[k[0]], scene.matrices[k[1]]))
     # (b) the reference on its own trees: tree-independent outputs
     o_trees = [oracle.tree_build(m.positions, m.normals, m.vertex_ids) for m in scene.meshes]
     ores = oracle_frame(oracle, scene, o_trees, port=port)

@@ -16,7 +16,7 @@ def _run(gpu_ctx, oracle, scene):
     cd = CollisionDetection(ctx=gpu_ctx)
     st, bp, ep, hits = gpu_frame(cd, scene, g_trees)
     ores = oracle_frame(oracle, scene, o_trees)
-    compare_frame(ores, st, bp, ep, hits)
+    compare_frame(ores, st, bp, ep, hits, rel_of=lambda k: oracle.pair_matrix(scene.matrices[k[0]], scene.matrices[k[1]]))
     return st, ores
 
 

@@ -5,7 +5,7 @@ import pytest
 
 import golden_io
 from inmyroom_vulkan_b200.collision import CollisionDetection, OBBtree
-from helpers import f32_bits, gpu_frame
+from helpers import contacts_close, f32_bits, gpu_frame
 
 pytestmark = pytest.mark.gpu
 
@@ -49,3 +49,11 @@ def test_frame_golden(gpu_ctx, port, name):
     assert o == g
     coll = {tuple(p) for p, s in zip(gold["pairs"].tolist(), summ) if s[6]}
     assert {(int(p["entry_first"]), int(p["entry_second"])) for p in ep} == coll
+    # contact reduction against the reference's own numbers: ray counts exact, contact points within 1e-5 relative
+    index = {tuple(p): k for k, p in enumerate(gold["pairs"].tolist())}
+    for p in ep:
+        k = index[(int(p["entry_first"]), int(p["entry_second"]))]
+        assert (int(p["n_rays_first"]), int(p["n_rays_second"])) == (int(summ[k][4]), int(summ[k][5]))
+        if summ[k][4] and summ[k][5]:
+            rel = port.pair_matrix(sc.matrices[int(p["entry_first"])], sc.matrices[int(p["entry_second"])])
+            assert contacts_close(np.concatenate([p["avg_first"], p["avg_second"]]), gold["avg"][k], rel)
