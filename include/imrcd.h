@@ -112,6 +112,15 @@ int imrcd_frame_add_entry(imrcd_ctx* ctx, const float current[16], const float p
                           uint8_t should_callback, uint32_t entity);
 int imrcd_frame_add_entries(imrcd_ctx* ctx, uint64_t n, const float* current, const float* previous,
                             const uint32_t* mesh_ids, const uint8_t* should_callback, const uint32_t* entities);
+/* Zero-copy submission: the caller writes the entries of this frame straight into the context's PINNED staging buffers
+ * (what AddCollisionDetectionEntry's push_back is to the reference, CollisionDetection.cpp:33-36) and then commits them.
+ * imrcd_frame_map_entries returns pointers to room for `n` more entries after the ones already added (any out pointer
+ * may be NULL); the memory keeps its previous contents, stays valid until the next map call that has to grow it, and
+ * must be completely filled before imrcd_frame_commit_entries(n).  `previous` may be left untouched when
+ * previous_valid == 0 (previous == current for every committed entry). */
+int imrcd_frame_map_entries(imrcd_ctx* ctx, uint64_t n, float** current, float** previous, uint32_t** mesh_ids,
+                            uint8_t** should_callback, uint32_t** entities);
+int imrcd_frame_commit_entries(imrcd_ctx* ctx, uint64_t n, int previous_valid);
 /* Multi-GPU: this context keeps only the broad-phase pairs whose owner entry (the larger entry index)
  * satisfies owner % n_ranks == rank.  Default (0,1) = everything. */
 int imrcd_frame_set_shard(imrcd_ctx* ctx, uint32_t rank, uint32_t n_ranks);

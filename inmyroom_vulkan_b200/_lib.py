@@ -56,6 +56,8 @@ _SIGS = [
     ("imrcd_frame_reset", C.c_int, [_P]),
     ("imrcd_frame_add_entry", C.c_int, [_P, _P, _P, C.c_uint32, C.c_uint8, C.c_uint32]),
     ("imrcd_frame_add_entries", C.c_int, [_P, C.c_uint64, _P, _P, _P, _P, _P]),
+    ("imrcd_frame_map_entries", C.c_int, [_P, C.c_uint64, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
+    ("imrcd_frame_commit_entries", C.c_int, [_P, C.c_uint64, C.c_int]),
     ("imrcd_frame_set_shard", C.c_int, [_P, C.c_uint32, C.c_uint32]),
     ("imrcd_frame_execute", C.c_int, [_P]),
     ("imrcd_frame_upload", C.c_int, [_P]),

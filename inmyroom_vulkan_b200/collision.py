@@ -201,6 +201,23 @@ class CollisionDetection:
         self.ctx.check(self.lib.imrcd_frame_add_entries(self.ctx.h, n, _ptr(m), _ptr(p), _ptr(mid), _ptr(cb), _ptr(ent)))
         self._n += n
 
+    def map_entries(self, n: int):
+        """Zero-copy submission: numpy views of the context's pinned staging for `n` more entries
+        (current (n,16) f32, previous (n,16) f32, mesh_ids (n,) u32, should_callback (n,) u8, entities (n,) u32).
+        Fill them, then call commit_entries(n)."""
+        from types import SimpleNamespace
+        ptrs = [C.c_void_p() for _ in range(5)]
+        self.ctx.check(self.lib.imrcd_frame_map_entries(self.ctx.h, n, *[C.byref(p) for p in ptrs]))
+        def view(p, ctype, shape):
+            return np.ctypeslib.as_array(C.cast(p, C.POINTER(ctype)), shape=shape)
+        return SimpleNamespace(current=view(ptrs[0], C.c_float, (n, 16)), previous=view(ptrs[1], C.c_float, (n, 16)),
+                               mesh_ids=view(ptrs[2], C.c_uint32, (n,)), should_callback=view(ptrs[3], C.c_uint8, (n,)),
+                               entities=view(ptrs[4], C.c_uint32, (n,)))
+
+    def commit_entries(self, n: int, previous_valid: bool = False):
+        self.ctx.check(self.lib.imrcd_frame_commit_entries(self.ctx.h, n, 1 if previous_valid else 0))
+        self._n += n
+
     def set_shard(self, rank: int, n_ranks: int):
         self.ctx.check(self.lib.imrcd_frame_set_shard(self.ctx.h, rank, n_ranks))
 

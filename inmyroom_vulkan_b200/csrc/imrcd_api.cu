@@ -30,6 +30,8 @@ extern "C" int imrcd_create(int device, void* cuda_stream, imrcd_ctx** out) {
     if (cuda_stream) { ctx->stream = static_cast<cudaStream_t>(cuda_stream); ctx->own_stream = false; }
     else { if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return IMRCD_E_CUDA; } ctx->own_stream = true; }
     for (auto& e : ctx->ev) if (cudaEventCreate(&e) != cudaSuccess) { delete ctx; return IMRCD_E_CUDA; }
+    if (cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return IMRCD_E_CUDA; }
     *out = ctx;
     return IMRCD_OK;
 }
@@ -46,6 +48,9 @@ extern "C" void imrcd_destroy(imrcd_ctx* ctx) {
     PinBuf* pins[] = { &ctx->p_cur, &ctx->p_prev, &ctx->p_mesh, &ctx->p_entity, &ctx->p_cb, &ctx->p_ctl, &ctx->p_epairs, &ctx->p_hits, &ctx->p_pairs, &ctx->p_combos };
     for (PinBuf* b : pins) b->release();
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -320,6 +325,59 @@ extern "C" int imrcd_frame_add_entries(imrcd_ctx* ctx, uint64_t n, const float* 
     }
     ctx->uploaded = ctx->ran = ctx->fetched = false;
     return IMRCD_OK;
+}
+
+static int entries_reserve(imrcd_ctx* ctx, uint64_t total, bool device_too) {
+    const uint64_t base = ctx->n_entries;
+    cudaStream_t s = ctx->stream;
+    IMR_CUDA(ctx, ctx->p_cur.reserve(64 * total, 64 * base, s));
+    IMR_CUDA(ctx, ctx->p_prev.reserve(64 * total, 64 * base, s));
+    IMR_CUDA(ctx, ctx->p_mesh.reserve(4 * total, 4 * base, s));
+    IMR_CUDA(ctx, ctx->p_entity.reserve(4 * total, 4 * base, s));
+    IMR_CUDA(ctx, ctx->p_cb.reserve(total, base, s));
+    if (device_too) {
+        IMR_CUDA(ctx, ctx->d_cur.reserve(64 * total, 64 * ctx->n_sent, s));
+        IMR_CUDA(ctx, ctx->d_mesh.reserve(4 * total, 4 * ctx->n_sent, s));
+        IMR_CUDA(ctx, ctx->d_entity.reserve(4 * total, 4 * ctx->n_sent, s));
+        IMR_CUDA(ctx, ctx->d_cb.reserve(total, ctx->n_sent, s));
+    }
+    return IMRCD_OK;
+}
+
+extern "C" int imrcd_frame_map_entries(imrcd_ctx* ctx, uint64_t n, float** current, float** previous, uint32_t** mesh_ids,
+                                       uint8_t** should_callback, uint32_t** entities) {
+    CHECK_CTX(ctx);
+    const uint64_t base = ctx->n_entries, total = base + n;
+    if (total >= (1ull << 32) - 1) { ctx->err = "too many entries"; return IMRCD_E_ARG; }
+    cudaSetDevice(ctx->device);
+    int rc = entries_reserve(ctx, total ? total : 1, false);
+    if (rc) return rc;
+    if (current) *current = ctx->p_cur.as<float>() + 16 * base;
+    if (previous) *previous = ctx->p_prev.as<float>() + 16 * base;
+    if (mesh_ids) *mesh_ids = ctx->p_mesh.as<uint32_t>() + base;
+    if (should_callback) *should_callback = ctx->p_cb.as<uint8_t>() + base;
+    if (entities) *entities = ctx->p_entity.as<uint32_t>() + base;
+    return IMRCD_OK;
+}
+
+extern "C" int imrcd_frame_commit_entries(imrcd_ctx* ctx, uint64_t n, int previous_valid) {
+    CHECK_CTX(ctx);
+    const uint64_t base = ctx->n_entries, total = base + n;
+    if (64 * total > ctx->p_cur.cap) { ctx->err = "imrcd_frame_commit_entries: more entries than were mapped"; return IMRCD_E_STATE; }
+    if (n == 0) return IMRCD_OK;
+    cudaSetDevice(ctx->device);
+    const uint32_t n_meshes = (uint32_t)ctx->meshes.size();
+    const uint32_t* pm = ctx->p_mesh.as<uint32_t>();
+    for (uint64_t i = base; i < total; ++i) if (pm[i] >= n_meshes) { ctx->err = "imrcd_frame_commit_entries: unknown mesh id"; return IMRCD_E_ARG; }
+    if (previous_valid) {
+        if (!ctx->prev_distinct && base) memcpy(ctx->p_prev.p, ctx->p_cur.p, 64 * base);
+        ctx->prev_distinct = true;
+    } else if (ctx->prev_distinct) memcpy(ctx->p_prev.as<char>() + 64 * base, ctx->p_cur.as<char>() + 64 * base, 64 * n);
+    int rc = entries_reserve(ctx, total, true);
+    if (rc) return rc;
+    ctx->n_entries = total;
+    ctx->uploaded = ctx->ran = ctx->fetched = false;
+    return entries_send(ctx, total);          // the DMA starts now; imrcd_frame_upload has nothing left to copy
 }
 
 extern "C" int imrcd_frame_add_entry(imrcd_ctx* ctx, const float current[16], const float previous[16], uint32_t mesh_id,

@@ -1097,9 +1097,14 @@ int imr_frame_run_device(imrcd_ctx* ctx) {
             unsigned long long* a_key = ctx->d_skey.as<unsigned long long>(); unsigned long long* a_vkey = ctx->d_svkey.as<unsigned long long>();
             const imrcd_tri_hit* a_hits = ctx->d_hits.as<imrcd_tri_hit>(); const HitAux* a_aux = ctx->d_aux.as<HitAux>();
             const PairRec* a_pr = ctx->d_pairrec.as<PairRec>(); const TriRec* a_tris = ctx->d_tris.as<TriRec>(); const uint32_t* a_vid = ctx->d_tri_vid.as<uint32_t>();
+            // the three size classes are independent: the two rarer ones run beside the common one on a second stream
+            IMR_CUDA(ctx, cudaEventRecord(ctx->ev_fork, s));
+            IMR_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
             k_pair_contacts<64, PC_S_MAX, 1024><<<ctx->sm_count * 16, 64, smem_s, s>>>(ctl, ctx->d_lsmall.as<uint32_t>(), 0, a_acc, a_grp, a_key, a_vkey, a_hits, a_aux, a_pr, a_tris, a_vid);
-            k_pair_contacts<256, PC_M_MAX, 4096><<<ctx->sm_count * 3, 256, smem_m, s>>>(ctl, ctx->d_lmid.as<uint32_t>(), 1, a_acc, a_grp, a_key, a_vkey, a_hits, a_aux, a_pr, a_tris, a_vid);
-            k_pair_contacts<512, 0, 2><<<ctx->sm_count * 2, 512, 0, s>>>(ctl, ctx->d_llarge.as<uint32_t>(), 2, a_acc, a_grp, a_key, a_vkey, a_hits, a_aux, a_pr, a_tris, a_vid);
+            k_pair_contacts<256, PC_M_MAX, 4096><<<ctx->sm_count * 3, 256, smem_m, ctx->stream2>>>(ctl, ctx->d_lmid.as<uint32_t>(), 1, a_acc, a_grp, a_key, a_vkey, a_hits, a_aux, a_pr, a_tris, a_vid);
+            k_pair_contacts<512, 0, 2><<<ctx->sm_count * 2, 512, 0, ctx->stream2>>>(ctl, ctx->d_llarge.as<uint32_t>(), 2, a_acc, a_grp, a_key, a_vkey, a_hits, a_aux, a_pr, a_tris, a_vid);
+            IMR_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->stream2));
+            IMR_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_join, 0));
         }
         launches += 8;      // layout, scan (2), lists, group, three size classes
         k_finalize<<<ctx->sm_count * 4, 256, 0, s>>>(ctl, ctx->cap_pairs, ctx->d_pairs.as<uint2>(), ctx->d_pairacc.as<PairAcc>(),

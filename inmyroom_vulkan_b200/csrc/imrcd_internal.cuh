@@ -151,6 +151,8 @@ struct imrcd_ctx {
     imrcd_frame_stats stats;
     bool hits_fetched = false;
     cudaEvent_t ev[8] = {};
+    cudaStream_t stream2 = nullptr;      // side stream for independent tail work of a frame
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int trav_blocks = 0, narrow_blocks = 0, trav_variant = 0;
     bool pc_attr_set = false;
     const void* trav_fn = nullptr;

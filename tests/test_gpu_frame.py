@@ -62,3 +62,35 @@ def test_should_callback_filter(gpu_ctx, oracle):
     scene = scenes.scene_instances(scenes.torus(40, 20), 200, seed=9)
     scene.should_callback[::2] = 0
     _run(gpu_ctx, oracle, scene)
+
+
+def test_zero_copy_submission_matches_add_entries(gpu_ctx):
+    """imrcd_frame_map_entries / commit_entries (entries written straight into pinned staging) == add_entries."""
+    mesh = scenes.torus(40, 20)
+    scene = scenes.scene_instances(mesh, 300, seed=17)
+    tree = OBBtree(gpu_ctx, mesh.positions, mesh.normals, mesh.vertex_ids)
+    ids = np.full(scene.n_entries, tree.mesh_id, np.uint32)
+    cd = CollisionDetection(ctx=gpu_ctx)
+
+    def snapshot():
+        cd.ExecuteCollisionDetection()
+        ep, hits = cd.results(True)
+        bp = cd.broad_pairs()
+        key = np.stack([bp[hits["pair"], 0], bp[hits["pair"], 1], hits["tri_first"], hits["tri_second"]], 1)
+        order = np.lexsort(key.T[::-1])
+        eo = np.lexsort((ep["entry_second"], ep["entry_first"]))
+        return cd.stats(), key[order], hits["source"][order], ep[eo]
+
+    cd.Reset(); cd.add_entries(scene.matrices, ids, scene.should_callback, scene.entities)
+    a = snapshot()
+    cd.Reset()
+    half = scene.n_entries // 2
+    for lo, hi in ((0, half), (half, scene.n_entries)):          # two map/commit rounds append
+        v = cd.map_entries(hi - lo)
+        v.current[:] = scene.matrices[lo:hi]; v.mesh_ids[:] = ids[lo:hi]; v.should_callback[:] = scene.should_callback[lo:hi]; v.entities[:] = scene.entities[lo:hi]
+        cd.commit_entries(hi - lo)
+    b = snapshot()
+    for k in ("n_pairs", "n_sat_tests", "n_combos", "n_tri_tests", "n_hits", "n_colliding", "n_rays"):
+        assert a[0][k] == b[0][k], k
+    assert np.array_equal(a[1], b[1]) and np.array_equal(a[2].view(np.uint32), b[2].view(np.uint32))
+    assert a[3].tobytes() == b[3].tobytes()                      # colliding pairs incl. ray counts and contact points: bit-identical
