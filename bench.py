@@ -224,6 +224,8 @@ def run_gpu_arm(args):
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     stream = torch.cuda.Stream()
     ctx = Context(local, stream.cuda_stream)
@@ -384,7 +386,7 @@ def run_gpu_arm(args):
         "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": desc, "entries": n_entries, "triangles_in_trees": n_tri_total, "bodies": args.bodies,
-                   "parallelism": f"pairs sharded by entity over {world} GPU(s); one end-of-frame NCCL gather" if world > 1 else "1 GPU",
+                   "parallelism": f"broad-phase sweep chunks (entity x window slice) dealt round-robin to {world} GPUs; one end-of-frame NCCL gather" if world > 1 else "1 GPU",
                    "l2": "flushed between timed steps (256 MiB write); inputs (~35 MB) would otherwise stay L2-resident",
                    "tree_build": "GPU Morton build (IMRCD_BUILD_MORTON)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

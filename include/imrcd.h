@@ -121,8 +121,9 @@ int imrcd_frame_add_entries(imrcd_ctx* ctx, uint64_t n, const float* current, co
 int imrcd_frame_map_entries(imrcd_ctx* ctx, uint64_t n, float** current, float** previous, uint32_t** mesh_ids,
                             uint8_t** should_callback, uint32_t** entities);
 int imrcd_frame_commit_entries(imrcd_ctx* ctx, uint64_t n, int previous_valid);
-/* Multi-GPU: this context keeps only the broad-phase pairs whose owner entry (the larger entry index)
- * satisfies owner % n_ranks == rank.  Default (0,1) = everything. */
+/* Multi-GPU: this context sweeps only every n_ranks-th chunk of the broad phase (chunk = one entity x 512 consecutive
+ * candidates of its U window) and so keeps a disjoint 1/n_ranks slice of the pairs; the slices of ranks 0..n_ranks-1
+ * add up to the full pair list.  Default (0,1) = everything. */
 int imrcd_frame_set_shard(imrcd_ctx* ctx, uint32_t rank, uint32_t n_ranks);
 /* ExecuteCollisionDetection() = upload + run + fetch.  The three steps are exposed so that a caller
  * can time the device part with inputs already resident. */

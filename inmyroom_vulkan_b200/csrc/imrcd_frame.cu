@@ -140,7 +140,10 @@ k_sweep(uint32_t n, const SweepRec* __restrict__ sorted, const SweepRec* __restr
     const uint32_t lane = lane_id();
     const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
     const uint32_t total = chunk_off[n];
-    for (uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; c < total; c += warps_total) {
+    // Multi-GPU: rank r sweeps the chunks c with c % n_ranks == r, so the sweep itself is sharded and every pair is found by
+    // exactly one rank.  A chunk is (one entity) x (512 consecutive candidates of its window): entities with short windows
+    // (the dynamic bodies) land whole on one rank, the long windows of large static parts are dealt round-robin.
+    for (uint32_t c = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * n_ranks + rank; c < total; c += warps_total * n_ranks) {
         const uint32_t p = warp_find_owner(chunk_off, n, c, lane);
         const SweepRec a = sorted[p];
         const SweepRec* list = a.cb ? sorted : sorted_c;
@@ -157,8 +160,7 @@ k_sweep(uint32_t n, const SweepRec* __restrict__ sorted, const SweepRec* __restr
                 if (a.cb | e.cb) {
                     const bool v_ok = (a.vmin <= e.vmin) ? !(a.vmax < e.vmin) : !(e.vmax < a.vmin);
                     const bool w_ok = (a.wmin <= e.wmin) ? !(a.wmax < e.wmin) : !(e.wmax < a.wmin);
-                    const uint32_t owner = a.idx > e.idx ? a.idx : e.idx;
-                    emit = v_ok && w_ok && (owner % n_ranks == rank);
+                    emit = v_ok && w_ok;
                 }
             }
             const uint32_t m = __ballot_sync(FULL_MASK, emit);

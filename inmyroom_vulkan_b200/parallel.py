@@ -1,9 +1,9 @@
-"""Multi-GPU plumbing of the collision frame: one process per GPU, pairs sharded by entity, ONE exchange per frame.
+"""Multi-GPU plumbing of the collision frame: one process per GPU, the broad-phase sweep sharded by chunk, ONE exchange per frame.
 
 The path shards naturally: trees and the entry table are replicated, every rank runs the (cheap) sort
-of the broad phase and keeps only the pairs whose owner entry -- the larger entry index of the pair -- satisfies
-owner % world == rank (imrcd_frame_set_shard), so each colliding entity pair and all of its triangle hits are produced
-by exactly one rank and the per-pair contact reduction needs no cross-GPU step.  The only collective is the
+of the broad phase and then sweeps only every world-th chunk of it (imrcd_frame_set_shard; a chunk is one entity x 512
+consecutive candidates of its window), so each candidate pair, all of its triangle hits and its contact reduction belong
+to exactly one rank and nothing crosses GPUs before the end of the frame.  The only collective is the
 end-of-frame merge of the colliding-pair records (80 B each): an all-gather of per-rank counts followed by an
 all-gather of max-padded record blocks, over NCCL on NVLink (gloo on CPU in the tests).
 
@@ -21,16 +21,6 @@ import torch.distributed as dist
 from .collision import PAIR_DTYPE
 
 RECORD_BYTES = PAIR_DTYPE.itemsize     # 80
-
-
-def owner_of_pairs(pairs: np.ndarray) -> np.ndarray:
-    """Shard key of broad-phase pairs: the larger entry index (k_sweep, csrc/imrcd_frame.cu)."""
-    pairs = np.asarray(pairs).reshape(-1, 2)
-    return np.maximum(pairs[:, 0], pairs[:, 1])
-
-
-def shard_mask(pairs: np.ndarray, rank: int, world: int) -> np.ndarray:
-    return (owner_of_pairs(pairs) % np.uint32(world)) == np.uint32(rank)
 
 
 def all_gather_varlen(local: torch.Tensor, group=None) -> torch.Tensor:
@@ -61,11 +51,15 @@ class _DevMem:
 
 
 class FrameGather:
-    """End-of-frame merge of the colliding entity pairs of all ranks."""
+    """End-of-frame merge of the colliding entity pairs of all ranks: ONE all-gather of fixed-capacity blocks whose first
+    row carries the rank's record count (no separate count exchange, no host round trip before the payload moves).
+    The capacity doubles (and the gather is repeated) on the rare frame where some rank outgrows it."""
 
-    def __init__(self, cd, world: int, rank: int, group=None):
+    def __init__(self, cd, world: int, rank: int, group=None, capacity: int = 4096):
         self.cd = cd; self.world = world; self.rank = rank; self.group = group
+        self.cap = capacity
         self.last = None
+        self._send = None; self._recv = None
 
     def _local_device_records(self) -> torch.Tensor:
         ctx = self.cd.ctx
@@ -76,12 +70,38 @@ class FrameGather:
         t = torch.as_tensor(_DevMem(dp.value, n.value * RECORD_BYTES), device="cuda")
         return t.view(n.value, RECORD_BYTES)
 
+    def _buffers(self, device):
+        if self._send is None or self._send.shape[0] != self.cap + 1 or self._send.device != device:
+            self._send = torch.zeros((self.cap + 1, RECORD_BYTES), dtype=torch.uint8, device=device)
+            self._recv = torch.empty((self.world * (self.cap + 1), RECORD_BYTES), dtype=torch.uint8, device=device)
+        return self._send, self._recv
+
+    def exchange(self, local: torch.Tensor):
+        """local: (n, 80) uint8 records of this rank (CUDA over NCCL, CPU over gloo).  Returns (blocks, counts) where
+        blocks is (world, cap + 1, 80) on the device and counts the per-rank record counts on the host."""
+        n = int(local.shape[0])
+        while True:          # every rank uses the same capacity in every collective: it only changes from the gathered counts
+            send, recv = self._buffers(local.device)
+            send[0, :8] = torch.tensor([n], dtype=torch.int64).view(torch.uint8).to(local.device, non_blocking=True)
+            k = min(n, self.cap)
+            if k:
+                send[1:k + 1] = local[:k]
+            dist.all_gather_into_tensor(recv, send, group=self.group)
+            blocks = recv.view(self.world, self.cap + 1, RECORD_BYTES)
+            counts = blocks[:, 0, :8].contiguous().view(torch.int64).reshape(-1).cpu().tolist()
+            if max(counts) <= self.cap:
+                return blocks, counts
+            self.cap = 1 << (max(counts) - 1).bit_length()      # somebody else outgrew the blocks: everyone retries
+
     def gather_device(self) -> torch.Tensor:
-        """Call after cd.run(): every rank ends up with all ranks' records in HBM."""
-        self.last = all_gather_varlen(self._local_device_records(), self.group)
-        return self.last
+        """Call after cd.run(): every rank ends up with all ranks' records in HBM (one collective)."""
+        blocks, counts = self.exchange(self._local_device_records())
+        self.last = (blocks, counts)
+        return blocks
 
     def gather_host(self) -> np.ndarray:
         """Call after cd.ExecuteCollisionDetection(): merged records as a numpy structured array."""
-        g = self.gather_device()
-        return g.cpu().numpy().reshape(-1).view(PAIR_DTYPE) if g.shape[0] else np.zeros(0, PAIR_DTYPE)
+        blocks, counts = self.exchange(self._local_device_records())
+        h = blocks.cpu().numpy()
+        parts = [h[r, 1:1 + c].reshape(-1) for r, c in enumerate(counts) if c]
+        return np.concatenate(parts).view(PAIR_DTYPE) if parts else np.zeros(0, PAIR_DTYPE)

@@ -94,3 +94,38 @@ def test_zero_copy_submission_matches_add_entries(gpu_ctx):
         assert a[0][k] == b[0][k], k
     assert np.array_equal(a[1], b[1]) and np.array_equal(a[2].view(np.uint32), b[2].view(np.uint32))
     assert a[3].tobytes() == b[3].tobytes()                      # colliding pairs incl. ray counts and contact points: bit-identical
+
+
+def test_shards_partition_the_frame(gpu_ctx):
+    """imrcd_frame_set_shard(r, n): the n slices are disjoint and add up to the unsharded frame (pairs, hits, colliding pairs)."""
+    static = scenes.atrium_static(detail=1)
+    keep = list(range(0, 8)) + list(range(60, 70))
+    static = ([static[0][i] for i in keep], static[1][keep])
+    scene = scenes.scene_static_vs_bodies(scenes.uv_sphere(24, 17), 2000, seed=11, body_scale=(0.5, 1.5), static=static)
+    trees = [OBBtree(gpu_ctx, m.positions, m.normals, m.vertex_ids) for m in scene.meshes]
+
+    def run(rank, world):
+        cd = CollisionDetection(ctx=gpu_ctx)
+        cd.set_shard(rank, world)
+        st, bp, ep, hits = gpu_frame(cd, scene, trees)
+        cd.set_shard(0, 1)
+        pairs = set(map(tuple, bp.tolist()))
+        assert len(pairs) == len(bp)
+        hk = {(int(bp[h["pair"]][0]), int(bp[h["pair"]][1]), int(h["tri_first"]), int(h["tri_second"])) for h in hits}
+        coll = {(int(p["entry_first"]), int(p["entry_second"])): (int(p["n_rays_first"]), int(p["n_rays_second"]), p["avg_first"].tobytes(), p["avg_second"].tobytes()) for p in ep}
+        return pairs, hk, coll
+
+    full = run(0, 1)
+    assert len(full[0]) > 500 and len(full[2]) > 20
+    for world in (2, 3, 8):
+        parts = [run(r, world) for r in range(world)]
+        for k in range(3):
+            keys = [set(p[k]) for p in parts]
+            assert sum(len(x) for x in keys) == len(set().union(*keys)), "shards overlap"
+            assert set().union(*keys) == set(full[k]), "shards do not add up to the frame"
+        merged = {}
+        for p in parts:
+            merged.update(p[2])
+        assert merged == full[2]                      # per-pair results do not depend on the shard that computed them
+        sizes = [len(p[0]) for p in parts]
+        assert max(sizes) <= 1.5 * (sum(sizes) / world) + 32

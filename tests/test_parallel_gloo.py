@@ -1,5 +1,5 @@
-"""CPU, world_size 2 over gloo: the N>1 host logic -- shard ownership partitions the pair list, and the end-of-frame
-variable-length gather reassembles every rank's records in rank order."""
+"""CPU, world_size 2 over gloo: the N>1 host logic -- the end-of-frame variable-length gather reassembles every rank's
+records in rank order (that the device-side shards partition the pair list is a GPU test: test_gpu_frame.py)."""
 import os
 import socket
 
@@ -9,16 +9,6 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from inmyroom_vulkan_b200 import parallel
-
-
-def test_shard_masks_partition_pairs():
-    rng = np.random.default_rng(0)
-    pairs = rng.integers(0, 5000, size=(20000, 2)).astype(np.uint32)
-    for world in (1, 2, 4, 8):
-        masks = [parallel.shard_mask(pairs, r, world) for r in range(world)]
-        assert (np.sum(masks, 0) == 1).all()                       # every pair owned by exactly one rank
-        counts = np.array([m.sum() for m in masks])
-        assert counts.max() < 1.2 * counts.mean() + 10             # owner % world balances random owners
 
 
 def _free_port():
@@ -39,6 +29,12 @@ def _worker(rank, world, port, out_dir):
         np.save(os.path.join(out_dir, f"merged{rank}.npy"), merged.numpy())
         empty = parallel.all_gather_varlen(torch.zeros((0, parallel.RECORD_BYTES), dtype=torch.uint8))
         assert empty.shape == (0, parallel.RECORD_BYTES)
+        # the frame gather: one fixed-capacity collective, capacity 4 so that rank 0's 7 records force the grow-and-retry path
+        fg = parallel.FrameGather(None, world, rank, capacity=4)
+        blocks, counts = fg.exchange(local)
+        got = torch.cat([blocks[r, 1:1 + c] for r, c in enumerate(counts)], 0)
+        np.save(os.path.join(out_dir, f"fg{rank}.npy"), got.numpy())
+        assert fg.cap >= 7
     finally:
         dist.destroy_process_group()
 
@@ -50,3 +46,4 @@ def test_all_gather_varlen_world2(tmp_path):
     expect = np.concatenate(locals_).view(np.uint8).reshape(-1, parallel.RECORD_BYTES)
     for r in range(world):
         assert np.array_equal(np.load(tmp_path / f"merged{r}.npy"), expect)
+        assert np.array_equal(np.load(tmp_path / f"fg{r}.npy"), expect)
