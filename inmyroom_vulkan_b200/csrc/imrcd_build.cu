@@ -23,6 +23,7 @@
 #include <cstring>
 
 int imr_mesh_arena_alloc(imrcd_ctx* ctx, uint64_t n_rec, uint64_t n_tri, MeshHost* mh);
+int imr_build_mesh_reference(imrcd_ctx* ctx, const float* pos, const float* nrm, const uint32_t* vid, uint64_t n_tri, MeshHost* mh);
 
 #define FULL_MASK 0xffffffffu
 
@@ -532,12 +533,7 @@ static int build_morton(imrcd_ctx* ctx, const float* h_pos, const float* h_nrm, 
 int imr_build_mesh_device(imrcd_ctx* ctx, const float* pos, const float* nrm, const uint32_t* vid, uint64_t n_tri, uint32_t mode, MeshHost* out) {
     if (n_tri >= (1ull << 31)) { ctx->err = "imrcd_mesh_create: too many triangles"; return IMRCD_E_ARG; }
     if (mode == IMRCD_BUILD_MORTON) return build_morton(ctx, pos, nrm, vid, n_tri, out);
-    ctx->err = "imrcd_mesh_create: IMRCD_BUILD_REFERENCE is not implemented yet";
-    return IMRCD_E_STATE;
-}
-
-extern "C" int imrcd_test_obb_fit(imrcd_ctx* ctx, uint64_t, const float*, float*) {
-    if (!ctx) return IMRCD_E_ARG;
-    ctx->err = "imrcd_test_obb_fit: not implemented yet";
-    return IMRCD_E_STATE;
+    if (mode == IMRCD_BUILD_REFERENCE) return imr_build_mesh_reference(ctx, pos, nrm, vid, n_tri, out);
+    ctx->err = "imrcd_mesh_create: unknown build mode";
+    return IMRCD_E_ARG;
 }
