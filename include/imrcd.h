@@ -103,6 +103,14 @@ int imrcd_mesh_info(imrcd_ctx* ctx, uint32_t mesh_id, uint64_t* n_tri, uint64_t*
 int imrcd_mesh_export_tree(imrcd_ctx* ctx, uint32_t mesh_id, float* boxes, int32_t* left, int32_t* right,
                            uint32_t* tri_off, uint32_t* tri_cnt, float* tri_pos, float* tri_nrm, uint32_t* tri_vid,
                            uint32_t* tri_orig);
+/* Re-posed meshes (BASELINE config 5; the engine re-poses skinned / morphed meshes on the GPU, IMR/shaders/dynamicMeshShader_glsl.comp:99-145,
+ * but never gives them collision trees: SURVEY finding 4).  imrcd_mesh_update_positions replaces the triangle positions (and normals
+ * when non-NULL) of a mesh, given in the ORIGINAL input order of imrcd_mesh_create / tri_orig of an imported tree; the topology of the
+ * tree is kept.  imrcd_mesh_refit recomputes every box of the listed meshes (NULL = all meshes updated since their last refit) in one
+ * batched pass: fresh PCA axes per node, boxes rounded outward. */
+int imrcd_mesh_update_positions(imrcd_ctx* ctx, uint32_t mesh_id, const float* positions, const float* normals);
+int imrcd_mesh_refit(imrcd_ctx* ctx, const uint32_t* mesh_ids, uint64_t n);
+int imrcd_mesh_last_refit_ms(imrcd_ctx* ctx, float* ms);
 /* device time of the last imrcd_mesh_create in ms */
 int imrcd_mesh_last_build_ms(imrcd_ctx* ctx, float* ms);
 

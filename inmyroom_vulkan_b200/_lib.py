@@ -53,6 +53,9 @@ _SIGS = [
     ("imrcd_mesh_info", C.c_int, [_P, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     ("imrcd_mesh_export_tree", C.c_int, [_P, C.c_uint32] + [_P] * 9),
     ("imrcd_mesh_last_build_ms", C.c_int, [_P, C.POINTER(C.c_float)]),
+    ("imrcd_mesh_update_positions", C.c_int, [_P, C.c_uint32, _P, _P]),
+    ("imrcd_mesh_refit", C.c_int, [_P, _P, C.c_uint64]),
+    ("imrcd_mesh_last_refit_ms", C.c_int, [_P, C.POINTER(C.c_float)]),
     ("imrcd_frame_reset", C.c_int, [_P]),
     ("imrcd_frame_add_entry", C.c_int, [_P, _P, _P, C.c_uint32, C.c_uint8, C.c_uint32]),
     ("imrcd_frame_add_entries", C.c_int, [_P, C.c_uint64, _P, _P, _P, _P, _P]),

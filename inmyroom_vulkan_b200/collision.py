@@ -91,6 +91,18 @@ class Context:
         return out
 
 
+def refit_meshes(ctx: "Context", trees=None) -> float:
+    """Batched refit of `trees` (None = every mesh updated since its last refit); returns the device time in ms."""
+    if trees is None:
+        ctx.check(ctx.lib.imrcd_mesh_refit(ctx.h, None, 0))
+    else:
+        ids = np.array([t.mesh_id for t in trees], np.uint32)
+        ctx.check(ctx.lib.imrcd_mesh_refit(ctx.h, _ptr(ids), len(ids)))
+    ms = C.c_float()
+    ctx.check(ctx.lib.imrcd_mesh_last_refit_ms(ctx.h, C.byref(ms)))
+    return ms.value
+
+
 class OBBtree:
     """Device-resident OBB tree of one mesh: the replacement for OBBtree::OBBtree(std::vector<Triangle>&&)."""
 
@@ -127,6 +139,17 @@ class OBBtree:
         ms = C.c_float()
         self.ctx.check(self.ctx.lib.imrcd_mesh_last_build_ms(self.ctx.h, C.byref(ms)))
         return ms.value
+
+    def update_positions(self, positions, normals=None):
+        """New triangle positions (original input order); call refit() / refit_meshes() before the next frame."""
+        pos = _c(positions, np.float32).reshape(-1, 9)
+        nrm = None if normals is None else _c(normals, np.float32).reshape(-1, 9)
+        assert pos.shape[0] == self.info()[0]
+        self.ctx.check(self.ctx.lib.imrcd_mesh_update_positions(self.ctx.h, self.mesh_id, _ptr(pos), _ptr(nrm)))
+
+    def refit(self):
+        ids = np.array([self.mesh_id], np.uint32)
+        self.ctx.check(self.ctx.lib.imrcd_mesh_refit(self.ctx.h, _ptr(ids), 1))
 
     def export(self):
         """Read the tree back in the flat pre-order form (returns a SimpleNamespace with FlatTree's fields)."""

@@ -40,7 +40,7 @@ extern "C" void imrcd_destroy(imrcd_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf* bufs[] = { &ctx->d_recs, &ctx->d_tris, &ctx->d_tri_nrm, &ctx->d_tri_vid, &ctx->d_meshes, &ctx->d_cur, &ctx->d_prev, &ctx->d_mesh,
+    DevBuf* bufs[] = { &ctx->d_recs, &ctx->d_tris, &ctx->d_tri_nrm, &ctx->d_tri_vid, &ctx->d_meshes, &ctx->d_rf_stage, &ctx->d_rf_segs, &ctx->d_rf_scratch, &ctx->d_cur, &ctx->d_prev, &ctx->d_mesh,
                        &ctx->d_cb, &ctx->d_entity, &ctx->d_inv, &ctx->d_ext, &ctx->d_keys, &ctx->d_keys2, &ctx->d_idx, &ctx->d_idx2,
                        &ctx->d_sorted, &ctx->d_sorted_c, &ctx->d_flag, &ctx->d_cpos, &ctx->d_wlen, &ctx->d_chunks, &ctx->d_chunkoff, &ctx->d_cubtmp, &ctx->d_pairs, &ctx->d_pairrec, &ctx->d_pairacc, &ctx->d_queue, &ctx->d_combos,
                        &ctx->d_hits, &ctx->d_epairs, &ctx->d_ctl, &ctx->d_aux, &ctx->d_grouped, &ctx->d_skey, &ctx->d_svkey, &ctx->d_padded, &ctx->d_padoff, &ctx->d_lsmall, &ctx->d_lmid, &ctx->d_llarge };
@@ -200,6 +200,26 @@ extern "C" int imrcd_mesh_create(imrcd_ctx* ctx, const float* positions, const f
     ctx->last_build_ms = mh.build_ms;
     return mesh_register(ctx, mh, mesh_id);
 }
+
+// ---- refit (BASELINE config 5) ----
+extern "C" int imrcd_mesh_update_positions(imrcd_ctx* ctx, uint32_t mesh_id, const float* positions, const float* normals) {
+    CHECK_CTX(ctx);
+    if (mesh_id >= ctx->meshes.size() || !positions) { ctx->err = "imrcd_mesh_update_positions: bad argument"; return IMRCD_E_ARG; }
+    cudaSetDevice(ctx->device);
+    return imr_mesh_update_positions_device(ctx, mesh_id, positions, normals);
+}
+extern "C" int imrcd_mesh_refit(imrcd_ctx* ctx, const uint32_t* mesh_ids, uint64_t n) {
+    CHECK_CTX(ctx);
+    cudaSetDevice(ctx->device);
+    std::vector<uint32_t> all;
+    if (!mesh_ids) {                                    // every mesh whose positions changed since its last refit
+        for (uint32_t i = 0; i < ctx->meshes.size(); ++i) if (ctx->meshes[i].needs_refit) all.push_back(i);
+        mesh_ids = all.data(); n = all.size();
+    }
+    for (uint64_t i = 0; i < n; ++i) if (mesh_ids[i] >= ctx->meshes.size()) { ctx->err = "imrcd_mesh_refit: bad mesh id"; return IMRCD_E_ARG; }
+    return imr_meshes_refit_device(ctx, mesh_ids, n, &ctx->last_refit_ms);
+}
+extern "C" int imrcd_mesh_last_refit_ms(imrcd_ctx* ctx, float* ms) { CHECK_CTX(ctx); if (ms) *ms = ctx->last_refit_ms; return IMRCD_OK; }
 
 extern "C" int imrcd_mesh_last_build_ms(imrcd_ctx* ctx, float* ms) { CHECK_CTX(ctx); if (ms) *ms = ctx->last_build_ms; return IMRCD_OK; }
 

@@ -430,6 +430,180 @@ __global__ void k_moments_small(uint32_t n, const TriRec* __restrict__ tris, con
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Refit (BASELINE config 5: re-posed meshes): new triangle positions, same topology.  Works on any tree in the arena
+// (Morton-built, reference-built or imported) and on many meshes per launch: the work of all meshes being refitted is
+// concatenated and every thread finds its mesh by binary search in a small segment table.
+//   k_rf_parents   parent link of every record                                     (top-down, trivial)
+//   k_rf_up        leaf records: triangle range + FP64 moments, then climb to the root with one ticket per record
+//   k_rf_axes / k_rf_extents / k_rf_boxes   the same fit as the Morton build (covariance -> closed-form eigen-solve ->
+//                  every triangle walks root -> leaf -> outward-rounded FP32 boxes)
+// The reference has no refit (SURVEY finding 4: skinned meshes never get collision trees); parity is defined against the
+// reference REBUILDING its tree from the re-posed triangles (tests/test_gpu_refit.py).
+// ---------------------------------------------------------------------------------------------------
+struct RefitSeg { uint32_t rec_base, tri_base, n_rec, n_tri, rec_prefix, tri_prefix; };
+
+__device__ __forceinline__ uint32_t rf_locate(const uint32_t* __restrict__ prefix, uint32_t n_seg, uint32_t g) {   // last s with prefix[s] <= g
+    uint32_t lo = 0, hi = n_seg;
+    while (hi - lo > 1u) { const uint32_t mid = (lo + hi) >> 1; if (prefix[mid] <= g) lo = mid; else hi = mid; }
+    return lo;
+}
+__device__ __forceinline__ void rf_origin(const TreeRec* recs, const RefitSeg& sg, double o[3]) {
+    const float4 q = recs[sg.rec_base].q0;            // centre of the old root box: a well-conditioned origin for the raw moments
+    o[0] = (double)q.x; o[1] = (double)q.y; o[2] = (double)q.z;
+}
+
+__global__ void k_rf_scatter(uint32_t n, TriRec* tris, float* nrm_out, const float* __restrict__ pos, const float* __restrict__ nrm) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    TriRec r = tris[t];
+    const uint32_t src = __float_as_uint(r.t0.w);
+    const float* p = pos + 9ull * src;
+    r.t0 = make_float4(p[0], p[1], p[2], r.t0.w); r.t1 = make_float4(p[3], p[4], p[5], 0.f); r.t2 = make_float4(p[6], p[7], p[8], 0.f);
+    { V3 N; float d; tt_plane(mk3(p[0], p[1], p[2]), mk3(p[3], p[4], p[5]), mk3(p[6], p[7], p[8]), N, d); r.t3 = make_float4(N.x, N.y, N.z, d); }
+    tris[t] = r;
+    if (nrm) { float* no = nrm_out + 9ull * t; const float* q = nrm + 9ull * src;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) no[k] = q[k]; }
+}
+
+__global__ void k_rf_parents(uint32_t total_rec, const RefitSeg* __restrict__ segs, const uint32_t* __restrict__ rec_prefix, uint32_t n_seg,
+                             const TreeRec* __restrict__ recs, uint32_t* __restrict__ parent, int* __restrict__ ticket) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total_rec) return;
+    const RefitSeg sg = segs[rf_locate(rec_prefix, n_seg, g)];
+    const uint32_t r = g - sg.rec_prefix;
+    ticket[g] = 0;
+    if (r == 0) parent[g] = 0xffffffffu;
+    if (r == 1) { parent[g] = 0xfffffffeu; return; }                       // padding record
+    const float4 q3 = recs[sg.rec_base + r].q3;
+    if (__float_as_uint(q3.w) == 0u) { const uint32_t c = __float_as_uint(q3.y); parent[sg.rec_prefix + c] = r; parent[sg.rec_prefix + c + 1u] = r; }
+}
+
+__global__ void k_rf_up(uint32_t total_rec, const RefitSeg* __restrict__ segs, const uint32_t* __restrict__ rec_prefix, uint32_t n_seg,
+                        const TreeRec* __restrict__ recs, const TriRec* __restrict__ tris, const uint32_t* __restrict__ parent,
+                        RecDesc* desc, double* mom, int* ticket) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total_rec) return;
+    const RefitSeg sg = segs[rf_locate(rec_prefix, n_seg, g)];
+    uint32_t r = g - sg.rec_prefix;
+    if (r == 1) { RecDesc d; d.first = d.last = d.split = d.child = 0; d.src = 1; d.kind = 2u; desc[g] = d; return; }      // kind 2 = padding
+    const float4 q3 = recs[sg.rec_base + r].q3;
+    if (__float_as_uint(q3.w) == 0u) return;                               // inner records are finished by their second child
+    double o[3]; rf_origin(recs, sg, o);
+    RecDesc d;
+    d.first = __float_as_uint(q3.y); const uint32_t cnt = __float_as_uint(q3.z);
+    d.last = cnt ? d.first + cnt - 1u : d.first; d.split = d.last; d.child = d.first; d.src = (int)g; d.kind = 1u;
+    double m[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) m[k] = 0.0;
+    for (uint32_t i = 0; i < cnt; ++i) { double tm[10]; tri_moments(tris[sg.tri_base + d.first + i], o, tm);
+#pragma unroll
+        for (int k = 0; k < 10; ++k) m[k] += tm[k]; }
+    desc[g] = d;
+#pragma unroll
+    for (int k = 0; k < 10; ++k) __stcg(mom + 10ull * g + k, m[k]);
+    uint32_t first = d.first, last = d.last;
+    for (;;) {
+        const uint32_t p = parent[sg.rec_prefix + r];
+        if (p >= 0xfffffffeu) return;                                      // reached the root
+        __threadfence();
+        if (atomicAdd(&ticket[sg.rec_prefix + p], 1) == 0) return;        // the sibling's subtree is not finished yet: it will continue
+        const uint32_t child = __float_as_uint(recs[sg.rec_base + p].q3.y);
+        const uint32_t sib = (r == child) ? child + 1u : child;
+        const RecDesc sd = desc[sg.rec_prefix + sib];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) m[k] += __ldcg(mom + 10ull * (sg.rec_prefix + sib) + k);
+        const RecDesc ld = (sib == child) ? sd : RecDesc{first, last, 0, 0, 0, 0};
+        first = min(first, sd.first); last = max(last, sd.last);
+        RecDesc pd; pd.first = first; pd.last = last; pd.split = ld.last; pd.child = child; pd.src = (int)(sg.rec_prefix + p); pd.kind = 0u;
+        desc[sg.rec_prefix + p] = pd;
+#pragma unroll
+        for (int k = 0; k < 10; ++k) __stcg(mom + 10ull * (sg.rec_prefix + p) + k, m[k]);
+        r = p;
+    }
+}
+
+__global__ void k_rf_axes(uint32_t total_rec, const RecDesc* __restrict__ desc, const double* __restrict__ mom, double* __restrict__ axes, unsigned long long* __restrict__ ext) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total_rec) return;
+    unsigned long long* e = ext + 6ull * g;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { e[2 * k] = 0xffffffffffffffffull; e[2 * k + 1] = 0ull; }
+    double* ax = axes + 9ull * g;
+    const RecDesc d = desc[g];
+    if (d.kind == 2u) { for (int k = 0; k < 9; ++k) ax[k] = (k % 4 == 0) ? 1.0 : 0.0; return; }   // padding record
+    double m[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) m[k] = mom[10ull * g + k];
+    if (!(m[9] > 0.0)) { for (int k = 0; k < 9; ++k) ax[k] = (k % 4 == 0) ? 1.0 : 0.0; return; }
+    const double in = 1.0 / m[9];
+    const double mx = m[0] * in, my = m[1] * in, mz = m[2] * in;
+    sym_eig3_axes(m[3] * in - mx * mx, m[4] * in - my * my, m[5] * in - mz * mz, m[6] * in - mx * my, m[7] * in - mx * mz, m[8] * in - my * mz, ax);
+}
+
+__global__ void k_rf_extents(uint32_t total_tri, const RefitSeg* __restrict__ segs, const uint32_t* __restrict__ tri_prefix, uint32_t n_seg,
+                             const TriRec* __restrict__ tris, const RecDesc* __restrict__ desc, const double* __restrict__ axes, unsigned long long* ext) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total_tri) return;
+    const RefitSeg sg = segs[rf_locate(tri_prefix, n_seg, g)];
+    const uint32_t t = g - sg.tri_prefix;
+    const TriRec tr = tris[sg.tri_base + t];
+    const double px[3] = { tr.t0.x, tr.t1.x, tr.t2.x }, py[3] = { tr.t0.y, tr.t1.y, tr.t2.y }, pz[3] = { tr.t0.z, tr.t1.z, tr.t2.z };
+    uint32_t node = 0;
+    for (int depth = 0; depth < 4096; ++depth) {
+        const RecDesc d = desc[sg.rec_prefix + node];
+        const double* ax = axes + 9ull * (sg.rec_prefix + node);
+        unsigned long long* e = ext + 6ull * (sg.rec_prefix + node);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            double mn = INFINITY, mx = -INFINITY;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { const double pr = ax[3 * a] * px[k] + ax[3 * a + 1] * py[k] + ax[3 * a + 2] * pz[k]; mn = fmin(mn, pr); mx = fmax(mx, pr); }
+            const unsigned long long smn = f64_sortable(mn), smx = f64_sortable(mx);
+            if (smn < e[2 * a]) atomicMin(&e[2 * a], smn);                 // plain read first: most visits do not move the bound
+            if (smx > e[2 * a + 1]) atomicMax(&e[2 * a + 1], smx);
+        }
+        if (d.kind == 1u) break;
+        node = d.child + (t > d.split ? 1u : 0u);
+    }
+}
+
+__global__ void k_rf_boxes(uint32_t total_rec, const RefitSeg* __restrict__ segs, const uint32_t* __restrict__ rec_prefix, uint32_t n_seg,
+                           const RecDesc* __restrict__ desc, const double* __restrict__ axes, const unsigned long long* __restrict__ ext, TreeRec* __restrict__ recs) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total_rec) return;
+    const RefitSeg sg = segs[rf_locate(rec_prefix, n_seg, g)];
+    const uint32_t r = g - sg.rec_prefix;
+    if (r == 1) return;                                                   // padding record stays as it is
+    const RecDesc d = desc[g];
+    const double* ax = axes + 9ull * g;
+    const unsigned long long* e = ext + 6ull * g;
+    double c[3] = { 0, 0, 0 }, half[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const double mn = f64_unsortable(e[2 * a]), mx = f64_unsortable(e[2 * a + 1]);
+        const double mid = 0.5 * (mx + mn);
+        half[a] = 0.5 * (mx - mn);
+        c[0] += mid * ax[3 * a]; c[1] += mid * ax[3 * a + 1]; c[2] += mid * ax[3 * a + 2];
+    }
+    const float cf[3] = { (float)c[0], (float)c[1], (float)c[2] };
+    const double cmax = fmax(fabs(c[0]), fmax(fabs(c[1]), fabs(c[2])));
+    const double hmax = fmax(half[0], fmax(half[1], half[2]));
+    const double pad = 4.0 * 5.9604644775390625e-8 * (cmax + hmax) + (double)FLT_EPSILON;     // same outward rounding as k_finalize_boxes
+    float s[9];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const double h = half[a] * (1.0 + 2.384185791015625e-7) + pad;
+        s[3 * a] = (float)(h * ax[3 * a]); s[3 * a + 1] = (float)(h * ax[3 * a + 1]); s[3 * a + 2] = (float)(h * ax[3 * a + 2]);
+    }
+    TreeRec out = recs[sg.rec_base + r];                                   // q3 (links, leaf range) is topology: unchanged
+    out.q0 = make_float4(cf[0], cf[1], cf[2], s[0]); out.q1 = make_float4(s[1], s[2], s[3], s[4]); out.q2 = make_float4(s[5], s[6], s[7], s[8]);
+    Box b; b.c = mk3(cf[0], cf[1], cf[2]); b.u = mk3(s[0], s[1], s[2]); b.v = mk3(s[3], s[4], s[5]); b.w = mk3(s[6], s[7], s[8]);
+    out.q3.x = box_surface(b);
+    recs[sg.rec_base + r] = out;
+}
+
+// ---------------------------------------------------------------------------------------------------
 static inline unsigned nb(uint64_t n, unsigned bs) { return (unsigned)((n + bs - 1) / bs); }
 
 static int build_morton(imrcd_ctx* ctx, const float* h_pos, const float* h_nrm, const uint32_t* h_vid, uint64_t n_tri, MeshHost* mh) {
@@ -536,4 +710,66 @@ int imr_build_mesh_device(imrcd_ctx* ctx, const float* pos, const float* nrm, co
     if (mode == IMRCD_BUILD_REFERENCE) return imr_build_mesh_reference(ctx, pos, nrm, vid, n_tri, out);
     ctx->err = "imrcd_mesh_create: unknown build mode";
     return IMRCD_E_ARG;
+}
+
+// ---- refit: host side --------------------------------------------------------------------------------
+int imr_mesh_update_positions_device(imrcd_ctx* ctx, uint32_t mesh_id, const float* h_pos, const float* h_nrm) {
+    MeshHost& mh = ctx->meshes[mesh_id];
+    const uint32_t n = mh.dev.n_tri;
+    if (n == 0) return IMRCD_OK;
+    cudaStream_t s = ctx->stream;
+    IMR_CUDA(ctx, ctx->d_rf_stage.reserve(36ull * n * (h_nrm ? 2 : 1), 0, s));
+    IMR_CUDA(ctx, cudaMemcpyAsync(ctx->d_rf_stage.p, h_pos, 36ull * n, cudaMemcpyHostToDevice, s));
+    if (h_nrm) IMR_CUDA(ctx, cudaMemcpyAsync(ctx->d_rf_stage.as<char>() + 36ull * n, h_nrm, 36ull * n, cudaMemcpyHostToDevice, s));
+    k_rf_scatter<<<nb(n, 256), 256, 0, s>>>(n, ctx->d_tris.as<TriRec>() + mh.dev.tri_base, ctx->d_tri_nrm.as<float>() + 9ull * mh.dev.tri_base,
+                                             ctx->d_rf_stage.as<float>(), h_nrm ? ctx->d_rf_stage.as<float>() + 9ull * n : nullptr);
+    IMR_CUDA(ctx, cudaGetLastError());
+    IMR_CUDA(ctx, cudaStreamSynchronize(s));           // the staging buffer is reused by the next update
+    mh.needs_refit = true;
+    return IMRCD_OK;
+}
+
+int imr_meshes_refit_device(imrcd_ctx* ctx, const uint32_t* ids, uint64_t n_ids, float* ms_out) {
+    std::vector<RefitSeg> segs; std::vector<uint32_t> recp, trip;
+    uint64_t tot_rec = 0, tot_tri = 0;
+    for (uint64_t k = 0; k < n_ids; ++k) {
+        MeshHost& mh = ctx->meshes[ids[k]];
+        RefitSeg sg; sg.rec_base = mh.dev.rec_base; sg.tri_base = mh.dev.tri_base; sg.n_rec = mh.dev.n_rec; sg.n_tri = mh.dev.n_tri;
+        sg.rec_prefix = (uint32_t)tot_rec; sg.tri_prefix = (uint32_t)tot_tri;
+        if (sg.n_tri == 0) continue;                    // nothing to fit
+        segs.push_back(sg); recp.push_back(sg.rec_prefix); trip.push_back(sg.tri_prefix);
+        tot_rec += sg.n_rec; tot_tri += sg.n_tri;
+        mh.needs_refit = false;
+    }
+    if (segs.empty()) { if (ms_out) *ms_out = 0.f; return IMRCD_OK; }
+    if (tot_rec >= (1ull << 32) || tot_tri >= (1ull << 32)) { ctx->err = "refit: too many records in one call"; return IMRCD_E_CAPACITY; }
+    cudaStream_t s = ctx->stream;
+    const uint32_t ns = (uint32_t)segs.size();
+    IMR_CUDA(ctx, ctx->d_rf_segs.reserve(sizeof(RefitSeg) * ns + 8ull * ns, 0, s));
+    RefitSeg* d_segs = ctx->d_rf_segs.as<RefitSeg>();
+    uint32_t* d_recp = reinterpret_cast<uint32_t*>(d_segs + ns); uint32_t* d_trip = d_recp + ns;
+    IMR_CUDA(ctx, cudaMemcpyAsync(d_segs, segs.data(), sizeof(RefitSeg) * ns, cudaMemcpyHostToDevice, s));
+    IMR_CUDA(ctx, cudaMemcpyAsync(d_recp, recp.data(), 4ull * ns, cudaMemcpyHostToDevice, s));
+    IMR_CUDA(ctx, cudaMemcpyAsync(d_trip, trip.data(), 4ull * ns, cudaMemcpyHostToDevice, s));
+    IMR_CUDA(ctx, ctx->d_rf_scratch.reserve((sizeof(RecDesc) + 80 + 72 + 48 + 4 + 4) * tot_rec, 0, s));
+    char* base = ctx->d_rf_scratch.as<char>();
+    double* mom = reinterpret_cast<double*>(base); double* axes = mom + 10ull * tot_rec;
+    unsigned long long* ext = reinterpret_cast<unsigned long long*>(axes + 9ull * tot_rec);
+    RecDesc* desc = reinterpret_cast<RecDesc*>(ext + 6ull * tot_rec);
+    uint32_t* parent = reinterpret_cast<uint32_t*>(desc + tot_rec); int* ticket = reinterpret_cast<int*>(parent + tot_rec);
+    const TreeRec* recs = ctx->d_recs.as<TreeRec>(); const TriRec* tris = ctx->d_tris.as<TriRec>();
+    cudaEvent_t e0 = ctx->ev[6], e1 = ctx->ev[7];
+    IMR_CUDA(ctx, cudaEventRecord(e0, s));
+    k_rf_parents<<<nb(tot_rec, 256), 256, 0, s>>>((uint32_t)tot_rec, d_segs, d_recp, ns, recs, parent, ticket);
+    k_rf_up<<<nb(tot_rec, 128), 128, 0, s>>>((uint32_t)tot_rec, d_segs, d_recp, ns, recs, tris, parent, desc, mom, ticket);
+    k_rf_axes<<<nb(tot_rec, 128), 128, 0, s>>>((uint32_t)tot_rec, desc, mom, axes, ext);
+    k_rf_extents<<<nb(tot_tri, 256), 256, 0, s>>>((uint32_t)tot_tri, d_segs, d_trip, ns, tris, desc, axes, ext);
+    k_rf_boxes<<<nb(tot_rec, 128), 128, 0, s>>>((uint32_t)tot_rec, d_segs, d_recp, ns, desc, axes, ext, ctx->d_recs.as<TreeRec>());
+    IMR_CUDA(ctx, cudaEventRecord(e1, s));
+    IMR_CUDA(ctx, cudaStreamSynchronize(s));
+    IMR_CUDA(ctx, cudaGetLastError());
+    float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
+    if (ms_out) *ms_out = ms;
+    // root boxes (host copies used nowhere on the hot path, kept coherent for imrcd_mesh_info-style queries)
+    return IMRCD_OK;
 }

@@ -115,6 +115,7 @@ struct MeshHost {
     MeshDev dev;
     float root_box[12];
     float build_ms = 0.f;
+    bool needs_refit = false;            // positions were updated since the last refit
 };
 
 struct imrcd_ctx {
@@ -127,6 +128,8 @@ struct imrcd_ctx {
     // mesh arena
     std::vector<MeshHost> meshes;
     DevBuf d_recs, d_tris, d_tri_nrm, d_tri_vid, d_meshes;
+    DevBuf d_rf_stage, d_rf_segs, d_rf_scratch;      // refit staging / segment table / scratch (imrcd_build.cu)
+    float last_refit_ms = 0.f;
     uint64_t n_rec_total = 0, n_tri_total = 0;
     bool meshes_dirty = false;
     float last_build_ms = 0.f;
@@ -166,3 +169,5 @@ int imr_mesh_finalize_tris(imrcd_ctx* ctx, uint32_t tri_base, uint32_t n_tri);  
 int imr_build_mesh_device(imrcd_ctx* ctx, const float* pos, const float* nrm, const uint32_t* vid, uint64_t n_tri,
                           uint32_t mode, MeshHost* out);
 int imr_frame_run_device(imrcd_ctx* ctx);
+int imr_mesh_update_positions_device(imrcd_ctx* ctx, uint32_t mesh_id, const float* pos, const float* nrm);
+int imr_meshes_refit_device(imrcd_ctx* ctx, const uint32_t* ids, uint64_t n_ids, float* ms_out);
