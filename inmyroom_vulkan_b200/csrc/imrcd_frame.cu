@@ -862,6 +862,191 @@ __device__ __forceinline__ SideSum pc_side(uint32_t side, uint32_t n, uint32_t m
     return acc;
 }
 
+// ---- size classes S and M: one block per pair, no sort --------------------------------------------------------------------
+// What a side needs of a pair's hits is a keyed reduction: per own triangle, AND of the not-outside bits and the sums of weight and
+// weight * midpoint over the hits of every combo whose weight is not 0 (TriangleCandidateRays::Merge, :51-57; IsNull, :22-25).  Weights are
+// >= 0, so a combo is dropped iff every one of its hits has weight 0: a hit with weight != 0 always contributes, and a hit with weight 0
+// contributes (its bits only) iff the same (own triangle, other LEAF) has another hit with weight != 0 - checked by a scan over the pair's
+// hits for those few.  The reduction runs in a shared-memory hash table, one thread per hit: AND and FP64 adds are order-free, so the FP32
+// result does not depend on which thread comes first.  Then one thread per table slot turns the candidate into rays (:139-166), vertex
+// rays going through the `emplaced` set (:139-141), and one thread per set entry adds its ray origin.
+struct PcSlot { double w, cx, cy, cz; };
+
+// Find or claim the slot of `tri`; `claimed` tells the caller to append the slot to the dense list of occupied slots (done
+// afterwards in converged code with one ballot, so that the later passes run over occupied slots only).
+__device__ __forceinline__ uint32_t pc_slot_of(uint32_t* keys, uint32_t mask, uint32_t tri, bool& claimed) {
+    uint32_t slot = ((tri * 2654435761u) >> 7) & mask;
+    for (;;) {
+        const uint32_t old = atomicCAS(&keys[slot], 0xffffffffu, tri);
+        if (old == 0xffffffffu) { claimed = true; return slot; }
+        if (old == tri) return slot;
+        slot = (slot + 1u) & mask;
+    }
+}
+
+// vertex set: entry = vid << 32 | smallest (triangle * 4 + corner) that has it; returns the slot when this call claimed it, else ~0
+__device__ __forceinline__ uint32_t vset_insert_m(unsigned long long* vset, uint32_t mask, unsigned long long ent) {
+    const uint32_t vid = (uint32_t)(ent >> 32);
+    uint32_t slot = ((vid * 2654435761u) >> 9) & mask;
+    for (;;) {
+        const unsigned long long old = atomicCAS(&vset[slot], ~0ull, ent);
+        if (old == ~0ull) return slot;
+        if ((uint32_t)(old >> 32) == vid) { atomicMin(&vset[slot], ent); return 0xffffffffu; }
+        slot = (slot + 1u) & mask;
+    }
+}
+
+// warp-aggregated append of `v` (for the lanes with `yes`) to list[*count ...]; converged code only
+__device__ __forceinline__ void pc_append(bool yes, uint32_t v, uint16_t* list, uint32_t* count, uint32_t lane) {
+    const uint32_t m = __ballot_sync(FULL_MASK, yes);
+    if (m == 0u) return;
+    const uint32_t leader = (uint32_t)__ffs(m) - 1u;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(count, (uint32_t)__popc(m));
+    base = __shfl_sync(FULL_MASK, base, leader);
+    if (yes) list[base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)v;
+}
+
+template <int T, uint32_t M_MAX>
+__global__ void __launch_bounds__(T)
+k_pair_contacts_hash(const FrameCtl* ctl, const uint32_t* __restrict__ list, int cls, PairAcc* acc, const uint32_t* __restrict__ grouped,
+                     const imrcd_tri_hit* __restrict__ hits, const HitAux* __restrict__ aux, const PairRec* __restrict__ pairrec,
+                     const TriRec* __restrict__ tris, const uint32_t* __restrict__ tri_vid) {
+    extern __shared__ __align__(16) unsigned char pc_smem[];
+    PcSlot* s_sum = reinterpret_cast<PcSlot*>(pc_smem);                                          // 2 M_MAX
+    unsigned long long* s_vset = reinterpret_cast<unsigned long long*>(s_sum + 2u * M_MAX);      // 4 M_MAX
+    uint32_t* s_key = reinterpret_cast<uint32_t*>(s_vset + 4u * M_MAX);                          // 2 M_MAX
+    uint32_t* s_bits = s_key + 2u * M_MAX;                                                       // 2 M_MAX
+    uint32_t* s_ta = s_bits + 2u * M_MAX;                                                        // M_MAX: the pair's hits, staged once for both sides
+    uint32_t* s_tb = s_ta + M_MAX;                                                               // M_MAX
+    uint32_t* s_fl = s_tb + M_MAX;                                                               // M_MAX: HitAux.flags | (weight != 0) << 31
+    uint16_t* s_cand = reinterpret_cast<uint16_t*>(s_fl + M_MAX);                                // M_MAX: claimed candidate slots
+    uint16_t* s_vert = s_cand + M_MAX;                                                           // 3 M_MAX: claimed vertex slots
+    __shared__ double s_red[3][T / 32];
+    __shared__ uint32_t s_redc[T / 32];
+    __shared__ uint32_t s_ncand, s_nvert;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    if (ctl->overflow & (OVF_PAIRS | OVF_QUEUE | OVF_COMBOS | OVF_HITS)) return;      // the frame is re-run with larger buffers
+    const unsigned long long n_list = ctl->n_class[cls * 16];
+    for (unsigned long long b = blockIdx.x; b < n_list; b += gridDim.x) {
+        const uint32_t p = list[b];
+        const uint32_t n = acc[p].n_hits;
+        uint32_t m = 16u; while (m < n) m <<= 1;                     // tables sized by the pair: 2m candidate slots (<= n distinct triangles), 4m vertex slots (<= 3n)
+        const uint32_t slots = 2u * m, vslots = 4u * m;
+        const uint32_t* grp = grouped + acc[p].off;
+        const float4* pp = reinterpret_cast<const float4*>(pairrec + p);
+        Rel rel; rel.r0 = __ldg(pp); rel.r1 = __ldg(pp + 1); rel.r2 = __ldg(pp + 2);
+        for (uint32_t k = tid; k < n; k += T) {
+            const uint32_t h = grp[k];
+            const HitAux x = aux[h];
+            s_ta[k] = x.triA; s_tb[k] = x.triB; s_fl[k] = x.flags | (hits[h].weight == 0.f ? 0u : 0x80000000u);
+        }
+        for (uint32_t side = 0; side < 2; ++side) {
+            for (uint32_t k = tid; k < slots; k += T) { s_key[k] = 0xffffffffu; s_bits[k] = 7u; s_sum[k].w = 0.0; s_sum[k].cx = 0.0; s_sum[k].cy = 0.0; s_sum[k].cz = 0.0; }
+            for (uint32_t k = tid; k < vslots; k += T) s_vset[k] = ~0ull;
+            if (tid == 0) { s_ncand = 0u; s_nvert = 0u; }
+            __syncthreads();
+            // ---- one thread per hit: merge into the own triangle's candidate ----
+            for (uint32_t k0 = 0; k0 < n; k0 += T) {
+                const uint32_t k = k0 + tid;
+                uint32_t slot = 0xffffffffu, bits = 7u;
+                double w = 0.0, cx = 0.0, cy = 0.0, cz = 0.0;
+                bool claimed = false;
+                if (k < n) {
+                    const uint32_t fl = s_fl[k];
+                    const uint32_t own = side ? s_tb[k] : s_ta[k];
+                    bool contributes = (fl >> 31) != 0u;
+                    if (!contributes) {                                                  // rare: is the combo's weight for this triangle 0? (:117-127)
+                        const uint32_t leaf = side ? s_ta[k] - ((fl >> 6) & 3u) : s_tb[k] - ((fl >> 8) & 3u);
+                        for (uint32_t q = 0; q < n && !contributes; ++q) {
+                            const uint32_t fl2 = s_fl[q];
+                            const uint32_t own2 = side ? s_tb[q] : s_ta[q];
+                            const uint32_t leaf2 = side ? s_ta[q] - ((fl2 >> 6) & 3u) : s_tb[q] - ((fl2 >> 8) & 3u);
+                            contributes = own2 == own && leaf2 == leaf && (fl2 >> 31) != 0u;
+                        }
+                    }
+                    if (contributes) {
+                        const imrcd_tri_hit hh = hits[grp[k]];
+                        const V3 sum = add3(mk3(hh.source[0], hh.source[1], hh.source[2]), mk3(hh.target[0], hh.target[1], hh.target[2]));
+                        slot = pc_slot_of(s_key, slots - 1u, own, claimed);
+                        bits = side ? ((fl >> 3) & 7u) : (fl & 7u);
+                        w = (double)hh.weight;
+                        cx = (double)((hh.weight * sum.x) / 2.f); cy = (double)((hh.weight * sum.y) / 2.f); cz = (double)((hh.weight * sum.z) / 2.f);   // :94-100
+                    }
+                }
+                pc_append(claimed, slot, s_cand, &s_ncand, lane);
+                // Hits come out of the narrow phase combo by combo, so one triangle's hits mostly sit in consecutive lanes (and a large triangle
+                // collects many): add up each run of equal slots inside the warp first (segmented scan), then one update per run.
+                const uint32_t prev = __shfl_up_sync(FULL_MASK, slot, 1);
+                const uint32_t heads = __ballot_sync(FULL_MASK, lane == 0u || prev != slot);
+                const uint32_t head = 31u - (uint32_t)__clz(heads & (0xffffffffu >> (31u - lane)));           // first lane of this lane's run
+                const uint32_t after = heads & ~(0xffffffffu >> (31u - lane));                                // run heads above this lane
+                const uint32_t tail = after ? (uint32_t)__ffs(after) - 2u : 31u;                              // last lane of the run
+#pragma unroll
+                for (uint32_t d = 1; d < 32u; d <<= 1) {
+                    const double vw = __shfl_up_sync(FULL_MASK, w, d), vx = __shfl_up_sync(FULL_MASK, cx, d), vy = __shfl_up_sync(FULL_MASK, cy, d), vz = __shfl_up_sync(FULL_MASK, cz, d);
+                    const uint32_t vb = __shfl_up_sync(FULL_MASK, bits, d);
+                    if (lane >= head + d) { w += vw; cx += vx; cy += vy; cz += vz; bits &= vb; }
+                }
+                if (lane == tail && slot != 0xffffffffu) {
+                    atomicAnd(&s_bits[slot], bits);
+                    atomicAdd(&s_sum[slot].w, w); atomicAdd(&s_sum[slot].cx, cx); atomicAdd(&s_sum[slot].cy, cy); atomicAdd(&s_sum[slot].cz, cz);
+                }
+            }
+            __syncthreads();
+            // ---- one thread per candidate: its rays (:139-166) ----
+            SideSum r; r.x = r.y = r.z = 0.0; r.rays = 0u;
+            const uint32_t n_cand = s_ncand;
+            for (uint32_t c0 = 0; c0 < n_cand; c0 += T) {
+                const uint32_t c = c0 + tid;
+                uint32_t q0 = 0xffffffffu, q1 = 0xffffffffu, q2 = 0xffffffffu;           // vertex slots claimed by this lane
+                if (c < n_cand) {
+                    const uint32_t k = s_cand[c];
+                    const uint32_t tri = s_key[k], bits = s_bits[k];
+                    if (bits == 0u) {                                                    // ray at the weighted average point (:34-37,160-163)
+                        // the quotient is taken in FP64 and rounded once: rounding the two sums first would turn the last-bit noise of the
+                        // order-free FP64 sums into FP32 differences whenever a sum sits on a rounding tie (two equal-exponent addends do)
+                        const double w = s_sum[k].w;
+                        r.x += (double)(float)(s_sum[k].cx / w); r.y += (double)(float)(s_sum[k].cy / w); r.z += (double)(float)(s_sum[k].cz / w); r.rays += 1u;
+                    } else {
+                        const uint32_t v0 = tri_vid[3ull * tri], v1 = tri_vid[3ull * tri + 1], v2 = tri_vid[3ull * tri + 2];
+                        if (bits & 1u) q0 = vset_insert_m(s_vset, vslots - 1u, ((unsigned long long)v0 << 32) | (unsigned long long)(tri * 4u));
+                        if (bits & 2u) q1 = vset_insert_m(s_vset, vslots - 1u, ((unsigned long long)v1 << 32) | (unsigned long long)(tri * 4u + 1u));
+                        if (bits & 4u) q2 = vset_insert_m(s_vset, vslots - 1u, ((unsigned long long)v2 << 32) | (unsigned long long)(tri * 4u + 2u));
+                    }
+                }
+                pc_append(q0 != 0xffffffffu, q0, s_vert, &s_nvert, lane);
+                pc_append(q1 != 0xffffffffu, q1, s_vert, &s_nvert, lane);
+                pc_append(q2 != 0xffffffffu, q2, s_vert, &s_nvert, lane);
+            }
+            __syncthreads();
+            // ---- vertex rays: one per distinct vertex id (the `emplaced` set, :139-141) ----
+            const uint32_t n_vert = s_nvert;
+            for (uint32_t c = tid; c < n_vert; c += T) {
+                const uint32_t ref = (uint32_t)s_vset[s_vert[c]];
+                const float4 q = __ldg(reinterpret_cast<const float4*>(tris + (ref >> 2)) + (ref & 3u));
+                V3 pos = mk3(q.x, q.y, q.z);
+                if (side) pos = rel_mul(rel, pos, 1.f);                                  // second's triangles live in first's space (:84,:134)
+                r.x += (double)pos.x; r.y += (double)pos.y; r.z += (double)pos.z; r.rays += 1u;
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                r.x += __shfl_down_sync(FULL_MASK, r.x, o); r.y += __shfl_down_sync(FULL_MASK, r.y, o); r.z += __shfl_down_sync(FULL_MASK, r.z, o);
+                r.rays += __shfl_down_sync(FULL_MASK, r.rays, o);
+            }
+            if (lane == 0u) { s_red[0][tid >> 5] = r.x; s_red[1][tid >> 5] = r.y; s_red[2][tid >> 5] = r.z; s_redc[tid >> 5] = r.rays; }
+            __syncthreads();
+            if (tid == 0) {
+                for (int w = 1; w < T / 32; ++w) { r.x += s_red[0][w]; r.y += s_red[1][w]; r.z += s_red[2][w]; r.rays += s_redc[w]; }
+                PairAcc* pa = acc + p;
+                double* sum = side ? pa->sum_b : pa->sum_a;
+                sum[0] = r.x; sum[1] = r.y; sum[2] = r.z;
+                if (side) pa->rays_b = r.rays; else pa->rays_a = r.rays;
+            }
+            __syncthreads();
+        }
+    }
+}
+
 template <int T, uint32_t M_MAX, uint32_t VSET>        // M_MAX == 0: scratch in global memory
 __global__ void __launch_bounds__(T)
 k_pair_contacts(const FrameCtl* ctl, const uint32_t* __restrict__ list, int cls, PairAcc* acc, const uint32_t* __restrict__ grouped,
@@ -931,9 +1116,9 @@ __global__ void k_finalize(FrameCtl* ctl, unsigned long long cap_pairs, const ui
         atomicAdd(&ctl->n_rays, (unsigned long long)(a.rays_a + a.rays_b));
         // average_point_first_modelspace = sum / count (:185-189); second: back to its own model space through
         // inverse(second_to_first_space_matrix) (:191-198).  0 rays on a side gives NaN exactly like the reference.
-        const float fa = (float)a.rays_a, fb = (float)a.rays_b;
-        o.avg_first[0] = (float)a.sum_a[0] / fa; o.avg_first[1] = (float)a.sum_a[1] / fa; o.avg_first[2] = (float)a.sum_a[2] / fa;
-        const V3 sb = mk3((float)a.sum_b[0] / fb, (float)a.sum_b[1] / fb, (float)a.sum_b[2] / fb);
+        const double fa = (double)a.rays_a, fb = (double)a.rays_b;            // FP64 quotient, rounded once (see k_pair_contacts_hash)
+        o.avg_first[0] = (float)(a.sum_a[0] / fa); o.avg_first[1] = (float)(a.sum_a[1] / fa); o.avg_first[2] = (float)(a.sum_a[2] / fa);
+        const V3 sb = mk3((float)(a.sum_b[0] / fb), (float)(a.sum_b[1] / fb), (float)(a.sum_b[2] / fb));
         float rel[16], rinv[16];
         mat4_mul(inv + 16 * (size_t)pr.x, cur + 16 * (size_t)pr.y, rel);            // the same rel as k_pair_setup (OBBtreesCollision.cpp:15)
         mat4_inverse(rel, rinv);
@@ -1090,9 +1275,9 @@ int imr_frame_run_device(imrcd_ctx* ctx) {
                                                        ctx->d_lsmall.as<uint32_t>(), ctx->d_lmid.as<uint32_t>(), ctx->d_llarge.as<uint32_t>());
         k_group_hits<<<ctx->sm_count * 8, 256, 0, s>>>(ctl, ctx->cap_hits, ctx->d_hits.as<imrcd_tri_hit>(), ctx->d_pairacc.as<PairAcc>(), ctx->d_grouped.as<uint32_t>());
         {
-            const size_t smem_s = PC_S_MAX * 8 + 1024 * 8 + PC_S_MAX * 24, smem_m = PC_M_MAX * 8 + 4096 * 8 + PC_M_MAX * 24;
+            const size_t smem_s = PC_S_MAX * (2 * (sizeof(PcSlot) + 8) + 4 * 8 + 12 + 8), smem_m = PC_M_MAX * (2 * (sizeof(PcSlot) + 8) + 4 * 8 + 12 + 8);
             if (!ctx->pc_attr_set) {
-                IMR_CUDA(ctx, cudaFuncSetAttribute(k_pair_contacts<256, PC_M_MAX, 4096>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m));
+                IMR_CUDA(ctx, cudaFuncSetAttribute(k_pair_contacts_hash<512, PC_M_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m));
                 ctx->pc_attr_set = true;
             }
             PairAcc* a_acc = ctx->d_pairacc.as<PairAcc>(); const uint32_t* a_grp = ctx->d_grouped.as<uint32_t>();
@@ -1102,8 +1287,8 @@ int imr_frame_run_device(imrcd_ctx* ctx) {
             // the three size classes are independent: the two rarer ones run beside the common one on a second stream
             IMR_CUDA(ctx, cudaEventRecord(ctx->ev_fork, s));
             IMR_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
-            k_pair_contacts<64, PC_S_MAX, 1024><<<ctx->sm_count * 16, 64, smem_s, s>>>(ctl, ctx->d_lsmall.as<uint32_t>(), 0, a_acc, a_grp, a_key, a_vkey, a_hits, a_aux, a_pr, a_tris, a_vid);
-            k_pair_contacts<256, PC_M_MAX, 4096><<<ctx->sm_count * 3, 256, smem_m, ctx->stream2>>>(ctl, ctx->d_lmid.as<uint32_t>(), 1, a_acc, a_grp, a_key, a_vkey, a_hits, a_aux, a_pr, a_tris, a_vid);
+            k_pair_contacts_hash<128, PC_S_MAX><<<ctx->sm_count * 8, 128, smem_s, s>>>(ctl, ctx->d_lsmall.as<uint32_t>(), 0, a_acc, a_grp, a_hits, a_aux, a_pr, a_tris, a_vid);
+            k_pair_contacts_hash<512, PC_M_MAX><<<ctx->sm_count, 512, smem_m, ctx->stream2>>>(ctl, ctx->d_lmid.as<uint32_t>(), 1, a_acc, a_grp, a_hits, a_aux, a_pr, a_tris, a_vid);
             k_pair_contacts<512, 0, 2><<<ctx->sm_count * 2, 512, 0, ctx->stream2>>>(ctl, ctx->d_llarge.as<uint32_t>(), 2, a_acc, a_grp, a_key, a_vkey, a_hits, a_aux, a_pr, a_tris, a_vid);
             IMR_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->stream2));
             IMR_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_join, 0));

@@ -8,6 +8,20 @@ def f32_bits(a):
     return np.ascontiguousarray(a, np.float32).view(np.uint32)
 
 
+def same_entity_pairs(a, b, rtol=1e-6):
+    """Two runs of the same frame: identical colliding pairs, hit and ray counts; contact points equal up to FP32 rounding.
+    The contact averages are sums over unordered sets (std::unordered_map iteration in the reference, CreateUncollideRays.cpp:138,185-198;
+    order-free FP64 atomics here), so the last bit of a component may differ between runs; everything integral is exact."""
+    assert len(a) == len(b)
+    for f in ("entry_first", "entry_second", "entity_first", "entity_second", "n_hits", "n_rays_first", "n_rays_second", "flags"):
+        assert np.array_equal(a[f], b[f]), f
+    for f in ("avg_first", "avg_second"):
+        x = np.asarray(a[f], np.float64); y = np.asarray(b[f], np.float64)
+        ok = np.linalg.norm(x - y, axis=1) <= rtol * np.maximum(np.linalg.norm(y, axis=1), 1e-30)
+        ok |= np.isnan(x).any(1) & np.isnan(y).any(1)           # 0 rays on a side: NaN like the reference
+        assert ok.all(), (f, x[~ok][:3], y[~ok][:3])
+
+
 def contacts_close(avg, gold, rel, rtol=1e-5):
     """Contact points agree within `rtol` relative (north star): average_point_first lives in first's model space;
     average_point_second is inverse(rel) * (a first-space point) (CreateUncollideRays.cpp:191-198), so its rounding noise

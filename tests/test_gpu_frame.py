@@ -5,7 +5,7 @@ import pytest
 
 from inmyroom_vulkan_b200 import scenes
 from inmyroom_vulkan_b200.collision import CollisionDetection, OBBtree
-from helpers import compare_frame, gpu_frame, oracle_frame
+from helpers import compare_frame, gpu_frame, oracle_frame, same_entity_pairs
 
 pytestmark = pytest.mark.gpu
 
@@ -93,7 +93,7 @@ def test_zero_copy_submission_matches_add_entries(gpu_ctx):
     for k in ("n_pairs", "n_sat_tests", "n_combos", "n_tri_tests", "n_hits", "n_colliding", "n_rays"):
         assert a[0][k] == b[0][k], k
     assert np.array_equal(a[1], b[1]) and np.array_equal(a[2].view(np.uint32), b[2].view(np.uint32))
-    assert a[3].tobytes() == b[3].tobytes()                      # colliding pairs incl. ray counts and contact points: bit-identical
+    same_entity_pairs(a[3], b[3])                                # colliding pairs, ray counts exact; contact points to FP32 rounding
 
 
 def test_shards_partition_the_frame(gpu_ctx):
@@ -112,7 +112,7 @@ def test_shards_partition_the_frame(gpu_ctx):
         pairs = set(map(tuple, bp.tolist()))
         assert len(pairs) == len(bp)
         hk = {(int(bp[h["pair"]][0]), int(bp[h["pair"]][1]), int(h["tri_first"]), int(h["tri_second"])) for h in hits}
-        coll = {(int(p["entry_first"]), int(p["entry_second"])): (int(p["n_rays_first"]), int(p["n_rays_second"]), p["avg_first"].tobytes(), p["avg_second"].tobytes()) for p in ep}
+        coll = {(int(p["entry_first"]), int(p["entry_second"])): (int(p["n_rays_first"]), int(p["n_rays_second"]), tuple(p["avg_first"].tolist()), tuple(p["avg_second"].tolist())) for p in ep}
         return pairs, hk, coll
 
     full = run(0, 1)
@@ -126,6 +126,12 @@ def test_shards_partition_the_frame(gpu_ctx):
         merged = {}
         for p in parts:
             merged.update(p[2])
-        assert merged == full[2]                      # per-pair results do not depend on the shard that computed them
+        assert merged.keys() == full[2].keys()        # per-pair results do not depend on the shard that computed them
+        for key, (ra, rb, pa, pb) in merged.items():
+            fa, fb, qa, qb = full[2][key]
+            assert (ra, rb) == (fa, fb)
+            for x, y in ((pa, qa), (pb, qb)):         # contact points: equal to FP32 rounding (order-free FP64 sums, see helpers.same_entity_pairs)
+                x = np.asarray(x, np.float64); y = np.asarray(y, np.float64)
+                assert (np.isnan(x).any() and np.isnan(y).any()) or np.linalg.norm(x - y) <= 1e-6 * max(np.linalg.norm(y), 1e-30)
         sizes = [len(p[0]) for p in parts]
         assert max(sizes) <= 1.5 * (sum(sizes) / world) + 32
