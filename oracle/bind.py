@@ -151,6 +151,25 @@ class _Base:
         f(out.ctypes.data)
         return out.reshape(3, 3)
 
+    # ---- response rays (Ray.cpp, ShootUncollideRays.cpp, CollisionDetection.cpp:80-103) ----
+    def ray_tree(self, tree, m16, origin, direction):
+        """Ray::IntersectOBBtree: (doIntersect, itBackfaces, distance, bary(2), leaf-order triangle index)."""
+        m16 = _c(m16, np.float32); o = _c(origin, np.float32); d = _c(direction, np.float32)
+        out = np.zeros(3, np.float32); tri = C.c_uint32(0); back = C.c_int(0)
+        f = self._fn("ray_tree"); f.restype = C.c_int
+        f.argtypes = [C.c_void_p] * 7
+        hit = f(tree.h, m16.ctypes.data, o.ctypes.data, d.ctypes.data, out.ctypes.data, C.byref(tri), C.byref(back))
+        return bool(hit), bool(back.value), out[0], out[1:3].copy(), int(tri.value)
+
+    def pair_delta(self, ta, ma, pa, tb, mb, pb):
+        """One ordered pair through CollisionDetection.cpp:44-103: (colliding, deltaVector first, deltaVector second)."""
+        ma = _c(ma, np.float32); mb = _c(mb, np.float32); pa = _c(pa, np.float32); pb = _c(pb, np.float32)
+        d = np.zeros(6, np.float32); extra = np.zeros(2, np.uint64)
+        f = self._fn("pair_delta"); f.restype = C.c_int
+        f.argtypes = [C.c_void_p] * 8
+        col = f(ta.h, ma.ctypes.data, pa.ctypes.data, tb.h, mb.ctypes.data, pb.ctypes.data, d.ctypes.data, extra.ctypes.data)
+        return bool(col), d[:3].copy(), d[3:].copy()
+
     # ---- trees ---------------------------------------------------------
     def tree_build(self, pos, nrm=None, vid=None):
         pos = _c(pos, np.float32).reshape(-1, 9)
@@ -278,6 +297,28 @@ class RefOracle(_Base):
                                   int(summ[4]), int(summ[5]), bool(summ[6]), avg, (float(secs[0]), float(secs[1])))
             cap = h
 
+    def shoot(self, ta, ma, tb, mb, rays_first, rays_second):
+        """ShootUncollideRays::ExecuteShootUncollideRays on explicit ray lists (n x 6, first's model space): world-space delta."""
+        ma = _c(ma, np.float32); mb = _c(mb, np.float32)
+        r1 = _c(rays_first, np.float32).reshape(-1, 6); r2 = _c(rays_second, np.float32).reshape(-1, 6)
+        d = np.zeros(3, np.float32)
+        f = self.lib.imr_ref_shoot; f.restype = None
+        f.argtypes = [C.c_void_p] * 5 + [C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p]
+        f(ta.h, ma.ctypes.data, tb.h, mb.ctypes.data, r1.ctypes.data, len(r1), r2.ctypes.data, len(r2), d.ctypes.data)
+        return d, None
+
+    def pair_rays(self, ta, ma, tb, mb):
+        """The rays of one ordered pair in the reference's own order (n x 6 each)."""
+        ma = _c(ma, np.float32); mb = _c(mb, np.float32)
+        f = self.lib.imr_ref_pair_rays; f.restype = None
+        f.argtypes = [C.c_void_p] * 6 + [C.c_uint64, C.c_void_p]
+        n2 = np.zeros(2, np.uint64)
+        f(ta.h, ma.ctypes.data, tb.h, mb.ctypes.data, None, None, 0, n2.ctypes.data)
+        cap = int(max(n2.max(), 1))
+        r1 = np.zeros((cap, 6), np.float32); r2 = np.zeros((cap, 6), np.float32)
+        f(ta.h, ma.ctypes.data, tb.h, mb.ctypes.data, r1.ctypes.data, r2.ctypes.data, cap, n2.ctypes.data)
+        return r1[:int(n2[0])].copy(), r2[:int(n2[1])].copy()
+
 
 class PortOracle(_Base):
     """The plain-C restatement (kind = "port")."""
@@ -387,6 +428,16 @@ class PortOracle(_Base):
                 return res
             cap = max(cap, h)
             ray_cap = max(ray_cap, int(summ[4]), int(summ[5]))
+
+    def shoot(self, ta, ma, tb, mb, rays_first, rays_second):
+        """ShootUncollideRays::ExecuteShootUncollideRays on explicit ray lists (n x 6, first's model space): world-space delta, responses."""
+        ma = _c(ma, np.float32); mb = _c(mb, np.float32)
+        r1 = _c(rays_first, np.float32).reshape(-1, 6); r2 = _c(rays_second, np.float32).reshape(-1, 6)
+        d = np.zeros(3, np.float32); nr = C.c_uint64(0)
+        f = self.lib.imro_shoot; f.restype = None
+        f.argtypes = [C.c_void_p] * 5 + [C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+        f(ta.h, ma.ctypes.data, tb.h, mb.ctypes.data, r1.ctypes.data, len(r1), r2.ctypes.data, len(r2), d.ctypes.data, C.byref(nr))
+        return d, int(nr.value)
 
 
 def frame_pairs(orc, mats, trees, pairs, threads: int = 1):

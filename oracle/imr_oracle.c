@@ -1044,6 +1044,254 @@ void imro_pair(const imro_tree* a, const float* mat_a, const imro_tree* b, const
     free(ma.map); free(ma.present); free(ma.order); free(mb.map); free(mb.present); free(mb.order);
 }
 
+/* ------------------------------------------------------------------ */
+/* response rays: Ray.cpp, ShootUncollideRays.cpp, CollisionDetection.cpp:80-103 */
+/* ------------------------------------------------------------------ */
+typedef struct { int hit, back; float dist; uint64_t tri; float bx, by; } rayhit_t;      /* RayOBBtreeIntersectInfo, Ray.h:17-24 */
+
+/* glm fork, glm/gtx/intersect.inl:29-97 (intersectRayTriangle with itBackfaces) */
+static int ray_triangle(v3 orig, v3 dir, v3 v0, v3 v1, v3 v2, float* bx, float* by, float* distance, int* back) {
+    v3 edge1 = sub3(v1, v0), edge2 = sub3(v2, v0);
+    v3 p = cross3(dir, edge2);
+    float det = dot3(edge1, p);
+    v3 perp = { 0.f, 0.f, 0.f };
+    float x, y;
+    if (det > FLT_EPSILON) {
+        v3 dist = sub3(orig, v0);
+        x = dot3(dist, p);
+        if (x < 0.f || x > det) return 0;
+        perp = cross3(dist, edge1);
+        y = dot3(dir, perp);
+        if (y < 0.f || (x + y) > det) return 0;
+        *back = 0;
+    } else if (det < -FLT_EPSILON) {
+        v3 dist = sub3(orig, v0);
+        x = dot3(dist, p);
+        if (x > 0.f || x < det) return 0;
+        perp = cross3(dist, edge1);
+        y = dot3(dir, perp);
+        if (y > 0.f || (x + y) < det) return 0;
+        *back = 1;
+    } else return 0;
+    float inv_det = 1.f / det;
+    *distance = dot3(edge2, perp) * inv_det;
+    *bx = x * inv_det; *by = y * inv_det;
+    return 1;
+}
+
+/* one slab of Ray::IntersectParalgram, Ray.cpp:49-75 (the U, V and W blocks are the same code) */
+static int ray_slab(v3 a, v3 b, v3 side, v3 ray_origin, v3 dir, float* mn, float* mx) {
+    v3 plane_dir = normalize3(cross3(a, b));
+    float d = -fabsf(dot3(plane_dir, side));
+    float c = dot3(plane_dir, ray_origin);
+    float v_n1 = +c + d;
+    float v_n2 = -c + d;
+    float vd = dot3(plane_dir, dir);
+    if (fabsf(vd) >= FLT_EPSILON) {
+        float vd_inv = 1.f / vd;
+        float t1 = -v_n1 * vd_inv;
+        float t2 = +v_n2 * vd_inv;
+        if (t1 > t2) { float t = t1; t1 = t2; t2 = t; }
+        *mn = (t1 < *mn) ? *mn : t1;               /* std::max(t1, min_distance) */
+        *mx = (*mx < t2) ? *mx : t2;               /* std::min(t2, max_distance) */
+        if (*mn > *mx || *mx < 0.f) return 0;
+    } else if (v_n1 > 0 || v_n2 > 0) return 0;
+    return 1;
+}
+/* Ray::IntersectParalgram, Ray.cpp:38-134; the ray's origin is always (0,0,0) here (Ray.cpp:138,153-158) */
+static int ray_box(v3 origin, v3 dir, const box_t* bx, float* tmin, float* tmax) {
+    float mn = -INFINITY, mx = +INFINITY;
+    v3 ro = sub3(origin, bx->c);
+    if (!ray_slab(bx->v, bx->w, bx->u, ro, dir, &mn, &mx)) return 0;       /* U test :48-75 */
+    if (!ray_slab(bx->w, bx->u, bx->v, ro, dir, &mn, &mx)) return 0;       /* V test :77-104 */
+    if (!ray_slab(bx->u, bx->v, bx->w, ro, dir, &mn, &mx)) return 0;       /* W test :106-133 */
+    *tmin = mn; *tmax = mx;
+    return 1;
+}
+
+/* Ray::IntersectOBBtreeRecursive, Ray.cpp:163-236 */
+static void ray_tree_rec(const imro_tree* t, int32_t v, const float* m, v3 dir, rayhit_t* best) {
+    const v3 zero = { 0.f, 0.f, 0.f };
+    if (t->left[v] >= 0) {
+        int32_t l = t->left[v], r = t->right[v];
+        box_t lb = box_transform(m, box_load(t->boxes + 12 * (uint64_t)l)), rb = box_transform(m, box_load(t->boxes + 12 * (uint64_t)r));
+        float lmin = 0.f, lmax = 0.f, rmin = 0.f, rmax = 0.f;
+        int lh = ray_box(zero, dir, &lb, &lmin, &lmax), rh = ray_box(zero, dir, &rb, &rmin, &rmax);
+        if (lh && rh) {
+            if (lmin < rmin) {
+                if (lmin < best->dist && lmax >= 0.f) ray_tree_rec(t, l, m, dir, best);
+                if (rmin < best->dist && rmax >= 0.f) ray_tree_rec(t, r, m, dir, best);
+            } else {
+                if (rmin < best->dist && rmax >= 0.f) ray_tree_rec(t, r, m, dir, best);
+                if (lmin < best->dist && lmax >= 0.f) ray_tree_rec(t, l, m, dir, best);
+            }
+        } else if (lh) {
+            if (lmin < best->dist && lmax >= 0.f) ray_tree_rec(t, l, m, dir, best);
+        } else if (rh) {
+            if (rmin < best->dist && rmax >= 0.f) ray_tree_rec(t, r, m, dir, best);
+        }
+    } else {
+        for (uint64_t i = t->tri_off[v]; i != (uint64_t)t->tri_off[v] + t->tri_cnt[v]; ++i) {
+            float tp[9];
+            tri_transform(m, t->tri_pos + 9 * i, tp);
+            v3 p0 = { tp[0], tp[1], tp[2] }, p1 = { tp[3], tp[4], tp[5] }, p2 = { tp[6], tp[7], tp[8] };
+            float bx = 0.f, by = 0.f, dist = INFINITY; int back = 0;
+            int hit = ray_triangle(zero, dir, p0, p1, p2, &bx, &by, &dist, &back);
+            if (hit && dist > 0.f && dist < best->dist) { best->hit = 1; best->back = back; best->dist = dist; best->tri = i; best->bx = bx; best->by = by; }
+        }
+    }
+}
+
+/* Ray::IntersectOBBtree, Ray.cpp:136-161 */
+static rayhit_t ray_tree(const imro_tree* t, const float* m16, v3 origin, v3 dir) {
+    rayhit_t best = { 0, 0, INFINITY, (uint64_t)-1, 0.f, 0.f };
+    float m[16]; memcpy(m, m16, 64);
+    if (!(origin.x == 0.f && origin.y == 0.f && origin.z == 0.f)) {        /* centered_matrix[3] -= vec4(origin, 0) */
+        m[12] = m[12] - origin.x; m[13] = m[13] - origin.y; m[14] = m[14] - origin.z; m[15] = m[15] - 0.f;
+    }
+    const v3 zero = { 0.f, 0.f, 0.f };
+    box_t root = box_transform(m, box_load(t->boxes));
+    float mn = 0.f, mx = 0.f;
+    if (ray_box(zero, dir, &root, &mn, &mx) && mx >= 0.f) ray_tree_rec(t, 0, m, dir, &best);
+    return best;
+}
+
+int imro_ray_tree(const imro_tree* t, const float* m16, const float* origin3, const float* dir3, float* out3, uint32_t* tri, int* back) {
+    v3 o = { origin3[0], origin3[1], origin3[2] }, d = { dir3[0], dir3[1], dir3[2] };
+    rayhit_t h = ray_tree(t, m16, o, d);
+    out3[0] = h.dist; out3[1] = h.bx; out3[2] = h.by;
+    *tri = (uint32_t)h.tri; *back = h.back;
+    return h.hit;
+}
+
+typedef struct { int ok; v3 response, normal; } hermann_t;
+
+/* ShootUncollideRays::HermannPass, ShootUncollideRays.cpp:116-148 (the ray is a copy: its origin is moved inside) */
+static hermann_t hermann_pass(const imro_tree* A, const imro_tree* B, const float* matA, const float* matB, const float* nmatB, v3 origin, v3 dir) {
+    hermann_t r; r.ok = 0; r.response.x = r.response.y = r.response.z = 0.f; r.normal = r.response;
+    rayhit_t p2 = ray_tree(B, matB, origin, dir);
+    if (p2.hit && p2.back) {
+        /* Ray::MoveOriginEpsilonTowardsDirection(4.f), Ray.cpp:13-21 */
+        float big = fabsf(origin.x); if (big < fabsf(origin.y)) big = fabsf(origin.y); if (big < fabsf(origin.z)) big = fabsf(origin.z);
+        float scaled = big * FLT_EPSILON;
+        v3 moved = add3(origin, scale3(dir, 4.f * scaled));
+        float eps_dist = length3(sub3(moved, origin));
+        rayhit_t p3 = ray_tree(A, matA, moved, dir);
+        if (p2.dist <= p3.dist + eps_dist) {
+            r.ok = 1;
+            r.response = scale3(dir, p2.dist);                                 /* distanceFromOrigin * ray.GetDirection() */
+            const float* tn = B->tri_nrm + 9 * p2.tri;
+            v3 n0 = { tn[0], tn[1], tn[2] }, n1 = { tn[3], tn[4], tn[5] }, n2 = { tn[6], tn[7], tn[8] };
+            float w0 = 1.f - p2.bx - p2.by;
+            v3 in = add3(add3(scale3(n0, w0), scale3(n1, p2.bx)), scale3(n2, p2.by));   /* Triangle.cpp:197-204 */
+            r.normal = normalize3(mat3_mul(nmatB, in));
+        }
+    }
+    return r;
+}
+
+/* ShootUncollideRays::CalcForceResponse, ShootUncollideRays.cpp:104-114 */
+static v3 force_response(const hermann_t* h) {
+    v3 dirn = normalize3(h->response);
+    float len = length3(h->response);
+    float c = dot3(h->normal, dirn);
+    return scale3(dirn, (c * c) * len);
+}
+
+typedef struct { v3 force; v3* resp; uint64_t n, cap; } shoot_acc;
+static void shoot_push(shoot_acc* a, v3 v) {
+    if (a->n == a->cap) { a->cap = a->cap ? 2 * a->cap : 64; a->resp = (v3*)realloc(a->resp, sizeof(v3) * a->cap); }
+    a->resp[a->n++] = v;
+}
+
+/* ShootUncollideRays::ExecuteShootUncollideRays, ShootUncollideRays.cpp:14-93.  rays: 6 floats each (origin, direction), first's model
+ * space.  Returns the world-space delta (first.current * vec4(localspace_response, 0)). */
+void imro_shoot(const imro_tree* a, const float* mat_a, const imro_tree* b, const float* mat_b,
+                const float* rays_first, uint64_t n_first, const float* rays_second, uint64_t n_second, float* delta3, uint64_t* n_responses) {
+    static const float ident4[16] = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1 };
+    static const float ident3[9] = { 1, 0, 0, 0, 1, 0, 0, 0, 1 };
+    float rel[16], nmat[9];
+    imro_pair_matrix(mat_a, mat_b, rel);
+    adjoint_transpose3(rel, nmat);
+    shoot_acc acc; memset(&acc, 0, sizeof(acc));
+    for (int phase = 0; phase < 2; ++phase) {
+        const float* rays = phase ? rays_second : rays_first;
+        uint64_t n = phase ? n_second : n_first;
+        for (uint64_t k = 0; k < n; ++k) {
+            v3 o = { rays[6 * k], rays[6 * k + 1], rays[6 * k + 2] }, d = { rays[6 * k + 3], rays[6 * k + 4], rays[6 * k + 5] };
+            for (int step = 0; step < 2; ++step) {
+                /* first_to_second when (phase == 0) == (step == 0), else second_to_first (:29-71) */
+                int f2s = (phase == 0) == (step == 0);
+                hermann_t h = f2s ? hermann_pass(a, b, ident4, rel, nmat, o, d) : hermann_pass(b, a, rel, ident4, ident3, o, d);
+                if (!h.ok) break;
+                v3 fr = force_response(&h);
+                if (f2s) { acc.force = sub3(acc.force, fr); v3 neg = { -h.response.x, -h.response.y, -h.response.z }; shoot_push(&acc, neg); }
+                else { acc.force = add3(acc.force, fr); shoot_push(&acc, h.response); }
+                /* ReflectHermannResult :95-101 */
+                o = add3(o, h.response);
+                d.x = -h.normal.x; d.y = -h.normal.y; d.z = -h.normal.z;
+            }
+        }
+    }
+    v3 local = { 0.f, 0.f, 0.f };
+    if (!(acc.force.x == 0.f && acc.force.y == 0.f && acc.force.z == 0.f)) {
+        v3 nf = normalize3(acc.force);
+        /* FindResponse :150-172; edges: cos(65 deg) .. cos(40 deg) (CollisionDetection.cpp:22-24, ShootUncollideRays.cpp:8-9) */
+        const float edge_b = cosf(0.01745329251994329576923690768489f * 40.f), edge_a = cosf(0.01745329251994329576923690768489f * 65.f);
+        float max_len = 0.f;
+        for (uint64_t k = 0; k < acc.n; ++k) {
+            v3 nr = normalize3(acc.resp[k]);
+            float c = dot3(nr, nf);
+            float len = length3(acc.resp[k]);
+            float need = len / c;
+            float tq = (c - edge_a) / (edge_b - edge_a);
+            float tmp = tq < 0.f ? 0.f : (1.f < tq ? 1.f : tq);                    /* std::clamp */
+            float ss = tmp * tmp * tmp * (tmp * (tmp * 6 - 15) + 10);               /* SmootherStep :174-178 */
+            float cand = ss * need;
+            max_len = max_len < cand ? cand : max_len;                             /* std::max(max_length, cand) */
+        }
+        local = scale3(scale3(nf, max_len), 1.01f);                                /* ray_distance_bias_multiplier * (max_length * n) */
+    }
+    v3 w = mat4_mul_point(mat_a, local, 0.f);
+    delta3[0] = w.x; delta3[1] = w.y; delta3[2] = w.z;
+    if (n_responses) *n_responses = acc.n;
+    free(acc.resp);
+}
+
+/* CollisionDetection::PointMovementBetweenFrames, CollisionDetection.cpp:143-150 */
+static float point_movement(v3 p, const float* m_first, const float* m_second) {
+    v3 a = mat4_mul_point(m_first, p, 1.f), b = mat4_mul_point(m_second, p, 1.f);
+    return length3(sub3(a, b));
+}
+
+/* CollisionDetection.cpp:60-103 for one ordered pair: rays, then (when either entry moved) the response.  delta6 = deltaVector of first, of second.
+ * Returns 1 when the pair is colliding (>= 1 ray). */
+int imro_pair_delta(const imro_tree* a, const float* mat_a, const float* prev_a, const imro_tree* b, const float* mat_b, const float* prev_b,
+                    float* delta6, uint64_t* n_responses) {
+    uint64_t summ[7]; float avg[6];
+    memset(delta6, 0, 24);
+    if (n_responses) *n_responses = 0;
+    imro_pair(a, mat_a, b, mat_b, NULL, NULL, 0, summ, avg, NULL, NULL, 0);
+    if (!summ[6]) return 0;
+    int moved = 0;                                     /* glm mat4 operator!= : any component differs (:80-81) */
+    for (int i = 0; i < 16; ++i) if (mat_a[i] != prev_a[i] || mat_b[i] != prev_b[i]) moved = 1;
+    if (!moved) return 1;
+    uint64_t ra = summ[4], rb = summ[5];
+    float* r1 = (float*)malloc(sizeof(float) * 6 * (ra ? ra : 1));
+    float* r2 = (float*)malloc(sizeof(float) * 6 * (rb ? rb : 1));
+    imro_pair(a, mat_a, b, mat_b, NULL, NULL, 0, summ, avg, r1, r2, ra > rb ? ra : rb);
+    float d[3];
+    imro_shoot(a, mat_a, b, mat_b, r1, ra, r2, rb, d, n_responses);
+    v3 pa = { avg[0], avg[1], avg[2] }, pb = { avg[3], avg[4], avg[5] };
+    float m1 = point_movement(pa, mat_a, prev_a), m2 = point_movement(pb, mat_b, prev_b);
+    float total = m1 + m2;
+    float f1 = m1 / total, f2 = m2 / total;
+    delta6[0] = -d[0] * f1; delta6[1] = -d[1] * f1; delta6[2] = -d[2] * f1;       /* - delta * (first / total) :88 */
+    delta6[3] = d[0] * f2; delta6[4] = d[1] * f2; delta6[5] = d[2] * f2;          /* + delta * (second / total) :89 */
+    free(r1); free(r2);
+    return 1;
+}
+
 /* Batch mid + narrow over a pair list: the loop of IMR/src/CollisionDetection/CollisionDetection.cpp:44-69 on
  * (first,second) entry-index pairs.  Re-entrant.  totals: [0] combos [1] tri-pair tests [2] colliding pairs
  * [3] pairs with >= 1 combo. */

@@ -419,6 +419,86 @@ void imr_ref_frame_pairs(const float* mats, void* const* trees, const uint32_t* 
     if (seconds) { seconds[0] = s_mid; seconds[1] = s_narrow; }
 }
 
+// ---- response rays --------------------------------------------------------------
+// Ray::IntersectOBBtree (Ray.cpp:136-161) on one ray.  out3 = distanceFromOrigin, baryPosition; tri = leaf-order triangle index.
+int imr_ref_ray_tree(void* tree, const float* m16, const float* origin3, const float* dir3, float* out3, uint32_t* tri, int* back) {
+    RefTree* t = static_cast<RefTree*>(tree);
+    Ray ray(glm::vec3(origin3[0], origin3[1], origin3[2]), glm::vec3(dir3[0], dir3[1], dir3[2]));
+    RayOBBtreeIntersectInfo r = ray.IntersectOBBtree(t->tree, load_mat(m16));
+    out3[0] = r.distanceFromOrigin; out3[1] = r.baryPosition.x; out3[2] = r.baryPosition.y;
+    *tri = uint32_t(r.triangle_index); *back = r.itBackfaces ? 1 : 0;
+    return r.doIntersect ? 1 : 0;
+}
+
+// One ordered pair through the engine's per-pair code, CollisionDetection.cpp:44-103 (the ECS fan-out after it needs an ECSwrapper and is
+// exercised by the host adapter test instead).  delta6 = CollisionCallbackData.deltaVector of first, of second.  Returns colliding (0/1).
+// PointMovementBetweenFrames is a private static of CollisionDetection (CollisionDetection.cpp:143-150); its six lines are repeated here.
+int imr_ref_pair_delta(void* tree_a, const float* mat_a, const float* prev_a, void* tree_b, const float* mat_b, const float* prev_b,
+                       float* delta6, uint64_t* n_rays2) {
+    RefTree* a = static_cast<RefTree*>(tree_a); RefTree* b = static_cast<RefTree*>(tree_b);
+    OBBtreesCollision mid;
+    CreateUncollideRays narrow;
+    ShootUncollideRays shoot(glm::radians(40.f), glm::radians(65.f), 1.01f);                 // CollisionDetection.cpp:22-24
+    std::memset(delta6, 0, 24);
+    auto pr = std::make_pair(make_entry(mat_a, prev_a, a, true, 1), make_entry(mat_b, prev_b, b, true, 2));
+    CDentriesPairTrianglesPairs m = mid.ExecuteOBBtreesCollision(pr);
+    if (m.OBBtreesIntersectInfoObj.candidateTriangleRangeCombinations.empty()) return 0;   // :51
+    CDentriesUncollideRays rays = narrow.ExecuteCreateUncollideRays(m);
+    if (n_rays2) { n_rays2[0] = rays.rays_from_first_to_second.size(); n_rays2[1] = rays.rays_from_second_to_first.size(); }
+    if (!(rays.rays_from_first_to_second.size() || rays.rays_from_second_to_first.size())) return 0;   // :63
+    if (rays.firstEntry.currentGlobalMatrix != rays.firstEntry.previousGlobalMatrix ||
+        rays.secondEntry.currentGlobalMatrix != rays.secondEntry.previousGlobalMatrix) {     // :80-81
+        glm::vec3 delta = shoot.ExecuteShootUncollideRays(rays);
+        auto movement = [](const glm::vec3 point, const glm::mat4& m_first, const glm::mat4& m_second) {
+            glm::vec3 p_first = glm::vec3(m_first * glm::vec4(point, 1.f));
+            glm::vec3 p_second = glm::vec3(m_second * glm::vec4(point, 1.f));
+            glm::vec3 v_diff = p_first - p_second;
+            return glm::length(v_diff);
+        };
+        float first_movement = movement(rays.average_point_first_modelspace, rays.firstEntry.currentGlobalMatrix, rays.firstEntry.previousGlobalMatrix);
+        float second_movement = movement(rays.average_point_second_modelspace, rays.secondEntry.currentGlobalMatrix, rays.secondEntry.previousGlobalMatrix);
+        float total_movement = first_movement + second_movement;
+        glm::vec3 d1 = - delta * (first_movement / total_movement);
+        glm::vec3 d2 = + delta * (second_movement / total_movement);
+        std::memcpy(delta6, &d1, 12); std::memcpy(delta6 + 3, &d2, 12);
+    }
+    return 1;
+}
+
+
+// ShootUncollideRays::ExecuteShootUncollideRays (ShootUncollideRays.cpp:14-93) on explicit ray lists (6 floats per ray: origin, direction,
+// first's model space), so that a restatement can be compared on the same rays in the same order.
+void imr_ref_shoot(void* tree_a, const float* mat_a, void* tree_b, const float* mat_b,
+                   const float* rays_first, uint64_t n_first, const float* rays_second, uint64_t n_second, float* delta3) {
+    RefTree* a = static_cast<RefTree*>(tree_a); RefTree* b = static_cast<RefTree*>(tree_b);
+    ShootUncollideRays shoot(glm::radians(40.f), glm::radians(65.f), 1.01f);                 // CollisionDetection.cpp:22-24
+    CDentriesUncollideRays in;
+    in.firstEntry = make_entry(mat_a, nullptr, a, true, 1);
+    in.secondEntry = make_entry(mat_b, nullptr, b, true, 2);
+    for (uint64_t k = 0; k < n_first; ++k) in.rays_from_first_to_second.emplace_back(glm::vec3(rays_first[6 * k], rays_first[6 * k + 1], rays_first[6 * k + 2]), glm::vec3(rays_first[6 * k + 3], rays_first[6 * k + 4], rays_first[6 * k + 5]));
+    for (uint64_t k = 0; k < n_second; ++k) in.rays_from_second_to_first.emplace_back(glm::vec3(rays_second[6 * k], rays_second[6 * k + 1], rays_second[6 * k + 2]), glm::vec3(rays_second[6 * k + 3], rays_second[6 * k + 4], rays_second[6 * k + 5]));
+    glm::vec3 d = shoot.ExecuteShootUncollideRays(in);
+    std::memcpy(delta3, &d, 12);
+}
+
+// The rays of one ordered pair in the reference's own order (CreateUncollideRays.cpp:180-184); returns the counts in n2.
+void imr_ref_pair_rays(void* tree_a, const float* mat_a, void* tree_b, const float* mat_b, float* rays_first, float* rays_second, uint64_t cap, uint64_t* n2) {
+    RefTree* a = static_cast<RefTree*>(tree_a); RefTree* b = static_cast<RefTree*>(tree_b);
+    OBBtreesCollision mid;
+    CreateUncollideRays narrow;
+    auto pr = std::make_pair(make_entry(mat_a, nullptr, a, true, 1), make_entry(mat_b, nullptr, b, true, 2));
+    CDentriesPairTrianglesPairs m = mid.ExecuteOBBtreesCollision(pr);
+    n2[0] = n2[1] = 0;
+    if (m.OBBtreesIntersectInfoObj.candidateTriangleRangeCombinations.empty()) return;
+    CDentriesUncollideRays rays = narrow.ExecuteCreateUncollideRays(m);
+    n2[0] = rays.rays_from_first_to_second.size(); n2[1] = rays.rays_from_second_to_first.size();
+    auto put = [&](const std::vector<Ray>& v, float* out) {
+        for (size_t k = 0; k < v.size() && k < cap; ++k) { glm::vec3 o = v[k].GetOrigin(), d = v[k].GetDirection(); std::memcpy(out + 6 * k, &o, 12); std::memcpy(out + 6 * k + 3, &d, 12); }
+    };
+    if (rays_first) put(rays.rays_from_first_to_second, rays_first);
+    if (rays_second) put(rays.rays_from_second_to_first, rays_second);
+}
+
 const char* imr_ref_build_info() { return "reference sources compiled in place: g++ -std=c++20 -O2 -ffp-contract=off"; }
 
 }  // extern "C"

@@ -82,3 +82,57 @@ def test_batch_frame_pairs_matches_per_pair(port, ref):
         for th in (1, 3):
             r = bind.frame_pairs(orc, sc.matrices, et, res["pairs"], threads=th)
             assert (r["combos"], r["tri_tests"], r["colliding"]) == (res["totals"]["combos"], res["totals"]["tri_tests"], res["totals"]["colliding"])
+
+
+def test_ray_tree_identical(port, ref):
+    """Ray::IntersectOBBtree (Ray.cpp:136-236): same hit flag, back-face flag, distance, barycentrics and triangle, bit for bit."""
+    rng = np.random.default_rng(31)
+    mesh = scenes.torus(40, 20)
+    tp = port.tree_build(mesh.positions, mesh.normals, mesh.vertex_ids); tr = ref.tree_build(mesh.positions, mesh.normals, mesh.vertex_ids)
+    mats = _rand_mats(rng, 40, tscale=0.3)
+    n_hit = 0
+    for k in range(2000):
+        m = mats[k % len(mats)]
+        o = (rng.normal(size=3) * (0.2 if k % 3 else 3.0)).astype(np.float32)
+        d = rng.normal(size=3); d = (d / np.linalg.norm(d)).astype(np.float32)
+        if k % 50 == 0:
+            o[:] = 0                                   # the un-centred branch (Ray.cpp:138)
+        a = port.ray_tree(tp, m, o, d); b = ref.ray_tree(tr, m, o, d)
+        assert a[0] == b[0] and a[1] == b[1] and a[4] == b[4], (k, a, b)
+        assert np.array_equal(f32_bits(np.array([a[2]])), f32_bits(np.array([b[2]]))) and np.array_equal(f32_bits(a[3]), f32_bits(b[3])), (k, a, b)
+        n_hit += a[0]
+    assert n_hit > 300
+
+
+def test_pair_delta_matches_reference(port, ref):
+    """deltaVector of both entities (ShootUncollideRays.cpp:14-93, CollisionDetection.cpp:80-103).  The rays of a pair come out of
+    std::unordered_map iteration in the reference and in merge order in the port, and the response is a float sum / max over them:
+    so the two agree to 1e-4 of the vector's length end to end; on the SAME rays in the SAME order (the reference's) the port is bit-identical."""
+    rng = np.random.default_rng(41)
+    sc = scenes.scene_instances(scenes.torus(40, 20), 60, seed=23, neighbours=6.0)
+    tp = [port.tree_build(m.positions, m.normals, m.vertex_ids) for m in sc.meshes]
+    tr = [ref.tree_build(m.positions, m.normals, m.vertex_ids) for m in sc.meshes]
+    pairs = oracle_frame(port, sc, tp, port=port)["pairs"]
+    prev = sc.matrices.copy()
+    prev[:, 12:15] += (rng.normal(size=(sc.n_entries, 3)) * 0.02).astype(np.float32)       # every entry moved a little since the last frame
+    n_col = n_nonzero = 0
+    for (i, j) in pairs.tolist():
+        cp, p1, p2 = port.pair_delta(tp[sc.mesh_index[i]], sc.matrices[i], prev[i], tp[sc.mesh_index[j]], sc.matrices[j], prev[j])
+        cr, r1, r2 = ref.pair_delta(tr[sc.mesh_index[i]], sc.matrices[i], prev[i], tr[sc.mesh_index[j]], sc.matrices[j], prev[j])
+        assert cp == cr
+        if not cr:
+            assert not p1.any() and not p2.any() and not r1.any() and not r2.any()
+            continue
+        n_col += 1
+        for a, b in ((p1, r1), (p2, r2)):
+            assert np.linalg.norm(a.astype(np.float64) - b) <= 1e-4 * max(np.linalg.norm(b), 1e-30) + 1e-12, ((i, j), a, b)
+        ta, tb = tr[sc.mesh_index[i]], tr[sc.mesh_index[j]]
+        r1, r2 = ref.pair_rays(ta, sc.matrices[i], tb, sc.matrices[j])
+        d_ref, _ = ref.shoot(ta, sc.matrices[i], tb, sc.matrices[j], r1, r2)
+        d_port, _ = port.shoot(tp[sc.mesh_index[i]], sc.matrices[i], tp[sc.mesh_index[j]], sc.matrices[j], r1, r2)
+        assert np.array_equal(f32_bits(d_ref), f32_bits(d_port)), ((i, j), d_ref, d_port)
+        n_nonzero += bool(r1.any() or r2.any())
+        # unmoved entries: the response is skipped (CollisionDetection.cpp:99-103)
+        c0, z1, z2 = port.pair_delta(tp[sc.mesh_index[i]], sc.matrices[i], sc.matrices[i], tp[sc.mesh_index[j]], sc.matrices[j], sc.matrices[j])
+        assert c0 and not z1.any() and not z2.any()
+    assert n_col > 10 and n_nonzero > 5
