@@ -46,7 +46,8 @@ typedef struct {
     uint32_t flags;                        /* bit0: colliding (>= 1 ray, CollisionDetection.cpp:63) */
     float    avg_first[3];                 /* average_point_first_modelspace  (CreateUncollideRays.cpp:185-189) */
     float    avg_second[3];                /* average_point_second_modelspace (CreateUncollideRays.cpp:191-198) */
-    float    delta_first[3];               /* CollisionCallbackData.deltaVector for first  (CollisionDetection.cpp:80-103) */
+    float    delta_first[3];               /* CollisionCallbackData.deltaVector for first (CollisionDetection.cpp:80-103): the response of
+                                              ShootUncollideRays.cpp:14-93 split by movement; zero when neither entity moved (:99-103) */
     float    delta_second[3];              /* ... for second */
 } imrcd_entity_pair;                       /* 80 bytes */
 
@@ -79,6 +80,9 @@ typedef struct {
     float    ms_broad, ms_pair_setup, ms_traverse, ms_narrow, ms_reduce;
     uint64_t n_contact_pairs;   /* pairs with at least one hit that went through the contact reduction (CreateUncollideRays.cpp:117-198) */
     uint64_t n_rays;            /* "uncollide" rays of the colliding pairs, both sides (CreateUncollideRays.cpp:131-178) */
+    uint64_t n_rays_shot;       /* rays of the pairs whose entities moved: each goes through the Hermann passes of ShootUncollideRays.cpp:73-89 */
+    uint64_t n_responses;       /* successful Hermann passes (entries of ray_responses, ShootUncollideRays.cpp:43,61) */
+    float    ms_response;       /* device time of the response stage (part of ms_reduce) */
 } imrcd_frame_stats;
 
 /* ---- context ---------------------------------------------------------------------------- */
@@ -157,6 +161,10 @@ int imrcd_test_tri_tri(imrcd_ctx* ctx, uint64_t n, const float* tris_a, const fl
                        uint8_t* flags, float* seg /* n*6 */);
 int imrcd_test_pair_matrix(imrcd_ctx* ctx, uint64_t n, const float* a, const float* b, float* out /* n*16 */);
 int imrcd_test_obb_fit(imrcd_ctx* ctx, uint64_t n_points, const float* points, float* out12);
+/* Ray::IntersectOBBtree (Ray.cpp:136-236) on n rays against one mesh: mats n*16 (tree -> ray space), origins / directions n*3;
+ * flags bit0 doIntersect, bit1 itBackfaces; out3 = distanceFromOrigin, baryPosition.x, .y; tri = LEAF-ORDER triangle index (0xffffffff: none) */
+int imrcd_test_ray_tree(imrcd_ctx* ctx, uint32_t mesh_id, uint64_t n, const float* mats, const float* origins, const float* directions,
+                        uint8_t* flags, float* out3, uint32_t* tri);
 
 #ifdef __cplusplus
 }

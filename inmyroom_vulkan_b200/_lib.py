@@ -35,7 +35,8 @@ class FrameStats(C.Structure):
                 ("n_tri_tests", C.c_uint64), ("n_hits", C.c_uint64), ("n_coplanar_hits", C.c_uint64), ("n_colliding", C.c_uint64),
                 ("traverse_launches", C.c_uint64), ("total_launches", C.c_uint64), ("n_queue_items", C.c_uint64), ("n_warp_iterations", C.c_uint64), ("trav_busy_cycles", C.c_uint64), ("trav_idle_polls", C.c_uint64), ("ms_total", C.c_float), ("ms_broad", C.c_float),
                 ("ms_pair_setup", C.c_float), ("ms_traverse", C.c_float), ("ms_narrow", C.c_float), ("ms_reduce", C.c_float),
-                ("n_contact_pairs", C.c_uint64), ("n_rays", C.c_uint64)]
+                ("n_contact_pairs", C.c_uint64), ("n_rays", C.c_uint64),
+                ("n_rays_shot", C.c_uint64), ("n_responses", C.c_uint64), ("ms_response", C.c_float)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -75,6 +76,7 @@ _SIGS = [
     ("imrcd_test_tri_tri", C.c_int, [_P, C.c_uint64, _P, _P, _P, _P, _P]),
     ("imrcd_test_pair_matrix", C.c_int, [_P, C.c_uint64, _P, _P, _P]),
     ("imrcd_test_obb_fit", C.c_int, [_P, C.c_uint64, _P, _P]),
+    ("imrcd_test_ray_tree", C.c_int, [_P, C.c_uint32, C.c_uint64, _P, _P, _P, _P, _P, _P]),
 ]
 EXPORTED_SYMBOLS = [s[0] for s in _SIGS]
 

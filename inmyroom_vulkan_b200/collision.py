@@ -90,6 +90,14 @@ class Context:
         self.check(self.lib.imrcd_test_obb_fit(self.h, p.shape[0], _ptr(p), _ptr(out)))
         return out
 
+    def test_ray_tree(self, tree, mats, origins, directions):
+        """Ray::IntersectOBBtree on n rays: (hit, backface, distance, bary (n,2), leaf-order triangle index)."""
+        m = _c(mats, np.float32).reshape(-1, 16); o = _c(origins, np.float32).reshape(-1, 3); d = _c(directions, np.float32).reshape(-1, 3)
+        n = m.shape[0]
+        flags = np.zeros(n, np.uint8); out = np.zeros((n, 3), np.float32); tri = np.zeros(n, np.uint32)
+        self.check(self.lib.imrcd_test_ray_tree(self.h, tree.mesh_id, n, _ptr(m), _ptr(o), _ptr(d), _ptr(flags), _ptr(out), _ptr(tri)))
+        return (flags & 1).astype(bool), (flags & 2).astype(bool), out[:, 0].copy(), out[:, 1:3].copy(), tri
+
 
 def refit_meshes(ctx: "Context", trees=None) -> float:
     """Batched refit of `trees` (None = every mesh updated since its last refit); returns the device time in ms."""

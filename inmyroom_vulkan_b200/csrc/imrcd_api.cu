@@ -43,7 +43,7 @@ extern "C" void imrcd_destroy(imrcd_ctx* ctx) {
     DevBuf* bufs[] = { &ctx->d_recs, &ctx->d_tris, &ctx->d_tri_nrm, &ctx->d_tri_vid, &ctx->d_meshes, &ctx->d_rf_stage, &ctx->d_rf_segs, &ctx->d_rf_scratch, &ctx->d_cur, &ctx->d_prev, &ctx->d_mesh,
                        &ctx->d_cb, &ctx->d_entity, &ctx->d_inv, &ctx->d_ext, &ctx->d_keys, &ctx->d_keys2, &ctx->d_idx, &ctx->d_idx2,
                        &ctx->d_sorted, &ctx->d_sorted_c, &ctx->d_flag, &ctx->d_cpos, &ctx->d_wlen, &ctx->d_chunks, &ctx->d_chunkoff, &ctx->d_cubtmp, &ctx->d_pairs, &ctx->d_pairrec, &ctx->d_pairacc, &ctx->d_queue, &ctx->d_combos,
-                       &ctx->d_hits, &ctx->d_epairs, &ctx->d_ctl, &ctx->d_aux, &ctx->d_grouped, &ctx->d_skey, &ctx->d_svkey, &ctx->d_padded, &ctx->d_padoff, &ctx->d_lsmall, &ctx->d_lmid, &ctx->d_llarge };
+                       &ctx->d_hits, &ctx->d_epairs, &ctx->d_ctl, &ctx->d_aux, &ctx->d_grouped, &ctx->d_lscratch, &ctx->d_rays, &ctx->d_resp, &ctx->d_epair_pair, &ctx->d_padded, &ctx->d_padoff, &ctx->d_lsmall, &ctx->d_lmid, &ctx->d_llarge };
     for (DevBuf* b : bufs) b->release();
     PinBuf* pins[] = { &ctx->p_cur, &ctx->p_prev, &ctx->p_mesh, &ctx->p_entity, &ctx->p_cb, &ctx->p_ctl, &ctx->p_epairs, &ctx->p_hits, &ctx->p_pairs, &ctx->p_combos };
     for (PinBuf* b : pins) b->release();
@@ -616,6 +616,19 @@ extern "C" int imrcd_test_tri_tri(imrcd_ctx* ctx, uint64_t n, const float* tris_
                                   k_test_tri<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(n, (const float*)i[0], (const float*)i[1], (const float*)i[2],
                                                                                                    (uint8_t*)o[0], (float*)o[1]);
                               });
+}
+extern "C" int imrcd_test_ray_tree(imrcd_ctx* ctx, uint32_t mesh_id, uint64_t n, const float* mats, const float* origins, const float* directions,
+                                   uint8_t* flags, float* out3, uint32_t* tri) {
+    CHECK_CTX(ctx);
+    if (mesh_id >= ctx->meshes.size()) { ctx->err = "bad mesh id"; return IMRCD_E_ARG; }
+    if (!n) return IMRCD_OK;
+    int inner = IMRCD_OK;
+    int rc = with_device_arrays(ctx, { {mats, 64 * n}, {origins, 12 * n}, {directions, 12 * n} }, { {flags, n}, {out3, 12 * n}, {tri, 4 * n} },
+                                [&](std::vector<void*>& i, std::vector<void*>& o) {
+                                    inner = imr_test_ray_tree_device(ctx, mesh_id, n, (const float*)i[0], (const float*)i[1], (const float*)i[2],
+                                                                     (uint8_t*)o[0], (float*)o[1], (uint32_t*)o[2]);
+                                });
+    return inner != IMRCD_OK ? inner : rc;
 }
 extern "C" int imrcd_test_pair_matrix(imrcd_ctx* ctx, uint64_t n, const float* a, const float* b, float* out) {
     CHECK_CTX(ctx);

@@ -20,19 +20,6 @@ __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned lon
 __device__ __forceinline__ long long ld_volatile_s64(const long long* p) { return *((const volatile long long*)p); }
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 
-__device__ __forceinline__ Box unpack_box(const float4& q0, const float4& q1, const float4& q2) {
-    Box b;
-    b.c = mk3(q0.x, q0.y, q0.z); b.u = mk3(q0.w, q1.x, q1.y); b.v = mk3(q1.z, q1.w, q2.x); b.w = mk3(q2.y, q2.z, q2.w);
-    return b;
-}
-__device__ __forceinline__ Rel rel_from_mat(const float* m) {   // rows of a column-major mat4
-    Rel r;
-    r.r0 = make_float4(m[0], m[4], m[8], m[12]);
-    r.r1 = make_float4(m[1], m[5], m[9], m[13]);
-    r.r2 = make_float4(m[2], m[6], m[10], m[14]);
-    return r;
-}
-
 // ------------------------------------------------------------------------------------------
 // broad phase
 // ------------------------------------------------------------------------------------------
@@ -181,16 +168,6 @@ k_sweep(uint32_t n, const SweepRec* __restrict__ sorted, const SweepRec* __restr
 // ------------------------------------------------------------------------------------------
 // pair setup
 // ------------------------------------------------------------------------------------------
-// Per broad-phase pair accumulators, 64 B.  sum_* / rays_* are the ray origins of CreateUncollideRays.cpp:131-178 summed per side
-// (first's model space), in FP64 so that the order of the atomic adds does not show in the FP32 result.
-struct __align__(16) PairAcc { uint32_t n_hits, flags, rays_a, rays_b, cursor, off, pad0, pad1; double sum_a[3], sum_b[3]; };   // 80 B
-
-// Side record of one hit for the contact reduction (the 40-B imrcd_tri_hit keeps source, target and weight), 12 B:
-// arena indices of the two triangles and flags = bitsA | bitsB << 3 | i << 6 | j << 8, where bitsX has bit k set iff vertex k of
-// that triangle is NOT outside the other triangle's plane (CreateUncollideRays.cpp:102-112) and (i, j) are the positions of the
-// triangles inside their leaves (so tri - i / tri - j name the leaf, i.e. the combo the hit came from).
-struct HitAux { uint32_t triA, triB, flags; };
-
 // Plane.cpp:5-21 through TrianglePosition::GetTrianglePlane: normal = normalize(cross(p1-p0, p2-p0)), d = -dot(p0, normal),
 // then the Plane ctor divides both by length(normal).
 struct PlaneN { V3 n; float d; };
@@ -213,9 +190,9 @@ __global__ void k_queue_init(FrameCtl* ctl, unsigned long long cap_pairs, unsign
 // One thread per pair: rel = glm::inverse(first.M) * second.M (OBBtreesCollision.cpp:15), the bases of the
 // two meshes, the pair's accumulators, and the root work item (root_obb vs root_obb, OBBtree.cpp:396-411).
 __global__ void k_pair_setup(const FrameCtl* ctl, unsigned long long cap_pairs, const uint2* __restrict__ pairs,
-                             const float* __restrict__ cur, const float* __restrict__ inv, const uint32_t* __restrict__ mesh_id,
-                             const MeshDev* __restrict__ meshes, PairRec* __restrict__ pairrec, PairAcc* __restrict__ acc,
-                             WorkItem* __restrict__ queue, unsigned long long cap_queue) {
+                             const float* __restrict__ cur, const float* __restrict__ prev /* or NULL: nothing moved */, const float* __restrict__ inv,
+                             const uint32_t* __restrict__ mesh_id, const MeshDev* __restrict__ meshes, PairRec* __restrict__ pairrec,
+                             PairAcc* __restrict__ acc, WorkItem* __restrict__ queue, unsigned long long cap_queue) {
     unsigned long long n = ctl->n_pairs < cap_pairs ? ctl->n_pairs : cap_pairs;
     for (unsigned long long p = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; p < n; p += (unsigned long long)gridDim.x * blockDim.x) {
         uint2 pr = pairs[p];
@@ -235,7 +212,15 @@ __global__ void k_pair_setup(const FrameCtl* ctl, unsigned long long cap_pairs, 
         o.r2 = make_float4(r[2], r[6], r[10], r[14]);
         o.recA = ma.rec_base; o.recB = mb.rec_base; o.triA = ma.tri_base; o.triB = mb.tri_base;
         pairrec[p] = o;
-        PairAcc z; z.n_hits = 0; z.flags = 0; z.rays_a = z.rays_b = 0; z.cursor = z.off = z.pad0 = z.pad1 = 0; z.sum_a[0] = z.sum_a[1] = z.sum_a[2] = 0.0; z.sum_b[0] = z.sum_b[1] = z.sum_b[2] = 0.0;
+        PairAcc z; memset(&z, 0, sizeof(z));
+        if (prev) {                                     // either matrix changed since the last frame (glm mat4 !=, CollisionDetection.cpp:80-81)
+            bool moved = false;
+            const float* cx = cur + 16 * (size_t)pr.x; const float* px = prev + 16 * (size_t)pr.x;
+            const float* py = prev + 16 * (size_t)pr.y;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) moved |= (cx[k] != px[k]) | (b[k] != py[k]);
+            if (moved) z.flags = PAIR_MOVED;
+        }
         acc[p] = z;
         if (p < cap_queue) queue[p] = make_uint4((uint32_t)p, 0u, 0u, 1u);
     }
@@ -651,18 +636,11 @@ k_tritri(FrameCtl* ctl, const Combo* __restrict__ combos, unsigned long long cap
 // pairs with their contact points (CreateUncollideRays.cpp:185-198, CollisionDetection.cpp:60-78)
 // ------------------------------------------------------------------------------------------
 // The hits of a frame come out in no particular order; the reduction of CreateUncollideRays.cpp:117-178 is per entity pair.
-// So: (1) k_hit_layout gives every pair with hits a slice of the scratch arrays (power-of-two sized, offsets by one scan) and
-// puts it on the list of small or large pairs; (2) k_group_hits drops each hit index into its pair's slice; (3) one warp
-// 128-thread block (small pairs) or one 512-thread block (large pairs) per pair sorts the slice and walks it:
-//     sort by (first's triangle, second's triangle)  ->  runs of equal first's triangle are its TriangleCandidateRays
-//     merged over combos (a run of equal second's LEAF inside it is one combo: dropped when its weight is 0, :117-121);
-//     bits != 0: every still-flagged vertex is a ray candidate (deduplicated by vertex id with a second sort = the
-//     `emplaced` set, :139-141); bits == 0: one ray at the weighted average point (:34-37, :160-163).
-//   The same again with the roles swapped for the second entity, whose triangles live in first's space (:84, :134).
-// Everything a pair needs sits in its own slice (L1-resident for the typical 200-hit pair); no global atomics, and the
-// result does not depend on the order in which the hits were produced.
-// three size classes: S (<= 256 hits: 64 threads, everything in shared memory), M (<= 1024 hits: 256 threads, shared memory),
-// L (more: 512 threads, scratch slices in global memory)
+// So: (1) k_hit_layout gives every pair with hits a slice of the grouping array (power-of-two sized, offsets by one scan) and
+// k_hit_lists puts it on the list of its size class; (2) k_group_hits drops each hit index into its pair's slice; (3) one block
+// per pair reduces the slice (k_pair_contacts_hash below).  Nothing depends on the order in which the hits were produced.
+// three size classes: S (<= 256 hits: 128 threads), M (<= 1024 hits: 512 threads), both with their tables in shared memory, and
+// L (more: 512 threads, tables in a bump-allocated global scratch)
 #define PC_S_MAX 256u
 #define PC_M_MAX 1024u
 
@@ -715,162 +693,21 @@ __global__ void k_group_hits(const FrameCtl* ctl, unsigned long long cap_hits, c
     }
 }
 
-template <int T> __device__ __forceinline__ void pc_sync() { if (T == 32) __syncwarp(); else __syncthreads(); }
-
-// in-place bitonic sort of m (power of two) 64-bit keys by T cooperating threads
-template <int T>
-__device__ __forceinline__ void pc_sort(unsigned long long* k, uint32_t m, uint32_t tid) {
-    for (uint32_t size = 2; size <= m; size <<= 1) {
-        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
-            for (uint32_t t = tid; t < (m >> 1); t += T) {
-                const uint32_t lo = 2u * t - (t & (stride - 1u)), hi = lo + stride;
-                const bool up = ((lo & size) == 0u);
-                const unsigned long long a = k[lo], b = k[hi];
-                if ((a > b) == up) { k[lo] = b; k[hi] = a; }
-            }
-            pc_sync<T>();
-        }
-    }
-}
-
 struct SideSum { double x, y, z; uint32_t rays; };
 
-// open-addressing vertex set in shared memory: entry = vid << 32 | smallest reference to a (sorted position, corner) that has it
-template <uint32_t VSET>
-__device__ __forceinline__ void vset_insert(unsigned long long* vset, unsigned long long ent) {
-    const uint32_t vid = (uint32_t)(ent >> 32);
-    uint32_t slot = (vid * 2654435761u) & (VSET - 1u);
-    for (;;) {
-        const unsigned long long old = atomicCAS(&vset[slot], ~0ull, ent);
-        if (old == ~0ull) return;
-        if ((uint32_t)(old >> 32) == vid) { atomicMin(&vset[slot], ent); return; }
-        slot = (slot + 1u) & (VSET - 1u);
-    }
-}
-
-// One side of one pair.  side 0: runs of first's triangle, combos = second's leaves;  side 1: the mirror image.
-// SMEM: key[] / hit_at[] / vset[] live in shared memory and ray vertices go straight into the set; otherwise key[] (m slots) and
-// vkey[] (8m slots: [0,4m) vertex list, [4m,5m) hit index per sorted position) are the pair's slices of the global scratch.
-template <int T, bool SMEM, uint32_t VSET>
-__device__ __forceinline__ SideSum pc_side(uint32_t side, uint32_t n, uint32_t m, const uint32_t* __restrict__ grp, unsigned long long* key, unsigned long long* vkey,
-                                           uint32_t* hit_at32, uint32_t* d_fl, float* d_w, float* d_cx, float* d_cy, float* d_cz,
-                                           uint32_t* s_count, unsigned long long* vset,
-                                           const imrcd_tri_hit* __restrict__ hits, const HitAux* __restrict__ aux,
-                                           const TriRec* __restrict__ tris, const uint32_t* __restrict__ tri_vid, const Rel& rel, uint32_t tid) {
-    // ---- sort the hits by (own triangle, other triangle) ----
-    // two hits of a pair never share (triA, triB): a leaf pair is visited once and tests each (i, j) once
-    for (uint32_t k = tid; k < m; k += T) {
-        unsigned long long v = ~0ull;
-        if (k < n) { const HitAux x = aux[grp[k]]; v = side ? (((unsigned long long)x.triB << 32) | x.triA) : (((unsigned long long)x.triA << 32) | x.triB); }
-        key[k] = v;
-    }
-    if (tid == 0) *s_count = 0u;
-    if (SMEM) for (uint32_t k = tid; k < VSET; k += T) vset[k] = ~0ull;
-    pc_sync<T>();
-    pc_sort<T>(key, m, tid);
-    // every hit finds its sorted position by binary search and leaves its index there
-    for (uint32_t k = tid; k < n; k += T) {
-        const uint32_t h = grp[k];
-        const HitAux x = aux[h];
-        const unsigned long long v = side ? (((unsigned long long)x.triB << 32) | x.triA) : (((unsigned long long)x.triA << 32) | x.triB);
-        uint32_t lo = 0, hi = n;
-        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (key[mid] < v) lo = mid + 1; else hi = mid; }
-        if (SMEM) hit_at32[lo] = h; else vkey[4u * m + lo] = (unsigned long long)h;
-    }
-    pc_sync<T>();
-    // what the run walk needs of every hit, in sorted order (one parallel gather instead of dependent loads inside the runs)
-    for (uint32_t e = tid; e < n; e += T) {
-        const uint32_t h = SMEM ? hit_at32[e] : (uint32_t)vkey[4u * m + e];
-        const HitAux x = aux[h];
-        const imrcd_tri_hit hh = hits[h];
-        const V3 sum = add3(mk3(hh.source[0], hh.source[1], hh.source[2]), mk3(hh.target[0], hh.target[1], hh.target[2]));
-        d_fl[e] = x.flags; d_w[e] = hh.weight;
-        d_cx[e] = (hh.weight * sum.x) / 2.f; d_cy[e] = (hh.weight * sum.y) / 2.f; d_cz[e] = (hh.weight * sum.z) / 2.f;       // :94-100
-    }
-    pc_sync<T>();
-    SideSum acc; acc.x = acc.y = acc.z = 0.0; acc.rays = 0u;
-    // ---- runs of equal own triangle: merge the combos' candidates (TriangleCandidateRays, :13-58,117-127) ----
-    for (uint32_t k = tid; k < n; k += T) {
-        const uint32_t tri = (uint32_t)(key[k] >> 32);
-        if (k > 0 && (uint32_t)(key[k - 1] >> 32) == tri) continue;              // not the head of a run
-        uint32_t bits = 7u; V3 wavg = mk3(0.f, 0.f, 0.f); float weight = 0.f; bool present = false;
-        uint32_t e = k;
-        while (e < n && (uint32_t)(key[e] >> 32) == tri) {
-            // one combo: hits whose other triangle lies in the same leaf
-            uint32_t cbits = 7u; V3 cw = mk3(0.f, 0.f, 0.f); float cwt = 0.f;
-            uint32_t leaf = 0xffffffffu;
-            while (e < n && (uint32_t)(key[e] >> 32) == tri) {
-                const uint32_t fl = d_fl[e];
-                const uint32_t other_pos = side ? ((fl >> 6) & 3u) : ((fl >> 8) & 3u);
-                const uint32_t this_leaf = (uint32_t)key[e] - other_pos;
-                if (leaf != 0xffffffffu && this_leaf != leaf) break;
-                leaf = this_leaf;
-                cw = add3(cw, mk3(d_cx[e], d_cy[e], d_cz[e]));
-                cwt += d_w[e];
-                cbits &= side ? ((fl >> 3) & 7u) : (fl & 7u);
-                ++e;
-            }
-            if (!(cwt == 0.f)) {                                                  // IsNull() (:22-25), MergeWithMap (:39-49)
-                if (!present) { present = true; bits = cbits; wavg = cw; weight = cwt; }
-                else { bits &= cbits; wavg = add3(wavg, cw); weight += cwt; }
-            }
-        }
-        if (!present) continue;
-        if (bits == 0u) {                                                         // ray at the weighted average point (:34-37,160-163)
-            acc.x += (double)(wavg.x / weight); acc.y += (double)(wavg.y / weight); acc.z += (double)(wavg.z / weight); acc.rays += 1u;
-        } else {
-#pragma unroll
-            for (uint32_t pi = 0; pi < 3; ++pi) {
-                if (!((bits >> pi) & 1u)) continue;
-                const unsigned long long ent = ((unsigned long long)tri_vid[3ull * tri + pi] << 32) | (unsigned long long)(k * 4u + pi);
-                if (SMEM) vset_insert<VSET>(vset, ent);
-                else vkey[atomicAdd(s_count, 1u)] = ent;
-            }
-        }
-    }
-    pc_sync<T>();
-    // ---- vertex rays: one per distinct vertex id (the `emplaced` set, :139-141) ----
-    if (SMEM) {
-        for (uint32_t k = tid; k < VSET; k += T) {
-            const unsigned long long ent = vset[k];
-            if (ent == ~0ull) continue;
-            const uint32_t ref = (uint32_t)ent, pi = ref & 3u;
-            const float4 q = __ldg(reinterpret_cast<const float4*>(tris + (uint32_t)(key[ref >> 2] >> 32)) + pi);
-            V3 pos = mk3(q.x, q.y, q.z);
-            if (side) pos = rel_mul(rel, pos, 1.f);                                // second's triangles live in first's space (:84,:134)
-            acc.x += (double)pos.x; acc.y += (double)pos.y; acc.z += (double)pos.z; acc.rays += 1u;
-        }
-    } else {
-        const uint32_t nv = *s_count;
-        if (nv) {
-            uint32_t mv = 1u; while (mv < nv) mv <<= 1;                           // nv <= 3n, so mv <= 4m: the vertex list owns vkey[0 .. 4m)
-            for (uint32_t k = nv + tid; k < mv; k += T) vkey[k] = ~0ull;
-            pc_sync<T>();
-            pc_sort<T>(vkey, mv, tid);
-            for (uint32_t k = tid; k < nv; k += T) {
-                const uint32_t vid = (uint32_t)(vkey[k] >> 32);
-                if (k > 0 && (uint32_t)(vkey[k - 1] >> 32) == vid) continue;
-                const uint32_t ref = (uint32_t)vkey[k], pi = ref & 3u;
-                const float4 q = __ldg(reinterpret_cast<const float4*>(tris + (uint32_t)(key[ref >> 2] >> 32)) + pi);
-                V3 pos = mk3(q.x, q.y, q.z);
-                if (side) pos = rel_mul(rel, pos, 1.f);
-                acc.x += (double)pos.x; acc.y += (double)pos.y; acc.z += (double)pos.z; acc.rays += 1u;
-            }
-        }
-    }
-    pc_sync<T>();
-    return acc;
-}
-
-// ---- size classes S and M: one block per pair, no sort --------------------------------------------------------------------
+// ---- one block per pair, no sort -----------------------------------------------------------------------------------------
 // What a side needs of a pair's hits is a keyed reduction: per own triangle, AND of the not-outside bits and the sums of weight and
 // weight * midpoint over the hits of every combo whose weight is not 0 (TriangleCandidateRays::Merge, :51-57; IsNull, :22-25).  Weights are
 // >= 0, so a combo is dropped iff every one of its hits has weight 0: a hit with weight != 0 always contributes, and a hit with weight 0
 // contributes (its bits only) iff the same (own triangle, other LEAF) has another hit with weight != 0 - checked by a scan over the pair's
-// hits for those few.  The reduction runs in a shared-memory hash table, one thread per hit: AND and FP64 adds are order-free, so the FP32
-// result does not depend on which thread comes first.  Then one thread per table slot turns the candidate into rays (:139-166), vertex
-// rays going through the `emplaced` set (:139-141), and one thread per set entry adds its ray origin.
+// staged hits for those few.  The reduction runs in a hash table, one thread per hit: AND and FP64 adds are order-free, so the FP32
+// result does not depend on which thread comes first.  Then one thread per occupied slot turns the candidate into rays (:139-166), vertex
+// rays going through the `emplaced` set (:139-141), and one thread per ray adds its origin and - for pairs whose entities moved since the
+// last frame, the only ones the response stage looks at (CollisionDetection.cpp:80-81) - writes the ray (origin, -normal) to the frame's ray array.
+// Size classes S and M keep the tables in shared memory; class L (M_MAX == 0, > 1024 hits) takes them from a bump-allocated global scratch.
 struct PcSlot { double w, cx, cy, cz; };
+
+template <bool G, class X> __device__ __forceinline__ X pc_ld(const X* p) { return G ? __ldcg(p) : *p; }
 
 // Find or claim the slot of `tri`; `claimed` tells the caller to append the slot to the dense list of occupied slots (done
 // afterwards in converged code with one ballot, so that the later passes run over occupied slots only).
@@ -897,45 +734,66 @@ __device__ __forceinline__ uint32_t vset_insert_m(unsigned long long* vset, uint
 }
 
 // warp-aggregated append of `v` (for the lanes with `yes`) to list[*count ...]; converged code only
-__device__ __forceinline__ void pc_append(bool yes, uint32_t v, uint16_t* list, uint32_t* count, uint32_t lane) {
+template <class LT>
+__device__ __forceinline__ void pc_append(bool yes, uint32_t v, LT* list, uint32_t* count, uint32_t lane) {
     const uint32_t m = __ballot_sync(FULL_MASK, yes);
     if (m == 0u) return;
     const uint32_t leader = (uint32_t)__ffs(m) - 1u;
     uint32_t base = 0;
     if (lane == leader) base = atomicAdd(count, (uint32_t)__popc(m));
     base = __shfl_sync(FULL_MASK, base, leader);
-    if (yes) list[base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)v;
+    if (yes) list[base + __popc(m & ((1u << lane) - 1u))] = (LT)v;
 }
+
+#define PC_BYTES_PER_HIT (2 * (sizeof(PcSlot) + 8) + 4 * 8 + 12 + 5 * sizeof(LT))      // tables + staging + lists, per (padded) hit
 
 template <int T, uint32_t M_MAX>
 __global__ void __launch_bounds__(T)
-k_pair_contacts_hash(const FrameCtl* ctl, const uint32_t* __restrict__ list, int cls, PairAcc* acc, const uint32_t* __restrict__ grouped,
+k_pair_contacts_hash(FrameCtl* ctl, const uint32_t* __restrict__ list, int cls, PairAcc* acc, const uint32_t* __restrict__ grouped,
                      const imrcd_tri_hit* __restrict__ hits, const HitAux* __restrict__ aux, const PairRec* __restrict__ pairrec,
-                     const TriRec* __restrict__ tris, const uint32_t* __restrict__ tri_vid) {
+                     const TriRec* __restrict__ tris, const uint32_t* __restrict__ tri_vid, const float* __restrict__ tri_nrm,
+                     RayRec* __restrict__ rays, unsigned long long cap_rays, unsigned char* scratch, unsigned long long cap_scratch) {
+    constexpr bool G = M_MAX == 0;                     // tables in global memory
+    typedef typename std::conditional<G, uint32_t, uint16_t>::type LT;
     extern __shared__ __align__(16) unsigned char pc_smem[];
-    PcSlot* s_sum = reinterpret_cast<PcSlot*>(pc_smem);                                          // 2 M_MAX
-    unsigned long long* s_vset = reinterpret_cast<unsigned long long*>(s_sum + 2u * M_MAX);      // 4 M_MAX
-    uint32_t* s_key = reinterpret_cast<uint32_t*>(s_vset + 4u * M_MAX);                          // 2 M_MAX
-    uint32_t* s_bits = s_key + 2u * M_MAX;                                                       // 2 M_MAX
-    uint32_t* s_ta = s_bits + 2u * M_MAX;                                                        // M_MAX: the pair's hits, staged once for both sides
-    uint32_t* s_tb = s_ta + M_MAX;                                                               // M_MAX
-    uint32_t* s_fl = s_tb + M_MAX;                                                               // M_MAX: HitAux.flags | (weight != 0) << 31
-    uint16_t* s_cand = reinterpret_cast<uint16_t*>(s_fl + M_MAX);                                // M_MAX: claimed candidate slots
-    uint16_t* s_vert = s_cand + M_MAX;                                                           // 3 M_MAX: claimed vertex slots
     __shared__ double s_red[3][T / 32];
     __shared__ uint32_t s_redc[T / 32];
-    __shared__ uint32_t s_ncand, s_nvert;
+    __shared__ uint32_t s_ncand, s_nvert, s_navg, s_raybase;
+    __shared__ unsigned long long s_scratch;
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
     if (ctl->overflow & (OVF_PAIRS | OVF_QUEUE | OVF_COMBOS | OVF_HITS)) return;      // the frame is re-run with larger buffers
     const unsigned long long n_list = ctl->n_class[cls * 16];
     for (unsigned long long b = blockIdx.x; b < n_list; b += gridDim.x) {
         const uint32_t p = list[b];
         const uint32_t n = acc[p].n_hits;
+        const bool keep_rays = (acc[p].flags & PAIR_MOVED) != 0u;
         uint32_t m = 16u; while (m < n) m <<= 1;                     // tables sized by the pair: 2m candidate slots (<= n distinct triangles), 4m vertex slots (<= 3n)
         const uint32_t slots = 2u * m, vslots = 4u * m;
+        const uint32_t cap = G ? m : M_MAX;                          // array stride
+        unsigned char* base;
+        if (!G) base = pc_smem;
+        else {
+            if (tid == 0) s_scratch = atomicAdd(&ctl->scratch_used, (unsigned long long)m * PC_BYTES_PER_HIT);
+            __syncthreads();
+            const unsigned long long at = s_scratch;
+            __syncthreads();
+            if (at + (unsigned long long)m * PC_BYTES_PER_HIT > cap_scratch) { if (tid == 0) atomicOr(&ctl->overflow, (unsigned)OVF_SCRATCH); continue; }
+            base = scratch + at;
+        }
+        PcSlot* s_sum = reinterpret_cast<PcSlot*>(base);                                             // 2 cap
+        unsigned long long* s_vset = reinterpret_cast<unsigned long long*>(s_sum + 2u * cap);        // 4 cap
+        uint32_t* s_key = reinterpret_cast<uint32_t*>(s_vset + 4u * cap);                            // 2 cap
+        uint32_t* s_bits = s_key + 2u * cap;                                                         // 2 cap
+        uint32_t* s_ta = s_bits + 2u * cap;                                                          // cap: the pair's hits, staged once for both sides
+        uint32_t* s_tb = s_ta + cap;                                                                 // cap
+        uint32_t* s_fl = s_tb + cap;                                                                 // cap: HitAux.flags | (weight != 0) << 31
+        LT* s_cand = reinterpret_cast<LT*>(s_fl + cap);                                              // cap: claimed candidate slots
+        LT* s_vert = s_cand + cap;                                                                   // 3 cap: claimed vertex slots
+        LT* s_avgl = s_vert + 3u * cap;                                                              // cap: candidates that fall back to the average point
         const uint32_t* grp = grouped + acc[p].off;
         const float4* pp = reinterpret_cast<const float4*>(pairrec + p);
         Rel rel; rel.r0 = __ldg(pp); rel.r1 = __ldg(pp + 1); rel.r2 = __ldg(pp + 2);
+        const M3 nmat = adjoint_transpose3(rel);                                                     // CreateUncollideRays.cpp:65
         for (uint32_t k = tid; k < n; k += T) {
             const uint32_t h = grp[k];
             const HitAux x = aux[h];
@@ -944,7 +802,8 @@ k_pair_contacts_hash(const FrameCtl* ctl, const uint32_t* __restrict__ list, int
         for (uint32_t side = 0; side < 2; ++side) {
             for (uint32_t k = tid; k < slots; k += T) { s_key[k] = 0xffffffffu; s_bits[k] = 7u; s_sum[k].w = 0.0; s_sum[k].cx = 0.0; s_sum[k].cy = 0.0; s_sum[k].cz = 0.0; }
             for (uint32_t k = tid; k < vslots; k += T) s_vset[k] = ~0ull;
-            if (tid == 0) { s_ncand = 0u; s_nvert = 0u; }
+            if (tid == 0) { s_ncand = 0u; s_nvert = 0u; s_navg = 0u; s_raybase = 0u; }
+            if (G) __threadfence();
             __syncthreads();
             // ---- one thread per hit: merge into the own triangle's candidate ----
             for (uint32_t k0 = 0; k0 < n; k0 += T) {
@@ -953,15 +812,15 @@ k_pair_contacts_hash(const FrameCtl* ctl, const uint32_t* __restrict__ list, int
                 double w = 0.0, cx = 0.0, cy = 0.0, cz = 0.0;
                 bool claimed = false;
                 if (k < n) {
-                    const uint32_t fl = s_fl[k];
-                    const uint32_t own = side ? s_tb[k] : s_ta[k];
+                    const uint32_t fl = pc_ld<G>(s_fl + k);
+                    const uint32_t own = side ? pc_ld<G>(s_tb + k) : pc_ld<G>(s_ta + k);
                     bool contributes = (fl >> 31) != 0u;
                     if (!contributes) {                                                  // rare: is the combo's weight for this triangle 0? (:117-127)
-                        const uint32_t leaf = side ? s_ta[k] - ((fl >> 6) & 3u) : s_tb[k] - ((fl >> 8) & 3u);
+                        const uint32_t leaf = side ? pc_ld<G>(s_ta + k) - ((fl >> 6) & 3u) : pc_ld<G>(s_tb + k) - ((fl >> 8) & 3u);
                         for (uint32_t q = 0; q < n && !contributes; ++q) {
-                            const uint32_t fl2 = s_fl[q];
-                            const uint32_t own2 = side ? s_tb[q] : s_ta[q];
-                            const uint32_t leaf2 = side ? s_ta[q] - ((fl2 >> 6) & 3u) : s_tb[q] - ((fl2 >> 8) & 3u);
+                            const uint32_t fl2 = pc_ld<G>(s_fl + q);
+                            const uint32_t own2 = side ? pc_ld<G>(s_tb + q) : pc_ld<G>(s_ta + q);
+                            const uint32_t leaf2 = side ? pc_ld<G>(s_ta + q) - ((fl2 >> 6) & 3u) : pc_ld<G>(s_tb + q) - ((fl2 >> 8) & 3u);
                             contributes = own2 == own && leaf2 == leaf && (fl2 >> 31) != 0u;
                         }
                     }
@@ -974,7 +833,7 @@ k_pair_contacts_hash(const FrameCtl* ctl, const uint32_t* __restrict__ list, int
                         cx = (double)((hh.weight * sum.x) / 2.f); cy = (double)((hh.weight * sum.y) / 2.f); cz = (double)((hh.weight * sum.z) / 2.f);   // :94-100
                     }
                 }
-                pc_append(claimed, slot, s_cand, &s_ncand, lane);
+                pc_append<LT>(claimed, slot, s_cand, &s_ncand, lane);
                 // Hits come out of the narrow phase combo by combo, so one triangle's hits mostly sit in consecutive lanes (and a large triangle
                 // collects many): add up each run of equal slots inside the warp first (segmented scan), then one update per run.
                 const uint32_t prev = __shfl_up_sync(FULL_MASK, slot, 1);
@@ -993,41 +852,78 @@ k_pair_contacts_hash(const FrameCtl* ctl, const uint32_t* __restrict__ list, int
                     atomicAdd(&s_sum[slot].w, w); atomicAdd(&s_sum[slot].cx, cx); atomicAdd(&s_sum[slot].cy, cy); atomicAdd(&s_sum[slot].cz, cz);
                 }
             }
+            if (G) __threadfence();
             __syncthreads();
-            // ---- one thread per candidate: its rays (:139-166) ----
-            SideSum r; r.x = r.y = r.z = 0.0; r.rays = 0u;
+            // ---- one thread per candidate: vertex rays into the `emplaced` set, average-point rays onto their list (:139-166) ----
             const uint32_t n_cand = s_ncand;
             for (uint32_t c0 = 0; c0 < n_cand; c0 += T) {
                 const uint32_t c = c0 + tid;
                 uint32_t q0 = 0xffffffffu, q1 = 0xffffffffu, q2 = 0xffffffffu;           // vertex slots claimed by this lane
+                uint32_t fallback = 0xffffffffu;
                 if (c < n_cand) {
-                    const uint32_t k = s_cand[c];
-                    const uint32_t tri = s_key[k], bits = s_bits[k];
-                    if (bits == 0u) {                                                    // ray at the weighted average point (:34-37,160-163)
-                        // the quotient is taken in FP64 and rounded once: rounding the two sums first would turn the last-bit noise of the
-                        // order-free FP64 sums into FP32 differences whenever a sum sits on a rounding tie (two equal-exponent addends do)
-                        const double w = s_sum[k].w;
-                        r.x += (double)(float)(s_sum[k].cx / w); r.y += (double)(float)(s_sum[k].cy / w); r.z += (double)(float)(s_sum[k].cz / w); r.rays += 1u;
-                    } else {
+                    const uint32_t k = pc_ld<G>(s_cand + c);
+                    const uint32_t tri = pc_ld<G>(s_key + k), bits = pc_ld<G>(s_bits + k);
+                    if (bits == 0u) fallback = k;                                        // ShouldFallbackToAvgPoint (:27-30)
+                    else {
                         const uint32_t v0 = tri_vid[3ull * tri], v1 = tri_vid[3ull * tri + 1], v2 = tri_vid[3ull * tri + 2];
                         if (bits & 1u) q0 = vset_insert_m(s_vset, vslots - 1u, ((unsigned long long)v0 << 32) | (unsigned long long)(tri * 4u));
                         if (bits & 2u) q1 = vset_insert_m(s_vset, vslots - 1u, ((unsigned long long)v1 << 32) | (unsigned long long)(tri * 4u + 1u));
                         if (bits & 4u) q2 = vset_insert_m(s_vset, vslots - 1u, ((unsigned long long)v2 << 32) | (unsigned long long)(tri * 4u + 2u));
                     }
                 }
-                pc_append(q0 != 0xffffffffu, q0, s_vert, &s_nvert, lane);
-                pc_append(q1 != 0xffffffffu, q1, s_vert, &s_nvert, lane);
-                pc_append(q2 != 0xffffffffu, q2, s_vert, &s_nvert, lane);
+                pc_append<LT>(q0 != 0xffffffffu, q0, s_vert, &s_nvert, lane);
+                pc_append<LT>(q1 != 0xffffffffu, q1, s_vert, &s_nvert, lane);
+                pc_append<LT>(q2 != 0xffffffffu, q2, s_vert, &s_nvert, lane);
+                pc_append<LT>(fallback != 0xffffffffu, fallback, s_avgl, &s_navg, lane);
             }
+            if (G) __threadfence();
             __syncthreads();
-            // ---- vertex rays: one per distinct vertex id (the `emplaced` set, :139-141) ----
-            const uint32_t n_vert = s_nvert;
+            const uint32_t n_vert = s_nvert, n_avg = s_navg;
+            bool emit = keep_rays;
+            if (keep_rays) {                                                             // the pair's slice of the frame's ray array
+                if (tid == 0) s_raybase = (uint32_t)atomicAdd(&ctl->n_rays_kept, (unsigned long long)(n_vert + n_avg));
+                __syncthreads();
+                if ((unsigned long long)s_raybase + n_vert + n_avg > cap_rays) { emit = false; if (tid == 0) atomicOr(&ctl->overflow, (unsigned)OVF_RAYS); }
+            }
+            const uint32_t ray_base = s_raybase;
+            SideSum r; r.x = r.y = r.z = 0.0; r.rays = 0u;
+            // ---- rays at the weighted average point (:34-37,157-166) ----
+            for (uint32_t c = tid; c < n_avg; c += T) {
+                const uint32_t k = pc_ld<G>(s_avgl + c);
+                // the quotient is taken in FP64 and rounded once: rounding the two sums first would turn the last-bit noise of the
+                // order-free FP64 sums into FP32 differences whenever a sum sits on a rounding tie (two equal-exponent addends do)
+                const double w = pc_ld<G>(&s_sum[k].w);
+                const V3 pos = mk3((float)(pc_ld<G>(&s_sum[k].cx) / w), (float)(pc_ld<G>(&s_sum[k].cy) / w), (float)(pc_ld<G>(&s_sum[k].cz) / w));
+                r.x += (double)pos.x; r.y += (double)pos.y; r.z += (double)pos.z; r.rays += 1u;
+                if (emit) {
+                    const uint32_t tri = pc_ld<G>(s_key + k);
+                    const float4* tp = reinterpret_cast<const float4*>(tris + tri);
+                    const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
+                    V3 p0 = mk3(t0.x, t0.y, t0.z), p1 = mk3(t1.x, t1.y, t1.z), p2 = mk3(t2.x, t2.y, t2.z);
+                    if (side) { p0 = rel_mul(rel, p0, 1.f); p1 = rel_mul(rel, p1, 1.f); p2 = rel_mul(rel, p2, 1.f); }     // :134
+                    float bx, by;
+                    tri_barycentric(p0, p1, p2, pos, bx, by);                            // :160
+                    const float* nn = tri_nrm + 9ull * tri;
+                    V3 nrm = tri_interp_normal(mk3(nn[0], nn[1], nn[2]), mk3(nn[3], nn[4], nn[5]), mk3(nn[6], nn[7], nn[8]), bx, by);
+                    nrm = normalize3(side ? m3_mul(nmat, nrm) : nrm);                    // :163-164, Triangle.cpp:197-212
+                    RayRec o; o.o = make_float4(pos.x, pos.y, pos.z, __uint_as_float(p)); o.d = make_float4(-nrm.x, -nrm.y, -nrm.z, __uint_as_float(side));
+                    rays[ray_base + c] = o;
+                }
+            }
+            // ---- vertex rays: one per distinct vertex id (the `emplaced` set, :139-155) ----
             for (uint32_t c = tid; c < n_vert; c += T) {
-                const uint32_t ref = (uint32_t)s_vset[s_vert[c]];
+                const uint32_t ref = (uint32_t)pc_ld<G>(s_vset + pc_ld<G>(s_vert + c));
                 const float4 q = __ldg(reinterpret_cast<const float4*>(tris + (ref >> 2)) + (ref & 3u));
                 V3 pos = mk3(q.x, q.y, q.z);
                 if (side) pos = rel_mul(rel, pos, 1.f);                                  // second's triangles live in first's space (:84,:134)
                 r.x += (double)pos.x; r.y += (double)pos.y; r.z += (double)pos.z; r.rays += 1u;
+                if (emit) {
+                    const float* nn = tri_nrm + 9ull * (ref >> 2) + 3u * (ref & 3u);
+                    V3 nrm = mk3(nn[0], nn[1], nn[2]);
+                    nrm = normalize3(side ? m3_mul(nmat, nrm) : nrm);                    // :150-151, Triangle.cpp:180-195
+                    RayRec o; o.o = make_float4(pos.x, pos.y, pos.z, __uint_as_float(p)); o.d = make_float4(-nrm.x, -nrm.y, -nrm.z, __uint_as_float(side));
+                    rays[ray_base + n_avg + c] = o;
+                }
             }
             for (int o = 16; o > 0; o >>= 1) {
                 r.x += __shfl_down_sync(FULL_MASK, r.x, o); r.y += __shfl_down_sync(FULL_MASK, r.y, o); r.z += __shfl_down_sync(FULL_MASK, r.z, o);
@@ -1040,67 +936,17 @@ k_pair_contacts_hash(const FrameCtl* ctl, const uint32_t* __restrict__ list, int
                 PairAcc* pa = acc + p;
                 double* sum = side ? pa->sum_b : pa->sum_a;
                 sum[0] = r.x; sum[1] = r.y; sum[2] = r.z;
-                if (side) pa->rays_b = r.rays; else pa->rays_a = r.rays;
+                if (side) { pa->rays_b = r.rays; pa->ray_off_b = ray_base; } else { pa->rays_a = r.rays; pa->ray_off_a = ray_base; }
+                if (!emit) pa->flags &= ~(uint32_t)PAIR_MOVED;                           // no rays kept: the response stage skips the pair
             }
             __syncthreads();
         }
     }
 }
 
-template <int T, uint32_t M_MAX, uint32_t VSET>        // M_MAX == 0: scratch in global memory
-__global__ void __launch_bounds__(T)
-k_pair_contacts(const FrameCtl* ctl, const uint32_t* __restrict__ list, int cls, PairAcc* acc, const uint32_t* __restrict__ grouped,
-                unsigned long long* scratch_key, unsigned long long* scratch_vkey, const imrcd_tri_hit* __restrict__ hits,
-                const HitAux* __restrict__ aux, const PairRec* __restrict__ pairrec, const TriRec* __restrict__ tris, const uint32_t* __restrict__ tri_vid) {
-    constexpr bool SMEM = M_MAX != 0;
-    extern __shared__ __align__(16) unsigned char pc_smem[];
-    unsigned long long* s_key = reinterpret_cast<unsigned long long*>(pc_smem);                  // M_MAX
-    unsigned long long* s_vset = s_key + M_MAX;                                                  // VSET
-    uint32_t* s_hit = reinterpret_cast<uint32_t*>(s_vset + (SMEM ? VSET : 0));                   // M_MAX, then 5 x M_MAX words of per-hit data
-    __shared__ uint32_t s_count;
-    __shared__ double s_red[3][T / 32];
-    __shared__ uint32_t s_redc[T / 32];
-    const uint32_t tid = threadIdx.x;
-    if (ctl->overflow & (OVF_PAIRS | OVF_QUEUE | OVF_COMBOS | OVF_HITS)) return;      // the frame is re-run with larger buffers
-    const unsigned long long n_list = ctl->n_class[cls * 16];
-    for (unsigned long long b = blockIdx.x; b < n_list; b += gridDim.x) {
-        const uint32_t p = list[b];
-        const uint32_t n = acc[p].n_hits, off = acc[p].off;
-        uint32_t m = 1u; while (m < n) m <<= 1;
-        const uint32_t* grp = grouped + off;
-        unsigned long long* key = SMEM ? s_key : scratch_key + off;
-        unsigned long long* vkey = scratch_vkey + 8ull * off;         // [0,4m) vertex list, [4m,5m) hit per sorted position, [5m,8m) per-hit data
-        uint32_t* d_fl = SMEM ? s_hit + M_MAX : reinterpret_cast<uint32_t*>(vkey + 5ull * m);
-        float* d_w = reinterpret_cast<float*>(d_fl + (SMEM ? M_MAX : m));
-        float* d_cx = d_w + (SMEM ? M_MAX : m); float* d_cy = d_cx + (SMEM ? M_MAX : m); float* d_cz = d_cy + (SMEM ? M_MAX : m);
-        const float4* pp = reinterpret_cast<const float4*>(pairrec + p);
-        Rel rel; rel.r0 = __ldg(pp); rel.r1 = __ldg(pp + 1); rel.r2 = __ldg(pp + 2);
-        for (uint32_t side = 0; side < 2; ++side) {
-            SideSum r = pc_side<T, SMEM, (SMEM ? VSET : 2u)>(side, n, m, grp, key, vkey, s_hit, d_fl, d_w, d_cx, d_cy, d_cz, &s_count, s_vset, hits, aux, tris, tri_vid, rel, tid);
-            // fixed-order reduction over the threads (deterministic)
-            for (int o = 16; o > 0; o >>= 1) {
-                r.x += __shfl_down_sync(FULL_MASK, r.x, o); r.y += __shfl_down_sync(FULL_MASK, r.y, o); r.z += __shfl_down_sync(FULL_MASK, r.z, o);
-                r.rays += __shfl_down_sync(FULL_MASK, r.rays, o);
-            }
-            if (T > 32) {
-                if ((tid & 31u) == 0u) { s_red[0][tid >> 5] = r.x; s_red[1][tid >> 5] = r.y; s_red[2][tid >> 5] = r.z; s_redc[tid >> 5] = r.rays; }
-                __syncthreads();
-                if (tid == 0) { for (int w = 1; w < T / 32; ++w) { r.x += s_red[0][w]; r.y += s_red[1][w]; r.z += s_red[2][w]; r.rays += s_redc[w]; } }
-                __syncthreads();
-            }
-            if (tid == 0) {
-                PairAcc* pa = acc + p;
-                double* sum = side ? pa->sum_b : pa->sum_a;
-                sum[0] = r.x; sum[1] = r.y; sum[2] = r.z;
-                if (side) pa->rays_b = r.rays; else pa->rays_a = r.rays;
-            }
-        }
-    }
-}
-
 __global__ void k_finalize(FrameCtl* ctl, unsigned long long cap_pairs, const uint2* __restrict__ pairs, const PairAcc* __restrict__ acc,
                            const uint32_t* __restrict__ entity, const float* __restrict__ cur, const float* __restrict__ inv,
-                           imrcd_entity_pair* __restrict__ out) {
+                           imrcd_entity_pair* __restrict__ out, uint32_t* __restrict__ out_pair) {
     unsigned long long n = ctl->n_pairs < cap_pairs ? ctl->n_pairs : cap_pairs;
     for (unsigned long long p = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; p < n; p += (unsigned long long)gridDim.x * blockDim.x) {
         if (!(acc[p].flags & 1u)) continue;
@@ -1125,6 +971,7 @@ __global__ void k_finalize(FrameCtl* ctl, unsigned long long cap_pairs, const ui
         const V3 back = rel_mul(rel_from_mat(rinv), sb, 1.f);
         o.avg_second[0] = back.x; o.avg_second[1] = back.y; o.avg_second[2] = back.z;
         out[slot] = o;
+        out_pair[slot] = (uint32_t)p;
     }
 }
 
@@ -1147,6 +994,8 @@ int imr_frame_run_device(imrcd_ctx* ctx) {
     if (ctx->cap_queue == 0) ctx->cap_queue = ctx->cap_pairs + (1ull << 22);
     if (ctx->cap_combos == 0) ctx->cap_combos = 1ull << 22;
     if (ctx->cap_hits == 0) ctx->cap_hits = 1ull << 20;
+    if (ctx->cap_rays == 0) ctx->cap_rays = 1ull << 18;
+    if (ctx->cap_lscratch == 0) ctx->cap_lscratch = 16ull << 20;
 
     IMR_CUDA(ctx, ctx->d_inv.reserve(64ull * n, 0, s));
     IMR_CUDA(ctx, ctx->d_ext.reserve(24ull * n, 0, s));
@@ -1208,8 +1057,12 @@ int imr_frame_run_device(imrcd_ctx* ctx) {
         // contact reduction scratch: per-pair slices are power-of-two padded, so at most 2 x hits slots in total
         IMR_CUDA(ctx, ctx->d_aux.reserve(sizeof(HitAux) * ctx->cap_hits, 0, s));
         IMR_CUDA(ctx, ctx->d_grouped.reserve(4ull * 2 * ctx->cap_hits, 0, s));
-        IMR_CUDA(ctx, ctx->d_skey.reserve(8ull * 2 * ctx->cap_hits, 0, s));
-        IMR_CUDA(ctx, ctx->d_svkey.reserve(64ull * 2 * ctx->cap_hits, 0, s));
+        IMR_CUDA(ctx, ctx->d_lscratch.reserve(ctx->cap_lscratch, 0, s));
+        IMR_CUDA(ctx, ctx->d_epair_pair.reserve(4ull * ctx->cap_pairs, 0, s));
+        if (ctx->prev_distinct) {
+            IMR_CUDA(ctx, ctx->d_rays.reserve(sizeof(RayRec) * ctx->cap_rays, 0, s));
+            IMR_CUDA(ctx, ctx->d_resp.reserve(32ull * ctx->cap_rays, 0, s));
+        }
         IMR_CUDA(ctx, ctx->d_padded.reserve(4ull * (ctx->cap_pairs + 1), 0, s));
         IMR_CUDA(ctx, ctx->d_padoff.reserve(4ull * (ctx->cap_pairs + 1), 0, s));
         IMR_CUDA(ctx, ctx->d_lsmall.reserve(4ull * ctx->cap_pairs, 0, s));
@@ -1248,7 +1101,7 @@ int imr_frame_run_device(imrcd_ctx* ctx) {
         IMR_CUDA(ctx, cudaEventRecord(ctx->ev[1], s));
         // ---- pair setup ----
         k_queue_init<<<1, 1, 0, s>>>(ctl, ctx->cap_pairs, ctx->cap_queue);
-        k_pair_setup<<<ctx->sm_count * 8, 128, 0, s>>>(ctl, ctx->cap_pairs, ctx->d_pairs.as<uint2>(), ctx->d_cur.as<float>(), ctx->d_inv.as<float>(),
+        k_pair_setup<<<ctx->sm_count * 8, 128, 0, s>>>(ctl, ctx->cap_pairs, ctx->d_pairs.as<uint2>(), ctx->d_cur.as<float>(), ctx->prev_distinct ? ctx->d_prev.as<float>() : nullptr, ctx->d_inv.as<float>(),
                                                         ctx->d_mesh.as<uint32_t>(), ctx->d_meshes.as<MeshDev>(), ctx->d_pairrec.as<PairRec>(),
                                                         ctx->d_pairacc.as<PairAcc>(), ctx->d_queue.as<WorkItem>(), ctx->cap_queue);
         launches += 2;
@@ -1275,29 +1128,32 @@ int imr_frame_run_device(imrcd_ctx* ctx) {
                                                        ctx->d_lsmall.as<uint32_t>(), ctx->d_lmid.as<uint32_t>(), ctx->d_llarge.as<uint32_t>());
         k_group_hits<<<ctx->sm_count * 8, 256, 0, s>>>(ctl, ctx->cap_hits, ctx->d_hits.as<imrcd_tri_hit>(), ctx->d_pairacc.as<PairAcc>(), ctx->d_grouped.as<uint32_t>());
         {
-            const size_t smem_s = PC_S_MAX * (2 * (sizeof(PcSlot) + 8) + 4 * 8 + 12 + 8), smem_m = PC_M_MAX * (2 * (sizeof(PcSlot) + 8) + 4 * 8 + 12 + 8);
+            const size_t per_hit = 2 * (sizeof(PcSlot) + 8) + 4 * 8 + 12 + 5 * sizeof(uint16_t);
+            const size_t smem_s = PC_S_MAX * per_hit, smem_m = PC_M_MAX * per_hit;
             if (!ctx->pc_attr_set) {
                 IMR_CUDA(ctx, cudaFuncSetAttribute(k_pair_contacts_hash<512, PC_M_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m));
                 ctx->pc_attr_set = true;
             }
             PairAcc* a_acc = ctx->d_pairacc.as<PairAcc>(); const uint32_t* a_grp = ctx->d_grouped.as<uint32_t>();
-            unsigned long long* a_key = ctx->d_skey.as<unsigned long long>(); unsigned long long* a_vkey = ctx->d_svkey.as<unsigned long long>();
             const imrcd_tri_hit* a_hits = ctx->d_hits.as<imrcd_tri_hit>(); const HitAux* a_aux = ctx->d_aux.as<HitAux>();
             const PairRec* a_pr = ctx->d_pairrec.as<PairRec>(); const TriRec* a_tris = ctx->d_tris.as<TriRec>(); const uint32_t* a_vid = ctx->d_tri_vid.as<uint32_t>();
+            const float* a_nrm = ctx->d_tri_nrm.as<float>(); RayRec* a_rays = ctx->d_rays.as<RayRec>(); unsigned char* a_scr = ctx->d_lscratch.as<unsigned char>();
             // the three size classes are independent: the two rarer ones run beside the common one on a second stream
             IMR_CUDA(ctx, cudaEventRecord(ctx->ev_fork, s));
             IMR_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
-            k_pair_contacts_hash<128, PC_S_MAX><<<ctx->sm_count * 8, 128, smem_s, s>>>(ctl, ctx->d_lsmall.as<uint32_t>(), 0, a_acc, a_grp, a_hits, a_aux, a_pr, a_tris, a_vid);
-            k_pair_contacts_hash<512, PC_M_MAX><<<ctx->sm_count, 512, smem_m, ctx->stream2>>>(ctl, ctx->d_lmid.as<uint32_t>(), 1, a_acc, a_grp, a_hits, a_aux, a_pr, a_tris, a_vid);
-            k_pair_contacts<512, 0, 2><<<ctx->sm_count * 2, 512, 0, ctx->stream2>>>(ctl, ctx->d_llarge.as<uint32_t>(), 2, a_acc, a_grp, a_key, a_vkey, a_hits, a_aux, a_pr, a_tris, a_vid);
+            k_pair_contacts_hash<128, PC_S_MAX><<<ctx->sm_count * 8, 128, smem_s, s>>>(ctl, ctx->d_lsmall.as<uint32_t>(), 0, a_acc, a_grp, a_hits, a_aux, a_pr, a_tris, a_vid, a_nrm, a_rays, ctx->cap_rays, a_scr, ctx->cap_lscratch);
+            k_pair_contacts_hash<512, PC_M_MAX><<<ctx->sm_count, 512, smem_m, ctx->stream2>>>(ctl, ctx->d_lmid.as<uint32_t>(), 1, a_acc, a_grp, a_hits, a_aux, a_pr, a_tris, a_vid, a_nrm, a_rays, ctx->cap_rays, a_scr, ctx->cap_lscratch);
+            k_pair_contacts_hash<512, 0><<<ctx->sm_count * 2, 512, 0, ctx->stream2>>>(ctl, ctx->d_llarge.as<uint32_t>(), 2, a_acc, a_grp, a_hits, a_aux, a_pr, a_tris, a_vid, a_nrm, a_rays, ctx->cap_rays, a_scr, ctx->cap_lscratch);
             IMR_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->stream2));
             IMR_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_join, 0));
         }
         launches += 8;      // layout, scan (2), lists, group, three size classes
         k_finalize<<<ctx->sm_count * 4, 256, 0, s>>>(ctl, ctx->cap_pairs, ctx->d_pairs.as<uint2>(), ctx->d_pairacc.as<PairAcc>(),
                                                       ctx->d_entity.as<uint32_t>(), ctx->d_cur.as<float>(), ctx->d_inv.as<float>(),
-                                                      ctx->d_epairs.as<imrcd_entity_pair>());
+                                                      ctx->d_epairs.as<imrcd_entity_pair>(), ctx->d_epair_pair.as<uint32_t>());
         launches += 1;
+        IMR_CUDA(ctx, cudaEventRecord(ctx->ev[6], s));
+        { int rc = imr_frame_shoot_device(ctx, ctl, &launches); if (rc != IMRCD_OK) return rc; }
         IMR_CUDA(ctx, cudaEventRecord(ctx->ev[5], s));
         IMR_CUDA(ctx, cudaMemcpyAsync(ctx->p_ctl.p, ctl, sizeof(FrameCtl), cudaMemcpyDeviceToHost, s));
         IMR_CUDA(ctx, cudaStreamSynchronize(s));
@@ -1312,6 +1168,9 @@ int imr_frame_run_device(imrcd_ctx* ctx) {
             if (ctx->cap_queue < ctx->cap_pairs) ctx->cap_queue = ctx->cap_pairs + (1ull << 22);
             if (c.overflow & OVF_COMBOS) ctx->cap_combos = std::max<uint64_t>(c.n_combos + c.n_combos / 8, ctx->cap_combos * 2);
             if (c.overflow & OVF_HITS) ctx->cap_hits = std::max<uint64_t>(c.n_hits + c.n_hits / 8, ctx->cap_hits * 2);
+            if (c.overflow & OVF_RAYS) ctx->cap_rays = std::max<uint64_t>(c.n_rays_kept + c.n_rays_kept / 8, ctx->cap_rays * 2);
+            if (c.overflow & OVF_SCRATCH) ctx->cap_lscratch = std::max<uint64_t>(c.scratch_used + c.scratch_used / 8, ctx->cap_lscratch * 2);
+            if (c.overflow & OVF_RAYSTACK) { ctx->err = "ray stack overflow (tree deeper than the per-thread stack of the response stage)"; return IMRCD_E_CAPACITY; }
 
             continue;   // re-run the frame with the larger buffers
         }
@@ -1327,6 +1186,8 @@ int imr_frame_run_device(imrcd_ctx* ctx) {
         cudaEventElapsedTime(&st.ms_traverse, ctx->ev[2], ctx->ev[3]);
         cudaEventElapsedTime(&st.ms_narrow, ctx->ev[3], ctx->ev[4]);
         cudaEventElapsedTime(&st.ms_reduce, ctx->ev[4], ctx->ev[5]);
+        cudaEventElapsedTime(&st.ms_response, ctx->ev[6], ctx->ev[5]);
+        st.n_rays_shot = c.n_rays_kept; st.n_responses = c.n_responses;
         return IMRCD_OK;
     }
     ctx->err = "frame buffers could not be grown enough (8 attempts)";

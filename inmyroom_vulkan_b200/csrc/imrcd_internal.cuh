@@ -39,6 +39,23 @@ typedef uint4 WorkItem;   // (pair, a, b, ready)
 // Leaf x leaf candidate (OBBtreesIntersectInfo::CandidateTriangleRangeCombination, OBBtree.h:9-18)
 typedef uint4 Combo;      // (pair, offA, offB, cntA | cntB << 16), offsets relative to the mesh
 
+// Per broad-phase pair accumulators, 112 B.  sum_* / rays_* are the ray origins of CreateUncollideRays.cpp:131-178 summed per side
+// (first's model space) and force is average_force_responses of ShootUncollideRays.cpp:26,42,60, all in FP64 so that the order of the
+// atomic adds does not show in the FP32 result.  ray_off_*: the pair's slices of the frame's ray array (only pairs that moved keep rays).
+struct __align__(16) PairAcc { uint32_t n_hits, flags, rays_a, rays_b, cursor, off, ray_off_a, ray_off_b; double sum_a[3], sum_b[3], force[3]; uint32_t n_resp, pad; };
+enum { PAIR_COLLIDING = 1u, PAIR_MOVED = 2u };
+
+// Side record of one hit for the contact reduction (the 40-B imrcd_tri_hit keeps source, target and weight), 12 B:
+// arena indices of the two triangles and flags = bitsA | bitsB << 3 | i << 6 | j << 8, where bitsX has bit k set iff vertex k of
+// that triangle is NOT outside the other triangle's plane (CreateUncollideRays.cpp:102-112) and (i, j) are the positions of the
+// triangles inside their leaves (so tri - i / tri - j name the leaf, i.e. the combo the hit came from).
+struct HitAux { uint32_t triA, triB, flags; };
+
+// One "uncollide" ray (CreateUncollideRays.cpp:153,165), first's model space, 32 B: o = (origin, pair index bits), d = (direction, side bits:
+// 0 = from first to second, 1 = from second to first).  Its up to two Hermann responses (ShootUncollideRays.cpp:73-89) are float4
+// (response with the sign it enters ray_responses with, valid ? 1 : 0) at resp[2 * ray + step].
+struct __align__(16) RayRec { float4 o, d; };
+
 // sorted sweep record, 32 B
 struct __align__(16) SweepRec { float umin, umax, vmin, vmax, wmin, wmax; uint32_t idx, cb; };
 
@@ -61,10 +78,27 @@ struct __align__(128) FrameCtl {
     unsigned long long n_iterations;       // traversal warp-iterations (diagnostic)
     unsigned long long busy_cycles, idle_polls;
     unsigned long long n_rays;             // rays of all colliding pairs, both sides
-    unsigned int overflow;                 // bit0 pairs, bit1 queue, bit2 combos, bit3 hits
+    unsigned long long n_rays_kept;        // rays written to the ray array (pairs that moved): bump allocator of the contact reduction
+    unsigned long long scratch_used;       // bytes of the large-pair scratch handed out (bump allocator)
+    unsigned long long n_responses;        // successful Hermann passes of the frame
+    unsigned int overflow;                 // bit0 pairs, bit1 queue, bit2 combos, bit3 hits, bit4 rays, bit5 large-pair scratch, bit6 ray stack
     unsigned int pad;
 };
-enum { OVF_PAIRS = 1, OVF_QUEUE = 2, OVF_COMBOS = 4, OVF_HITS = 8 };
+enum { OVF_PAIRS = 1, OVF_QUEUE = 2, OVF_COMBOS = 4, OVF_HITS = 8, OVF_RAYS = 16, OVF_SCRATCH = 32, OVF_RAYSTACK = 64 };
+
+// ---- device helpers shared by the .cu files ----
+__device__ __forceinline__ Box unpack_box(const float4& q0, const float4& q1, const float4& q2) {
+    Box b;
+    b.c = mk3(q0.x, q0.y, q0.z); b.u = mk3(q0.w, q1.x, q1.y); b.v = mk3(q1.z, q1.w, q2.x); b.w = mk3(q2.y, q2.z, q2.w);
+    return b;
+}
+__device__ __forceinline__ Rel rel_from_mat(const float* m) {   // rows of a column-major mat4
+    Rel r;
+    r.r0 = make_float4(m[0], m[4], m[8], m[12]);
+    r.r1 = make_float4(m[1], m[5], m[9], m[13]);
+    r.r2 = make_float4(m[2], m[6], m[10], m[14]);
+    return r;
+}
 
 // ------------------------------------------------------------------------------------------
 // host-side helpers
@@ -145,8 +179,9 @@ struct imrcd_ctx {
     // frame, device side
     DevBuf d_cur, d_prev, d_mesh, d_cb, d_entity, d_inv, d_ext, d_keys, d_keys2, d_idx, d_idx2, d_sorted, d_sorted_c, d_flag, d_cpos, d_wlen, d_chunks, d_chunkoff, d_cubtmp;
     DevBuf d_pairs, d_pairrec, d_pairacc, d_queue, d_combos, d_hits, d_epairs, d_ctl;
-    DevBuf d_aux, d_grouped, d_skey, d_svkey, d_padded, d_padoff, d_lsmall, d_lmid, d_llarge;      // contact reduction scratch (imrcd_frame.cu)
-    uint64_t cap_pairs = 0, cap_queue = 0, cap_combos = 0, cap_hits = 0;
+    DevBuf d_aux, d_grouped, d_lscratch, d_padded, d_padoff, d_lsmall, d_lmid, d_llarge;      // contact reduction scratch (imrcd_frame.cu)
+    DevBuf d_rays, d_resp, d_epair_pair;                                                    // response stage (imrcd_rays.cu)
+    uint64_t cap_pairs = 0, cap_queue = 0, cap_combos = 0, cap_hits = 0, cap_rays = 0, cap_lscratch = 0;
     uint64_t queue_dirty = 0;            // slots whose ready flag may still be set
     // results
     PinBuf p_ctl, p_epairs, p_hits, p_pairs, p_combos;
@@ -169,5 +204,9 @@ int imr_mesh_finalize_tris(imrcd_ctx* ctx, uint32_t tri_base, uint32_t n_tri);  
 int imr_build_mesh_device(imrcd_ctx* ctx, const float* pos, const float* nrm, const uint32_t* vid, uint64_t n_tri,
                           uint32_t mode, MeshHost* out);
 int imr_frame_run_device(imrcd_ctx* ctx);
+// response stage: one thread per kept ray (Hermann passes), then one warp per colliding pair that moved (imrcd_rays.cu)
+int imr_frame_shoot_device(imrcd_ctx* ctx, FrameCtl* ctl, uint64_t* launches);
+int imr_test_ray_tree_device(imrcd_ctx* ctx, uint32_t mesh_id, uint64_t n, const float* mats, const float* origins, const float* dirs,
+                             uint8_t* flags, float* out3, uint32_t* tri);
 int imr_mesh_update_positions_device(imrcd_ctx* ctx, uint32_t mesh_id, const float* pos, const float* nrm);
 int imr_meshes_refit_device(imrcd_ctx* ctx, const uint32_t* ids, uint64_t n_ids, float* ms_out);

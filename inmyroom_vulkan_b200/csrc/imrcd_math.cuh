@@ -337,3 +337,40 @@ IMR_HD uint32_t float_orderable(float f) {
 #endif
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
+
+// ---- normals of the "uncollide" rays (CreateUncollideRays.cpp:150-163, IMR/src/Geometry/Triangle.cpp:148-212) ---------------
+// glm::adjointTranspose(mat3(m)) (glm/gtc/matrix_inverse.inl:133-147; Triangle.cpp:175-178), column-major: a[3 * c + r]
+struct M3 { float a[9]; };
+IMR_HD M3 m3_identity() { M3 o; o.a[0] = 1.f; o.a[1] = 0.f; o.a[2] = 0.f; o.a[3] = 0.f; o.a[4] = 1.f; o.a[5] = 0.f; o.a[6] = 0.f; o.a[7] = 0.f; o.a[8] = 1.f; return o; }
+IMR_HD M3 adjoint_transpose3(const Rel& m) {
+    // A(c, r) = m[c][r]; rows of Rel: r0 = (m[0][0], m[1][0], m[2][0], .), r1 = (m[0][1], ...), r2 = (m[0][2], ...)
+    const float a00 = m.r0.x, a01 = m.r1.x, a02 = m.r2.x, a10 = m.r0.y, a11 = m.r1.y, a12 = m.r2.y, a20 = m.r0.z, a21 = m.r1.z, a22 = m.r2.z;
+    M3 o;
+    o.a[0] = +(a11 * a22 - a21 * a12);
+    o.a[1] = -(a10 * a22 - a20 * a12);
+    o.a[2] = +(a10 * a21 - a20 * a11);
+    o.a[3] = -(a01 * a22 - a21 * a02);
+    o.a[4] = +(a00 * a22 - a20 * a02);
+    o.a[5] = -(a00 * a21 - a20 * a01);
+    o.a[6] = +(a01 * a12 - a11 * a02);
+    o.a[7] = -(a00 * a12 - a10 * a02);
+    o.a[8] = +(a00 * a11 - a10 * a01);
+    return o;
+}
+// type_mat3x3.inl:468-474 : (m[0] * v.x + m[1] * v.y) + m[2] * v.z
+IMR_HD V3 m3_mul(const M3& m, V3 v) {
+    return mk3((m.a[0] * v.x + m.a[3] * v.y) + m.a[6] * v.z, (m.a[1] * v.x + m.a[4] * v.y) + m.a[7] * v.z, (m.a[2] * v.x + m.a[5] * v.y) + m.a[8] * v.z);
+}
+// TrianglePosition::GetBarycentricOfPoint, Triangle.cpp:148-163
+IMR_HD void tri_barycentric(V3 p0, V3 p1, V3 p2, V3 point, float& bx, float& by) {
+    const V3 v0 = sub3(p1, p0), v1 = sub3(p2, p0), v2 = sub3(point, p0);
+    const float d00 = dot3(v0, v0), d01 = dot3(v0, v1), d11 = dot3(v1, v1), d20 = dot3(v2, v0), d21 = dot3(v2, v1);
+    const float denom = d00 * d11 - d01 * d01;
+    bx = (d11 * d20 - d01 * d21) / denom;
+    by = (d00 * d21 - d01 * d20) / denom;
+}
+// TriangleNormal::GetNormal(baryCoords[, corrected_matrix]), Triangle.cpp:197-212 (before the normalisation)
+IMR_HD V3 tri_interp_normal(V3 n0, V3 n1, V3 n2, float bx, float by) {
+    const float w0 = (1.f - bx) - by;
+    return add3(add3(scale3(n0, w0), scale3(n1, bx)), scale3(n2, by));
+}
