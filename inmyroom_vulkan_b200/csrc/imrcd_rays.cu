@@ -158,45 +158,148 @@ __device__ Hermann hermann_pass(const TreeRec* recsA, const TriRec* trisA, const
 
 __device__ __forceinline__ Rel rel_identity() { Rel r; r.r0 = make_float4(1.f, 0.f, 0.f, 0.f); r.r1 = make_float4(0.f, 1.f, 0.f, 0.f); r.r2 = make_float4(0.f, 0.f, 1.f, 0.f); return r; }
 
-// One thread per kept ray: ExecuteShootUncollideRays' two lambdas (ShootUncollideRays.cpp:29-89).
+// box `idx` of a tree, moved into the ray's space, against the ray from the origin (Ray.cpp:169-173); one copy of the slab code
+__device__ __noinline__ bool ray_node_box(const TreeRec* __restrict__ recs, uint32_t idx, const Rel& m, V3 dir, float& mn, float& mx) {
+    const float4* rp = reinterpret_cast<const float4*>(recs + idx);
+    const Box b = box_transform(m, unpack_box(__ldg(rp), __ldg(rp + 1), __ldg(rp + 2)));
+    return ray_box0(dir, b, mn, mx);
+}
+
+// One lane per kept ray: ExecuteShootUncollideRays' two lambdas (ShootUncollideRays.cpp:29-89) as a state machine.  A ray goes through up to
+// four tree queries (step 0: the other object, then its own; step 1, the reflected ray: the same with the roles swapped); every lane of a
+// warp advances its own query by ONE tree node per iteration of a common loop, so lanes in different queries - or on different rays: a lane
+// that finishes fetches its next ray - still execute the same node code together.  (The first version ran the four queries as four inlined
+// copies of the descent: 12 of 32 lanes active and 65 % of the issue slots lost to instruction-cache misses, ncu.)
 __global__ void __launch_bounds__(128)
 k_shoot(FrameCtl* ctl, unsigned long long cap_rays, const RayRec* __restrict__ rays, float4* __restrict__ resp, PairAcc* acc, const PairRec* __restrict__ pairrec,
         const TreeRec* __restrict__ recs, const TriRec* __restrict__ tris, const float* __restrict__ tri_nrm) {
     if (ctl->overflow) return;
     const unsigned long long n = ctl->n_rays_kept < cap_rays ? ctl->n_rays_kept : cap_rays;
-    for (unsigned long long k = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; k < n; k += (unsigned long long)gridDim.x * blockDim.x) {
-        const RayRec ray = rays[k];
-        const uint32_t p = __float_as_uint(ray.o.w), side = __float_as_uint(ray.d.w);
-        const PairRec pr = pairrec[p];
-        Rel rel; rel.r0 = pr.r0; rel.r1 = pr.r1; rel.r2 = pr.r2;
-        const M3 nmat = adjoint_transpose3(rel), ident3 = m3_identity();
-        const Rel ident = rel_identity();
-        const TreeRec* recs1 = recs + pr.recA; const TreeRec* recs2 = recs + pr.recB;
-        const TriRec* tris1 = tris + pr.triA; const TriRec* tris2 = tris + pr.triB;
-        V3 o = mk3(ray.o.x, ray.o.y, ray.o.z), d = mk3(ray.d.x, ray.d.y, ray.d.z);
-        double fx = 0.0, fy = 0.0, fz = 0.0;
-        uint32_t n_ok = 0;
-        float4 out[2] = { make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f) };
-        for (int step = 0; step < 2; ++step) {
-            const bool f2s = (side == 0u) == (step == 0);                   // first_to_second_ray_execute, else second_to_first (:29-71)
-            const Hermann h = f2s ? hermann_pass(recs1, tris1, ident, recs2, tris2, rel, nmat, tri_nrm, pr.triB, o, d, &ctl->overflow)
-                                  : hermann_pass(recs2, tris2, rel, recs1, tris1, ident, ident3, tri_nrm, pr.triA, o, d, &ctl->overflow);
-            if (!h.ok) break;
-            // CalcForceResponse (:104-114)
-            const V3 dirn = normalize3(h.response);
-            const float len = length3(h.response);
-            const float c = dot3(h.normal, dirn);
-            const V3 fr = scale3(dirn, (c * c) * len);
-            if (f2s) { fx -= (double)fr.x; fy -= (double)fr.y; fz -= (double)fr.z; out[step] = make_float4(-h.response.x, -h.response.y, -h.response.z, 1.f); }
-            else { fx += (double)fr.x; fy += (double)fr.y; fz += (double)fr.z; out[step] = make_float4(h.response.x, h.response.y, h.response.z, 1.f); }
-            ++n_ok;
-            o = add3(o, h.response);                                        // ReflectHermannResult (:95-101)
-            d = mk3(-h.normal.x, -h.normal.y, -h.normal.z);
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    unsigned long long next = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    uint32_t st_node[RAY_STACK]; float st_min[RAY_STACK];
+    int sp = 0;
+    bool active = false, root_pending = false;
+    // per-ray state
+    unsigned long long k = 0; uint32_t p = 0, side = 0; int step = 0, phase = 0;
+    V3 o = mk3(0, 0, 0), d = mk3(0, 0, 0), q_origin = mk3(0, 0, 0);
+    Rel rel, m; rel.r0 = rel.r1 = rel.r2 = make_float4(0, 0, 0, 0); m = rel;
+    uint32_t recA = 0, recB = 0, triA = 0, triB = 0;                        // first's / second's arena bases
+    const TreeRec* q_recs = recs; const TriRec* q_tris = tris;             // the tree of the running query
+    RayHit best, p2;
+    best.hit = false; best.back = false; best.dist = INFINITY; best.tri = 0xffffffffu; best.bx = best.by = 0.f; p2 = best;
+    float eps_dist = 0.f;
+    double fx = 0.0, fy = 0.0, fz = 0.0; uint32_t n_ok = 0;
+    float4 out0 = make_float4(0, 0, 0, 0), out1 = out0;
+
+    for (;;) {
+        if (!active) {
+            if (next < n) {                                                 // fetch the lane's next ray
+                k = next; next += stride;
+                const RayRec ray = rays[k];
+                p = __float_as_uint(ray.o.w); side = __float_as_uint(ray.d.w);
+                const PairRec pr = pairrec[p];
+                rel.r0 = pr.r0; rel.r1 = pr.r1; rel.r2 = pr.r2; recA = pr.recA; recB = pr.recB; triA = pr.triA; triB = pr.triB;
+                o = mk3(ray.o.x, ray.o.y, ray.o.z); d = mk3(ray.d.x, ray.d.y, ray.d.z);
+                step = 0; phase = 0; fx = fy = fz = 0.0; n_ok = 0; out0 = out1 = make_float4(0, 0, 0, 0);
+                active = true; root_pending = true; q_origin = o;
+            }
         }
-        resp[2 * k] = out[0]; resp[2 * k + 1] = out[1];
-        if (n_ok) {
-            atomicAdd(&acc[p].force[0], fx); atomicAdd(&acc[p].force[1], fy); atomicAdd(&acc[p].force[2], fz);
-            atomicAdd(&acc[p].n_resp, n_ok);
+        if (!__any_sync(FULL_MASK, active)) break;
+        if (!active) continue;
+
+        // f2s: first_to_second_ray_execute (objects: A = first, B = second), else second_to_first (A = second, B = first)  (:29-71)
+        const bool f2s = (side == 0u) == (step == 0);
+        if (root_pending) {
+            // start a query (Ray::IntersectOBBtree, Ray.cpp:136-161): phase 0 looks at B (point2), phase 1 at A (point3)
+            const bool on_second = (phase == 0) == f2s;                     // which tree: second's (matrix rel) or first's (identity)
+            q_recs = recs + (on_second ? recB : recA); q_tris = tris + (on_second ? triB : triA);
+            m = on_second ? rel : rel_identity();
+            if (!(q_origin.x == 0.f && q_origin.y == 0.f && q_origin.z == 0.f)) {      // centered_matrix[3] -= vec4(origin, 0)
+                m.r0.w = m.r0.w - q_origin.x; m.r1.w = m.r1.w - q_origin.y; m.r2.w = m.r2.w - q_origin.z;
+            }
+            best.hit = false; best.back = false; best.dist = INFINITY; best.tri = 0xffffffffu; best.bx = best.by = 0.f;
+            float mn, mx;
+            sp = 0;
+            if (ray_node_box(q_recs, 0u, m, d, mn, mx) && mx >= 0.f) { st_node[0] = 0u; st_min[0] = -INFINITY; sp = 1; }   // :144-147
+            root_pending = false;
+        } else if (sp > 0) {
+            // one node of the descent (Ray::IntersectOBBtreeRecursive, Ray.cpp:163-236)
+            --sp;
+            const uint32_t node = st_node[sp];
+            if (st_min[sp] < best.dist) {                                   // the recursion's `min < best_so_far` at call time
+                const float4 q3 = __ldg(reinterpret_cast<const float4*>(q_recs + node) + 3);
+                const uint32_t child = __float_as_uint(q3.y);
+                if (__float_as_uint(q3.w) == 0u) {                          // inner: children are records child (left), child + 1 (right)
+                    float lmin = 0.f, lmax = 0.f, rmin = 0.f, rmax = 0.f;
+                    const bool lh = ray_node_box(q_recs, child, m, d, lmin, lmax), rh = ray_node_box(q_recs, child + 1u, m, d, rmin, rmax);
+                    const bool lgo = lh && lmax >= 0.f, rgo = rh && rmax >= 0.f;
+                    const bool left_first = !(lh && rh) || (lmin < rmin);   // :182-204
+                    if (sp + 2 > RAY_STACK) { atomicOr(&ctl->overflow, (unsigned)OVF_RAYSTACK); sp = 0; }
+                    else if (left_first) {
+                        if (rgo) { st_node[sp] = child + 1u; st_min[sp] = rmin; ++sp; }
+                        if (lgo) { st_node[sp] = child; st_min[sp] = lmin; ++sp; }
+                    } else {
+                        if (lgo) { st_node[sp] = child; st_min[sp] = lmin; ++sp; }
+                        if (rgo) { st_node[sp] = child + 1u; st_min[sp] = rmin; ++sp; }
+                    }
+                } else {
+                    const uint32_t cnt = __float_as_uint(q3.z);
+                    for (uint32_t i = 0; i < cnt; ++i) {                    // :221-234
+                        const float4* tp = reinterpret_cast<const float4*>(q_tris + child + i);
+                        const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
+                        const V3 p0 = rel_mul(m, mk3(t0.x, t0.y, t0.z), 1.f), p1 = rel_mul(m, mk3(t1.x, t1.y, t1.z), 1.f), p2v = rel_mul(m, mk3(t2.x, t2.y, t2.z), 1.f);
+                        float bx = 0.f, by = 0.f, dist = INFINITY; bool back = false;
+                        if (ray_triangle0(d, p0, p1, p2v, bx, by, dist, back) && dist > 0.f && dist < best.dist) {
+                            best.hit = true; best.back = back; best.dist = dist; best.tri = child + i; best.bx = bx; best.by = by;
+                        }
+                    }
+                }
+            }
+        } else {
+            // the query is over: HermannPass (ShootUncollideRays.cpp:116-148)
+            bool ray_done = false;
+            if (phase == 0) {
+                if (best.hit && best.back) {                                // point2: the other object, hit from inside
+                    p2 = best;
+                    // Ray::MoveOriginEpsilonTowardsDirection(4.f), Ray.cpp:13-21
+                    float big = fabsf(o.x); if (big < fabsf(o.y)) big = fabsf(o.y); if (big < fabsf(o.z)) big = fabsf(o.z);
+                    const float scaled = big * FLT_EPSILON;
+                    q_origin = add3(o, scale3(d, 4.f * scaled));
+                    eps_dist = length3(sub3(q_origin, o));
+                    phase = 1; root_pending = true;
+                } else ray_done = true;
+            } else {
+                if (p2.dist <= best.dist + eps_dist) {                      // :134 (best = point3, the ray's own object)
+                    const V3 response = scale3(d, p2.dist);
+                    const uint32_t tri_base = f2s ? triB : triA;           // object B of this pass
+                    const float* nn = tri_nrm + 9ull * (tri_base + p2.tri);
+                    const V3 in = tri_interp_normal(mk3(nn[0], nn[1], nn[2]), mk3(nn[3], nn[4], nn[5]), mk3(nn[6], nn[7], nn[8]), p2.bx, p2.by);
+                    const V3 normal = normalize3(f2s ? m3_mul(adjoint_transpose3(rel), in) : m3_mul(m3_identity(), in));     // Triangle.cpp:197-204
+                    // CalcForceResponse (:104-114)
+                    const V3 dirn = normalize3(response);
+                    const float len = length3(response);
+                    const float c = dot3(normal, dirn);
+                    const V3 fr = scale3(dirn, (c * c) * len);
+                    float4 rec;
+                    if (f2s) { fx -= (double)fr.x; fy -= (double)fr.y; fz -= (double)fr.z; rec = make_float4(-response.x, -response.y, -response.z, 1.f); }
+                    else { fx += (double)fr.x; fy += (double)fr.y; fz += (double)fr.z; rec = make_float4(response.x, response.y, response.z, 1.f); }
+                    if (step == 0) out0 = rec; else out1 = rec;
+                    ++n_ok;
+                    if (step == 0) {                                        // ReflectHermannResult (:95-101), then the opposite direction (:73-89)
+                        o = add3(o, response); d = mk3(-normal.x, -normal.y, -normal.z);
+                        step = 1; phase = 0; root_pending = true; q_origin = o;
+                    } else ray_done = true;
+                } else ray_done = true;
+            }
+            if (ray_done) {
+                resp[2 * k] = out0; resp[2 * k + 1] = out1;
+                if (n_ok) {
+                    atomicAdd(&acc[p].force[0], fx); atomicAdd(&acc[p].force[1], fy); atomicAdd(&acc[p].force[2], fz);
+                    atomicAdd(&acc[p].n_resp, n_ok);
+                }
+                active = false;
+            }
         }
     }
 }
@@ -263,7 +366,9 @@ int imr_frame_shoot_device(imrcd_ctx* ctx, FrameCtl* ctl, uint64_t* launches) {
     cudaStream_t s = ctx->stream;
     // glm::radians(40.f), glm::radians(65.f) -> cos (CollisionDetection.cpp:22-23, ShootUncollideRays.cpp:8-9): smoothstep runs from cos 65 to cos 40
     const float edge_b = cosf(0.01745329251994329576923690768489f * 40.f), edge_a = cosf(0.01745329251994329576923690768489f * 65.f);
-    k_shoot<<<ctx->sm_count * 8, 128, 0, s>>>(ctl, ctx->cap_rays, ctx->d_rays.as<RayRec>(), ctx->d_resp.as<float4>(), ctx->d_pairacc.as<PairAcc>(),
+    static int shoot_blocks_per_sm = 0;
+    if (!shoot_blocks_per_sm) { IMR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&shoot_blocks_per_sm, k_shoot, 128, 0)); if (shoot_blocks_per_sm < 1) shoot_blocks_per_sm = 1; }
+    k_shoot<<<ctx->sm_count * shoot_blocks_per_sm, 128, 0, s>>>(ctl, ctx->cap_rays, ctx->d_rays.as<RayRec>(), ctx->d_resp.as<float4>(), ctx->d_pairacc.as<PairAcc>(),
                                                ctx->d_pairrec.as<PairRec>(), ctx->d_recs.as<TreeRec>(), ctx->d_tris.as<TriRec>(), ctx->d_tri_nrm.as<float>());
     k_delta<<<ctx->sm_count * 4, 256, 0, s>>>(ctl, ctx->d_epair_pair.as<uint32_t>(), ctx->d_epairs.as<imrcd_entity_pair>(), ctx->d_pairacc.as<PairAcc>(),
                                                ctx->d_resp.as<float4>(), ctx->d_cur.as<float>(), ctx->d_prev.as<float>(), edge_a, edge_b);
