@@ -355,6 +355,25 @@ def run_gpu_arm(args):
     h2d = n_entries * (64 + 4 + 4 + 1 + (64 if scene.previous is not None else 0))   # previous == current is not re-sent
     d2h = int(len(res)) * 80 + 1280
 
+    # ---- response stage: the same scene with every dynamic body moved since the last frame, so that the deltaVector of
+    #      every colliding pair is computed (ShootUncollideRays.cpp:14-93); reported beside the headline, not inside it ----
+    ns_static = len(scene.meshes) - 1 if args.workload == "c3" else 0
+    prev = scene.matrices.copy()
+    prev[ns_static:, 12:15] += (np.random.default_rng(1).normal(size=(scene.n_entries - ns_static, 3)) * 0.02).astype(np.float32)
+    cd.Reset(); cd.add_entries(scene.matrices, mesh_ids, scene.should_callback, scene.entities, prev); cd.upload()
+    for _ in range(args.warmup):
+        l2_flush(); device_step()
+    barrier()
+    resp_ms = 0.0; moved_ms = 0.0
+    for _ in range(args.steps):
+        l2_flush(); device_step()
+        stm = cd.stats()
+        resp_ms += stm["ms_response"]; moved_ms += stm["ms_total"]; launches_moved = stm["total_launches"]
+    barrier()
+    response = {"ms_response": resp_ms / args.steps, "ms_frame_with_response": moved_ms / args.steps, "rays_shot": global_sum(float(stm["n_rays_shot"])),
+                "responses": global_sum(float(stm["n_responses"])), "rays_per_s": stm["n_rays_shot"] / (resp_ms / args.steps * 1e-3) if resp_ms > 0 else 0.0,
+                "scene": "every dynamic body translated by N(0, 0.02) since the previous frame (this rank's shard)"}
+
     # ---- roofline of the dominant kernel (stage times from CUDA events on the launching stream, this rank) ----
     peaks = measured_peaks()
     ms_trav = st_acc["ms_traverse"] / args.steps; ms_nar = st_acc["ms_narrow"] / args.steps
@@ -394,7 +413,7 @@ def run_gpu_arm(args):
                 "from_pageable_numpy": {"value": tests_total * args.steps / e2e_pageable_s, "ms_per_step": e2e_pageable_s / args.steps * 1e3}},
         "gpu_launches": int(launches),
         "clocks": clk,
-        "roofline": dominant, "roofline_other": other,
+        "roofline": dominant, "roofline_other": other, "response": response,
         "frame": {"pairs": pairs_total, "sat_tests": sat_total, "tri_tests": tests_total, "hits": hits_total, "colliding_pairs": coll_total,
                   "ms_broad": st_acc["ms_broad"] / args.steps, "ms_pair_setup": st_acc["ms_pair_setup"] / args.steps,
                   "ms_traverse": ms_trav, "ms_narrow": ms_nar, "ms_reduce": st_acc["ms_reduce"] / args.steps,
@@ -408,6 +427,25 @@ def run_gpu_arm(args):
         sample = sample_scene(scene, args.workload, args.cpu_sample)
         ctrees = [orc.tree_build(m.positions, m.normals, m.vertex_ids) for m in sample.meshes]
         r = cpu_frame(orc, port, sample, ctrees, threads=1)
+        # response stage on the CPU: the reference's per-pair code with and without movement on the first colliding pairs of the sample
+        try:
+            et = [ctrees[m] for m in sample.mesh_index]
+            cpairs, _ = (orc.broad if (orc.kind != "reference" or sample.n_entries <= 65534) else port.broad)(sample.matrices, et, sample.should_callback)
+            rngp = np.random.default_rng(1); t_moved = t_still = 0.0; n_rays_cpu = 0; n_used = 0
+            for (i, j) in cpairs.tolist():
+                rr = orc.pair(et[i], sample.matrices[i], et[j], sample.matrices[j])
+                if not rr.colliding:
+                    continue
+                pi = sample.matrices[i].copy(); pj = sample.matrices[j].copy(); pj[12:15] += (rngp.normal(size=3) * 0.02).astype(np.float32)
+                t0 = time.perf_counter(); orc.pair_delta(et[i], sample.matrices[i], pi, et[j], sample.matrices[j], pj); t1 = time.perf_counter()
+                orc.pair_delta(et[i], sample.matrices[i], pi, et[j], sample.matrices[j], sample.matrices[j]); t2 = time.perf_counter()
+                t_moved += t1 - t0; t_still += t2 - t1; n_rays_cpu += rr.rays_first + rr.rays_second; n_used += 1
+                if n_used >= 150 or t_moved > 8.0:
+                    break
+            if n_used and t_moved > t_still:
+                line["response"]["cpu_reference"] = {"rays_per_s": n_rays_cpu / (t_moved - t_still), "pairs": n_used, "rays": n_rays_cpu, "cores": 1, "kind": orc.kind}
+        except Exception as e:          # the response figure is informational
+            line["response"]["cpu_reference"] = {"error": str(e)[:200]}
         line["cpu_baseline"] = {"value": r["tri_tests"] / r["frame_s"], "unit": UNIT, "cores": 1, "kind": orc.kind,
                                 "sample": (f"{sample.n_entries} entries (all static nodes + first {args.cpu_sample} bodies), {r['pairs']} pairs, "
                                            f"{r['tri_tests']} tri-pair tests; broad {r['broad_s']:.2f} s + mid {r['mid_s']:.2f} s + narrow {r['narrow_s']:.2f} s, "

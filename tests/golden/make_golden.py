@@ -52,9 +52,48 @@ def degenerate_tris(rng, count=800):
     return np.array(A, np.float32), np.array(B, np.float32)
 
 
+def make_response(ref):
+    """response.npz: Ray::IntersectOBBtree on one tree, and the response stage (rays in the reference's order, the delta
+    ShootUncollideRays returns for them, the deltaVectors of CollisionDetection.cpp:80-103) on the torus_instances frame."""
+    import golden_io
+    rng = np.random.default_rng(20261018)
+    out = {}
+    mesh = scenes.torus(20, 10)
+    tree = ref.tree_build(mesh.positions, mesh.normals, mesh.vertex_ids)
+    n = 1500
+    mats = rand_mats(rng, n, 0.3)
+    o = (rng.normal(size=(n, 3)) * np.where(np.arange(n) % 3 == 0, 3.0, 0.2)[:, None]).astype(np.float32); o[::50] = 0
+    d = rng.normal(size=(n, 3)); d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    res = [ref.ray_tree(tree, mats[k], o[k], d[k]) for k in range(n)]
+    out["ray.mats"] = mats; out["ray.origins"] = o; out["ray.dirs"] = d
+    out["ray.hit"] = np.array([r[0] for r in res], np.uint8); out["ray.back"] = np.array([r[1] for r in res], np.uint8)
+    out["ray.dist"] = np.array([r[2] for r in res], np.float32); out["ray.bary"] = np.stack([r[3] for r in res]).astype(np.float32)
+    out["ray.tri"] = np.array([r[4] & 0xffffffff for r in res], np.uint32)
+    sc, gold = golden_io.golden_frame(golden_io.load("frames"), "torus_instances")
+    trees = [ref.tree_build(m.positions, m.normals, m.vertex_ids) for m in sc.meshes]
+    prev = sc.matrices.copy()
+    prev[:, 12:15] += (rng.normal(size=(sc.n_entries, 3)) * 0.03).astype(np.float32)
+    prev[::5] = sc.matrices[::5]
+    rays1, rays2, cnt, shoot, delta, col = [], [], [], [], [], []
+    for (i, j) in gold["pairs"].tolist():
+        ta, tb = trees[sc.mesh_index[i]], trees[sc.mesh_index[j]]
+        r1, r2 = ref.pair_rays(ta, sc.matrices[i], tb, sc.matrices[j])
+        dd, _ = ref.shoot(ta, sc.matrices[i], tb, sc.matrices[j], r1, r2) if (len(r1) or len(r2)) else (np.zeros(3, np.float32), None)
+        c, d1, d2 = ref.pair_delta(ta, sc.matrices[i], prev[i], tb, sc.matrices[j], prev[j])
+        rays1.append(r1); rays2.append(r2); cnt.append([len(r1), len(r2)]); shoot.append(dd); delta.append(np.concatenate([d1, d2])); col.append(int(c))
+    out["frame.previous"] = prev
+    out["frame.rays_first"] = np.concatenate(rays1).astype(np.float32).reshape(-1, 6); out["frame.rays_second"] = np.concatenate(rays2).astype(np.float32).reshape(-1, 6)
+    out["frame.ray_counts"] = np.array(cnt, np.int64); out["frame.shoot"] = np.array(shoot, np.float32); out["frame.delta"] = np.array(delta, np.float32)
+    out["frame.colliding"] = np.array(col, np.uint8)
+    np.savez_compressed(os.path.join(HERE, "response.npz"), **out)
+    print("response: rays hit", int(out["ray.hit"].sum()), "of", n, "; colliding pairs", int(sum(col)), "non-zero deltas", int((np.abs(np.nan_to_num(out["frame.delta"])).sum(1) > 0).sum()))
+
+
 def main():
     bind.build("ref")
     ref = bind.RefOracle()
+    if len(sys.argv) > 1 and sys.argv[1] == "response":
+        return make_response(ref)
     rng = np.random.default_rng(20261017)
 
     # ---- predicates ----
@@ -150,6 +189,7 @@ def main():
         frames[f"{name}.avg"] = np.array(avg, np.float32).reshape(-1, 6)
         print(name, "entries", sc.n_entries, "pairs", len(pairs), "totals", res["totals"])
     np.savez_compressed(os.path.join(HERE, "frames.npz"), **frames)
+    make_response(ref)
     for fn in sorted(os.listdir(HERE)):
         if fn.endswith(".npz"):
             print(fn, os.path.getsize(os.path.join(HERE, fn)))

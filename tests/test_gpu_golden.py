@@ -57,3 +57,42 @@ def test_frame_golden(gpu_ctx, port, name):
         if summ[k][4] and summ[k][5]:
             rel = port.pair_matrix(sc.matrices[int(p["entry_first"])], sc.matrices[int(p["entry_second"])])
             assert contacts_close(np.concatenate([p["avg_first"], p["avg_second"]]), gold["avg"][k], rel)
+
+
+def test_ray_tree_golden(gpu_ctx):
+    """Ray::IntersectOBBtree on the device against the reference's answers (tests/golden/response.npz), with the reference's tree: bit-exact."""
+    z = golden_io.load("response")
+    gold_tree, mesh = golden_io.golden_tree(golden_io.load("trees"), "torus20x10")
+    gt = OBBtree.from_flat(gpu_ctx, gold_tree)
+    hit, back, dist, bary, tri = gpu_ctx.test_ray_tree(gt, z["ray.mats"], z["ray.origins"], z["ray.dirs"])
+    assert np.array_equal(hit, z["ray.hit"].astype(bool))
+    sel = hit
+    assert np.array_equal(back[sel], z["ray.back"].astype(bool)[sel]) and np.array_equal(tri[sel], z["ray.tri"][sel])
+    assert np.array_equal(f32_bits(dist[sel]), f32_bits(z["ray.dist"][sel])) and np.array_equal(f32_bits(bary[sel]), f32_bits(z["ray.bary"][sel]))
+
+
+def test_delta_golden(gpu_ctx):
+    """deltaVector of every colliding pair of the golden frame against the reference's (1e-4 of the vector's length: the rays of a pair
+    are summed in a different order)."""
+    z = golden_io.load("response")
+    sc, gold = golden_io.golden_frame(golden_io.load("frames"), "torus_instances")
+    sc.previous = z["frame.previous"]
+    tz = golden_io.load("trees")
+    gold_tree, _ = golden_io.golden_tree(tz, "torus20x10")
+    trees = [OBBtree.from_flat(gpu_ctx, gold_tree) for _ in sc.meshes]
+    cd = CollisionDetection(ctx=gpu_ctx)
+    st, bp, ep, hits = gpu_frame(cd, sc, trees)
+    want = {tuple(p): (z["frame.delta"][k], int(z["frame.colliding"][k])) for k, p in enumerate(gold["pairs"].tolist())}
+    assert len(ep) == sum(c for _, c in want.values())
+    n_checked = 0
+    for p in ep:
+        g, col = want[(int(p["entry_first"]), int(p["entry_second"]))]
+        assert col
+        for a, b in ((p["delta_first"], g[:3]), (p["delta_second"], g[3:])):
+            a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+            if np.isnan(b).any():
+                assert np.isnan(a).any()
+            else:
+                assert np.linalg.norm(a - b) <= 1e-4 * max(np.linalg.norm(b), 1e-30) + 1e-12, (a, b)
+                n_checked += bool(b.any())
+    assert n_checked > 20

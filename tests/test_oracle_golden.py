@@ -73,3 +73,44 @@ def test_frame(port, name):
         if r.colliding:   # contact averages: unordered_map iteration order leaks into the float sums (SURVEY trap 11)
             rel = port.pair_matrix(sc.matrices[key[0]], sc.matrices[key[1]])
             assert contacts_close(r.avg, gold["avg"][k], rel), f"pair {key}: {r.avg} vs {gold['avg'][k]}"
+
+
+def test_ray_tree_golden(port):
+    """Ray::IntersectOBBtree (Ray.cpp:136-236) against the reference's answers: bit-exact."""
+    z = golden_io.load("response")
+    from inmyroom_vulkan_b200 import scenes
+    mesh = scenes.torus(20, 10)
+    tree = port.tree_build(mesh.positions, mesh.normals, mesh.vertex_ids)
+    for k in range(z["ray.mats"].shape[0]):
+        h, b, dist, bary, tri = port.ray_tree(tree, z["ray.mats"][k], z["ray.origins"][k], z["ray.dirs"][k])
+        assert h == bool(z["ray.hit"][k]) and b == bool(z["ray.back"][k]) and (tri & 0xffffffff) == int(z["ray.tri"][k]), k
+        assert f32_bits(np.array([dist]))[0] == f32_bits(z["ray.dist"][k:k + 1])[0] and np.array_equal(f32_bits(bary), f32_bits(z["ray.bary"][k])), k
+    assert z["ray.hit"].sum() > 300
+
+
+def test_response_golden(port):
+    """ShootUncollideRays on the reference's rays in the reference's order: bit-exact; deltaVectors end to end (the port's ray order
+    differs from std::unordered_map's): 1e-4 of the vector's length."""
+    z = golden_io.load("response")
+    sc, gold = golden_io.golden_frame(golden_io.load("frames"), "torus_instances")
+    trees = [port.tree_build(m.positions, m.normals, m.vertex_ids) for m in sc.meshes]
+    prev = z["frame.previous"]
+    o1 = o2 = 0
+    n_checked = 0
+    for k, (i, j) in enumerate(gold["pairs"].tolist()):
+        c1, c2 = z["frame.ray_counts"][k].tolist()
+        r1 = z["frame.rays_first"][o1:o1 + c1]; r2 = z["frame.rays_second"][o2:o2 + c2]; o1 += c1; o2 += c2
+        ta, tb = trees[sc.mesh_index[i]], trees[sc.mesh_index[j]]
+        if c1 or c2:
+            d, _ = port.shoot(ta, sc.matrices[i], tb, sc.matrices[j], r1, r2)
+            assert np.array_equal(f32_bits(d), f32_bits(z["frame.shoot"][k])), (k, d, z["frame.shoot"][k])
+        col, d1, d2 = port.pair_delta(ta, sc.matrices[i], prev[i], tb, sc.matrices[j], prev[j])
+        assert int(col) == int(z["frame.colliding"][k])
+        g = z["frame.delta"][k].astype(np.float64)
+        for a, b in ((d1, g[:3]), (d2, g[3:])):
+            if np.isnan(b).any():
+                assert np.isnan(a).any()
+            else:
+                assert np.linalg.norm(a - b) <= 1e-4 * max(np.linalg.norm(b), 1e-30) + 1e-12, (k, a, b)
+                n_checked += bool(b.any())
+    assert n_checked > 20
