@@ -31,7 +31,8 @@ extern "C" int imrcd_create(int device, void* cuda_stream, imrcd_ctx** out) {
     else { if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return IMRCD_E_CUDA; } ctx->own_stream = true; }
     for (auto& e : ctx->ev) if (cudaEventCreate(&e) != cudaSuccess) { delete ctx; return IMRCD_E_CUDA; }
     if (cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return IMRCD_E_CUDA; }
+        cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream3, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_join3, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return IMRCD_E_CUDA; }
     *out = ctx;
     return IMRCD_OK;
 }
@@ -51,6 +52,8 @@ extern "C" void imrcd_destroy(imrcd_ctx* ctx) {
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+    if (ctx->stream3) cudaStreamDestroy(ctx->stream3);
+    if (ctx->ev_join3) cudaEventDestroy(ctx->ev_join3);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

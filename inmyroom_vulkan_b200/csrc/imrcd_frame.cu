@@ -642,7 +642,9 @@ k_tritri(FrameCtl* ctl, const Combo* __restrict__ combos, unsigned long long cap
 // three size classes: S (<= 256 hits: 128 threads), M (<= 1024 hits: 512 threads), both with their tables in shared memory, and
 // L (more: 512 threads, tables in a bump-allocated global scratch)
 #define PC_S_MAX 256u
+#define PC_M1_MAX 512u
 #define PC_M_MAX 1024u
+#define PC_CLASSES 4
 
 __global__ void k_hit_layout(const FrameCtl* ctl, unsigned long long cap_pairs, const PairAcc* __restrict__ acc, uint32_t* __restrict__ padded) {
     const unsigned long long n = ctl->n_pairs < cap_pairs ? ctl->n_pairs : cap_pairs;
@@ -654,22 +656,22 @@ __global__ void k_hit_layout(const FrameCtl* ctl, unsigned long long cap_pairs, 
 }
 
 __global__ void k_hit_lists(FrameCtl* ctl, unsigned long long cap_pairs, PairAcc* acc, const uint32_t* __restrict__ padded_off,
-                            uint32_t* __restrict__ list_s, uint32_t* __restrict__ list_m, uint32_t* __restrict__ list_l) {
+                            uint32_t* __restrict__ lists /* PC_CLASSES x cap_pairs */) {
     const unsigned long long n = ctl->n_pairs < cap_pairs ? ctl->n_pairs : cap_pairs;
     const uint32_t lane = lane_id();
     for (unsigned long long p0 = (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x) & ~31ull; p0 < n; p0 += (unsigned long long)gridDim.x * blockDim.x) {
         const unsigned long long p = p0 + lane;
         uint32_t h = 0;
         if (p < n) { h = acc[p].n_hits; acc[p].off = padded_off[p]; }
-        const int cls = h == 0 ? -1 : (h <= PC_S_MAX ? 0 : (h <= PC_M_MAX ? 1 : 2));
+        const int cls = h == 0 ? -1 : (h <= PC_S_MAX ? 0 : (h <= PC_M1_MAX ? 1 : (h <= PC_M_MAX ? 2 : 3)));
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
+        for (int c = 0; c < PC_CLASSES; ++c) {
             const uint32_t mm = __ballot_sync(FULL_MASK, cls == c);
             if (mm) {
                 unsigned long long b = 0;
                 if (lane == 0) b = atomicAdd(&ctl->n_class[c * 16], (unsigned long long)__popc(mm));
                 b = __shfl_sync(FULL_MASK, b, 0);
-                uint32_t* list = c == 0 ? list_s : (c == 1 ? list_m : list_l);
+                uint32_t* list = lists + (unsigned long long)c * cap_pairs;
                 if (cls == c) list[b + __popc(mm & ((1u << lane) - 1u))] = (uint32_t)p;
             }
         }
@@ -1065,9 +1067,7 @@ int imr_frame_run_device(imrcd_ctx* ctx) {
         }
         IMR_CUDA(ctx, ctx->d_padded.reserve(4ull * (ctx->cap_pairs + 1), 0, s));
         IMR_CUDA(ctx, ctx->d_padoff.reserve(4ull * (ctx->cap_pairs + 1), 0, s));
-        IMR_CUDA(ctx, ctx->d_lsmall.reserve(4ull * ctx->cap_pairs, 0, s));
-        IMR_CUDA(ctx, ctx->d_llarge.reserve(4ull * ctx->cap_pairs, 0, s));
-        IMR_CUDA(ctx, ctx->d_lmid.reserve(4ull * ctx->cap_pairs, 0, s));
+        IMR_CUDA(ctx, ctx->d_lsmall.reserve(4ull * PC_CLASSES * ctx->cap_pairs, 0, s));      // the size-class lists, cap_pairs entries each
         {
             size_t scan_bytes = 0;
             cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, ctx->d_padded.as<uint32_t>(), ctx->d_padoff.as<uint32_t>(), (int)(ctx->cap_pairs + 1), s);
@@ -1125,12 +1125,13 @@ int imr_frame_run_device(imrcd_ctx* ctx) {
         k_hit_layout<<<ctx->sm_count * 8, 256, 0, s>>>(ctl, ctx->cap_pairs, ctx->d_pairacc.as<PairAcc>(), ctx->d_padded.as<uint32_t>());
         cub::DeviceScan::ExclusiveSum(ctx->d_cubtmp.p, cub_bytes, ctx->d_padded.as<uint32_t>(), ctx->d_padoff.as<uint32_t>(), (int)(ctx->cap_pairs + 1), s);
         k_hit_lists<<<ctx->sm_count * 4, 256, 0, s>>>(ctl, ctx->cap_pairs, ctx->d_pairacc.as<PairAcc>(), ctx->d_padoff.as<uint32_t>(),
-                                                       ctx->d_lsmall.as<uint32_t>(), ctx->d_lmid.as<uint32_t>(), ctx->d_llarge.as<uint32_t>());
+                                                       ctx->d_lsmall.as<uint32_t>());
         k_group_hits<<<ctx->sm_count * 8, 256, 0, s>>>(ctl, ctx->cap_hits, ctx->d_hits.as<imrcd_tri_hit>(), ctx->d_pairacc.as<PairAcc>(), ctx->d_grouped.as<uint32_t>());
         {
             const size_t per_hit = 2 * (sizeof(PcSlot) + 8) + 4 * 8 + 12 + 5 * sizeof(uint16_t);
-            const size_t smem_s = PC_S_MAX * per_hit, smem_m = PC_M_MAX * per_hit;
+            const size_t smem_s = PC_S_MAX * per_hit, smem_m1 = PC_M1_MAX * per_hit, smem_m = PC_M_MAX * per_hit;
             if (!ctx->pc_attr_set) {
+                IMR_CUDA(ctx, cudaFuncSetAttribute(k_pair_contacts_hash<256, PC_M1_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m1));
                 IMR_CUDA(ctx, cudaFuncSetAttribute(k_pair_contacts_hash<512, PC_M_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m));
                 ctx->pc_attr_set = true;
             }
@@ -1138,16 +1139,22 @@ int imr_frame_run_device(imrcd_ctx* ctx) {
             const imrcd_tri_hit* a_hits = ctx->d_hits.as<imrcd_tri_hit>(); const HitAux* a_aux = ctx->d_aux.as<HitAux>();
             const PairRec* a_pr = ctx->d_pairrec.as<PairRec>(); const TriRec* a_tris = ctx->d_tris.as<TriRec>(); const uint32_t* a_vid = ctx->d_tri_vid.as<uint32_t>();
             const float* a_nrm = ctx->d_tri_nrm.as<float>(); RayRec* a_rays = ctx->d_rays.as<RayRec>(); unsigned char* a_scr = ctx->d_lscratch.as<unsigned char>();
-            // the three size classes are independent: the two rarer ones run beside the common one on a second stream
+            const uint32_t* l0 = ctx->d_lsmall.as<uint32_t>(); const uint32_t* l1 = l0 + ctx->cap_pairs; const uint32_t* l2 = l1 + ctx->cap_pairs; const uint32_t* l3 = l2 + ctx->cap_pairs;
+            // the size classes are independent: the rarer ones run beside the common one on a second stream, the ones with the largest
+            // shared-memory footprint first (a 137-KB block would otherwise wait for the small-class blocks to drain)
             IMR_CUDA(ctx, cudaEventRecord(ctx->ev_fork, s));
             IMR_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
-            k_pair_contacts_hash<128, PC_S_MAX><<<ctx->sm_count * 8, 128, smem_s, s>>>(ctl, ctx->d_lsmall.as<uint32_t>(), 0, a_acc, a_grp, a_hits, a_aux, a_pr, a_tris, a_vid, a_nrm, a_rays, ctx->cap_rays, a_scr, ctx->cap_lscratch);
-            k_pair_contacts_hash<512, PC_M_MAX><<<ctx->sm_count, 512, smem_m, ctx->stream2>>>(ctl, ctx->d_lmid.as<uint32_t>(), 1, a_acc, a_grp, a_hits, a_aux, a_pr, a_tris, a_vid, a_nrm, a_rays, ctx->cap_rays, a_scr, ctx->cap_lscratch);
-            k_pair_contacts_hash<512, 0><<<ctx->sm_count * 2, 512, 0, ctx->stream2>>>(ctl, ctx->d_llarge.as<uint32_t>(), 2, a_acc, a_grp, a_hits, a_aux, a_pr, a_tris, a_vid, a_nrm, a_rays, ctx->cap_rays, a_scr, ctx->cap_lscratch);
+            IMR_CUDA(ctx, cudaStreamWaitEvent(ctx->stream3, ctx->ev_fork, 0));
+            k_pair_contacts_hash<512, PC_M_MAX><<<ctx->sm_count, 512, smem_m, ctx->stream2>>>(ctl, l2, 2, a_acc, a_grp, a_hits, a_aux, a_pr, a_tris, a_vid, a_nrm, a_rays, ctx->cap_rays, a_scr, ctx->cap_lscratch);
+            k_pair_contacts_hash<512, 0><<<ctx->sm_count * 2, 512, 0, ctx->stream2>>>(ctl, l3, 3, a_acc, a_grp, a_hits, a_aux, a_pr, a_tris, a_vid, a_nrm, a_rays, ctx->cap_rays, a_scr, ctx->cap_lscratch);
+            k_pair_contacts_hash<256, PC_M1_MAX><<<ctx->sm_count * 3, 256, smem_m1, ctx->stream3>>>(ctl, l1, 1, a_acc, a_grp, a_hits, a_aux, a_pr, a_tris, a_vid, a_nrm, a_rays, ctx->cap_rays, a_scr, ctx->cap_lscratch);
+            k_pair_contacts_hash<128, PC_S_MAX><<<ctx->sm_count * 8, 128, smem_s, s>>>(ctl, l0, 0, a_acc, a_grp, a_hits, a_aux, a_pr, a_tris, a_vid, a_nrm, a_rays, ctx->cap_rays, a_scr, ctx->cap_lscratch);
             IMR_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->stream2));
+            IMR_CUDA(ctx, cudaEventRecord(ctx->ev_join3, ctx->stream3));
             IMR_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_join, 0));
+            IMR_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_join3, 0));
         }
-        launches += 8;      // layout, scan (2), lists, group, three size classes
+        launches += 9;      // layout, scan (2), lists, group, four size classes
         k_finalize<<<ctx->sm_count * 4, 256, 0, s>>>(ctl, ctx->cap_pairs, ctx->d_pairs.as<uint2>(), ctx->d_pairacc.as<PairAcc>(),
                                                       ctx->d_entity.as<uint32_t>(), ctx->d_cur.as<float>(), ctx->d_inv.as<float>(),
                                                       ctx->d_epairs.as<imrcd_entity_pair>(), ctx->d_epair_pair.as<uint32_t>());
@@ -1178,7 +1185,7 @@ int imr_frame_run_device(imrcd_ctx* ctx) {
         imrcd_frame_stats& st = ctx->stats;
         st.n_pairs = c.n_pairs; st.n_sat_tests = c.n_sat; st.n_combos = c.n_combos; st.n_tri_tests = c.n_tri_tests;
         st.n_hits = c.n_hits; st.n_coplanar_hits = c.n_coplanar; st.n_colliding = c.n_colliding;
-        st.n_contact_pairs = c.n_class[0] + c.n_class[16] + c.n_class[32]; st.n_rays = c.n_rays;
+        st.n_contact_pairs = c.n_class[0] + c.n_class[16] + c.n_class[32] + c.n_class[48]; st.n_rays = c.n_rays;
         st.traverse_launches = 1; st.total_launches = launches; st.n_queue_items = c.n_donated; st.n_warp_iterations = c.n_iterations; st.trav_busy_cycles = c.busy_cycles; st.trav_idle_polls = c.idle_polls;
         cudaEventElapsedTime(&st.ms_total, ctx->ev[0], ctx->ev[5]);
         cudaEventElapsedTime(&st.ms_broad, ctx->ev[0], ctx->ev[1]);

@@ -70,7 +70,7 @@ struct __align__(128) FrameCtl {
     unsigned long long n_combos;    unsigned long long _p5[15];
     unsigned long long n_hits;      unsigned long long _p6[15];
     unsigned long long n_colliding; unsigned long long _p7[15];
-    unsigned long long n_class[48];                               // pairs with hits per size class of the contact reduction ([0], [16], [32])
+    unsigned long long n_class[64];                               // pairs with hits per size class of the contact reduction ([0], [16], [32], [48])
     unsigned long long n_coplanar;
     unsigned long long n_sat;
     unsigned long long n_tri_tests;
@@ -189,8 +189,8 @@ struct imrcd_ctx {
     imrcd_frame_stats stats;
     bool hits_fetched = false;
     cudaEvent_t ev[8] = {};
-    cudaStream_t stream2 = nullptr;      // side stream for independent tail work of a frame
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t stream2 = nullptr, stream3 = nullptr;      // side streams for independent tail work of a frame
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join3 = nullptr;
     int trav_blocks = 0, narrow_blocks = 0, trav_variant = 0;
     bool pc_attr_set = false;
     const void* trav_fn = nullptr;
