@@ -656,14 +656,14 @@ __global__ void k_hit_layout(const FrameCtl* ctl, unsigned long long cap_pairs, 
 }
 
 __global__ void k_hit_lists(FrameCtl* ctl, unsigned long long cap_pairs, PairAcc* acc, const uint32_t* __restrict__ padded_off,
-                            uint32_t* __restrict__ lists /* PC_CLASSES x cap_pairs */) {
+                            uint32_t* __restrict__ lists /* PC_CLASSES x cap_pairs */, uint32_t large_min) {
     const unsigned long long n = ctl->n_pairs < cap_pairs ? ctl->n_pairs : cap_pairs;
     const uint32_t lane = lane_id();
     for (unsigned long long p0 = (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x) & ~31ull; p0 < n; p0 += (unsigned long long)gridDim.x * blockDim.x) {
         const unsigned long long p = p0 + lane;
         uint32_t h = 0;
         if (p < n) { h = acc[p].n_hits; acc[p].off = padded_off[p]; }
-        const int cls = h == 0 ? -1 : (h <= PC_S_MAX ? 0 : (h <= PC_M1_MAX ? 1 : (h <= PC_M_MAX ? 2 : 3)));
+        const int cls = h == 0 ? -1 : (h > large_min ? 3 : (h <= PC_S_MAX ? 0 : (h <= PC_M1_MAX ? 1 : 2)));
 #pragma unroll
         for (int c = 0; c < PC_CLASSES; ++c) {
             const uint32_t mm = __ballot_sync(FULL_MASK, cls == c);
@@ -946,6 +946,247 @@ k_pair_contacts_hash(FrameCtl* ctl, const uint32_t* __restrict__ list, int cls, 
     }
 }
 
+// ---- size class L (> 1024 hits): all large pairs together, the whole machine on them ---------------------------------------
+// A block per pair is the wrong shape for a pair with tens of thousands of hits (two deeply interpenetrating meshes: C2, C5): the same keyed
+// reduction runs here as a short sequence of grid-wide passes over ALL large pairs, tables in a global scratch (2m candidate slots and 4m vertex
+// slots per side for a pair padded to m hits), every atomic a native L2 RED (AND, FP64 add, 64-bit min).  `pref` = exclusive prefix of the
+// pairs' padded sizes: thread t of a pass serves unit t - pref[i] of pair i (found by binary search).
+struct LargeSide { uint32_t n_avg, n_vert, ray_base, cursor; };
+#define PCL_BYTES_PER_UNIT 224ull      // per padded hit, both sides: 2 x (2 keys + 2 bits + 2 PcSlot + 4 vertex entries)
+
+struct LargeTables { uint32_t* key; uint32_t* bits; PcSlot* sum; unsigned long long* vset; };
+__device__ __forceinline__ LargeTables pcl_tables(unsigned char* scratch, unsigned long long unit0, uint32_t m, uint32_t side) {
+    unsigned char* b = scratch + unit0 * PCL_BYTES_PER_UNIT + (unsigned long long)side * 112ull * m;
+    LargeTables t;
+    t.sum = reinterpret_cast<PcSlot*>(b);                                    // 2m x 32 B
+    t.vset = reinterpret_cast<unsigned long long*>(b + 64ull * m);           // 4m x 8 B
+    t.key = reinterpret_cast<uint32_t*>(b + 96ull * m);                      // 2m x 4 B
+    t.bits = reinterpret_cast<uint32_t*>(b + 104ull * m);                    // 2m x 4 B
+    return t;
+}
+__device__ __forceinline__ uint32_t pcl_padded(uint32_t n) { uint32_t m = 16u; while (m < n) m <<= 1; return m; }
+
+// one block: exclusive prefix of the padded sizes of the large pairs, scratch budget check, per-pair-side counters
+__global__ void __launch_bounds__(1024)
+k_large_layout(FrameCtl* ctl, const uint32_t* __restrict__ list, const PairAcc* __restrict__ acc, unsigned long long* __restrict__ pref, LargeSide* __restrict__ sides,
+               unsigned long long cap_scratch) {
+    __shared__ unsigned long long s_part[1024];
+    const unsigned long long n_list = (ctl->overflow & (OVF_PAIRS | OVF_QUEUE | OVF_COMBOS | OVF_HITS)) ? 0ull : ctl->n_class[3 * 16];
+    const uint32_t tid = threadIdx.x;
+    const unsigned long long per = (n_list + 1023ull) / 1024ull, lo = tid * per, hi = lo + per < n_list ? lo + per : n_list;
+    unsigned long long sum = 0;
+    for (unsigned long long i = lo; i < hi; ++i) sum += pcl_padded(acc[list[i]].n_hits);
+    s_part[tid] = sum;
+    __syncthreads();
+    if (tid == 0) { unsigned long long run = 0; for (int k = 0; k < 1024; ++k) { const unsigned long long v = s_part[k]; s_part[k] = run; run += v; } pref[n_list] = run;
+                    ctl->scratch_used = run * PCL_BYTES_PER_UNIT; if (run * PCL_BYTES_PER_UNIT > cap_scratch) { atomicOr(&ctl->overflow, (unsigned)OVF_SCRATCH); pref[n_list] = 0; } }
+    __syncthreads();
+    unsigned long long run = s_part[tid];
+    for (unsigned long long i = lo; i < hi; ++i) {
+        pref[i] = run; run += pcl_padded(acc[list[i]].n_hits);
+        LargeSide z; z.n_avg = z.n_vert = z.ray_base = z.cursor = 0u; sides[2 * i] = z; sides[2 * i + 1] = z;
+    }
+}
+
+// largest i in [0, n) with pref[i] <= t  (pref is non-decreasing, pref[0] = 0)
+__device__ __forceinline__ uint32_t pcl_find(const unsigned long long* __restrict__ pref, uint32_t n, unsigned long long t) {
+    uint32_t lo = 0, hi = n;
+    while (hi - lo > 1u) { const uint32_t mid = (lo + hi) >> 1; if (pref[mid] <= t) lo = mid; else hi = mid; }
+    return lo;
+}
+
+__global__ void k_large_init(const FrameCtl* ctl, const uint32_t* __restrict__ list, const PairAcc* __restrict__ acc, const unsigned long long* __restrict__ pref, unsigned char* scratch) {
+    const uint32_t n_list = (uint32_t)ctl->n_class[3 * 16];
+    if (ctl->overflow) return;
+    const unsigned long long total = pref[n_list];
+    for (unsigned long long t = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; t < total; t += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint32_t i = pcl_find(pref, n_list, t);
+        const uint32_t m = pcl_padded(acc[list[i]].n_hits), u = (uint32_t)(t - pref[i]);
+#pragma unroll
+        for (uint32_t side = 0; side < 2; ++side) {
+            const LargeTables tb = pcl_tables(scratch, pref[i], m, side);
+#pragma unroll
+            for (uint32_t q = 0; q < 2; ++q) { const uint32_t k = 2u * u + q; tb.key[k] = 0xffffffffu; tb.bits[k] = 7u; tb.sum[k].w = 0.0; tb.sum[k].cx = 0.0; tb.sum[k].cy = 0.0; tb.sum[k].cz = 0.0; }
+#pragma unroll
+            for (uint32_t q = 0; q < 4; ++q) tb.vset[4u * u + q] = ~0ull;
+        }
+    }
+}
+
+// one thread per hit of a large pair, both sides
+__global__ void __launch_bounds__(256)
+k_large_hits(const FrameCtl* ctl, const uint32_t* __restrict__ list, const PairAcc* __restrict__ acc, const unsigned long long* __restrict__ pref, unsigned char* scratch,
+             const uint32_t* __restrict__ grouped, const imrcd_tri_hit* __restrict__ hits, const HitAux* __restrict__ aux) {
+    const uint32_t n_list = (uint32_t)ctl->n_class[3 * 16];
+    if (ctl->overflow) return;
+    const unsigned long long total = pref[n_list];
+    const uint32_t lane = lane_id();
+    for (unsigned long long t0 = (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x) & ~31ull; t0 < total; t0 += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long t = t0 + lane;
+        bool have = false;
+        uint32_t i = 0, m = 0, n = 0, k = 0;
+        const uint32_t* grp = nullptr;
+        HitAux x; x.triA = x.triB = x.flags = 0u;
+        imrcd_tri_hit hh; hh.weight = 0.f; hh.source[0] = hh.source[1] = hh.source[2] = hh.target[0] = hh.target[1] = hh.target[2] = 0.f;
+        if (t < total) {
+            i = pcl_find(pref, n_list, t);
+            const PairAcc& pa = acc[list[i]];
+            n = pa.n_hits; m = pcl_padded(n); k = (uint32_t)(t - pref[i]); grp = grouped + pa.off;
+            if (k < n) { have = true; const uint32_t h = grp[k]; x = aux[h]; hh = hits[h]; }
+        }
+#pragma unroll
+        for (uint32_t side = 0; side < 2; ++side) {
+            uint32_t slot = 0xffffffffu, bits = 7u, tab = 0xffffffffu;
+            double w = 0.0, cx = 0.0, cy = 0.0, cz = 0.0;
+            LargeTables tb; tb.key = nullptr; tb.bits = nullptr; tb.sum = nullptr; tb.vset = nullptr;
+            if (have) {
+                const uint32_t own = side ? x.triB : x.triA;
+                bool contributes = !(hh.weight == 0.f);
+                if (!contributes) {                                                      // rare: is the combo's weight for this triangle 0? (:117-127)
+                    const uint32_t leaf = side ? x.triA - ((x.flags >> 6) & 3u) : x.triB - ((x.flags >> 8) & 3u);
+                    for (uint32_t q = 0; q < n && !contributes; ++q) {
+                        const uint32_t h2 = grp[q];
+                        const HitAux y = aux[h2];
+                        const uint32_t own2 = side ? y.triB : y.triA;
+                        const uint32_t leaf2 = side ? y.triA - ((y.flags >> 6) & 3u) : y.triB - ((y.flags >> 8) & 3u);
+                        contributes = own2 == own && leaf2 == leaf && !(hits[h2].weight == 0.f);
+                    }
+                }
+                if (contributes) {
+                    tb = pcl_tables(scratch, pref[i], m, side);
+                    bool claimed = false;
+                    slot = pc_slot_of(tb.key, 2u * m - 1u, own, claimed);
+                    tab = i;
+                    const V3 sum = add3(mk3(hh.source[0], hh.source[1], hh.source[2]), mk3(hh.target[0], hh.target[1], hh.target[2]));
+                    bits = side ? ((x.flags >> 3) & 7u) : (x.flags & 7u);
+                    w = (double)hh.weight;
+                    cx = (double)((hh.weight * sum.x) / 2.f); cy = (double)((hh.weight * sum.y) / 2.f); cz = (double)((hh.weight * sum.z) / 2.f);   // :94-100
+                }
+            }
+            // runs of equal (pair, slot) in consecutive lanes are added up inside the warp first (see k_pair_contacts_hash)
+            const uint32_t prev_s = __shfl_up_sync(FULL_MASK, slot, 1), prev_t = __shfl_up_sync(FULL_MASK, tab, 1);
+            const uint32_t heads = __ballot_sync(FULL_MASK, lane == 0u || prev_s != slot || prev_t != tab);
+            const uint32_t head = 31u - (uint32_t)__clz(heads & (0xffffffffu >> (31u - lane)));
+            const uint32_t after = heads & ~(0xffffffffu >> (31u - lane));
+            const uint32_t tail = after ? (uint32_t)__ffs(after) - 2u : 31u;
+#pragma unroll
+            for (uint32_t d = 1; d < 32u; d <<= 1) {
+                const double vw = __shfl_up_sync(FULL_MASK, w, d), vx = __shfl_up_sync(FULL_MASK, cx, d), vy = __shfl_up_sync(FULL_MASK, cy, d), vz = __shfl_up_sync(FULL_MASK, cz, d);
+                const uint32_t vb = __shfl_up_sync(FULL_MASK, bits, d);
+                if (lane >= head + d) { w += vw; cx += vx; cy += vy; cz += vz; bits &= vb; }
+            }
+            if (lane == tail && slot != 0xffffffffu) {
+                atomicAnd(&tb.bits[slot], bits);
+                atomicAdd(&tb.sum[slot].w, w); atomicAdd(&tb.sum[slot].cx, cx); atomicAdd(&tb.sum[slot].cy, cy); atomicAdd(&tb.sum[slot].cz, cz);
+            }
+        }
+    }
+}
+
+// one thread per candidate slot (2m per side): vertex rays into the `emplaced` set, average-point rays counted (:139-166)
+__global__ void __launch_bounds__(256)
+k_large_candidates(const FrameCtl* ctl, const uint32_t* __restrict__ list, const PairAcc* __restrict__ acc, const unsigned long long* __restrict__ pref, unsigned char* scratch,
+                   LargeSide* __restrict__ sides, const uint32_t* __restrict__ tri_vid) {
+    const uint32_t n_list = (uint32_t)ctl->n_class[3 * 16];
+    if (ctl->overflow) return;
+    const unsigned long long total = pref[n_list] * 4ull;                       // 2 sides x 2m slots per padded hit
+    for (unsigned long long t = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; t < total; t += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint32_t i = pcl_find(pref, n_list, t >> 2);
+        const uint32_t m = pcl_padded(acc[list[i]].n_hits);
+        const unsigned long long r = t - pref[i] * 4ull;                          // [0, 4m)
+        const uint32_t side = (uint32_t)(r / (2ull * m)), k = (uint32_t)(r % (2ull * m));
+        const LargeTables tb = pcl_tables(scratch, pref[i], m, side);
+        const uint32_t tri = __ldcg(tb.key + k);
+        if (tri == 0xffffffffu) continue;
+        const uint32_t bits = __ldcg(tb.bits + k);
+        if (bits == 0u) atomicAdd(&sides[2 * i + side].n_avg, 1u);                // ShouldFallbackToAvgPoint (:27-30)
+        else {
+            uint32_t claimed = 0;
+#pragma unroll
+            for (uint32_t pi = 0; pi < 3; ++pi)
+                if ((bits >> pi) & 1u)
+                    claimed += vset_insert_m(tb.vset, 4u * m - 1u, ((unsigned long long)tri_vid[3ull * tri + pi] << 32) | (unsigned long long)(tri * 4u + pi)) != 0xffffffffu;
+            if (claimed) atomicAdd(&sides[2 * i + side].n_vert, claimed);
+        }
+    }
+}
+
+// one thread per pair side: ray counts, the pair's slice of the ray array
+__global__ void k_large_alloc(FrameCtl* ctl, const uint32_t* __restrict__ list, PairAcc* acc, LargeSide* __restrict__ sides, unsigned long long cap_rays) {
+    const uint32_t n_list = (uint32_t)ctl->n_class[3 * 16];
+    if (ctl->overflow & ~(unsigned)OVF_RAYS) return;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < 2u * n_list; t += gridDim.x * blockDim.x) {
+        const uint32_t i = t >> 1, side = t & 1u;
+        PairAcc* pa = acc + list[i];
+        LargeSide& sd = sides[t];
+        const uint32_t cnt = sd.n_avg + sd.n_vert;
+        if (side) pa->rays_b = cnt; else pa->rays_a = cnt;
+        if (pa->flags & PAIR_MOVED) {
+            const unsigned long long base = atomicAdd(&ctl->n_rays_kept, (unsigned long long)cnt);
+            if (base + cnt > cap_rays) { atomicOr(&ctl->overflow, (unsigned)OVF_RAYS); sd.ray_base = 0xffffffffu; }
+            else { sd.ray_base = (uint32_t)base; if (side) pa->ray_off_b = (uint32_t)base; else pa->ray_off_a = (uint32_t)base; }
+        } else sd.ray_base = 0xffffffffu;
+    }
+}
+
+// one thread per candidate slot and per vertex slot: the ray's origin into the pair's FP64 sum, the ray into the pair's slice
+__global__ void __launch_bounds__(256)
+k_large_rays(const FrameCtl* ctl, const uint32_t* __restrict__ list, PairAcc* acc, const unsigned long long* __restrict__ pref, unsigned char* scratch,
+             LargeSide* __restrict__ sides, const PairRec* __restrict__ pairrec, const TriRec* __restrict__ tris, const float* __restrict__ tri_nrm, RayRec* __restrict__ rays) {
+    const uint32_t n_list = (uint32_t)ctl->n_class[3 * 16];
+    if (ctl->overflow) return;
+    const unsigned long long total = pref[n_list] * 12ull;                      // per padded hit: 2 sides x (2 candidate slots + 4 vertex slots)
+    for (unsigned long long t = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; t < total; t += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint32_t i = pcl_find(pref, n_list, t / 12ull);
+        const uint32_t p = list[i];
+        const uint32_t m = pcl_padded(acc[p].n_hits);
+        const unsigned long long r = t - pref[i] * 12ull;                         // [0, 12m)
+        const uint32_t side = (uint32_t)(r / (6ull * m)), k = (uint32_t)(r % (6ull * m));
+        const LargeTables tb = pcl_tables(scratch, pref[i], m, side);
+        LargeSide& sd = sides[2 * i + side];
+        V3 pos, nrm;
+        if (k < 2u * m) {                                                      // candidate slot: only the average-point rays (:157-166)
+            const uint32_t tri = __ldcg(tb.key + k);
+            if (tri == 0xffffffffu || __ldcg(tb.bits + k) != 0u) continue;
+            const double w = __ldcg(&tb.sum[k].w);
+            pos = mk3((float)(__ldcg(&tb.sum[k].cx) / w), (float)(__ldcg(&tb.sum[k].cy) / w), (float)(__ldcg(&tb.sum[k].cz) / w));     // FP64 quotient, rounded once
+            if (sd.ray_base != 0xffffffffu) {
+                const float4* pp = reinterpret_cast<const float4*>(pairrec + p);
+                Rel rel; rel.r0 = __ldg(pp); rel.r1 = __ldg(pp + 1); rel.r2 = __ldg(pp + 2);
+                const float4* tp = reinterpret_cast<const float4*>(tris + tri);
+                const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
+                V3 p0 = mk3(t0.x, t0.y, t0.z), p1 = mk3(t1.x, t1.y, t1.z), p2 = mk3(t2.x, t2.y, t2.z);
+                if (side) { p0 = rel_mul(rel, p0, 1.f); p1 = rel_mul(rel, p1, 1.f); p2 = rel_mul(rel, p2, 1.f); }
+                float bx, by;
+                tri_barycentric(p0, p1, p2, pos, bx, by);
+                const float* nn = tri_nrm + 9ull * tri;
+                nrm = tri_interp_normal(mk3(nn[0], nn[1], nn[2]), mk3(nn[3], nn[4], nn[5]), mk3(nn[6], nn[7], nn[8]), bx, by);
+                nrm = normalize3(side ? m3_mul(adjoint_transpose3(rel), nrm) : nrm);
+            }
+        } else {                                                               // vertex slot (:139-155)
+            const unsigned long long ent = __ldcg(tb.vset + (k - 2u * m));
+            if (ent == ~0ull) continue;
+            const uint32_t ref = (uint32_t)ent;
+            const float4 q = __ldg(reinterpret_cast<const float4*>(tris + (ref >> 2)) + (ref & 3u));
+            pos = mk3(q.x, q.y, q.z);
+            const float4* pp = reinterpret_cast<const float4*>(pairrec + p);
+            Rel rel; rel.r0 = __ldg(pp); rel.r1 = __ldg(pp + 1); rel.r2 = __ldg(pp + 2);
+            if (side) pos = rel_mul(rel, pos, 1.f);
+            if (sd.ray_base != 0xffffffffu) {
+                const float* nn = tri_nrm + 9ull * (ref >> 2) + 3u * (ref & 3u);
+                nrm = mk3(nn[0], nn[1], nn[2]);
+                nrm = normalize3(side ? m3_mul(adjoint_transpose3(rel), nrm) : nrm);
+            }
+        }
+        double* sum = side ? acc[p].sum_b : acc[p].sum_a;
+        atomicAdd(sum, (double)pos.x); atomicAdd(sum + 1, (double)pos.y); atomicAdd(sum + 2, (double)pos.z);
+        if (sd.ray_base != 0xffffffffu) {
+            RayRec o; o.o = make_float4(pos.x, pos.y, pos.z, __uint_as_float(p)); o.d = make_float4(-nrm.x, -nrm.y, -nrm.z, __uint_as_float(side));
+            rays[sd.ray_base + atomicAdd(&sd.cursor, 1u)] = o;
+        }
+    }
+}
+
 __global__ void k_finalize(FrameCtl* ctl, unsigned long long cap_pairs, const uint2* __restrict__ pairs, const PairAcc* __restrict__ acc,
                            const uint32_t* __restrict__ entity, const float* __restrict__ cur, const float* __restrict__ inv,
                            imrcd_entity_pair* __restrict__ out, uint32_t* __restrict__ out_pair) {
@@ -997,7 +1238,11 @@ int imr_frame_run_device(imrcd_ctx* ctx) {
     if (ctx->cap_combos == 0) ctx->cap_combos = 1ull << 22;
     if (ctx->cap_hits == 0) ctx->cap_hits = 1ull << 20;
     if (ctx->cap_rays == 0) ctx->cap_rays = 1ull << 18;
-    if (ctx->cap_lscratch == 0) ctx->cap_lscratch = 16ull << 20;
+    if (ctx->cap_lscratch == 0) {
+        ctx->cap_lscratch = 16ull << 20;
+        const char* ev = getenv("IMRCD_PC_LARGE_MIN");                 // pairs with more hits than this take the grid-wide passes (tuning knob)
+        if (ev) ctx->pc_large_min = std::min<uint32_t>((uint32_t)atoi(ev), PC_M_MAX);
+    }
 
     IMR_CUDA(ctx, ctx->d_inv.reserve(64ull * n, 0, s));
     IMR_CUDA(ctx, ctx->d_ext.reserve(24ull * n, 0, s));
@@ -1060,6 +1305,8 @@ int imr_frame_run_device(imrcd_ctx* ctx) {
         IMR_CUDA(ctx, ctx->d_aux.reserve(sizeof(HitAux) * ctx->cap_hits, 0, s));
         IMR_CUDA(ctx, ctx->d_grouped.reserve(4ull * 2 * ctx->cap_hits, 0, s));
         IMR_CUDA(ctx, ctx->d_lscratch.reserve(ctx->cap_lscratch, 0, s));
+        IMR_CUDA(ctx, ctx->d_lpref.reserve(8ull * (ctx->cap_pairs + 1), 0, s));
+        IMR_CUDA(ctx, ctx->d_lsides.reserve(sizeof(LargeSide) * 2ull * ctx->cap_pairs, 0, s));
         IMR_CUDA(ctx, ctx->d_epair_pair.reserve(4ull * ctx->cap_pairs, 0, s));
         if (ctx->prev_distinct) {
             IMR_CUDA(ctx, ctx->d_rays.reserve(sizeof(RayRec) * ctx->cap_rays, 0, s));
@@ -1125,7 +1372,7 @@ int imr_frame_run_device(imrcd_ctx* ctx) {
         k_hit_layout<<<ctx->sm_count * 8, 256, 0, s>>>(ctl, ctx->cap_pairs, ctx->d_pairacc.as<PairAcc>(), ctx->d_padded.as<uint32_t>());
         cub::DeviceScan::ExclusiveSum(ctx->d_cubtmp.p, cub_bytes, ctx->d_padded.as<uint32_t>(), ctx->d_padoff.as<uint32_t>(), (int)(ctx->cap_pairs + 1), s);
         k_hit_lists<<<ctx->sm_count * 4, 256, 0, s>>>(ctl, ctx->cap_pairs, ctx->d_pairacc.as<PairAcc>(), ctx->d_padoff.as<uint32_t>(),
-                                                       ctx->d_lsmall.as<uint32_t>());
+                                                       ctx->d_lsmall.as<uint32_t>(), ctx->pc_large_min);
         k_group_hits<<<ctx->sm_count * 8, 256, 0, s>>>(ctl, ctx->cap_hits, ctx->d_hits.as<imrcd_tri_hit>(), ctx->d_pairacc.as<PairAcc>(), ctx->d_grouped.as<uint32_t>());
         {
             const size_t per_hit = 2 * (sizeof(PcSlot) + 8) + 4 * 8 + 12 + 5 * sizeof(uint16_t);
@@ -1145,16 +1392,29 @@ int imr_frame_run_device(imrcd_ctx* ctx) {
             IMR_CUDA(ctx, cudaEventRecord(ctx->ev_fork, s));
             IMR_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
             IMR_CUDA(ctx, cudaStreamWaitEvent(ctx->stream3, ctx->ev_fork, 0));
+            IMR_CUDA(ctx, cudaStreamWaitEvent(ctx->stream4, ctx->ev_fork, 0));
             k_pair_contacts_hash<512, PC_M_MAX><<<ctx->sm_count, 512, smem_m, ctx->stream2>>>(ctl, l2, 2, a_acc, a_grp, a_hits, a_aux, a_pr, a_tris, a_vid, a_nrm, a_rays, ctx->cap_rays, a_scr, ctx->cap_lscratch);
-            k_pair_contacts_hash<512, 0><<<ctx->sm_count * 2, 512, 0, ctx->stream2>>>(ctl, l3, 3, a_acc, a_grp, a_hits, a_aux, a_pr, a_tris, a_vid, a_nrm, a_rays, ctx->cap_rays, a_scr, ctx->cap_lscratch);
+            {   // large pairs: grid-wide passes (k_large_*), on their own side stream
+                cudaStream_t s2 = ctx->stream4;
+                unsigned long long* a_pref = ctx->d_lpref.as<unsigned long long>(); LargeSide* a_sides = ctx->d_lsides.as<LargeSide>();
+                const unsigned gl = ctx->sm_count * 4;
+                k_large_layout<<<1, 1024, 0, s2>>>(ctl, l3, a_acc, a_pref, a_sides, ctx->cap_lscratch);
+                k_large_init<<<gl, 256, 0, s2>>>(ctl, l3, a_acc, a_pref, a_scr);
+                k_large_hits<<<gl, 256, 0, s2>>>(ctl, l3, a_acc, a_pref, a_scr, a_grp, a_hits, a_aux);
+                k_large_candidates<<<gl, 256, 0, s2>>>(ctl, l3, a_acc, a_pref, a_scr, a_sides, a_vid);
+                k_large_alloc<<<ctx->sm_count, 256, 0, s2>>>(ctl, l3, a_acc, a_sides, ctx->cap_rays);
+                k_large_rays<<<gl, 256, 0, s2>>>(ctl, l3, a_acc, a_pref, a_scr, a_sides, a_pr, a_tris, a_nrm, a_rays);
+            }
             k_pair_contacts_hash<256, PC_M1_MAX><<<ctx->sm_count * 3, 256, smem_m1, ctx->stream3>>>(ctl, l1, 1, a_acc, a_grp, a_hits, a_aux, a_pr, a_tris, a_vid, a_nrm, a_rays, ctx->cap_rays, a_scr, ctx->cap_lscratch);
             k_pair_contacts_hash<128, PC_S_MAX><<<ctx->sm_count * 8, 128, smem_s, s>>>(ctl, l0, 0, a_acc, a_grp, a_hits, a_aux, a_pr, a_tris, a_vid, a_nrm, a_rays, ctx->cap_rays, a_scr, ctx->cap_lscratch);
             IMR_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->stream2));
             IMR_CUDA(ctx, cudaEventRecord(ctx->ev_join3, ctx->stream3));
+            IMR_CUDA(ctx, cudaEventRecord(ctx->ev_join4, ctx->stream4));
             IMR_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_join, 0));
             IMR_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_join3, 0));
+            IMR_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_join4, 0));
         }
-        launches += 9;      // layout, scan (2), lists, group, four size classes
+        launches += 14;     // layout, scan (2), lists, group, three per-pair size classes, six passes over the large pairs
         k_finalize<<<ctx->sm_count * 4, 256, 0, s>>>(ctl, ctx->cap_pairs, ctx->d_pairs.as<uint2>(), ctx->d_pairacc.as<PairAcc>(),
                                                       ctx->d_entity.as<uint32_t>(), ctx->d_cur.as<float>(), ctx->d_inv.as<float>(),
                                                       ctx->d_epairs.as<imrcd_entity_pair>(), ctx->d_epair_pair.as<uint32_t>());

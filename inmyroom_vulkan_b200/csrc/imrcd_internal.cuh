@@ -179,7 +179,7 @@ struct imrcd_ctx {
     // frame, device side
     DevBuf d_cur, d_prev, d_mesh, d_cb, d_entity, d_inv, d_ext, d_keys, d_keys2, d_idx, d_idx2, d_sorted, d_sorted_c, d_flag, d_cpos, d_wlen, d_chunks, d_chunkoff, d_cubtmp;
     DevBuf d_pairs, d_pairrec, d_pairacc, d_queue, d_combos, d_hits, d_epairs, d_ctl;
-    DevBuf d_aux, d_grouped, d_lscratch, d_padded, d_padoff, d_lsmall, d_lmid, d_llarge;      // contact reduction scratch (imrcd_frame.cu)
+    DevBuf d_aux, d_grouped, d_lscratch, d_lpref, d_lsides, d_padded, d_padoff, d_lsmall, d_lmid, d_llarge;      // contact reduction scratch (imrcd_frame.cu)
     DevBuf d_rays, d_resp, d_epair_pair;                                                    // response stage (imrcd_rays.cu)
     uint64_t cap_pairs = 0, cap_queue = 0, cap_combos = 0, cap_hits = 0, cap_rays = 0, cap_lscratch = 0;
     uint64_t queue_dirty = 0;            // slots whose ready flag may still be set
@@ -189,10 +189,11 @@ struct imrcd_ctx {
     imrcd_frame_stats stats;
     bool hits_fetched = false;
     cudaEvent_t ev[8] = {};
-    cudaStream_t stream2 = nullptr, stream3 = nullptr;      // side streams for independent tail work of a frame
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join3 = nullptr;
+    cudaStream_t stream2 = nullptr, stream3 = nullptr, stream4 = nullptr;      // side streams for independent tail work of a frame
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join3 = nullptr, ev_join4 = nullptr;
     int trav_blocks = 0, narrow_blocks = 0, trav_variant = 0;
     bool pc_attr_set = false;
+    uint32_t pc_large_min = 1024;        // contact reduction: pairs with more hits go to the grid-wide passes
     const void* trav_fn = nullptr;
 };
 
