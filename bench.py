@@ -280,6 +280,8 @@ def run_gpu_arm(args):
             e1.record(stream)
         return e0, e1
 
+    if gather is not None:                               # settle the gather's block capacity before anything is timed
+        cd.run(); gather.gather_host()
     clocks = ClockSampler(local); clocks.start()          # sampled from the warm-up to the end of the e2e loop
     for _ in range(args.warmup):
         l2_flush(); device_step()
@@ -293,6 +295,8 @@ def run_gpu_arm(args):
             st_acc[k] = st_acc.get(k, 0.0) + st[k]
         launches += st["total_launches"]
     barrier()
+    if gather is not None and gather.counts() is None:
+        raise SystemExit("bench.py: the frame gather outgrew its blocks during the timed loop")
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     st = cd.stats()
     dev_ms_max = global_max(dev_ms)

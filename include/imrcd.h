@@ -154,6 +154,10 @@ int imrcd_frame_get_stats(imrcd_ctx* ctx, imrcd_frame_stats* out);
 /* Device pointers of the result arrays (for an NCCL gather by the caller): hits, entity pairs. */
 int imrcd_frame_results_device(imrcd_ctx* ctx, void** d_pairs, uint64_t* n_pairs, void** d_hits, uint64_t* n_hits);
 
+/* The same records as one contiguous device block for a fixed-capacity collective: row 0 (80 B) starts with the u64 record count, the
+ * records follow from row 1; `capacity` = rows allocated after the header (rows past the count hold stale data). */
+int imrcd_frame_results_block(imrcd_ctx* ctx, void** d_block, uint64_t* n_pairs, uint64_t* capacity);
+
 /* ---- unit-level entry points used by the parity tests (device kernels on flat arrays) ---- */
 int imrcd_test_sat(imrcd_ctx* ctx, uint64_t n, const float* boxes_a, const float* boxes_b, const float* mats /* n*16 or NULL */,
                    uint8_t* verdict, float* surface_a, float* surface_b);

@@ -72,6 +72,7 @@ _SIGS = [
     ("imrcd_frame_combos", C.c_int, [_P, C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.c_uint64)]),
     ("imrcd_frame_get_stats", C.c_int, [_P, C.POINTER(FrameStats)]),
     ("imrcd_frame_results_device", C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_uint64), C.POINTER(_P), C.POINTER(C.c_uint64)]),
+    ("imrcd_frame_results_block", C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     ("imrcd_test_sat", C.c_int, [_P, C.c_uint64, _P, _P, _P, _P, _P, _P]),
     ("imrcd_test_tri_tri", C.c_int, [_P, C.c_uint64, _P, _P, _P, _P, _P]),
     ("imrcd_test_pair_matrix", C.c_int, [_P, C.c_uint64, _P, _P, _P]),

@@ -460,7 +460,7 @@ extern "C" int imrcd_frame_fetch(imrcd_ctx* ctx) {
     const uint64_t nc = ctx->ctl_host.n_colliding;
     if (nc) {
         IMR_CUDA(ctx, ctx->p_epairs.reserve(sizeof(imrcd_entity_pair) * nc));
-        IMR_CUDA(ctx, cudaMemcpyAsync(ctx->p_epairs.p, ctx->d_epairs.p, sizeof(imrcd_entity_pair) * nc, cudaMemcpyDeviceToHost, ctx->stream));
+        IMR_CUDA(ctx, cudaMemcpyAsync(ctx->p_epairs.p, ctx->d_epairs.as<imrcd_entity_pair>() + 1, sizeof(imrcd_entity_pair) * nc, cudaMemcpyDeviceToHost, ctx->stream));
         IMR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
     ctx->fetched = true;
@@ -534,10 +534,19 @@ extern "C" int imrcd_frame_get_stats(imrcd_ctx* ctx, imrcd_frame_stats* out) {
 extern "C" int imrcd_frame_results_device(imrcd_ctx* ctx, void** d_pairs, uint64_t* n_pairs, void** d_hits, uint64_t* n_hits) {
     CHECK_CTX(ctx);
     if (!ctx->ran) { ctx->err = "imrcd_frame_results_device before imrcd_frame_run"; return IMRCD_E_STATE; }
-    if (d_pairs) *d_pairs = ctx->d_epairs.p;
+    if (d_pairs) *d_pairs = ctx->d_epairs.as<imrcd_entity_pair>() + 1;
     if (n_pairs) *n_pairs = ctx->ctl_host.n_colliding;
     if (d_hits) *d_hits = ctx->d_hits.p;
     if (n_hits) *n_hits = ctx->ctl_host.n_hits;
+    return IMRCD_OK;
+}
+
+extern "C" int imrcd_frame_results_block(imrcd_ctx* ctx, void** d_block, uint64_t* n_pairs, uint64_t* capacity) {
+    CHECK_CTX(ctx);
+    if (!ctx->ran) { ctx->err = "imrcd_frame_results_block before imrcd_frame_run"; return IMRCD_E_STATE; }
+    if (d_block) *d_block = ctx->d_epairs.p;
+    if (n_pairs) *n_pairs = ctx->ctl_host.n_colliding;
+    if (capacity) *capacity = ctx->d_epairs.p ? ctx->d_epairs.cap / sizeof(imrcd_entity_pair) - 1 : 0;
     return IMRCD_OK;
 }
 

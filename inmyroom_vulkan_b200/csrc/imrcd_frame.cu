@@ -1187,6 +1187,14 @@ k_large_rays(const FrameCtl* ctl, const uint32_t* __restrict__ list, PairAcc* ac
     }
 }
 
+// row 0 of the result block: the number of records that follow (what a fixed-capacity all-gather of the block needs to carry)
+__global__ void k_epairs_header(const FrameCtl* ctl, imrcd_entity_pair* block) {
+    imrcd_entity_pair h; memset(&h, 0, sizeof(h));
+    const unsigned long long n = ctl->n_colliding;
+    h.entry_first = (uint32_t)n; h.entry_second = (uint32_t)(n >> 32);
+    block[0] = h;
+}
+
 __global__ void k_finalize(FrameCtl* ctl, unsigned long long cap_pairs, const uint2* __restrict__ pairs, const PairAcc* __restrict__ acc,
                            const uint32_t* __restrict__ entity, const float* __restrict__ cur, const float* __restrict__ inv,
                            imrcd_entity_pair* __restrict__ out, uint32_t* __restrict__ out_pair) {
@@ -1297,7 +1305,7 @@ int imr_frame_run_device(imrcd_ctx* ctx) {
         IMR_CUDA(ctx, ctx->d_pairs.reserve(8ull * ctx->cap_pairs, 0, s));
         IMR_CUDA(ctx, ctx->d_pairrec.reserve(sizeof(PairRec) * ctx->cap_pairs, 0, s));
         IMR_CUDA(ctx, ctx->d_pairacc.reserve(sizeof(PairAcc) * ctx->cap_pairs, 0, s));
-        IMR_CUDA(ctx, ctx->d_epairs.reserve(sizeof(imrcd_entity_pair) * ctx->cap_pairs, 0, s));
+        IMR_CUDA(ctx, ctx->d_epairs.reserve(sizeof(imrcd_entity_pair) * (ctx->cap_pairs + 1), 0, s));      // row 0 = header (record count), see imrcd_frame_results_block
         if (16ull * ctx->cap_queue > ctx->d_queue.cap) { IMR_CUDA(ctx, ctx->d_queue.reserve(16ull * ctx->cap_queue, 0, s)); ctx->queue_dirty = ctx->cap_queue; }
         IMR_CUDA(ctx, ctx->d_combos.reserve(16ull * ctx->cap_combos, 0, s));
         IMR_CUDA(ctx, ctx->d_hits.reserve(sizeof(imrcd_tri_hit) * ctx->cap_hits, 0, s));
@@ -1417,8 +1425,9 @@ int imr_frame_run_device(imrcd_ctx* ctx) {
         launches += 14;     // layout, scan (2), lists, group, three per-pair size classes, six passes over the large pairs
         k_finalize<<<ctx->sm_count * 4, 256, 0, s>>>(ctl, ctx->cap_pairs, ctx->d_pairs.as<uint2>(), ctx->d_pairacc.as<PairAcc>(),
                                                       ctx->d_entity.as<uint32_t>(), ctx->d_cur.as<float>(), ctx->d_inv.as<float>(),
-                                                      ctx->d_epairs.as<imrcd_entity_pair>(), ctx->d_epair_pair.as<uint32_t>());
-        launches += 1;
+                                                      ctx->d_epairs.as<imrcd_entity_pair>() + 1, ctx->d_epair_pair.as<uint32_t>());
+        k_epairs_header<<<1, 1, 0, s>>>(ctl, ctx->d_epairs.as<imrcd_entity_pair>());
+        launches += 2;
         IMR_CUDA(ctx, cudaEventRecord(ctx->ev[6], s));
         { int rc = imr_frame_shoot_device(ctx, ctl, &launches); if (rc != IMRCD_OK) return rc; }
         IMR_CUDA(ctx, cudaEventRecord(ctx->ev[5], s));

@@ -370,7 +370,7 @@ int imr_frame_shoot_device(imrcd_ctx* ctx, FrameCtl* ctl, uint64_t* launches) {
     if (!shoot_blocks_per_sm) { IMR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&shoot_blocks_per_sm, k_shoot, 128, 0)); if (shoot_blocks_per_sm < 1) shoot_blocks_per_sm = 1; }
     k_shoot<<<ctx->sm_count * shoot_blocks_per_sm, 128, 0, s>>>(ctl, ctx->cap_rays, ctx->d_rays.as<RayRec>(), ctx->d_resp.as<float4>(), ctx->d_pairacc.as<PairAcc>(),
                                                ctx->d_pairrec.as<PairRec>(), ctx->d_recs.as<TreeRec>(), ctx->d_tris.as<TriRec>(), ctx->d_tri_nrm.as<float>());
-    k_delta<<<ctx->sm_count * 4, 256, 0, s>>>(ctl, ctx->d_epair_pair.as<uint32_t>(), ctx->d_epairs.as<imrcd_entity_pair>(), ctx->d_pairacc.as<PairAcc>(),
+    k_delta<<<ctx->sm_count * 4, 256, 0, s>>>(ctl, ctx->d_epair_pair.as<uint32_t>(), ctx->d_epairs.as<imrcd_entity_pair>() + 1, ctx->d_pairacc.as<PairAcc>(),
                                                ctx->d_resp.as<float4>(), ctx->d_cur.as<float>(), ctx->d_prev.as<float>(), edge_a, edge_b);
     *launches += 2;
     return IMRCD_OK;

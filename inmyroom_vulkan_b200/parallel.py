@@ -4,8 +4,8 @@ The path shards naturally: trees and the entry table are replicat
 of the broad phase and then sweeps only every world-th chunk of it (imrcd_frame_set_shard; a chunk is one entity x 512
 consecutive candidates of its window), so each candidate pair, all of its triangle hits and its contact reduction belong
 to exactly one rank and nothing crosses GPUs before the end of the frame.  The only collective is the
-end-of-frame merge of the colliding-pair records (80 B each): an all-gather of per-rank counts followed by an
-all-gather of max-padded record blocks, over NCCL on NVLink (gloo on CPU in the tests).
+end-of-frame merge of the colliding-pair records (80 B each): ONE all-gather of fixed-capacity blocks whose header row carries
+the rank's record count, taken straight from the library's result block in HBM, over NCCL on NVLink (gloo on CPU in the tests).
 
 The reference has no counterpart (it is a single-threaded host loop, CollisionDetection.cpp:44-129); what is kept is
 its contract: after ExecuteCollisionDetection every consumer sees the complete colliding set of the frame.
@@ -93,15 +93,53 @@ class FrameGather:
                 return blocks, counts
             self.cap = 1 << (max(counts) - 1).bit_length()      # somebody else outgrew the blocks: everyone retries
 
+    # ---- device path: the library keeps the records behind a header row (imrcd_frame_results_block), so the frame's block goes into the
+    #      collective as it lies in HBM: no count exchange, no staging copy, no host round trip before or after the payload moves ----
+    def _block_view(self):
+        ctx = self.cd.ctx
+        dp = C.c_void_p(); n = C.c_uint64(); cap = C.c_uint64()
+        ctx.check(ctx.lib.imrcd_frame_results_block(ctx.h, C.byref(dp), C.byref(n), C.byref(cap)))
+        if not dp.value:
+            raise RuntimeError("imrcd_frame_results_block: no result block (run a frame first)")
+        self.cap = min(self.cap, int(cap.value))
+        key = (dp.value, self.cap)
+        if getattr(self, "_view_key", None) != key:
+            self._view = torch.as_tensor(_DevMem(dp.value, (self.cap + 1) * RECORD_BYTES), device="cuda").view(self.cap + 1, RECORD_BYTES)
+            self._view_key = key
+            self._recv = torch.empty((self.world * (self.cap + 1), RECORD_BYTES), dtype=torch.uint8, device="cuda")
+            self._hdr = torch.empty((self.world, 8), dtype=torch.uint8).pin_memory()
+        return self._view, int(n.value), int(cap.value)
+
     def gather_device(self) -> torch.Tensor:
-        """Call after cd.run(): every rank ends up with all ranks' records in HBM (one collective)."""
-        blocks, counts = self.exchange(self._local_device_records())
-        self.last = (blocks, counts)
+        """Call after cd.run(): every rank ends up with all ranks' blocks in HBM (ONE collective, nothing else on the stream).
+        The per-rank counts travel in the blocks' header rows; counts() reads them (and tells when the capacity was too small)."""
+        send, n, cap_alloc = self._block_view()
+        dist.all_gather_into_tensor(self._recv, send, group=self.group)
+        blocks = self._recv.view(self.world, self.cap + 1, RECORD_BYTES)
+        self._hdr.copy_(blocks[:, 0, :8], non_blocking=True)
+        self._hdr_event = torch.cuda.Event(); self._hdr_event.record()
+        self.last = (blocks, None)
+        self._cap_alloc = cap_alloc
         return blocks
+
+    def counts(self):
+        """Per-rank record counts of the last gather_device(); None when some rank had more records than the capacity (the capacity
+        is raised for the next gather, every rank sees the same headers and decides alike)."""
+        self._hdr_event.synchronize()
+        counts = self._hdr.view(torch.int64).reshape(-1).tolist()
+        if max(counts) > self.cap:
+            self.cap = min(1 << (max(counts) - 1).bit_length(), self._cap_alloc)
+            return None
+        self.last = (self.last[0], counts)
+        return counts
 
     def gather_host(self) -> np.ndarray:
         """Call after cd.ExecuteCollisionDetection(): merged records as a numpy structured array."""
-        blocks, counts = self.exchange(self._local_device_records())
+        while True:
+            blocks = self.gather_device()
+            counts = self.counts()
+            if counts is not None:
+                break
         h = blocks.cpu().numpy()
         parts = [h[r, 1:1 + c].reshape(-1) for r, c in enumerate(counts) if c]
         return np.concatenate(parts).view(PAIR_DTYPE) if parts else np.zeros(0, PAIR_DTYPE)
