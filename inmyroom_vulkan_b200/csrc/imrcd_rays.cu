@@ -166,20 +166,28 @@ __device__ __noinline__ bool ray_node_box(const TreeRec* __restrict__ recs, uint
 }
 
 // One lane per kept ray: ExecuteShootUncollideRays' two lambdas (ShootUncollideRays.cpp:29-89) as a state machine.  A ray goes through up to
-// four tree queries (step 0: the other object, then its own; step 1, the reflected ray: the same with the roles swapped); every lane of a
-// warp advances its own query by ONE tree node per iteration of a common loop, so lanes in different queries - or on different rays: a lane
-// that finishes fetches its next ray - still execute the same node code together.  (The first version ran the four queries as four inlined
-// copies of the descent: 12 of 32 lanes active and 65 % of the issue slots lost to instruction-cache misses, ncu.)
-__global__ void __launch_bounds__(128)
+// four tree queries (step 0: the other object, then its own; step 1, the reflected ray: the same with the roles swapped).  A lane is always
+// in one of four states - a box test due (the root of a new query, or the two children of an inner node), a leaf due, a query finished
+// (Hermann bookkeeping due), or out of rays - and every iteration of the warp's loop runs the ONE kind of work that most lanes are waiting
+// for, the others sitting the iteration out: each code path (boxes ~900 instructions, leaf ~600, bookkeeping ~200) executes with as many lanes
+// as can take it instead of all three running back to back for a handful of lanes each.  The order of events inside one lane's query is the
+// recursion's, so the hit is the reference's bit for bit.  (History: four inlined descents per ray, 12/32 lanes and 65 % of the issue slots
+// lost to instruction-cache misses: 9.2 ms for 669 k rays on C3; one node per lane per iteration, all paths every iteration: 5.7 ms; majority
+// path + rays handed out dynamically, since their costs differ by two orders of magnitude + 6 blocks per SM: 3.7 ms; C2: 28 -> 10 ms.)
+enum { LANE_POP = 0, LANE_BOX = 1, LANE_LEAF = 2, LANE_ROOT = 3, LANE_DONE = 4 };
+
+__global__ void __launch_bounds__(128, 6)
 k_shoot(FrameCtl* ctl, unsigned long long cap_rays, const RayRec* __restrict__ rays, float4* __restrict__ resp, PairAcc* acc, const PairRec* __restrict__ pairrec,
         const TreeRec* __restrict__ recs, const TriRec* __restrict__ tris, const float* __restrict__ tri_nrm) {
     if (ctl->overflow) return;
     const unsigned long long n = ctl->n_rays_kept < cap_rays ? ctl->n_rays_kept : cap_rays;
-    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    unsigned long long next = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31u;
+    bool exhausted = false;                                                 // the frame's rays have all been handed out
     uint32_t st_node[RAY_STACK]; float st_min[RAY_STACK];
     int sp = 0;
-    bool active = false, root_pending = false;
+    bool active = false;
+    int kind = LANE_POP;
+    uint32_t cur = 0, cur_cnt = 0;                                          // the node / leaf range the lane is about to work on
     // per-ray state
     unsigned long long k = 0; uint32_t p = 0, side = 0; int step = 0, phase = 0;
     V3 o = mk3(0, 0, 0), d = mk3(0, 0, 0), q_origin = mk3(0, 0, 0);
@@ -193,70 +201,95 @@ k_shoot(FrameCtl* ctl, unsigned long long cap_rays, const RayRec* __restrict__ r
     float4 out0 = make_float4(0, 0, 0, 0), out1 = out0;
 
     for (;;) {
-        if (!active) {
-            if (next < n) {                                                 // fetch the lane's next ray
-                k = next; next += stride;
-                const RayRec ray = rays[k];
-                p = __float_as_uint(ray.o.w); side = __float_as_uint(ray.d.w);
-                const PairRec pr = pairrec[p];
-                rel.r0 = pr.r0; rel.r1 = pr.r1; rel.r2 = pr.r2; recA = pr.recA; recB = pr.recB; triA = pr.triA; triB = pr.triB;
-                o = mk3(ray.o.x, ray.o.y, ray.o.z); d = mk3(ray.d.x, ray.d.y, ray.d.z);
-                step = 0; phase = 0; fx = fy = fz = 0.0; n_ok = 0; out0 = out1 = make_float4(0, 0, 0, 0);
-                active = true; root_pending = true; q_origin = o;
+        // idle lanes take the next rays of the frame (one atomic per warp)
+        const uint32_t m_idle = __ballot_sync(FULL_MASK, !active && !exhausted);
+        if (m_idle) {
+            const uint32_t leader = (uint32_t)__ffs(m_idle) - 1u;
+            unsigned long long base = 0;
+            if (lane == leader) base = atomicAdd(&ctl->ray_cursor, (unsigned long long)__popc(m_idle));
+            base = __shfl_sync(FULL_MASK, base, leader);
+            if (!active && !exhausted) { k = base + __popc(m_idle & ((1u << lane) - 1u)); if (k >= n) exhausted = true; }
+        }
+        if (!active && !exhausted) {
+            const RayRec ray = rays[k];
+            p = __float_as_uint(ray.o.w); side = __float_as_uint(ray.d.w);
+            const PairRec pr = pairrec[p];
+            rel.r0 = pr.r0; rel.r1 = pr.r1; rel.r2 = pr.r2; recA = pr.recA; recB = pr.recB; triA = pr.triA; triB = pr.triB;
+            o = mk3(ray.o.x, ray.o.y, ray.o.z); d = mk3(ray.d.x, ray.d.y, ray.d.z);
+            step = 0; phase = 0; fx = fy = fz = 0.0; n_ok = 0; out0 = out1 = make_float4(0, 0, 0, 0);
+            active = true; kind = LANE_ROOT; q_origin = o;
+        }
+        // next event of the lane's query: drop pruned stack entries (the recursion's `min < best_so_far` at call time, Ray.cpp:182-216)
+        if (active && kind == LANE_POP) {
+            kind = LANE_DONE;
+            while (sp > 0) {
+                --sp;
+                if (st_min[sp] < best.dist) {
+                    const uint32_t node = st_node[sp];
+                    const float4 q3 = __ldg(reinterpret_cast<const float4*>(q_recs + node) + 3);
+                    cur = __float_as_uint(q3.y); cur_cnt = __float_as_uint(q3.z);
+                    kind = __float_as_uint(q3.w) == 0u ? LANE_BOX : LANE_LEAF;
+                    break;
+                }
             }
         }
-        if (!__any_sync(FULL_MASK, active)) break;
-        if (!active) continue;
+        const uint32_t m_box = __ballot_sync(FULL_MASK, active && (kind == LANE_BOX || kind == LANE_ROOT));
+        const uint32_t m_leaf = __ballot_sync(FULL_MASK, active && kind == LANE_LEAF);
+        const uint32_t m_done = __ballot_sync(FULL_MASK, active && kind == LANE_DONE);
+        if ((m_box | m_leaf | m_done) == 0u) break;                         // no lane has a ray left
+        const int n_box = __popc(m_box), n_leaf = __popc(m_leaf), n_done = __popc(m_done);
+        const int path = (n_box >= n_leaf && n_box >= n_done) ? 0 : (n_leaf >= n_done ? 1 : 2);
 
         // f2s: first_to_second_ray_execute (objects: A = first, B = second), else second_to_first (A = second, B = first)  (:29-71)
         const bool f2s = (side == 0u) == (step == 0);
-        if (root_pending) {
-            // start a query (Ray::IntersectOBBtree, Ray.cpp:136-161): phase 0 looks at B (point2), phase 1 at A (point3)
-            const bool on_second = (phase == 0) == f2s;                     // which tree: second's (matrix rel) or first's (identity)
-            q_recs = recs + (on_second ? recB : recA); q_tris = tris + (on_second ? triB : triA);
-            m = on_second ? rel : rel_identity();
-            if (!(q_origin.x == 0.f && q_origin.y == 0.f && q_origin.z == 0.f)) {      // centered_matrix[3] -= vec4(origin, 0)
-                m.r0.w = m.r0.w - q_origin.x; m.r1.w = m.r1.w - q_origin.y; m.r2.w = m.r2.w - q_origin.z;
+        if (path == 0) {
+            if (active && kind == LANE_ROOT) {
+                // start a query (Ray::IntersectOBBtree, Ray.cpp:136-161): phase 0 looks at B (point2), phase 1 at A (point3)
+                const bool on_second = (phase == 0) == f2s;                 // which tree: second's (matrix rel) or first's (identity)
+                q_recs = recs + (on_second ? recB : recA); q_tris = tris + (on_second ? triB : triA);
+                m = on_second ? rel : rel_identity();
+                if (!(q_origin.x == 0.f && q_origin.y == 0.f && q_origin.z == 0.f)) {      // centered_matrix[3] -= vec4(origin, 0)
+                    m.r0.w = m.r0.w - q_origin.x; m.r1.w = m.r1.w - q_origin.y; m.r2.w = m.r2.w - q_origin.z;
+                }
+                best.hit = false; best.back = false; best.dist = INFINITY; best.tri = 0xffffffffu; best.bx = best.by = 0.f;
+                sp = 0;
             }
-            best.hit = false; best.back = false; best.dist = INFINITY; best.tri = 0xffffffffu; best.bx = best.by = 0.f;
-            float mn, mx;
-            sp = 0;
-            if (ray_node_box(q_recs, 0u, m, d, mn, mx) && mx >= 0.f) { st_node[0] = 0u; st_min[0] = -INFINITY; sp = 1; }   // :144-147
-            root_pending = false;
-        } else if (sp > 0) {
-            // one node of the descent (Ray::IntersectOBBtreeRecursive, Ray.cpp:163-236)
-            --sp;
-            const uint32_t node = st_node[sp];
-            if (st_min[sp] < best.dist) {                                   // the recursion's `min < best_so_far` at call time
-                const float4 q3 = __ldg(reinterpret_cast<const float4*>(q_recs + node) + 3);
-                const uint32_t child = __float_as_uint(q3.y);
-                if (__float_as_uint(q3.w) == 0u) {                          // inner: children are records child (left), child + 1 (right)
-                    float lmin = 0.f, lmax = 0.f, rmin = 0.f, rmax = 0.f;
-                    const bool lh = ray_node_box(q_recs, child, m, d, lmin, lmax), rh = ray_node_box(q_recs, child + 1u, m, d, rmin, rmax);
+            if (active && (kind == LANE_BOX || kind == LANE_ROOT)) {
+                const bool root = kind == LANE_ROOT;
+                float lmin = 0.f, lmax = 0.f, rmin = 0.f, rmax = 0.f;
+                const bool lh = ray_node_box(q_recs, root ? 0u : cur, m, d, lmin, lmax);
+                bool rh = false;
+                if (!root) rh = ray_node_box(q_recs, cur + 1u, m, d, rmin, rmax);
+                if (root) {
+                    if (lh && lmax >= 0.f) { st_node[0] = 0u; st_min[0] = -INFINITY; sp = 1; }     // :144-147
+                } else {
                     const bool lgo = lh && lmax >= 0.f, rgo = rh && rmax >= 0.f;
                     const bool left_first = !(lh && rh) || (lmin < rmin);   // :182-204
                     if (sp + 2 > RAY_STACK) { atomicOr(&ctl->overflow, (unsigned)OVF_RAYSTACK); sp = 0; }
                     else if (left_first) {
-                        if (rgo) { st_node[sp] = child + 1u; st_min[sp] = rmin; ++sp; }
-                        if (lgo) { st_node[sp] = child; st_min[sp] = lmin; ++sp; }
+                        if (rgo) { st_node[sp] = cur + 1u; st_min[sp] = rmin; ++sp; }
+                        if (lgo) { st_node[sp] = cur; st_min[sp] = lmin; ++sp; }
                     } else {
-                        if (lgo) { st_node[sp] = child; st_min[sp] = lmin; ++sp; }
-                        if (rgo) { st_node[sp] = child + 1u; st_min[sp] = rmin; ++sp; }
-                    }
-                } else {
-                    const uint32_t cnt = __float_as_uint(q3.z);
-                    for (uint32_t i = 0; i < cnt; ++i) {                    // :221-234
-                        const float4* tp = reinterpret_cast<const float4*>(q_tris + child + i);
-                        const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
-                        const V3 p0 = rel_mul(m, mk3(t0.x, t0.y, t0.z), 1.f), p1 = rel_mul(m, mk3(t1.x, t1.y, t1.z), 1.f), p2v = rel_mul(m, mk3(t2.x, t2.y, t2.z), 1.f);
-                        float bx = 0.f, by = 0.f, dist = INFINITY; bool back = false;
-                        if (ray_triangle0(d, p0, p1, p2v, bx, by, dist, back) && dist > 0.f && dist < best.dist) {
-                            best.hit = true; best.back = back; best.dist = dist; best.tri = child + i; best.bx = bx; best.by = by;
-                        }
+                        if (lgo) { st_node[sp] = cur; st_min[sp] = lmin; ++sp; }
+                        if (rgo) { st_node[sp] = cur + 1u; st_min[sp] = rmin; ++sp; }
                     }
                 }
+                kind = LANE_POP;
             }
-        } else {
+        } else if (path == 1) {
+            if (active && kind == LANE_LEAF) {
+                for (uint32_t i = 0; i < cur_cnt; ++i) {                    // :221-234
+                    const float4* tp = reinterpret_cast<const float4*>(q_tris + cur + i);
+                    const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
+                    const V3 p0 = rel_mul(m, mk3(t0.x, t0.y, t0.z), 1.f), p1 = rel_mul(m, mk3(t1.x, t1.y, t1.z), 1.f), p2v = rel_mul(m, mk3(t2.x, t2.y, t2.z), 1.f);
+                    float bx = 0.f, by = 0.f, dist = INFINITY; bool back = false;
+                    if (ray_triangle0(d, p0, p1, p2v, bx, by, dist, back) && dist > 0.f && dist < best.dist) {
+                        best.hit = true; best.back = back; best.dist = dist; best.tri = cur + i; best.bx = bx; best.by = by;
+                    }
+                }
+                kind = LANE_POP;
+            }
+        } else if (active && kind == LANE_DONE) {
             // the query is over: HermannPass (ShootUncollideRays.cpp:116-148)
             bool ray_done = false;
             if (phase == 0) {
@@ -267,7 +300,7 @@ k_shoot(FrameCtl* ctl, unsigned long long cap_rays, const RayRec* __restrict__ r
                     const float scaled = big * FLT_EPSILON;
                     q_origin = add3(o, scale3(d, 4.f * scaled));
                     eps_dist = length3(sub3(q_origin, o));
-                    phase = 1; root_pending = true;
+                    phase = 1; kind = LANE_ROOT;
                 } else ray_done = true;
             } else {
                 if (p2.dist <= best.dist + eps_dist) {                      // :134 (best = point3, the ray's own object)
@@ -288,7 +321,7 @@ k_shoot(FrameCtl* ctl, unsigned long long cap_rays, const RayRec* __restrict__ r
                     ++n_ok;
                     if (step == 0) {                                        // ReflectHermannResult (:95-101), then the opposite direction (:73-89)
                         o = add3(o, response); d = mk3(-normal.x, -normal.y, -normal.z);
-                        step = 1; phase = 0; root_pending = true; q_origin = o;
+                        step = 1; phase = 0; kind = LANE_ROOT; q_origin = o;
                     } else ray_done = true;
                 } else ray_done = true;
             }
@@ -298,7 +331,7 @@ k_shoot(FrameCtl* ctl, unsigned long long cap_rays, const RayRec* __restrict__ r
                     atomicAdd(&acc[p].force[0], fx); atomicAdd(&acc[p].force[1], fy); atomicAdd(&acc[p].force[2], fz);
                     atomicAdd(&acc[p].n_resp, n_ok);
                 }
-                active = false;
+                active = false; kind = LANE_POP;
             }
         }
     }

@@ -55,7 +55,7 @@ class FrameGather:
     row carries the rank's record count (no separate count exchange, no host round trip before the payload moves).
     The capacity doubles (and the gather is repeated) on the rare frame where some rank outgrows it."""
 
-    def __init__(self, cd, world: int, rank: int, group=None, capacity: int = 4096):
+    def __init__(self, cd, world: int, rank: int, group=None, capacity: int = 256):
         self.cd = cd; self.world = world; self.rank = rank; self.group = group
         self.cap = capacity
         self.last = None
