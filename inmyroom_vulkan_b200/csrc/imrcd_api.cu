@@ -231,6 +231,15 @@ extern "C" int imrcd_mesh_last_build_ms(imrcd_ctx* ctx, float* ms) { CHECK_CTX(c
 
 // used by imr_build_mesh_device
 int imr_mesh_arena_alloc(imrcd_ctx* ctx, uint64_t n_rec, uint64_t n_tri, MeshHost* mh) { return mesh_alloc(ctx, n_rec, n_tri, mh); }
+// grow the arena's capacity for a mesh of at most n_rec records / n_tri triangles without placing it (keeps allocation out of timed regions)
+int imr_mesh_arena_reserve(imrcd_ctx* ctx, uint64_t n_rec, uint64_t n_tri) {
+    cudaStream_t s = ctx->stream;
+    IMR_CUDA(ctx, ctx->d_recs.reserve(sizeof(TreeRec) * (ctx->n_rec_total + n_rec), sizeof(TreeRec) * ctx->n_rec_total, s));
+    IMR_CUDA(ctx, ctx->d_tris.reserve(sizeof(TriRec) * (ctx->n_tri_total + n_tri), sizeof(TriRec) * ctx->n_tri_total, s));
+    IMR_CUDA(ctx, ctx->d_tri_nrm.reserve(36ull * (ctx->n_tri_total + n_tri), 36ull * ctx->n_tri_total, s));
+    IMR_CUDA(ctx, ctx->d_tri_vid.reserve(12ull * (ctx->n_tri_total + n_tri), 12ull * ctx->n_tri_total, s));
+    return IMRCD_OK;
+}
 
 extern "C" int imrcd_mesh_info(imrcd_ctx* ctx, uint32_t mesh_id, uint64_t* n_tri, uint64_t* n_vertices) {
     CHECK_CTX(ctx);

@@ -23,6 +23,7 @@
 #include <cstring>
 
 int imr_mesh_arena_alloc(imrcd_ctx* ctx, uint64_t n_rec, uint64_t n_tri, MeshHost* mh);
+int imr_mesh_arena_reserve(imrcd_ctx* ctx, uint64_t n_rec, uint64_t n_tri);
 int imr_build_mesh_reference(imrcd_ctx* ctx, const float* pos, const float* nrm, const uint32_t* vid, uint64_t n_tri, MeshHost* mh);
 
 #define FULL_MASK 0xffffffffu
@@ -325,10 +326,18 @@ __global__ void k_axes(uint32_t n_rec, const RecDesc* __restrict__ desc, const T
 }
 
 // ---- 7. extents: each triangle walks root -> leaf --------------------------------------------------
-__global__ void k_extents(uint32_t n, const TriRec* __restrict__ tris, const RecDesc* __restrict__ desc, const double* __restrict__ axes,
-                          unsigned long long* ext) {
+// Triangles are in leaf (= sorted) order and every node covers a contiguous range of them, so the lanes of a warp that sit in the same node are
+// consecutive: their minima / maxima are folded by a segmented scan first, and a run that fills whole warps is folded across the block in
+// shared memory, before one atomic per run and box face.  (First version: plain per-lane atomics unless the whole warp was in one node; the 6
+// words of the top nodes then took one atomic per warp of the mesh each: 6.5 of the 11 ms of kernel time of a 10 M-triangle build.)
+#define EXT_BLOCK 512
+__global__ void __launch_bounds__(EXT_BLOCK)
+k_extents(uint32_t n, const TriRec* __restrict__ tris, const RecDesc* __restrict__ desc, const double* __restrict__ axes,
+          unsigned long long* ext) {
+    __shared__ double s_v[EXT_BLOCK / 32][6];
+    __shared__ uint32_t s_node[EXT_BLOCK / 32];
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const bool valid = t < n;
     double px[3] = { 0, 0, 0 }, py[3] = { 0, 0, 0 }, pz[3] = { 0, 0, 0 };
     if (valid) {
@@ -337,8 +346,8 @@ __global__ void k_extents(uint32_t n, const TriRec* __restrict__ tris, const Rec
     }
     uint32_t node = 0;
     bool active = valid;
-    for (int depth = 0; depth < 4096 && __any_sync(FULL_MASK, active); ++depth) {
-        double mn[3] = { INFINITY, INFINITY, INFINITY }, mx[3] = { -INFINITY, -INFINITY, -INFINITY };
+    for (int depth = 0; depth < 4096 && __syncthreads_or(active); ++depth) {
+        double v[6] = { INFINITY, -INFINITY, INFINITY, -INFINITY, INFINITY, -INFINITY };      // min, max per axis
         RecDesc d; d.kind = 1u; d.child = 0; d.split = 0;
         if (active) {
             d = desc[node];
@@ -349,25 +358,50 @@ __global__ void k_extents(uint32_t n, const TriRec* __restrict__ tris, const Rec
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
                     const double pr = ux * px[k] + uy * py[k] + uz * pz[k];
-                    mn[a] = fmin(mn[a], pr); mx[a] = fmax(mx[a], pr);
+                    v[2 * a] = fmin(v[2 * a], pr); v[2 * a + 1] = fmax(v[2 * a + 1], pr);
                 }
             }
         }
-        // warp aggregation: near the root all 32 (sorted-adjacent) triangles sit in the same node
-        const uint32_t first_node = __shfl_sync(FULL_MASK, node, 0);
-        const bool uniform = __all_sync(FULL_MASK, active && node == first_node);
-        if (uniform) {
+        // segmented scan over runs of equal node in consecutive lanes (inactive lanes: node id ~0)
+        const uint32_t key = active ? node : 0xffffffffu;
+        const uint32_t prev = __shfl_up_sync(FULL_MASK, key, 1);
+        const uint32_t heads = __ballot_sync(FULL_MASK, lane == 0u || prev != key);
+        const uint32_t head = 31u - (uint32_t)__clz(heads & (0xffffffffu >> (31u - lane)));
+        const uint32_t after = heads & ~(0xffffffffu >> (31u - lane));
+        const uint32_t tail = after ? (uint32_t)__ffs(after) - 2u : 31u;
 #pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                for (int o = 16; o > 0; o >>= 1) { mn[a] = fmin(mn[a], __shfl_xor_sync(FULL_MASK, mn[a], o)); mx[a] = fmax(mx[a], __shfl_xor_sync(FULL_MASK, mx[a], o)); }
+        for (uint32_t o = 1; o < 32u; o <<= 1) {
+#pragma unroll
+            for (int q = 0; q < 6; ++q) {
+                const double w = __shfl_up_sync(FULL_MASK, v[q], o);
+                if (lane >= head + o) v[q] = (q & 1) ? fmax(v[q], w) : fmin(v[q], w);
             }
-            if (lane == 0) {
+        }
+        const bool whole = heads == 1u && active;                       // the warp is one run (uniform in lane 31's view: key != ~0)
+        // runs that fill whole warps go through shared memory: the last warp of a run of equal nodes adds up the run
+        if (lane == 31u) {
+            s_node[warp] = whole ? node : 0xffffffffu;
+            if (whole) {
 #pragma unroll
-                for (int a = 0; a < 3; ++a) { atomicMin(&ext[6ull * node + 2 * a], f64_sortable(mn[a])); atomicMax(&ext[6ull * node + 2 * a + 1], f64_sortable(mx[a])); }
+                for (int q = 0; q < 6; ++q) s_v[warp][q] = v[q];
             }
-        } else if (active) {
+        }
+        __syncthreads();
+        if (lane == tail && active) {
+            bool publish = true;
+            if (whole) {
+                if (warp + 1u < EXT_BLOCK / 32 && s_node[warp + 1u] == node) publish = false;      // a later warp of the block carries the run on
+                else {
+                    for (int w = (int)warp - 1; w >= 0 && s_node[w] == node; --w) {
 #pragma unroll
-            for (int a = 0; a < 3; ++a) { atomicMin(&ext[6ull * node + 2 * a], f64_sortable(mn[a])); atomicMax(&ext[6ull * node + 2 * a + 1], f64_sortable(mx[a])); }
+                        for (int q = 0; q < 6; ++q) v[q] = (q & 1) ? fmax(v[q], s_v[w][q]) : fmin(v[q], s_v[w][q]);
+                    }
+                }
+            }
+            if (publish) {
+#pragma unroll
+                for (int a = 0; a < 3; ++a) { atomicMin(&ext[6ull * node + 2 * a], f64_sortable(v[2 * a])); atomicMax(&ext[6ull * node + 2 * a + 1], f64_sortable(v[2 * a + 1])); }
+            }
         }
         if (active) {
             if (d.kind == 1u) active = false;
@@ -541,30 +575,82 @@ __global__ void k_rf_axes(uint32_t total_rec, const RecDesc* __restrict__ desc, 
     sym_eig3_axes(m[3] * in - mx * mx, m[4] * in - my * my, m[5] * in - mz * mz, m[6] * in - mx * my, m[7] * in - mx * mz, m[8] * in - my * mz, ax);
 }
 
-__global__ void k_rf_extents(uint32_t total_tri, const RefitSeg* __restrict__ segs, const uint32_t* __restrict__ tri_prefix, uint32_t n_seg,
-                             const TriRec* __restrict__ tris, const RecDesc* __restrict__ desc, const double* __restrict__ axes, unsigned long long* ext) {
+__global__ void __launch_bounds__(EXT_BLOCK)
+k_rf_extents(uint32_t total_tri, const RefitSeg* __restrict__ segs, const uint32_t* __restrict__ tri_prefix, uint32_t n_seg,
+             const TriRec* __restrict__ tris, const RecDesc* __restrict__ desc, const double* __restrict__ axes, unsigned long long* ext) {
+    // same folding as k_extents: runs of equal record in consecutive lanes, whole-warp runs across the block, one atomic per run and face
+    __shared__ double s_v[EXT_BLOCK / 32][6];
+    __shared__ uint32_t s_node[EXT_BLOCK / 32];
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= total_tri) return;
-    const RefitSeg sg = segs[rf_locate(tri_prefix, n_seg, g)];
-    const uint32_t t = g - sg.tri_prefix;
-    const TriRec tr = tris[sg.tri_base + t];
-    const double px[3] = { tr.t0.x, tr.t1.x, tr.t2.x }, py[3] = { tr.t0.y, tr.t1.y, tr.t2.y }, pz[3] = { tr.t0.z, tr.t1.z, tr.t2.z };
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    bool active = g < total_tri;
+    RefitSeg sg; sg.rec_base = sg.tri_base = sg.n_rec = sg.n_tri = sg.rec_prefix = sg.tri_prefix = 0u;
+    uint32_t t = 0;
+    double px[3] = { 0, 0, 0 }, py[3] = { 0, 0, 0 }, pz[3] = { 0, 0, 0 };
+    if (active) {
+        sg = segs[rf_locate(tri_prefix, n_seg, g)];
+        t = g - sg.tri_prefix;
+        const TriRec tr = tris[sg.tri_base + t];
+        px[0] = tr.t0.x; px[1] = tr.t1.x; px[2] = tr.t2.x; py[0] = tr.t0.y; py[1] = tr.t1.y; py[2] = tr.t2.y; pz[0] = tr.t0.z; pz[1] = tr.t1.z; pz[2] = tr.t2.z;
+    }
     uint32_t node = 0;
-    for (int depth = 0; depth < 4096; ++depth) {
-        const RecDesc d = desc[sg.rec_prefix + node];
-        const double* ax = axes + 9ull * (sg.rec_prefix + node);
-        unsigned long long* e = ext + 6ull * (sg.rec_prefix + node);
+    for (int depth = 0; depth < 4096 && __syncthreads_or(active); ++depth) {
+        double v[6] = { INFINITY, -INFINITY, INFINITY, -INFINITY, INFINITY, -INFINITY };
+        RecDesc d; d.kind = 1u; d.child = 0; d.split = 0;
+        const uint32_t rec = sg.rec_prefix + node;
+        if (active) {
+            d = desc[rec];
+            const double* ax = axes + 9ull * rec;
 #pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            double mn = INFINITY, mx = -INFINITY;
+            for (int a = 0; a < 3; ++a) {
 #pragma unroll
-            for (int k = 0; k < 3; ++k) { const double pr = ax[3 * a] * px[k] + ax[3 * a + 1] * py[k] + ax[3 * a + 2] * pz[k]; mn = fmin(mn, pr); mx = fmax(mx, pr); }
-            const unsigned long long smn = f64_sortable(mn), smx = f64_sortable(mx);
-            if (smn < e[2 * a]) atomicMin(&e[2 * a], smn);                 // plain read first: most visits do not move the bound
-            if (smx > e[2 * a + 1]) atomicMax(&e[2 * a + 1], smx);
+                for (int k = 0; k < 3; ++k) { const double pr = ax[3 * a] * px[k] + ax[3 * a + 1] * py[k] + ax[3 * a + 2] * pz[k]; v[2 * a] = fmin(v[2 * a], pr); v[2 * a + 1] = fmax(v[2 * a + 1], pr); }
+            }
         }
-        if (d.kind == 1u) break;
-        node = d.child + (t > d.split ? 1u : 0u);
+        const uint32_t key = active ? rec : 0xffffffffu;
+        const uint32_t prev = __shfl_up_sync(FULL_MASK, key, 1);
+        const uint32_t heads = __ballot_sync(FULL_MASK, lane == 0u || prev != key);
+        const uint32_t head = 31u - (uint32_t)__clz(heads & (0xffffffffu >> (31u - lane)));
+        const uint32_t after = heads & ~(0xffffffffu >> (31u - lane));
+        const uint32_t tail = after ? (uint32_t)__ffs(after) - 2u : 31u;
+#pragma unroll
+        for (uint32_t o = 1; o < 32u; o <<= 1) {
+#pragma unroll
+            for (int q = 0; q < 6; ++q) {
+                const double w = __shfl_up_sync(FULL_MASK, v[q], o);
+                if (lane >= head + o) v[q] = (q & 1) ? fmax(v[q], w) : fmin(v[q], w);
+            }
+        }
+        const bool whole = heads == 1u && active;
+        if (lane == 31u) {
+            s_node[warp] = whole ? rec : 0xffffffffu;
+            if (whole) {
+#pragma unroll
+                for (int q = 0; q < 6; ++q) s_v[warp][q] = v[q];
+            }
+        }
+        __syncthreads();
+        if (lane == tail && active) {
+            bool publish = true;
+            if (whole) {
+                if (warp + 1u < EXT_BLOCK / 32 && s_node[warp + 1u] == rec) publish = false;
+                else {
+                    for (int w = (int)warp - 1; w >= 0 && s_node[w] == rec; --w) {
+#pragma unroll
+                        for (int q = 0; q < 6; ++q) v[q] = (q & 1) ? fmax(v[q], s_v[w][q]) : fmin(v[q], s_v[w][q]);
+                    }
+                }
+            }
+            if (publish) {
+                unsigned long long* e = ext + 6ull * rec;
+#pragma unroll
+                for (int a = 0; a < 3; ++a) { atomicMin(&e[2 * a], f64_sortable(v[2 * a])); atomicMax(&e[2 * a + 1], f64_sortable(v[2 * a + 1])); }
+            }
+        }
+        if (active) {
+            if (d.kind == 1u) active = false;
+            else node = d.child + (t > d.split ? 1u : 0u);
+        }
     }
 }
 
@@ -642,16 +728,25 @@ static int build_morton(imrcd_ctx* ctx, const float* h_pos, const float* h_nrm, 
     BUILD_CUDA(d_flag.reserve(4ull * (n_int + 1), 0, s)); BUILD_CUDA(d_slot.reserve(4ull * (n_int + 1), 0, s));
     BUILD_CUDA(d_mom.reserve(80ull * (n_int + 1), 0, s)); BUILD_CUDA(d_ticket.reserve(4ull * (n_int + 1), 0, s));
 
+    // every allocation happens before the timed region: sort / scan scratch, the worst-case record count (every inner node kept), the arena
+    size_t tmp_bytes = 0, scan_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys.as<unsigned long long>(), d_keys2.as<unsigned long long>(), d_idx.as<uint32_t>(), d_idx2.as<uint32_t>(), (int)n, 0, 63, s);
+    cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, d_flag.as<uint32_t>(), d_slot.as<uint32_t>(), (int)(n_int + 1), s);
+    BUILD_CUDA(d_tmp.reserve(std::max(tmp_bytes, scan_bytes), 0, s));
+    {
+        const uint64_t n_rec_max = 2ull + 2ull * n_int;
+        BUILD_CUDA(d_desc.reserve(sizeof(RecDesc) * n_rec_max, 0, s));
+        BUILD_CUDA(d_axes.reserve(72ull * n_rec_max, 0, s));
+        BUILD_CUDA(d_ext.reserve(48ull * n_rec_max, 0, s));
+        int rrc = imr_mesh_arena_reserve(ctx, n_rec_max, n);
+        if (rrc) { free_all(); return rrc; }
+    }
     cudaEvent_t e0 = ctx->ev[6], e1 = ctx->ev[7];
     BUILD_CUDA(cudaEventRecord(e0, s));
     // 1. keys + sort
     k_bounds_init<<<1, 32, 0, s>>>(d_bounds.as<uint32_t>());
     k_bounds<<<std::min<unsigned>(nb(n, 256), ctx->sm_count * 8), 256, 0, s>>>(n, d_pos.as<float>(), d_bounds.as<uint32_t>());
     k_morton<<<nb(n, 256), 256, 0, s>>>(n, d_pos.as<float>(), d_bounds.as<uint32_t>(), d_keys.as<unsigned long long>(), d_idx.as<uint32_t>());
-    size_t tmp_bytes = 0, scan_bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys.as<unsigned long long>(), d_keys2.as<unsigned long long>(), d_idx.as<uint32_t>(), d_idx2.as<uint32_t>(), (int)n, 0, 63, s);
-    cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, d_flag.as<uint32_t>(), d_slot.as<uint32_t>(), (int)(n_int + 1), s);
-    BUILD_CUDA(d_tmp.reserve(std::max(tmp_bytes, scan_bytes), 0, s));
     cub::DeviceRadixSort::SortPairs(d_tmp.p, tmp_bytes, d_keys.as<unsigned long long>(), d_keys2.as<unsigned long long>(), d_idx.as<uint32_t>(), d_idx2.as<uint32_t>(), (int)n, 0, 63, s);
 
     // how many records?  known only after the scan -> reserve the worst case (every inner node kept) in the arena first
@@ -689,7 +784,7 @@ static int build_morton(imrcd_ctx* ctx, const float* h_pos, const float* h_nrm, 
     }
     k_axes<<<nb(n_rec, 128), 128, 0, s>>>((uint32_t)n_rec, d_desc.as<RecDesc>(), tris, d_mom.as<double>(), d_bounds.as<uint32_t>(), d_axes.as<double>(),
                                           d_ext.as<unsigned long long>());
-    k_extents<<<nb(n, 256), 256, 0, s>>>(n, tris, d_desc.as<RecDesc>(), d_axes.as<double>(), d_ext.as<unsigned long long>());
+    k_extents<<<nb(n, EXT_BLOCK), EXT_BLOCK, 0, s>>>(n, tris, d_desc.as<RecDesc>(), d_axes.as<double>(), d_ext.as<unsigned long long>());
     k_finalize_boxes<<<nb(n_rec, 128), 128, 0, s>>>((uint32_t)n_rec, d_desc.as<RecDesc>(), d_axes.as<double>(), d_ext.as<unsigned long long>(), recs);
     BUILD_CUDA(cudaEventRecord(e1, s));
     TreeRec root;
@@ -763,7 +858,7 @@ int imr_meshes_refit_device(imrcd_ctx* ctx, const uint32_t* ids, uint64_t n_ids,
     k_rf_parents<<<nb(tot_rec, 256), 256, 0, s>>>((uint32_t)tot_rec, d_segs, d_recp, ns, recs, parent, ticket);
     k_rf_up<<<nb(tot_rec, 128), 128, 0, s>>>((uint32_t)tot_rec, d_segs, d_recp, ns, recs, tris, parent, desc, mom, ticket);
     k_rf_axes<<<nb(tot_rec, 128), 128, 0, s>>>((uint32_t)tot_rec, desc, mom, axes, ext);
-    k_rf_extents<<<nb(tot_tri, 256), 256, 0, s>>>((uint32_t)tot_tri, d_segs, d_trip, ns, tris, desc, axes, ext);
+    k_rf_extents<<<nb(tot_tri, EXT_BLOCK), EXT_BLOCK, 0, s>>>((uint32_t)tot_tri, d_segs, d_trip, ns, tris, desc, axes, ext);
     k_rf_boxes<<<nb(tot_rec, 128), 128, 0, s>>>((uint32_t)tot_rec, d_segs, d_recp, ns, desc, axes, ext, ctx->d_recs.as<TreeRec>());
     IMR_CUDA(ctx, cudaEventRecord(e1, s));
     IMR_CUDA(ctx, cudaStreamSynchronize(s));
