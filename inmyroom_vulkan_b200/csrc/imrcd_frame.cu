@@ -706,10 +706,9 @@ struct SideSum { double x, y, z; uint32_t rays; };
 // result does not depend on which thread comes first.  Then one thread per occupied slot turns the candidate into rays (:139-166), vertex
 // rays going through the `emplaced` set (:139-141), and one thread per ray adds its origin and - for pairs whose entities moved since the
 // last frame, the only ones the response stage looks at (CollisionDetection.cpp:80-81) - writes the ray (origin, -normal) to the frame's ray array.
-// Size classes S and M keep the tables in shared memory; class L (M_MAX == 0, > 1024 hits) takes them from a bump-allocated global scratch.
+// The three per-pair size classes keep their tables in shared memory; pairs with more than 1024 hits go through the grid-wide passes (k_large_*).
 struct PcSlot { double w, cx, cy, cz; };
 
-template <bool G, class X> __device__ __forceinline__ X pc_ld(const X* p) { return G ? __ldcg(p) : *p; }
 
 // Find or claim the slot of `tri`; `claimed` tells the caller to append the slot to the dense list of occupied slots (done
 // afterwards in converged code with one ballot, so that the later passes run over occupied slots only).
@@ -747,21 +746,18 @@ __device__ __forceinline__ void pc_append(bool yes, uint32_t v, LT* list, uint32
     if (yes) list[base + __popc(m & ((1u << lane) - 1u))] = (LT)v;
 }
 
-#define PC_BYTES_PER_HIT (2 * (sizeof(PcSlot) + 8) + 4 * 8 + 12 + 5 * sizeof(LT))      // tables + staging + lists, per (padded) hit
 
 template <int T, uint32_t M_MAX>
 __global__ void __launch_bounds__(T)
 k_pair_contacts_hash(FrameCtl* ctl, const uint32_t* __restrict__ list, int cls, PairAcc* acc, const uint32_t* __restrict__ grouped,
                      const imrcd_tri_hit* __restrict__ hits, const HitAux* __restrict__ aux, const PairRec* __restrict__ pairrec,
                      const TriRec* __restrict__ tris, const uint32_t* __restrict__ tri_vid, const float* __restrict__ tri_nrm,
-                     RayRec* __restrict__ rays, unsigned long long cap_rays, unsigned char* scratch, unsigned long long cap_scratch) {
-    constexpr bool G = M_MAX == 0;                     // tables in global memory
-    typedef typename std::conditional<G, uint32_t, uint16_t>::type LT;
+                     RayRec* __restrict__ rays, unsigned long long cap_rays) {
+    typedef uint16_t LT;                               // slot indices (< 4 M_MAX <= 4096)
     extern __shared__ __align__(16) unsigned char pc_smem[];
     __shared__ double s_red[3][T / 32];
     __shared__ uint32_t s_redc[T / 32];
     __shared__ uint32_t s_ncand, s_nvert, s_navg, s_raybase;
-    __shared__ unsigned long long s_scratch;
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
     if (ctl->overflow & (OVF_PAIRS | OVF_QUEUE | OVF_COMBOS | OVF_HITS)) return;      // the frame is re-run with larger buffers
     const unsigned long long n_list = ctl->n_class[cls * 16];
@@ -771,17 +767,8 @@ k_pair_contacts_hash(FrameCtl* ctl, const uint32_t* __restrict__ list, int cls, 
         const bool keep_rays = (acc[p].flags & PAIR_MOVED) != 0u;
         uint32_t m = 16u; while (m < n) m <<= 1;                     // tables sized by the pair: 2m candidate slots (<= n distinct triangles), 4m vertex slots (<= 3n)
         const uint32_t slots = 2u * m, vslots = 4u * m;
-        const uint32_t cap = G ? m : M_MAX;                          // array stride
-        unsigned char* base;
-        if (!G) base = pc_smem;
-        else {
-            if (tid == 0) s_scratch = atomicAdd(&ctl->scratch_used, (unsigned long long)m * PC_BYTES_PER_HIT);
-            __syncthreads();
-            const unsigned long long at = s_scratch;
-            __syncthreads();
-            if (at + (unsigned long long)m * PC_BYTES_PER_HIT > cap_scratch) { if (tid == 0) atomicOr(&ctl->overflow, (unsigned)OVF_SCRATCH); continue; }
-            base = scratch + at;
-        }
+        const uint32_t cap = M_MAX;                                  // array stride
+        unsigned char* base = pc_smem;
         PcSlot* s_sum = reinterpret_cast<PcSlot*>(base);                                             // 2 cap
         unsigned long long* s_vset = reinterpret_cast<unsigned long long*>(s_sum + 2u * cap);        // 4 cap
         uint32_t* s_key = reinterpret_cast<uint32_t*>(s_vset + 4u * cap);                            // 2 cap
@@ -805,7 +792,6 @@ k_pair_contacts_hash(FrameCtl* ctl, const uint32_t* __restrict__ list, int cls, 
             for (uint32_t k = tid; k < slots; k += T) { s_key[k] = 0xffffffffu; s_bits[k] = 7u; s_sum[k].w = 0.0; s_sum[k].cx = 0.0; s_sum[k].cy = 0.0; s_sum[k].cz = 0.0; }
             for (uint32_t k = tid; k < vslots; k += T) s_vset[k] = ~0ull;
             if (tid == 0) { s_ncand = 0u; s_nvert = 0u; s_navg = 0u; s_raybase = 0u; }
-            if (G) __threadfence();
             __syncthreads();
             // ---- one thread per hit: merge into the own triangle's candidate ----
             for (uint32_t k0 = 0; k0 < n; k0 += T) {
@@ -814,15 +800,15 @@ k_pair_contacts_hash(FrameCtl* ctl, const uint32_t* __restrict__ list, int cls, 
                 double w = 0.0, cx = 0.0, cy = 0.0, cz = 0.0;
                 bool claimed = false;
                 if (k < n) {
-                    const uint32_t fl = pc_ld<G>(s_fl + k);
-                    const uint32_t own = side ? pc_ld<G>(s_tb + k) : pc_ld<G>(s_ta + k);
+                    const uint32_t fl = s_fl[k];
+                    const uint32_t own = side ? s_tb[k] : s_ta[k];
                     bool contributes = (fl >> 31) != 0u;
                     if (!contributes) {                                                  // rare: is the combo's weight for this triangle 0? (:117-127)
-                        const uint32_t leaf = side ? pc_ld<G>(s_ta + k) - ((fl >> 6) & 3u) : pc_ld<G>(s_tb + k) - ((fl >> 8) & 3u);
+                        const uint32_t leaf = side ? s_ta[k] - ((fl >> 6) & 3u) : s_tb[k] - ((fl >> 8) & 3u);
                         for (uint32_t q = 0; q < n && !contributes; ++q) {
-                            const uint32_t fl2 = pc_ld<G>(s_fl + q);
-                            const uint32_t own2 = side ? pc_ld<G>(s_tb + q) : pc_ld<G>(s_ta + q);
-                            const uint32_t leaf2 = side ? pc_ld<G>(s_ta + q) - ((fl2 >> 6) & 3u) : pc_ld<G>(s_tb + q) - ((fl2 >> 8) & 3u);
+                            const uint32_t fl2 = s_fl[q];
+                            const uint32_t own2 = side ? s_tb[q] : s_ta[q];
+                            const uint32_t leaf2 = side ? s_ta[q] - ((fl2 >> 6) & 3u) : s_tb[q] - ((fl2 >> 8) & 3u);
                             contributes = own2 == own && leaf2 == leaf && (fl2 >> 31) != 0u;
                         }
                     }
@@ -854,7 +840,6 @@ k_pair_contacts_hash(FrameCtl* ctl, const uint32_t* __restrict__ list, int cls, 
                     atomicAdd(&s_sum[slot].w, w); atomicAdd(&s_sum[slot].cx, cx); atomicAdd(&s_sum[slot].cy, cy); atomicAdd(&s_sum[slot].cz, cz);
                 }
             }
-            if (G) __threadfence();
             __syncthreads();
             // ---- one thread per candidate: vertex rays into the `emplaced` set, average-point rays onto their list (:139-166) ----
             const uint32_t n_cand = s_ncand;
@@ -863,8 +848,8 @@ k_pair_contacts_hash(FrameCtl* ctl, const uint32_t* __restrict__ list, int cls, 
                 uint32_t q0 = 0xffffffffu, q1 = 0xffffffffu, q2 = 0xffffffffu;           // vertex slots claimed by this lane
                 uint32_t fallback = 0xffffffffu;
                 if (c < n_cand) {
-                    const uint32_t k = pc_ld<G>(s_cand + c);
-                    const uint32_t tri = pc_ld<G>(s_key + k), bits = pc_ld<G>(s_bits + k);
+                    const uint32_t k = s_cand[c];
+                    const uint32_t tri = s_key[k], bits = s_bits[k];
                     if (bits == 0u) fallback = k;                                        // ShouldFallbackToAvgPoint (:27-30)
                     else {
                         const uint32_t v0 = tri_vid[3ull * tri], v1 = tri_vid[3ull * tri + 1], v2 = tri_vid[3ull * tri + 2];
@@ -878,7 +863,6 @@ k_pair_contacts_hash(FrameCtl* ctl, const uint32_t* __restrict__ list, int cls, 
                 pc_append<LT>(q2 != 0xffffffffu, q2, s_vert, &s_nvert, lane);
                 pc_append<LT>(fallback != 0xffffffffu, fallback, s_avgl, &s_navg, lane);
             }
-            if (G) __threadfence();
             __syncthreads();
             const uint32_t n_vert = s_nvert, n_avg = s_navg;
             bool emit = keep_rays;
@@ -891,14 +875,14 @@ k_pair_contacts_hash(FrameCtl* ctl, const uint32_t* __restrict__ list, int cls, 
             SideSum r; r.x = r.y = r.z = 0.0; r.rays = 0u;
             // ---- rays at the weighted average point (:34-37,157-166) ----
             for (uint32_t c = tid; c < n_avg; c += T) {
-                const uint32_t k = pc_ld<G>(s_avgl + c);
+                const uint32_t k = s_avgl[c];
                 // the quotient is taken in FP64 and rounded once: rounding the two sums first would turn the last-bit noise of the
                 // order-free FP64 sums into FP32 differences whenever a sum sits on a rounding tie (two equal-exponent addends do)
-                const double w = pc_ld<G>(&s_sum[k].w);
-                const V3 pos = mk3((float)(pc_ld<G>(&s_sum[k].cx) / w), (float)(pc_ld<G>(&s_sum[k].cy) / w), (float)(pc_ld<G>(&s_sum[k].cz) / w));
+                const double w = s_sum[k].w;
+                const V3 pos = mk3((float)(s_sum[k].cx / w), (float)(s_sum[k].cy / w), (float)(s_sum[k].cz / w));
                 r.x += (double)pos.x; r.y += (double)pos.y; r.z += (double)pos.z; r.rays += 1u;
                 if (emit) {
-                    const uint32_t tri = pc_ld<G>(s_key + k);
+                    const uint32_t tri = s_key[k];
                     const float4* tp = reinterpret_cast<const float4*>(tris + tri);
                     const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
                     V3 p0 = mk3(t0.x, t0.y, t0.z), p1 = mk3(t1.x, t1.y, t1.z), p2 = mk3(t2.x, t2.y, t2.z);
@@ -914,7 +898,7 @@ k_pair_contacts_hash(FrameCtl* ctl, const uint32_t* __restrict__ list, int cls, 
             }
             // ---- vertex rays: one per distinct vertex id (the `emplaced` set, :139-155) ----
             for (uint32_t c = tid; c < n_vert; c += T) {
-                const uint32_t ref = (uint32_t)pc_ld<G>(s_vset + pc_ld<G>(s_vert + c));
+                const uint32_t ref = (uint32_t)s_vset[s_vert[c]];
                 const float4 q = __ldg(reinterpret_cast<const float4*>(tris + (ref >> 2)) + (ref & 3u));
                 V3 pos = mk3(q.x, q.y, q.z);
                 if (side) pos = rel_mul(rel, pos, 1.f);                                  // second's triangles live in first's space (:84,:134)
@@ -1401,7 +1385,7 @@ int imr_frame_run_device(imrcd_ctx* ctx) {
             IMR_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
             IMR_CUDA(ctx, cudaStreamWaitEvent(ctx->stream3, ctx->ev_fork, 0));
             IMR_CUDA(ctx, cudaStreamWaitEvent(ctx->stream4, ctx->ev_fork, 0));
-            k_pair_contacts_hash<512, PC_M_MAX><<<ctx->sm_count, 512, smem_m, ctx->stream2>>>(ctl, l2, 2, a_acc, a_grp, a_hits, a_aux, a_pr, a_tris, a_vid, a_nrm, a_rays, ctx->cap_rays, a_scr, ctx->cap_lscratch);
+            k_pair_contacts_hash<512, PC_M_MAX><<<ctx->sm_count, 512, smem_m, ctx->stream2>>>(ctl, l2, 2, a_acc, a_grp, a_hits, a_aux, a_pr, a_tris, a_vid, a_nrm, a_rays, ctx->cap_rays);
             {   // large pairs: grid-wide passes (k_large_*), on their own side stream
                 cudaStream_t s2 = ctx->stream4;
                 unsigned long long* a_pref = ctx->d_lpref.as<unsigned long long>(); LargeSide* a_sides = ctx->d_lsides.as<LargeSide>();
@@ -1413,8 +1397,8 @@ int imr_frame_run_device(imrcd_ctx* ctx) {
                 k_large_alloc<<<ctx->sm_count, 256, 0, s2>>>(ctl, l3, a_acc, a_sides, ctx->cap_rays);
                 k_large_rays<<<gl, 256, 0, s2>>>(ctl, l3, a_acc, a_pref, a_scr, a_sides, a_pr, a_tris, a_nrm, a_rays);
             }
-            k_pair_contacts_hash<256, PC_M1_MAX><<<ctx->sm_count * 3, 256, smem_m1, ctx->stream3>>>(ctl, l1, 1, a_acc, a_grp, a_hits, a_aux, a_pr, a_tris, a_vid, a_nrm, a_rays, ctx->cap_rays, a_scr, ctx->cap_lscratch);
-            k_pair_contacts_hash<128, PC_S_MAX><<<ctx->sm_count * 8, 128, smem_s, s>>>(ctl, l0, 0, a_acc, a_grp, a_hits, a_aux, a_pr, a_tris, a_vid, a_nrm, a_rays, ctx->cap_rays, a_scr, ctx->cap_lscratch);
+            k_pair_contacts_hash<256, PC_M1_MAX><<<ctx->sm_count * 3, 256, smem_m1, ctx->stream3>>>(ctl, l1, 1, a_acc, a_grp, a_hits, a_aux, a_pr, a_tris, a_vid, a_nrm, a_rays, ctx->cap_rays);
+            k_pair_contacts_hash<128, PC_S_MAX><<<ctx->sm_count * 8, 128, smem_s, s>>>(ctl, l0, 0, a_acc, a_grp, a_hits, a_aux, a_pr, a_tris, a_vid, a_nrm, a_rays, ctx->cap_rays);
             IMR_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->stream2));
             IMR_CUDA(ctx, cudaEventRecord(ctx->ev_join3, ctx->stream3));
             IMR_CUDA(ctx, cudaEventRecord(ctx->ev_join4, ctx->stream4));
