@@ -1,0 +1,86 @@
+"""GPU parity at BASELINE.json's full size (configs[2]: 163 static nodes + 100,000 dynamic bodies, 100,163 entries -- more than the
+reference's own broad phase can index, Entity being uint16_t: SURVEY finding 5), through properties that do not need the reference to
+run the whole frame: the broad-phase pair set against the 32-bit restatement of the sweep, a sample of pairs against the port oracle
+traversing the exported GPU trees (bit-exact hits, exact ray counts), the shards adding up to the frame, and two runs agreeing."""
+import numpy as np
+import pytest
+
+import bench
+from inmyroom_vulkan_b200.collision import CollisionDetection, OBBtree
+from helpers import f32_bits, gpu_frame, same_entity_pairs
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def c3(gpu_ctx):
+    scene, _ = bench.make_workload("c3", 100000)
+    trees = [OBBtree(gpu_ctx, m.positions, m.normals, m.vertex_ids) for m in scene.meshes]
+    cd = CollisionDetection(ctx=gpu_ctx)
+    st, bp, ep, hits = gpu_frame(cd, scene, trees)
+    return scene, trees, cd, st, bp, ep, hits
+
+
+def test_fullsize_counts_and_broad_phase(c3, port):
+    scene, trees, cd, st, bp, ep, hits = c3
+    assert st["n_entries"] == 100163 and scene.n_entries > 65534
+    assert st["n_pairs"] == len(bp) > 50000 and st["n_hits"] == len(hits) > 500000 and st["n_colliding"] == len(ep) > 3000
+    # the whole pair list, ordered pairs included, against the 32-bit restatement of SweepAndPrune.cpp:15-88 on the same root boxes
+    roots = np.stack([t.export().boxes[0] for t in trees]).astype(np.float32)[scene.mesh_index]
+    want, _ = port.broad(scene.matrices, roots, scene.should_callback)
+    got = set(map(tuple, bp.tolist())); assert len(got) == len(bp)
+    assert got == set(map(tuple, want.tolist()))
+    # no dynamic-dynamic pair survives the shouldCallback rule (SweepAndPrune.cpp:60): the bodies carry shouldCallback = false
+    ns = len(scene.meshes) - 1
+    assert ((bp < ns).sum(1) >= 1).all() and ((bp < ns).sum(1) == 1).sum() > 50000
+    # every hit belongs to a listed pair, every colliding pair has hits and rays
+    assert hits["pair"].max() < len(bp)
+    assert (ep["n_hits"] > 0).all() and ((ep["n_rays_first"] + ep["n_rays_second"]) > 0).all()
+    assert int(ep["n_hits"].sum()) <= st["n_hits"]
+
+
+def test_fullsize_sampled_pairs_against_the_oracle(c3, port):
+    scene, trees, cd, st, bp, ep, hits = c3
+    p_trees = [port.tree_import(t.export()) for t in trees]
+    rng = np.random.default_rng(5)
+    order = np.argsort(hits["pair"], kind="stable"); hp = hits["pair"][order]
+    with_hits = np.unique(hp)
+    sample = np.concatenate([rng.choice(with_hits, 120, replace=False), rng.choice(len(bp), 80, replace=False)])
+    ep_by_key = {(int(p["entry_first"]), int(p["entry_second"])): p for p in ep}
+    n_checked_hits = 0
+    for k in sample.tolist():
+        i, j = bp[k].tolist()
+        r = port.pair(p_trees[scene.mesh_index[i]], scene.matrices[i], p_trees[scene.mesh_index[j]], scene.matrices[j])
+        lo, hi = np.searchsorted(hp, k), np.searchsorted(hp, k, side="right")
+        gh = hits[order[lo:hi]]
+        assert len(gh) == r.n_hits, (k, len(gh), r.n_hits)
+        o_rec = {(int(a), int(b)): f32_bits(seg).tobytes() for (a, b), seg in zip(r.hit_ids.tolist(), r.hit_seg)}
+        g_rec = {(int(h["tri_first"]), int(h["tri_second"])): f32_bits(np.concatenate([h["source"], h["target"], [h["weight"]]])).tobytes() for h in gh}
+        assert o_rec == g_rec, k
+        n_checked_hits += r.n_hits
+        p = ep_by_key.get((i, j))
+        assert (p is not None) == r.colliding
+        if p is not None:
+            assert (int(p["n_rays_first"]), int(p["n_rays_second"])) == (r.rays_first, r.rays_second)
+    assert n_checked_hits > 5000
+
+
+def test_fullsize_shards_add_up_and_runs_agree(c3):
+    scene, trees, cd, st, bp, ep, hits = c3
+    key = lambda e: np.lexsort((e["entry_second"], e["entry_first"]))
+    full = ep[key(ep)]
+    st2, bp2, ep2, hits2 = gpu_frame(cd, scene, trees)                       # the same frame again
+    for f in ("n_pairs", "n_sat_tests", "n_combos", "n_tri_tests", "n_hits", "n_colliding", "n_rays"):
+        assert st[f] == st2[f], f
+    same_entity_pairs(full, ep2[key(ep2)])
+    world = 8
+    parts, n_pairs, n_hits = [], 0, 0
+    for r in range(world):
+        cd.set_shard(r, world)
+        s, b, e, h = gpu_frame(cd, scene, trees)
+        parts.append(e); n_pairs += s["n_pairs"]; n_hits += s["n_hits"]
+        assert s["n_pairs"] <= 1.3 * st["n_pairs"] / world + 64              # the sweep chunks are dealt evenly
+    cd.set_shard(0, 1)
+    assert n_pairs == st["n_pairs"] and n_hits == st["n_hits"]
+    merged = np.concatenate(parts)
+    same_entity_pairs(full, merged[key(merged)])
