@@ -98,6 +98,19 @@ const char* imrcd_version(void);
  * Triangle.cpp:214-234); vertex_ids: n_tri*3 u32 (TriangleIndices, Triangle.cpp:242-250) or NULL. */
 int imrcd_mesh_create(imrcd_ctx* ctx, const float* positions, const float* normals, const uint32_t* vertex_ids,
                       uint64_t n_tri, uint32_t build_mode, uint32_t* mesh_id);
+/* The engine's own way in: PrimitivesOfMeshes::StartRecordOBBtree / one PrimitiveOBBtreeData per glTF primitive /
+ * GetOBBtreeAndReset (IMR/src/Graphics/Meshes/PrimitivesOfMeshes.cpp:637-671,835-863).  A primitive is handed over as it lies in the glTF
+ * buffers -- points (stride 3 or 4 floats: the engine keeps vec4), optional normals (same stride), optional u32 indices, the glTF draw mode
+ * (IMR/include/glTFenum.h:27-36: 0 points, 1 lines, 3 line strip, 4 triangles, 5 triangle strip, 6 triangle fan; 2 = line loop yields no
+ * triangles, as in the reference) -- and Triangle::CreateTriangleList (IMR/src/Geometry/Triangle.cpp:9-62,214-280) runs on the device:
+ * positions, normals (the face normal when the primitive has none, Triangle.cpp:141-147,223-232) and vertex ids of every triangle, the
+ * primitives of a mesh concatenated in the order given.  indices == NULL means 0 .. n_points-1 (the reference sizes that iota by the FLOAT
+ * count, PrimitivesOfMeshes.cpp:662, and reads out of bounds; no shipped asset has a non-indexed primitive). */
+int imrcd_mesh_begin(imrcd_ctx* ctx);
+int imrcd_mesh_add_primitive(imrcd_ctx* ctx, const float* points, uint64_t n_points, uint32_t stride_floats, const float* normals,
+                             const uint32_t* indices, uint64_t n_indices, uint32_t gltf_mode);
+int imrcd_mesh_end(imrcd_ctx* ctx, uint32_t build_mode, uint32_t* mesh_id);
+
 /* Test-only: upload a tree built elsewhere (flat pre-order form, see oracle/imr_oracle.h). */
 int imrcd_mesh_import_tree(imrcd_ctx* ctx, uint64_t n_vertices, const float* boxes, const int32_t* left, const int32_t* right,
                            const uint32_t* tri_off, const uint32_t* tri_cnt, uint64_t n_tri, const float* tri_pos,

@@ -50,6 +50,9 @@ _SIGS = [
     ("imrcd_last_error", C.c_char_p, [_P]),
     ("imrcd_version", C.c_char_p, []),
     ("imrcd_mesh_create", C.c_int, [_P, _P, _P, _P, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint32)]),
+    ("imrcd_mesh_begin", C.c_int, [_P]),
+    ("imrcd_mesh_add_primitive", C.c_int, [_P, _P, C.c_uint64, C.c_uint32, _P, _P, C.c_uint64, C.c_uint32]),
+    ("imrcd_mesh_end", C.c_int, [_P, C.c_uint32, C.POINTER(C.c_uint32)]),
     ("imrcd_mesh_import_tree", C.c_int, [_P, C.c_uint64, _P, _P, _P, _P, _P, C.c_uint64, _P, _P, _P, _P, C.POINTER(C.c_uint32)]),
     ("imrcd_mesh_info", C.c_int, [_P, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     ("imrcd_mesh_export_tree", C.c_int, [_P, C.c_uint32] + [_P] * 9),

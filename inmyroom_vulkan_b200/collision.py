@@ -148,6 +148,24 @@ class OBBtree:
         self.ctx.check(self.ctx.lib.imrcd_mesh_last_build_ms(self.ctx.h, C.byref(ms)))
         return ms.value
 
+    @classmethod
+    def from_primitives(cls, ctx: Context, primitives, build_mode: int = IMRCD_BUILD_MORTON):
+        """The engine's way in (PrimitivesOfMeshes::StartRecordOBBtree / GetOBBtreeAndReset): `primitives` is a sequence of
+        (points (n, 3 or 4), normals or None, indices or None, glTF draw mode); Triangle::CreateTriangleList runs on the device."""
+        ctx.check(ctx.lib.imrcd_mesh_begin(ctx.h))
+        for points, normals, indices, mode in primitives:
+            pts = _c(points, np.float32)
+            stride = pts.shape[1]
+            nrm = None if normals is None else _c(normals, np.float32)
+            assert nrm is None or nrm.shape == pts.shape
+            idx = None if indices is None else _c(indices, np.uint32).reshape(-1)
+            ctx.check(ctx.lib.imrcd_mesh_add_primitive(ctx.h, _ptr(pts), pts.shape[0], stride, _ptr(nrm), _ptr(idx), 0 if idx is None else len(idx), int(mode)))
+        mid = C.c_uint32()
+        ctx.check(ctx.lib.imrcd_mesh_end(ctx.h, int(build_mode), C.byref(mid)))
+        self = cls.__new__(cls)
+        self.ctx = ctx; self.mesh_id = mid.value
+        return self
+
     def update_positions(self, positions, normals=None):
         """New triangle positions (original input order); call refit() / refit_meshes() before the next frame."""
         pos = _c(positions, np.float32).reshape(-1, 9)

@@ -54,6 +54,19 @@ public:
         return id;
     }
 
+    // the engine's own route, PrimitivesOfMeshes::StartRecordOBBtree / one PrimitiveOBBtreeData per primitive / GetOBBtreeAndReset
+    // (IMR/src/Graphics/Meshes/PrimitivesOfMeshes.cpp:637-671,835-863): Triangle::CreateTriangleList runs on the device.
+    // points / normals: n_points * stride floats (stride 4 = the engine's vec4 arrays), indices may be null, draw_mode = glTFmode.
+    void StartRecordOBBtree() { check(imrcd_mesh_begin(ctx_)); }
+    void RecordPrimitive(const float* points, uint64_t n_points, uint32_t stride, const float* normals, const uint32_t* indices, uint64_t n_indices, uint32_t draw_mode) {
+        check(imrcd_mesh_add_primitive(ctx_, points, n_points, stride, normals, indices, n_indices, draw_mode));
+    }
+    uint32_t GetOBBtreeAndReset(uint32_t build_mode = IMRCD_BUILD_MORTON) {
+        uint32_t id = 0;
+        check(imrcd_mesh_end(ctx_, build_mode, &id));
+        return id;
+    }
+
     void Reset() {                                                       // CollisionDetection.cpp:28
         check(imrcd_frame_reset(ctx_));
         n_ = 0; mapped_ = 0; pending_ = 0; any_previous_ = false;

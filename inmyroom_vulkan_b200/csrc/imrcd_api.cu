@@ -38,7 +38,9 @@ extern "C" int imrcd_create(int device, void* cuda_stream, imrcd_ctx** out) {
     return IMRCD_OK;
 }
 
+static void recording_clear(imrcd_ctx* ctx);
 extern "C" void imrcd_destroy(imrcd_ctx* ctx) {
+    if (ctx) recording_clear(ctx);
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
@@ -202,6 +204,61 @@ extern "C" int imrcd_mesh_create(imrcd_ctx* ctx, const float* positions, const f
     cudaSetDevice(ctx->device);
     MeshHost mh;
     int rc = imr_build_mesh_device(ctx, positions, normals, vertex_ids, n_tri, build_mode, &mh);
+    if (rc) return rc;
+    ctx->last_build_ms = mh.build_ms;
+    return mesh_register(ctx, mh, mesh_id);
+}
+
+// ---- mesh recording: the engine's StartRecordOBBtree / AddPrimitive / GetOBBtreeAndReset (PrimitivesOfMeshes.cpp:835-863) ----
+static uint64_t gltf_triangle_count(uint32_t mode, uint64_t ni) {       // CreateIndicesTriplets, Triangle.cpp:9-62
+    switch (mode) {
+        case 0: return ni;
+        case 1: return ni / 2;
+        case 3: return ni ? ni - 1 : 0;
+        case 4: return ni / 3;
+        case 5: case 6: return ni >= 2 ? ni - 2 : 0;
+        default: return 0;                                               // line loop: not handled by the reference's switch
+    }
+}
+static void recording_clear(imrcd_ctx* ctx) {
+    for (auto& r : ctx->recording) { r.points.release(); r.normals.release(); r.indices.release(); }
+    ctx->recording.clear(); ctx->recording_open = false;
+}
+extern "C" int imrcd_mesh_begin(imrcd_ctx* ctx) {
+    CHECK_CTX(ctx);
+    recording_clear(ctx);
+    ctx->recording_open = true;
+    return IMRCD_OK;
+}
+extern "C" int imrcd_mesh_add_primitive(imrcd_ctx* ctx, const float* points, uint64_t n_points, uint32_t stride_floats, const float* normals,
+                                        const uint32_t* indices, uint64_t n_indices, uint32_t gltf_mode) {
+    CHECK_CTX(ctx);
+    if (!ctx->recording_open) { ctx->err = "imrcd_mesh_add_primitive before imrcd_mesh_begin"; return IMRCD_E_STATE; }
+    if ((n_points && !points) || (stride_floats != 3 && stride_floats != 4) || gltf_mode > 6) { ctx->err = "imrcd_mesh_add_primitive: bad argument"; return IMRCD_E_ARG; }
+    cudaSetDevice(ctx->device);
+    cudaStream_t s = ctx->stream;
+    ctx->recording.emplace_back();
+    imrcd_ctx::RecordedPrimitive& r = ctx->recording.back();
+    r.n_points = n_points; r.stride = stride_floats; r.mode = gltf_mode;
+    r.n_indices = indices ? n_indices : n_points;
+    r.n_tri = gltf_triangle_count(gltf_mode, r.n_indices);
+    const size_t pbytes = 4ull * stride_floats * n_points;
+    if (pbytes) {
+        IMR_CUDA(ctx, r.points.reserve(pbytes, 0, s));
+        IMR_CUDA(ctx, cudaMemcpyAsync(r.points.p, points, pbytes, cudaMemcpyDefault, s));
+        if (normals) { IMR_CUDA(ctx, r.normals.reserve(pbytes, 0, s)); IMR_CUDA(ctx, cudaMemcpyAsync(r.normals.p, normals, pbytes, cudaMemcpyDefault, s)); }
+    }
+    if (indices && n_indices) { IMR_CUDA(ctx, r.indices.reserve(4ull * n_indices, 0, s)); IMR_CUDA(ctx, cudaMemcpyAsync(r.indices.p, indices, 4ull * n_indices, cudaMemcpyDefault, s)); }
+    IMR_CUDA(ctx, cudaStreamSynchronize(s));                            // the caller may reuse its buffers
+    return IMRCD_OK;
+}
+extern "C" int imrcd_mesh_end(imrcd_ctx* ctx, uint32_t build_mode, uint32_t* mesh_id) {
+    CHECK_CTX(ctx);
+    if (!ctx->recording_open || !mesh_id) { ctx->err = "imrcd_mesh_end: no mesh is being recorded"; return IMRCD_E_STATE; }
+    cudaSetDevice(ctx->device);
+    MeshHost mh;
+    int rc = imr_mesh_assemble_device(ctx, build_mode, &mh);
+    recording_clear(ctx);
     if (rc) return rc;
     ctx->last_build_ms = mh.build_ms;
     return mesh_register(ctx, mh, mesh_id);

@@ -715,9 +715,9 @@ static int build_morton(imrcd_ctx* ctx, const float* h_pos, const float* h_nrm, 
                             for (DevBuf* b : all) b->release(); };
 #define BUILD_CUDA(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(_e); free_all(); return IMRCD_E_CUDA; } } while (0)
     BUILD_CUDA(d_pos.reserve(36ull * n, 0, s));
-    BUILD_CUDA(cudaMemcpyAsync(d_pos.p, h_pos, 36ull * n, cudaMemcpyHostToDevice, s));
-    if (h_nrm) { BUILD_CUDA(d_nrm.reserve(36ull * n, 0, s)); BUILD_CUDA(cudaMemcpyAsync(d_nrm.p, h_nrm, 36ull * n, cudaMemcpyHostToDevice, s)); }
-    if (h_vid) { BUILD_CUDA(d_vid.reserve(12ull * n, 0, s)); BUILD_CUDA(cudaMemcpyAsync(d_vid.p, h_vid, 12ull * n, cudaMemcpyHostToDevice, s)); }
+    BUILD_CUDA(cudaMemcpyAsync(d_pos.p, h_pos, 36ull * n, cudaMemcpyDefault, s));
+    if (h_nrm) { BUILD_CUDA(d_nrm.reserve(36ull * n, 0, s)); BUILD_CUDA(cudaMemcpyAsync(d_nrm.p, h_nrm, 36ull * n, cudaMemcpyDefault, s)); }
+    if (h_vid) { BUILD_CUDA(d_vid.reserve(12ull * n, 0, s)); BUILD_CUDA(cudaMemcpyAsync(d_vid.p, h_vid, 12ull * n, cudaMemcpyDefault, s)); }
     BUILD_CUDA(d_bounds.reserve(64, 0, s));
     BUILD_CUDA(d_keys.reserve(8ull * n, 0, s)); BUILD_CUDA(d_keys2.reserve(8ull * n, 0, s));
     BUILD_CUDA(d_idx.reserve(4ull * n, 0, s)); BUILD_CUDA(d_idx2.reserve(4ull * n, 0, s));
@@ -867,4 +867,76 @@ int imr_meshes_refit_device(imrcd_ctx* ctx, const uint32_t* ids, uint64_t n_ids,
     if (ms_out) *ms_out = ms;
     // root boxes (host copies used nowhere on the hot path, kept coherent for imrcd_mesh_info-style queries)
     return IMRCD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Triangle::CreateTriangleList on the device: the primitives of a mesh, as they lie in the glTF buffers, become the flat
+// triangle arrays (positions, normals, vertex ids) the builds start from.  CreateIndicesTriplets, IMR/src/Geometry/Triangle.cpp:9-62:
+//   points          (i, i, i)                          line strip      (i, i, i+1)
+//   lines           (2i, 2i, 2i+1)                     triangles       (3i, 3i+1, 3i+2)
+//   triangle strip  (i, i + (1 + i % 2), i + (2 - i % 2))              triangle fan   (i+1, i+2, 0)
+// Normals are the vertex normals through the same triplets, or the triangle's face normal three times when the primitive has none
+// (Triangle.cpp:141-147,223-232); vertex ids are the index values themselves (Triangle.cpp:242-250).
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void gltf_triplet(uint32_t mode, uint32_t i, uint32_t& a, uint32_t& b, uint32_t& c) {
+    switch (mode) {
+        case 0: a = i; b = i; c = i; break;
+        case 1: a = 2u * i; b = 2u * i; c = 2u * i + 1u; break;
+        case 3: a = i; b = i; c = i + 1u; break;
+        case 4: a = 3u * i; b = 3u * i + 1u; c = 3u * i + 2u; break;
+        case 5: a = i; b = i + (1u + i % 2u); c = i + (2u - i % 2u); break;
+        default: a = i + 1u; b = i + 2u; c = 0u; break;      // triangle fan
+    }
+}
+
+__global__ void k_assemble_primitive(uint32_t n_tri, uint32_t mode, uint32_t stride, const float* __restrict__ points, const float* __restrict__ normals,
+                                     const uint32_t* __restrict__ indices, float* __restrict__ pos_out, float* __restrict__ nrm_out, uint32_t* __restrict__ vid_out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_tri) return;
+    uint32_t k[3];
+    gltf_triplet(mode, i, k[0], k[1], k[2]);
+    uint32_t v[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) v[q] = indices ? indices[k[q]] : k[q];
+    float p[9];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) { const float* s = points + (size_t)stride * v[q]; p[3 * q] = s[0]; p[3 * q + 1] = s[1]; p[3 * q + 2] = s[2]; }
+#pragma unroll
+    for (int q = 0; q < 9; ++q) pos_out[9ull * i + q] = p[q];
+    if (normals) {
+#pragma unroll
+        for (int q = 0; q < 3; ++q) { const float* s = normals + (size_t)stride * v[q]; nrm_out[9ull * i + 3 * q] = s[0]; nrm_out[9ull * i + 3 * q + 1] = s[1]; nrm_out[9ull * i + 3 * q + 2] = s[2]; }
+    } else {
+        const V3 n = normalize3(cross3(sub3(mk3(p[3], p[4], p[5]), mk3(p[0], p[1], p[2])), sub3(mk3(p[6], p[7], p[8]), mk3(p[0], p[1], p[2]))));   // Triangle.cpp:141-147
+#pragma unroll
+        for (int q = 0; q < 3; ++q) { nrm_out[9ull * i + 3 * q] = n.x; nrm_out[9ull * i + 3 * q + 1] = n.y; nrm_out[9ull * i + 3 * q + 2] = n.z; }
+    }
+    vid_out[3ull * i] = v[0]; vid_out[3ull * i + 1] = v[1]; vid_out[3ull * i + 2] = v[2];
+}
+
+int imr_mesh_assemble_device(imrcd_ctx* ctx, uint32_t build_mode, MeshHost* out) {
+    cudaStream_t s = ctx->stream;
+    uint64_t n_tri = 0;
+    for (const auto& r : ctx->recording) n_tri += r.n_tri;
+    if (n_tri >= (1ull << 32)) { ctx->err = "mesh exceeds 2^32 triangles"; return IMRCD_E_CAPACITY; }
+    DevBuf d_pos, d_nrm, d_vid;
+    auto free_all = [&]() { d_pos.release(); d_nrm.release(); d_vid.release(); };
+    if (n_tri) {
+        cudaError_t e;
+        if ((e = d_pos.reserve(36ull * n_tri, 0, s)) != cudaSuccess || (e = d_nrm.reserve(36ull * n_tri, 0, s)) != cudaSuccess || (e = d_vid.reserve(12ull * n_tri, 0, s)) != cudaSuccess) {
+            ctx->err = std::string("imr_mesh_assemble_device: ") + cudaGetErrorString(e); free_all(); return IMRCD_E_CUDA;
+        }
+        uint64_t at = 0;
+        for (const auto& r : ctx->recording) {
+            if (!r.n_tri) continue;
+            k_assemble_primitive<<<nb(r.n_tri, 256), 256, 0, s>>>((uint32_t)r.n_tri, r.mode, r.stride, r.points.as<float>(), r.normals.p ? r.normals.as<float>() : nullptr,
+                                                                   r.indices.p ? r.indices.as<uint32_t>() : nullptr, d_pos.as<float>() + 9ull * at, d_nrm.as<float>() + 9ull * at,
+                                                                   d_vid.as<uint32_t>() + 3ull * at);
+            at += r.n_tri;
+        }
+        if ((e = cudaGetLastError()) != cudaSuccess) { ctx->err = std::string("k_assemble_primitive: ") + cudaGetErrorString(e); free_all(); return IMRCD_E_CUDA; }
+    }
+    const int rc = imr_build_mesh_device(ctx, d_pos.as<float>(), n_tri ? d_nrm.as<float>() : nullptr, n_tri ? d_vid.as<uint32_t>() : nullptr, n_tri, build_mode, out);
+    free_all();
+    return rc;
 }

@@ -282,9 +282,9 @@ int imr_build_mesh_reference(imrcd_ctx* ctx, const float* h_pos, const float* h_
     auto free_all = [&]() { DevBuf* all[] = { &d_pos, &d_nrm, &d_vid, &d_idx_a, &d_idx_b, &d_list_a, &d_list_b, &d_cnt, &d_u32, &d_u8, &d_box, &d_tmp }; for (DevBuf* b : all) b->release(); };
 #define REF_CUDA(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(_e); free_all(); return IMRCD_E_CUDA; } } while (0)
     REF_CUDA(d_pos.reserve(36ull * std::max<uint32_t>(n, 1), 0, s));
-    if (n) REF_CUDA(cudaMemcpyAsync(d_pos.p, h_pos, 36ull * n, cudaMemcpyHostToDevice, s));
-    if (h_nrm && n) { REF_CUDA(d_nrm.reserve(36ull * n, 0, s)); REF_CUDA(cudaMemcpyAsync(d_nrm.p, h_nrm, 36ull * n, cudaMemcpyHostToDevice, s)); }
-    if (h_vid && n) { REF_CUDA(d_vid.reserve(12ull * n, 0, s)); REF_CUDA(cudaMemcpyAsync(d_vid.p, h_vid, 12ull * n, cudaMemcpyHostToDevice, s)); }
+    if (n) REF_CUDA(cudaMemcpyAsync(d_pos.p, h_pos, 36ull * n, cudaMemcpyDefault, s));
+    if (h_nrm && n) { REF_CUDA(d_nrm.reserve(36ull * n, 0, s)); REF_CUDA(cudaMemcpyAsync(d_nrm.p, h_nrm, 36ull * n, cudaMemcpyDefault, s)); }
+    if (h_vid && n) { REF_CUDA(d_vid.reserve(12ull * n, 0, s)); REF_CUDA(cudaMemcpyAsync(d_vid.p, h_vid, 12ull * n, cudaMemcpyDefault, s)); }
     REF_CUDA(d_idx_a.reserve(4ull * std::max<uint32_t>(n, 1), 0, s)); REF_CUDA(d_idx_b.reserve(4ull * std::max<uint32_t>(n, 1), 0, s));
     REF_CUDA(d_list_a.reserve(4ull * cap, 0, s)); REF_CUDA(d_list_b.reserve(4ull * cap, 0, s));
     REF_CUDA(d_cnt.reserve(64, 0, s));

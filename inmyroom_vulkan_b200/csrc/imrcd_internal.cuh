@@ -169,6 +169,11 @@ struct imrcd_ctx {
     bool meshes_dirty = false;
     float last_build_ms = 0.f;
 
+    // mesh recording (imrcd_mesh_begin / add_primitive / end): the primitives' buffers wait in HBM until the mesh is closed
+    struct RecordedPrimitive { DevBuf points, normals, indices; uint64_t n_points, n_indices, n_tri; uint32_t stride, mode; };
+    std::vector<RecordedPrimitive> recording;
+    bool recording_open = false;
+
     // frame, host side: the entry table is written straight into pinned memory (one host copy per entry) and goes to
     // HBM in chunks while the caller is still adding entries
     PinBuf p_cur, p_prev, p_mesh, p_entity, p_cb;
@@ -205,6 +210,7 @@ int imr_mesh_finalize_records(imrcd_ctx* ctx, uint32_t rec_base, uint32_t n_rec)
 int imr_mesh_finalize_tris(imrcd_ctx* ctx, uint32_t tri_base, uint32_t n_tri);               // triangle planes (TriRec.t3)
 int imr_build_mesh_device(imrcd_ctx* ctx, const float* pos, const float* nrm, const uint32_t* vid, uint64_t n_tri,
                           uint32_t mode, MeshHost* out);
+int imr_mesh_assemble_device(imrcd_ctx* ctx, uint32_t build_mode, MeshHost* out);      // Triangle::CreateTriangleList on the device, then the build
 int imr_frame_run_device(imrcd_ctx* ctx);
 // response stage: one thread per kept ray (Hermann passes), then one warp per colliding pair that moved (imrcd_rays.cu)
 int imr_frame_shoot_device(imrcd_ctx* ctx, FrameCtl* ctl, uint64_t* launches);

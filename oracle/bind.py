@@ -170,6 +170,23 @@ class _Base:
         col = f(ta.h, ma.ctypes.data, pa.ctypes.data, tb.h, mb.ctypes.data, pb.ctypes.data, d.ctypes.data, extra.ctypes.data)
         return bool(col), d[:3].copy(), d[3:].copy()
 
+    def triangle_list(self, points, normals, indices, mode):
+        """Triangle::CreateTriangleList on one primitive: (positions (n,9), normals (n,9), vertex ids (n,3))."""
+        pts = _c(points, np.float32).reshape(-1, 3); idx = _c(indices, np.uint32).reshape(-1)
+        nrm = None if normals is None else _c(normals, np.float32).reshape(-1, 3)
+        f = self._fn("triangle_list"); f.restype = C.c_uint64
+        if self.kind == "reference":
+            f.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+            call = lambda p9, n9, v3: f(pts.ctypes.data, len(pts), _opt(nrm), idx.ctypes.data, len(idx), int(mode), p9, n9, v3)
+        else:
+            f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+            call = lambda p9, n9, v3: f(pts.ctypes.data, _opt(nrm), idx.ctypes.data, len(idx), int(mode), p9, n9, v3)
+        n = int(call(None, None, None))
+        pos = np.zeros((n, 9), np.float32); nr = np.zeros((n, 9), np.float32); vid = np.zeros((n, 3), np.uint32)
+        if n:
+            call(pos.ctypes.data, nr.ctypes.data, vid.ctypes.data)
+        return pos, nr, vid
+
     # ---- trees ---------------------------------------------------------
     def tree_build(self, pos, nrm=None, vid=None):
         pos = _c(pos, np.float32).reshape(-1, 9)

@@ -1292,6 +1292,40 @@ int imro_pair_delta(const imro_tree* a, const float* mat_a, const float* prev_a,
     return 1;
 }
 
+/* ------------------------------------------------------------------ */
+/* Triangle::CreateTriangleList (IMR/src/Geometry/Triangle.cpp:9-62,214-280) */
+/* ------------------------------------------------------------------ */
+static uint64_t triplet_count(uint32_t mode, uint64_t ni) {
+    switch (mode) { case 0: return ni; case 1: return ni / 2; case 3: return ni ? ni - 1 : 0; case 4: return ni / 3; case 5: case 6: return ni >= 2 ? ni - 2 : 0; default: return 0; }
+}
+static void triplet(uint32_t mode, uint64_t i, uint64_t* a, uint64_t* b, uint64_t* c) {      /* CreateIndicesTriplets :14-59 */
+    switch (mode) {
+        case 0: *a = i; *b = i; *c = i; break;
+        case 1: *a = 2 * i; *b = 2 * i; *c = 2 * i + 1; break;
+        case 3: *a = i; *b = i; *c = i + 1; break;
+        case 4: *a = 3 * i; *b = 3 * i + 1; *c = 3 * i + 2; break;
+        case 5: *a = i; *b = i + (1 + i % 2); *c = i + (2 - i % 2); break;
+        default: *a = i + 1; *b = i + 2; *c = 0; break;
+    }
+}
+/* points / normals: n_points x 3 floats (normals may be NULL: face normals, :223-232); out arrays sized by the return value of a first call with NULLs */
+uint64_t imro_triangle_list(const float* points, const float* normals, const uint32_t* indices, uint64_t n_indices, uint32_t mode,
+                            float* pos9, float* nrm9, uint32_t* vid3) {
+    uint64_t n = triplet_count(mode, n_indices);
+    if (!pos9) return n;
+    for (uint64_t i = 0; i < n; ++i) {
+        uint64_t k[3]; triplet(mode, i, &k[0], &k[1], &k[2]);
+        for (int q = 0; q < 3; ++q) {
+            uint32_t v = indices[k[q]];
+            memcpy(pos9 + 9 * i + 3 * q, points + 3 * (uint64_t)v, 12);
+            if (normals) memcpy(nrm9 + 9 * i + 3 * q, normals + 3 * (uint64_t)v, 12);
+            vid3[3 * i + q] = v;                                       /* CreateTriangleIndicesList :242-250: iota data, so the index itself */
+        }
+        if (!normals) { v3 fn = face_normal(pos9 + 9 * i); for (int q = 0; q < 3; ++q) { nrm9[9 * i + 3 * q] = fn.x; nrm9[9 * i + 3 * q + 1] = fn.y; nrm9[9 * i + 3 * q + 2] = fn.z; } }
+    }
+    return n;
+}
+
 /* Batch mid + narrow over a pair list: the loop of IMR/src/CollisionDetection/CollisionDetection.cpp:44-69 on
  * (first,second) entry-index pairs.  Re-entrant.  totals: [0] combos [1] tri-pair tests [2] colliding pairs
  * [3] pairs with >= 1 combo. */

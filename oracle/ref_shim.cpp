@@ -499,6 +499,25 @@ void imr_ref_pair_rays(void* tree_a, const float* mat_a, void* tree_b, const flo
     if (rays_second) put(rays.rays_from_second_to_first, rays_second);
 }
 
+// Triangle::CreateTriangleList (Triangle.cpp:259-280) on one primitive; returns the triangle count, fills the arrays when pos9 != nullptr.
+uint64_t imr_ref_triangle_list(const float* points, uint64_t n_points, const float* normals, const uint32_t* indices, uint64_t n_indices, uint32_t mode,
+                               float* pos9, float* nrm9, uint32_t* vid3) {
+    std::vector<glm::vec3> pts(n_points), nrm;
+    for (uint64_t i = 0; i < n_points; ++i) pts[i] = glm::vec3(points[3 * i], points[3 * i + 1], points[3 * i + 2]);
+    if (normals) { nrm.resize(n_points); for (uint64_t i = 0; i < n_points; ++i) nrm[i] = glm::vec3(normals[3 * i], normals[3 * i + 1], normals[3 * i + 2]); }
+    std::vector<uint32_t> idx(indices, indices + n_indices);
+    std::vector<Triangle> tris = Triangle::CreateTriangleList(pts, nrm, idx, static_cast<glTFmode>(mode));
+    if (pos9) {
+        for (size_t i = 0; i < tris.size(); ++i)
+            for (int q = 0; q < 3; ++q) {
+                glm::vec3 p = tris[i].GetP(q), n = tris[i].GetN(q);
+                std::memcpy(pos9 + 9 * i + 3 * q, &p, 12); std::memcpy(nrm9 + 9 * i + 3 * q, &n, 12);
+                vid3[3 * i + q] = tris[i].GetI(q);
+            }
+    }
+    return tris.size();
+}
+
 const char* imr_ref_build_info() { return "reference sources compiled in place: g++ -std=c++20 -O2 -ffp-contract=off"; }
 
 }  // extern "C"
