@@ -135,3 +135,24 @@ def test_shards_partition_the_frame(gpu_ctx):
                 assert (np.isnan(x).any() and np.isnan(y).any()) or np.linalg.norm(x - y) <= 1e-6 * max(np.linalg.norm(y), 1e-30)
         sizes = [len(p[0]) for p in parts]
         assert max(sizes) <= 1.5 * (sum(sizes) / world) + 32
+
+
+def test_zero_weight_hits_follow_the_combo_rule(gpu_ctx, oracle):
+    """A triangle pair that touches in one point is an intersecting, non-coplanar hit whose segment has length 0: its candidate is dropped
+    unless the same combo gives the triangle another hit with weight (TriangleCandidateRays::IsNull, CreateUncollideRays.cpp:22-25,117-127).
+    Exact small-integer coordinates, identity matrices: (a) the touching pair alone: one hit, no ray, not colliding; (b) with a second
+    triangle of the same leaf cutting through: both hits count for first's triangle, only the cutting one for second's."""
+    A = np.array([[0, 0, 0, 4, 0, 0, 0, 4, 0], [0, 0, -5, 4, 0, -5, 0, 4, -5]], np.float32)            # second triangle far below: never hit
+    touch = np.array([[1, 1, 0, 1, 1, 2, 2, 1, 2]], np.float32)                                       # vertex (1,1,0) lies inside A0
+    cut = np.array([[2, 1, -1, 2, 1, 1, 2, 2, 1]], np.float32)                                        # crosses z = 0 inside A0
+    ident = np.eye(4, dtype=np.float32).reshape(1, 16)
+    for name, B, want_hits in (("touch", touch, 1), ("touch+cut", np.concatenate([touch, cut]), 2)):
+        meshes = [scenes.Mesh(m, np.tile(np.array([0, 0, 1], np.float32), (m.shape[0], 3)), np.arange(3 * m.shape[0], dtype=np.uint32).reshape(-1, 3), nm)
+                  for m, nm in ((A, "A"), (B, "B"))]
+        scene = scenes.Scene(meshes, np.array([0, 1], np.uint32), np.concatenate([ident, ident]), np.ones(2, np.uint8), np.array([1, 2], np.uint32))
+        st, ores = _run(gpu_ctx, oracle, scene)
+        assert st["n_hits"] == want_hits and st["n_coplanar_hits"] == 0, name
+        r = next(iter(ores["per_pair"].values()))
+        assert r.n_hits == want_hits and (r.colliding, st["n_colliding"]) == ((want_hits == 2), int(want_hits == 2)), name
+        if want_hits == 1:
+            assert float(r.hit_seg[0, 6]) == 0.0 and (r.rays_first, r.rays_second) == (0, 0)
