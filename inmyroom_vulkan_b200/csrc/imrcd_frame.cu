@@ -1225,7 +1225,7 @@ int imr_frame_run_device(imrcd_ctx* ctx) {
     if (n < 2) return IMRCD_OK;                                   // CollisionDetection.cpp:40
 
     // capacities (persist across frames; grown on overflow)
-    if (ctx->cap_pairs == 0) ctx->cap_pairs = std::max<uint64_t>(1u << 16, 32ull * n);
+    if (ctx->cap_pairs == 0) ctx->cap_pairs = std::max<uint64_t>(1u << 16, 4ull * n);      // grown (and the frame re-run) when a frame has more pairs
     if (ctx->cap_queue == 0) ctx->cap_queue = ctx->cap_pairs + (1ull << 22);
     if (ctx->cap_combos == 0) ctx->cap_combos = 1ull << 22;
     if (ctx->cap_hits == 0) ctx->cap_hits = 1ull << 20;

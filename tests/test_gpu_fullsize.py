@@ -1,4 +1,4 @@
-"""GPU parity at BASELINE.json's full size (configs[2]: 163 static nodes + 100,000 dynamic bodies, 100,163 entries -- more than the
+"""GPU parity at BASELINE.json's full sizes (configs[1]: 4,096 tori; configs[2]: 163 static nodes + 100,000 dynamic bodies, 100,163 entries -- more than the
 reference's own broad phase can index, Entity being uint16_t: SURVEY finding 5), through properties that do not need the reference to
 run the whole frame: the broad-phase pair set against the 32-bit restatement of the sweep, a sample of pairs against the port oracle
 traversing the exported GPU trees (bit-exact hits, exact ray counts), the shards adding up to the frame, and two runs agreeing."""
@@ -12,9 +12,10 @@ from helpers import f32_bits, gpu_frame, same_entity_pairs
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def c3(gpu_ctx):
-    scene, _ = bench.make_workload("c3", 100000)
+@pytest.fixture(scope="module", params=["c3", "c2"])
+def c3(gpu_ctx, request):
+    """The two full-size bench workloads: configs[2] (C3, 100,163 entries) and configs[1] (C2: 4,096 instances of a 10,000-triangle torus)."""
+    scene, _ = bench.make_workload(request.param, 100000 if request.param == "c3" else 4096)
     trees = [OBBtree(gpu_ctx, m.positions, m.normals, m.vertex_ids) for m in scene.meshes]
     cd = CollisionDetection(ctx=gpu_ctx)
     st, bp, ep, hits = gpu_frame(cd, scene, trees)
@@ -23,16 +24,17 @@ def c3(gpu_ctx):
 
 def test_fullsize_counts_and_broad_phase(c3, port):
     scene, trees, cd, st, bp, ep, hits = c3
-    assert st["n_entries"] == 100163 and scene.n_entries > 65534
-    assert st["n_pairs"] == len(bp) > 50000 and st["n_hits"] == len(hits) > 500000 and st["n_colliding"] == len(ep) > 3000
+    big = scene.n_entries > 65534
+    assert st["n_entries"] == (100163 if big else 4096)
+    assert st["n_pairs"] == len(bp) > 30000 and st["n_hits"] == len(hits) > 500000 and st["n_colliding"] == len(ep) > 3000
     # the whole pair list, ordered pairs included, against the 32-bit restatement of SweepAndPrune.cpp:15-88 on the same root boxes
     roots = np.stack([t.export().boxes[0] for t in trees]).astype(np.float32)[scene.mesh_index]
     want, _ = port.broad(scene.matrices, roots, scene.should_callback)
     got = set(map(tuple, bp.tolist())); assert len(got) == len(bp)
     assert got == set(map(tuple, want.tolist()))
-    # no dynamic-dynamic pair survives the shouldCallback rule (SweepAndPrune.cpp:60): the bodies carry shouldCallback = false
-    ns = len(scene.meshes) - 1
-    assert ((bp < ns).sum(1) >= 1).all() and ((bp < ns).sum(1) == 1).sum() > 50000
+    if big:   # no dynamic-dynamic pair survives the shouldCallback rule (SweepAndPrune.cpp:60): the bodies carry shouldCallback = false
+        ns = len(scene.meshes) - 1
+        assert ((bp < ns).sum(1) >= 1).all() and ((bp < ns).sum(1) == 1).sum() > 50000
     # every hit belongs to a listed pair, every colliding pair has hits and rays
     assert hits["pair"].max() < len(bp)
     assert (ep["n_hits"] > 0).all() and ((ep["n_rays_first"] + ep["n_rays_second"]) > 0).all()
