@@ -295,6 +295,9 @@ def run_gpu_arm(args):
             st_acc[k] = st_acc.get(k, 0.0) + st[k]
         launches += st["total_launches"]
     barrier()
+    if os.environ.get("IMRCD_BENCH_DEBUG"):               # per-rank stage sums: where a multi-GPU step spends its time
+        print(f"[rank {rank}] dev_ms/step {sum(a.elapsed_time(b) for a, b in ev) / args.steps:.3f} stages " +
+              " ".join(f"{k}={v / args.steps:.3f}" for k, v in st_acc.items()) + f" pairs={cd.stats()['n_pairs']} hits={cd.stats()['n_hits']}", file=sys.stderr)
     if gather is not None and gather.counts() is None:
         raise SystemExit("bench.py: the frame gather outgrew its blocks during the timed loop")
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)

@@ -147,17 +147,27 @@ IMR_HD V3 sat_axis(const Box& l, const Box& r, int k) {
 }
 // Paralgram.cpp:17-173.  The verdict does not depend on evaluation order or early exit
 // (each axis test is a pure function of the two boxes), so the device evaluates all 15 and ANDs.
-template <bool STRAIGHT>
+// MODE 0: lane-level early exit after every axis (branches); 1: straight-line, all 15 axes; 2: the six face-normal axes straight-line,
+// one exit, then the nine edge-edge axes straight-line (most separated pairs are caught by a face normal).
+template <int MODE>
 IMR_HD bool box_sat_t(const Box& l, const Box& r) {
     bool ok = true;
+    if (MODE == 2) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) ok = ok & axis_overlap(l, r, sat_axis(l, r, k));
+        if (!ok) return false;
+#pragma unroll
+        for (int k = 6; k < 15; ++k) ok = ok & axis_overlap(l, r, sat_axis(l, r, k));
+        return ok;
+    }
 #pragma unroll
     for (int k = 0; k < 15; ++k) {
-        if (STRAIGHT) ok = ok & axis_overlap(l, r, sat_axis(l, r, k));     // straight-line: no per-axis branches
+        if (MODE == 1) ok = ok & axis_overlap(l, r, sat_axis(l, r, k));     // straight-line: no per-axis branches
         else ok = ok && axis_overlap(l, r, sat_axis(l, r, k));             // lane-level early exit (branches)
     }
     return ok;
 }
-IMR_HD bool box_sat(const Box& l, const Box& r) { return box_sat_t<false>(l, r); }
+IMR_HD bool box_sat(const Box& l, const Box& r) { return box_sat_t<0>(l, r); }
 // Paralgram.cpp:203-210
 IMR_HD float box_surface(const Box& b) {
     float uv = length3(cross3(b.u, b.v));
