@@ -555,7 +555,8 @@ k_tritri(FrameCtl* ctl, const Combo* __restrict__ combos, unsigned long long cap
                 }
             }
             const uint32_t km = __ballot_sync(FULL_MASK, keep);
-            if (keep) sm.test[n_surv + __popc(km & lt_mask)] = (uint16_t)code;     // after the ballot: every lane has read its test[t]
+            __syncwarp();                                                         // every lane has read its test[t]: the writes below trail the reads
+            if (keep) sm.test[n_surv + __popc(km & lt_mask)] = (uint16_t)code;
             n_surv += (uint32_t)__popc(km);
         }
         __syncwarp();
@@ -757,7 +758,8 @@ k_pair_contacts_hash(FrameCtl* ctl, const uint32_t* __restrict__ list, int cls, 
     extern __shared__ __align__(16) unsigned char pc_smem[];
     __shared__ double s_red[3][T / 32];
     __shared__ uint32_t s_redc[T / 32];
-    __shared__ uint32_t s_ncand, s_nvert, s_navg, s_raybase;
+    __shared__ uint32_t s_ncand, s_nvert, s_navg;
+    __shared__ __align__(16) uint32_t s_raybase;      // on its own 16 bytes: never part of a vector load of the counters
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
     if (ctl->overflow & (OVF_PAIRS | OVF_QUEUE | OVF_COMBOS | OVF_HITS)) return;      // the frame is re-run with larger buffers
     const unsigned long long n_list = ctl->n_class[cls * 16];
@@ -791,7 +793,7 @@ k_pair_contacts_hash(FrameCtl* ctl, const uint32_t* __restrict__ list, int cls, 
         for (uint32_t side = 0; side < 2; ++side) {
             for (uint32_t k = tid; k < slots; k += T) { s_key[k] = 0xffffffffu; s_bits[k] = 7u; s_sum[k].w = 0.0; s_sum[k].cx = 0.0; s_sum[k].cy = 0.0; s_sum[k].cz = 0.0; }
             for (uint32_t k = tid; k < vslots; k += T) s_vset[k] = ~0ull;
-            if (tid == 0) { s_ncand = 0u; s_nvert = 0u; s_navg = 0u; s_raybase = 0u; }
+            if (tid == 0) { s_ncand = 0u; s_nvert = 0u; s_navg = 0u; }
             __syncthreads();
             // ---- one thread per hit: merge into the own triangle's candidate ----
             for (uint32_t k0 = 0; k0 < n; k0 += T) {
@@ -865,13 +867,12 @@ k_pair_contacts_hash(FrameCtl* ctl, const uint32_t* __restrict__ list, int cls, 
             }
             __syncthreads();
             const uint32_t n_vert = s_nvert, n_avg = s_navg;
-            bool emit = keep_rays;
-            if (keep_rays) {                                                             // the pair's slice of the frame's ray array
-                if (tid == 0) s_raybase = (uint32_t)atomicAdd(&ctl->n_rays_kept, (unsigned long long)(n_vert + n_avg));
-                __syncthreads();
-                if ((unsigned long long)s_raybase + n_vert + n_avg > cap_rays) { emit = false; if (tid == 0) atomicOr(&ctl->overflow, (unsigned)OVF_RAYS); }
-            }
+            // the pair's slice of the frame's ray array (pairs that moved only)
+            if (tid == 0) s_raybase = keep_rays ? (uint32_t)atomicAdd(&ctl->n_rays_kept, (unsigned long long)(n_vert + n_avg)) : 0u;
+            __syncthreads();
             const uint32_t ray_base = s_raybase;
+            const bool emit = keep_rays && (unsigned long long)ray_base + n_vert + n_avg <= cap_rays;
+            if (keep_rays && !emit && tid == 0) atomicOr(&ctl->overflow, (unsigned)OVF_RAYS);
             SideSum r; r.x = r.y = r.z = 0.0; r.rays = 0u;
             // ---- rays at the weighted average point (:34-37,157-166) ----
             for (uint32_t c = tid; c < n_avg; c += T) {
