@@ -637,8 +637,8 @@ k_tritri(FrameCtl* ctl, const Combo* __restrict__ combos, unsigned long long cap
 // pairs with their contact points (CreateUncollideRays.cpp:185-198, CollisionDetection.cpp:60-78)
 // ------------------------------------------------------------------------------------------
 // The hits of a frame come out in no particular order; the reduction of CreateUncollideRays.cpp:117-178 is per entity pair.
-// So: (1) k_hit_layout gives every pair with hits a slice of the grouping array (power-of-two sized, offsets by one scan) and
-// k_hit_lists puts it on the list of its size class; (2) k_group_hits drops each hit index into its pair's slice; (3) one block
+// So: (1) k_hit_lists gives every pair with hits a slice of the grouping array (power-of-two sized, one atomic per warp of pairs) and
+// puts it on the list of its size class; (2) k_group_hits drops each hit index into its pair's slice; (3) one block
 // per pair reduces the slice (k_pair_contacts_hash below).  Nothing depends on the order in which the hits were produced.
 // three size classes: S (<= 256 hits: 128 threads), M (<= 1024 hits: 512 threads), both with their tables in shared memory, and
 // L (more: 512 threads, tables in a bump-allocated global scratch)
@@ -647,23 +647,27 @@ k_tritri(FrameCtl* ctl, const Combo* __restrict__ combos, unsigned long long cap
 #define PC_M_MAX 1024u
 #define PC_CLASSES 4
 
-__global__ void k_hit_layout(const FrameCtl* ctl, unsigned long long cap_pairs, const PairAcc* __restrict__ acc, uint32_t* __restrict__ padded) {
-    const unsigned long long n = ctl->n_pairs < cap_pairs ? ctl->n_pairs : cap_pairs;
-    for (unsigned long long p = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; p <= cap_pairs; p += (unsigned long long)gridDim.x * blockDim.x) {
-        uint32_t m = 0;
-        if (p < n) { const uint32_t h = acc[p].n_hits; if (h) { m = 1u; while (m < h) m <<= 1; } }
-        padded[p] = m;                                     // zeros from n on; the scan runs over cap_pairs + 1 elements
-    }
-}
-
-__global__ void k_hit_lists(FrameCtl* ctl, unsigned long long cap_pairs, PairAcc* acc, const uint32_t* __restrict__ padded_off,
+__global__ void k_hit_lists(FrameCtl* ctl, unsigned long long cap_pairs, PairAcc* acc,
                             uint32_t* __restrict__ lists /* PC_CLASSES x cap_pairs */, uint32_t large_min) {
     const unsigned long long n = ctl->n_pairs < cap_pairs ? ctl->n_pairs : cap_pairs;
     const uint32_t lane = lane_id();
     for (unsigned long long p0 = (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x) & ~31ull; p0 < n; p0 += (unsigned long long)gridDim.x * blockDim.x) {
         const unsigned long long p = p0 + lane;
         uint32_t h = 0;
-        if (p < n) { h = acc[p].n_hits; acc[p].off = padded_off[p]; }
+        if (p < n) h = acc[p].n_hits;
+        // the pair's slice of the grouping array: power-of-two sized, handed out by one atomic per warp (no scan over all pairs)
+        uint32_t m = 0;
+        if (h) { m = 1u; while (m < h) m <<= 1; }
+        uint32_t incl = m;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(FULL_MASK, incl, o); if (lane >= (uint32_t)o) incl += v; }
+        const uint32_t warp_total = __shfl_sync(FULL_MASK, incl, 31);
+        if (warp_total) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(&ctl->grouped_used, (unsigned long long)warp_total);
+            base = __shfl_sync(FULL_MASK, base, 0);
+            if (h) acc[p].off = (uint32_t)(base + incl - m);
+        }
         const int cls = h == 0 ? -1 : (h > large_min ? 3 : (h <= PC_S_MAX ? 0 : (h <= PC_M1_MAX ? 1 : 2)));
 #pragma unroll
         for (int c = 0; c < PC_CLASSES; ++c) {
@@ -1308,14 +1312,7 @@ int imr_frame_run_device(imrcd_ctx* ctx) {
             IMR_CUDA(ctx, ctx->d_rays.reserve(sizeof(RayRec) * ctx->cap_rays, 0, s));
             IMR_CUDA(ctx, ctx->d_resp.reserve(32ull * ctx->cap_rays, 0, s));
         }
-        IMR_CUDA(ctx, ctx->d_padded.reserve(4ull * (ctx->cap_pairs + 1), 0, s));
-        IMR_CUDA(ctx, ctx->d_padoff.reserve(4ull * (ctx->cap_pairs + 1), 0, s));
         IMR_CUDA(ctx, ctx->d_lsmall.reserve(4ull * PC_CLASSES * ctx->cap_pairs, 0, s));      // the size-class lists, cap_pairs entries each
-        {
-            size_t scan_bytes = 0;
-            cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, ctx->d_padded.as<uint32_t>(), ctx->d_padoff.as<uint32_t>(), (int)(ctx->cap_pairs + 1), s);
-            if (scan_bytes > cub_bytes) { cub_bytes = scan_bytes; IMR_CUDA(ctx, ctx->d_cubtmp.reserve(cub_bytes, 0, s)); }
-        }
         FrameCtl* ctl = ctx->d_ctl.as<FrameCtl>();
         uint64_t launches = 0;
         IMR_CUDA(ctx, cudaEventRecord(ctx->ev[0], s));
@@ -1365,9 +1362,7 @@ int imr_frame_run_device(imrcd_ctx* ctx) {
         launches += 1;
         IMR_CUDA(ctx, cudaEventRecord(ctx->ev[4], s));
         // ---- reduce ----
-        k_hit_layout<<<ctx->sm_count * 8, 256, 0, s>>>(ctl, ctx->cap_pairs, ctx->d_pairacc.as<PairAcc>(), ctx->d_padded.as<uint32_t>());
-        cub::DeviceScan::ExclusiveSum(ctx->d_cubtmp.p, cub_bytes, ctx->d_padded.as<uint32_t>(), ctx->d_padoff.as<uint32_t>(), (int)(ctx->cap_pairs + 1), s);
-        k_hit_lists<<<ctx->sm_count * 4, 256, 0, s>>>(ctl, ctx->cap_pairs, ctx->d_pairacc.as<PairAcc>(), ctx->d_padoff.as<uint32_t>(),
+        k_hit_lists<<<ctx->sm_count * 4, 256, 0, s>>>(ctl, ctx->cap_pairs, ctx->d_pairacc.as<PairAcc>(),
                                                        ctx->d_lsmall.as<uint32_t>(), ctx->pc_large_min);
         k_group_hits<<<ctx->sm_count * 8, 256, 0, s>>>(ctl, ctx->cap_hits, ctx->d_hits.as<imrcd_tri_hit>(), ctx->d_pairacc.as<PairAcc>(), ctx->d_grouped.as<uint32_t>());
         {
@@ -1410,7 +1405,7 @@ int imr_frame_run_device(imrcd_ctx* ctx) {
             IMR_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_join3, 0));
             IMR_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_join4, 0));
         }
-        launches += 14;     // layout, scan (2), lists, group, three per-pair size classes, six passes over the large pairs
+        launches += 11;     // lists, group, three per-pair size classes, six passes over the large pairs
         k_finalize<<<ctx->sm_count * 4, 256, 0, s>>>(ctl, ctx->cap_pairs, ctx->d_pairs.as<uint2>(), ctx->d_pairacc.as<PairAcc>(),
                                                       ctx->d_entity.as<uint32_t>(), ctx->d_cur.as<float>(), ctx->d_inv.as<float>(),
                                                       ctx->d_epairs.as<imrcd_entity_pair>() + 1, ctx->d_epair_pair.as<uint32_t>());

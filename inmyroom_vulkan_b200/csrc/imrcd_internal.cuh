@@ -81,6 +81,7 @@ struct __align__(128) FrameCtl {
     unsigned long long n_rays_kept;        // rays written to the ray array (pairs that moved): bump allocator of the contact reduction
     unsigned long long scratch_used;       // bytes of the large-pair scratch handed out (bump allocator)
     unsigned long long n_responses;        // successful Hermann passes of the frame
+    unsigned long long grouped_used;       // slots of the hit-grouping array handed out (contact reduction)
     unsigned long long ray_cursor;         // next ray to hand out (k_shoot fetches dynamically: ray costs differ by two orders of magnitude)
     unsigned int overflow;                 // bit0 pairs, bit1 queue, bit2 combos, bit3 hits, bit4 rays, bit5 large-pair scratch, bit6 ray stack
     unsigned int pad;
