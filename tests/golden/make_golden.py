@@ -89,11 +89,31 @@ def make_response(ref):
     print("response: rays hit", int(out["ray.hit"].sum()), "of", n, "; colliding pairs", int(sum(col)), "non-zero deltas", int((np.abs(np.nan_to_num(out["frame.delta"])).sum(1) > 0).sum()))
 
 
+def make_primitives(ref):
+    """primitives.npz: Triangle::CreateTriangleList (Triangle.cpp:9-62,259-280) on every draw mode, with and without normals."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_primitives import _cases
+    out = {}
+    names = []
+    for name, pts, nrm, idx, mode in _cases():
+        p, n, v = ref.triangle_list(pts, nrm, idx, mode)
+        names.append(name)
+        out[f"{name}.points"] = pts; out[f"{name}.indices"] = idx; out[f"{name}.mode"] = np.array([mode])
+        if nrm is not None:
+            out[f"{name}.normals"] = nrm
+        out[f"{name}.pos"] = p; out[f"{name}.nrm"] = n; out[f"{name}.vid"] = v
+    out["names"] = np.array(names)
+    np.savez_compressed(os.path.join(HERE, "primitives.npz"), **out)
+    print("primitives:", len(names), "cases,", sum(len(out[f"{k}.pos"]) for k in names), "triangles")
+
+
 def main():
     bind.build("ref")
     ref = bind.RefOracle()
     if len(sys.argv) > 1 and sys.argv[1] == "response":
         return make_response(ref)
+    if len(sys.argv) > 1 and sys.argv[1] == "primitives":
+        return make_primitives(ref)
     rng = np.random.default_rng(20261017)
 
     # ---- predicates ----
@@ -190,6 +210,7 @@ def main():
         print(name, "entries", sc.n_entries, "pairs", len(pairs), "totals", res["totals"])
     np.savez_compressed(os.path.join(HERE, "frames.npz"), **frames)
     make_response(ref)
+    make_primitives(ref)
     for fn in sorted(os.listdir(HERE)):
         if fn.endswith(".npz"):
             print(fn, os.path.getsize(os.path.join(HERE, fn)))

@@ -41,6 +41,34 @@ def test_port_triangle_list_matches_reference(port, ref, case):
     assert np.array_equal(f32_bits(a[0]), f32_bits(b[0])) and np.array_equal(f32_bits(a[1]), f32_bits(b[1])) and np.array_equal(a[2], b[2])
 
 
+def _nan_equal_bits(a, b):
+    nan = np.isnan(b)
+    return np.array_equal(np.isnan(a), nan) and np.array_equal(f32_bits(a)[~nan], f32_bits(b)[~nan])
+
+
+def test_port_triangle_list_matches_golden(port):
+    """The committed vectors (tests/golden/primitives.npz, outputs of the reference) pin the port where /root/reference is absent."""
+    import golden_io
+    z = golden_io.load("primitives")
+    for name in z["names"].tolist():
+        nrm = z[f"{name}.normals"] if f"{name}.normals" in z.files else None
+        p, n, v = port.triangle_list(z[f"{name}.points"], nrm, z[f"{name}.indices"], int(z[f"{name}.mode"][0]))
+        assert np.array_equal(f32_bits(p), f32_bits(z[f"{name}.pos"])) and _nan_equal_bits(n, z[f"{name}.nrm"]) and np.array_equal(v, z[f"{name}.vid"]), name
+
+
+@pytest.mark.gpu
+def test_device_assembly_matches_golden(gpu_ctx):
+    from inmyroom_vulkan_b200.collision import OBBtree
+    import golden_io
+    z = golden_io.load("primitives")
+    names = [n for n in z["names"].tolist() if len(z[f"{n}.pos"])]
+    prims = [(z[f"{n}.points"], z[f"{n}.normals"] if f"{n}.normals" in z.files else None, z[f"{n}.indices"], int(z[f"{n}.mode"][0])) for n in names]
+    flat = OBBtree.from_primitives(gpu_ctx, prims).export()
+    back = np.argsort(flat.tri_orig)
+    want_p = np.concatenate([z[f"{n}.pos"] for n in names]); want_n = np.concatenate([z[f"{n}.nrm"] for n in names]); want_v = np.concatenate([z[f"{n}.vid"] for n in names])
+    assert np.array_equal(f32_bits(flat.tri_pos[back]), f32_bits(want_p)) and _nan_equal_bits(flat.tri_nrm[back], want_n) and np.array_equal(flat.tri_vid[back], want_v)
+
+
 @pytest.mark.gpu
 def test_device_assembly_matches_oracle(gpu_ctx, oracle):
     """A mesh of several primitives (all draw modes, vec3 and vec4 strides, with and without normals, with and without indices):
