@@ -115,6 +115,8 @@ def cpu_frame(orc, port, scene, trees, threads: int):
 
 
 def load_cpu_checker():
+    """The single doorway from measurement code to oracle/: bench.py's cpu_baseline and --impl reference legs, and the cpu_reference legs of
+    scripts/build_bench.py (C4) and scripts/refit_bench.py (C5).  The product (inmyroom_vulkan_b200/) never comes through here."""
     from oracle import bind
     bind.build("port")
     port = bind.PortOracle()

@@ -35,8 +35,8 @@ if n <= 3_000_000 or "--check" in sys.argv:
     out["tree_vertices"] = int(flat.nv)
 if "--reference-cpu" in sys.argv:
     k = int(sys.argv[sys.argv.index("--reference-cpu") + 1])
-    from oracle import bind
-    orc = bind.load()
+    import bench                                  # the CPU checker is reached only through bench.py's cpu_baseline doorway
+    orc, _ = bench.load_cpu_checker()
     sub = scenes.grid_sheet(int((k / 2) ** 0.5 * 2 ** 0.5), int((k / 2) ** 0.5 / 2 ** 0.5), 1500.0, 750.0, bump=40.0)
     t0 = time.perf_counter(); orc.tree_build(sub.positions, sub.normals, sub.vertex_ids); dt = time.perf_counter() - t0
     out["cpu_reference"] = {"kind": orc.kind, "triangles": sub.n_tri, "seconds": dt, "mtri_per_s": sub.n_tri / dt / 1e6, "cores": 1}

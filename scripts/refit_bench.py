@@ -59,8 +59,8 @@ out = {"workload": f"C5: {n_char} characters x {base.n_tri} triangles re-posed p
        "refit_algorithmic_bytes_per_tri": 72, "refit_achieved_gbs": n_tri * 72 / (med["refit_ms_device"] * 1e-3) / 1e9, "initial_build_s": build_s}
 if "--reference-cpu" in sys.argv:
     k = int(sys.argv[sys.argv.index("--reference-cpu") + 1])
-    from oracle import bind
-    orc = bind.load()
+    import bench                                  # the CPU checker is reached only through bench.py's cpu_baseline doorway
+    orc, _ = bench.load_cpu_checker()
     t0 = time.perf_counter()
     for c in range(k):
         orc.tree_build(poses[c % P], base.normals, base.vertex_ids)
