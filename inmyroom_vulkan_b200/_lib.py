@@ -70,6 +70,8 @@ _SIGS = [
     ("imrcd_frame_upload", C.c_int, [_P]),
     ("imrcd_frame_run", C.c_int, [_P]),
     ("imrcd_frame_fetch", C.c_int, [_P]),
+    ("imrcd_frame_run_async", C.c_int, [_P]),
+    ("imrcd_frame_finish", C.c_int, [_P]),
     ("imrcd_frame_results", C.c_int, [_P, C.POINTER(C.POINTER(EntityPair)), C.POINTER(C.c_uint64), C.POINTER(C.POINTER(TriHit)), C.POINTER(C.c_uint64)]),
     ("imrcd_frame_pairs", C.c_int, [_P, C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.c_uint64)]),
     ("imrcd_frame_combos", C.c_int, [_P, C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.c_uint64)]),

@@ -276,6 +276,17 @@ class CollisionDetection:
     def run(self):
         self.ctx.check(self.lib.imrcd_frame_run(self.ctx.h))
 
+    def run_async(self):
+        """Enqueue every kernel of the frame and return at once (imrcd_frame_run_async); finish() must follow."""
+        self.ctx.check(self.lib.imrcd_frame_run_async(self.ctx.h))
+
+    def finish(self) -> bool:
+        """Wait for a frame started with run_async(); True when a buffer overflowed and the frame was run again."""
+        rc = self.lib.imrcd_frame_finish(self.ctx.h)
+        if rc < 0:
+            self.ctx.check(rc)
+        return rc == 1
+
     def fetch(self):
         self.ctx.check(self.lib.imrcd_frame_fetch(self.ctx.h))
 

@@ -519,6 +519,28 @@ extern "C" int imrcd_frame_run(imrcd_ctx* ctx) {
     return IMRCD_OK;
 }
 
+extern "C" int imrcd_frame_run_async(imrcd_ctx* ctx) {
+    CHECK_CTX(ctx);
+    if (!ctx->uploaded) { ctx->err = "imrcd_frame_run_async before imrcd_frame_upload"; return IMRCD_E_STATE; }
+    cudaSetDevice(ctx->device);
+    ctx->enqueue_only = true;
+    const int rc = imr_frame_run_device(ctx);
+    ctx->enqueue_only = false;
+    if (rc) return rc;
+    ctx->async_pending = true; ctx->ran = false; ctx->fetched = false;
+    return IMRCD_OK;
+}
+extern "C" int imrcd_frame_finish(imrcd_ctx* ctx) {
+    CHECK_CTX(ctx);
+    if (!ctx->async_pending) { ctx->err = "imrcd_frame_finish without imrcd_frame_run_async"; return IMRCD_E_STATE; }
+    cudaSetDevice(ctx->device);
+    ctx->async_pending = false;
+    const int rc = imr_frame_finish_device(ctx);
+    if (rc < 0) return rc;
+    ctx->ran = true; ctx->fetched = false;
+    return rc;                                            // 1: the frame was re-run with larger buffers (anything enqueued behind it saw stale results)
+}
+
 extern "C" int imrcd_frame_fetch(imrcd_ctx* ctx) {
     CHECK_CTX(ctx);
     if (!ctx->ran) { ctx->err = "imrcd_frame_fetch before imrcd_frame_run"; return IMRCD_E_STATE; }
@@ -609,7 +631,7 @@ extern "C" int imrcd_frame_results_device(imrcd_ctx* ctx, void** d_pairs, uint64
 
 extern "C" int imrcd_frame_results_block(imrcd_ctx* ctx, void** d_block, uint64_t* n_pairs, uint64_t* capacity) {
     CHECK_CTX(ctx);
-    if (!ctx->ran) { ctx->err = "imrcd_frame_results_block before imrcd_frame_run"; return IMRCD_E_STATE; }
+    if (!ctx->ran && !ctx->async_pending) { ctx->err = "imrcd_frame_results_block before imrcd_frame_run"; return IMRCD_E_STATE; }
     if (d_block) *d_block = ctx->d_epairs.p;
     if (n_pairs) *n_pairs = ctx->ctl_host.n_colliding;
     if (capacity) *capacity = ctx->d_epairs.p ? ctx->d_epairs.cap / sizeof(imrcd_entity_pair) - 1 : 0;

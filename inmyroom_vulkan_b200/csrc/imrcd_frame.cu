@@ -1220,6 +1220,48 @@ __global__ void k_finalize(FrameCtl* ctl, unsigned long long cap_pairs, const ui
 // ------------------------------------------------------------------------------------------
 static inline unsigned blocks_for(unsigned long long n, unsigned bs) { return (unsigned)((n + bs - 1) / bs); }
 
+// Second half of a frame: wait for the stream, read the control block back, grow whatever overflowed (the caller re-runs the frame) or
+// fill in the statistics.  Split from the enqueue half so that a caller can put more work (the end-of-frame collective) on the stream
+// before the host looks at the frame (imrcd_frame_run_async / imrcd_frame_finish).
+static int frame_complete(imrcd_ctx* ctx, uint64_t launches, bool* retry) {
+    cudaStream_t s = ctx->stream;
+    *retry = false;
+    IMR_CUDA(ctx, cudaStreamSynchronize(s));
+    IMR_CUDA(ctx, cudaGetLastError());
+    ctx->ctl_host = *ctx->p_ctl.as<FrameCtl>();
+    const FrameCtl& c = ctx->ctl_host;
+    ctx->queue_dirty = std::min<uint64_t>(std::max(c.q_tail, c.q_head), ctx->cap_queue);
+
+    if (c.overflow) {
+        if (c.overflow & OVF_PAIRS) ctx->cap_pairs = std::max<uint64_t>(c.n_pairs + c.n_pairs / 8, ctx->cap_pairs * 2);
+        if (c.overflow & OVF_QUEUE) ctx->cap_queue = std::max<uint64_t>(ctx->cap_queue * 2, ctx->cap_pairs + (1ull << 22));
+        if (ctx->cap_queue < ctx->cap_pairs) ctx->cap_queue = ctx->cap_pairs + (1ull << 22);
+        if (c.overflow & OVF_COMBOS) ctx->cap_combos = std::max<uint64_t>(c.n_combos + c.n_combos / 8, ctx->cap_combos * 2);
+        if (c.overflow & OVF_HITS) ctx->cap_hits = std::max<uint64_t>(c.n_hits + c.n_hits / 8, ctx->cap_hits * 2);
+        if (c.overflow & OVF_RAYS) ctx->cap_rays = std::max<uint64_t>(c.n_rays_kept + c.n_rays_kept / 8, ctx->cap_rays * 2);
+        if (c.overflow & OVF_SCRATCH) ctx->cap_lscratch = std::max<uint64_t>(c.scratch_used + c.scratch_used / 8, ctx->cap_lscratch * 2);
+        if (c.overflow & OVF_RAYSTACK) { ctx->err = "ray stack overflow (tree deeper than the per-thread stack of the response stage)"; return IMRCD_E_CAPACITY; }
+
+        *retry = true;   // re-run the frame with the larger buffers
+        return IMRCD_OK;
+    }
+
+    imrcd_frame_stats& st = ctx->stats;
+    st.n_pairs = c.n_pairs; st.n_sat_tests = c.n_sat; st.n_combos = c.n_combos; st.n_tri_tests = c.n_tri_tests;
+    st.n_hits = c.n_hits; st.n_coplanar_hits = c.n_coplanar; st.n_colliding = c.n_colliding;
+    st.n_contact_pairs = c.n_class[0] + c.n_class[16] + c.n_class[32] + c.n_class[48]; st.n_rays = c.n_rays;
+    st.traverse_launches = 1; st.total_launches = launches; st.n_queue_items = c.n_donated; st.n_warp_iterations = c.n_iterations; st.trav_busy_cycles = c.busy_cycles; st.trav_idle_polls = c.idle_polls;
+    cudaEventElapsedTime(&st.ms_total, ctx->ev[0], ctx->ev[5]);
+    cudaEventElapsedTime(&st.ms_broad, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&st.ms_pair_setup, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&st.ms_traverse, ctx->ev[2], ctx->ev[3]);
+    cudaEventElapsedTime(&st.ms_narrow, ctx->ev[3], ctx->ev[4]);
+    cudaEventElapsedTime(&st.ms_reduce, ctx->ev[4], ctx->ev[5]);
+    cudaEventElapsedTime(&st.ms_response, ctx->ev[6], ctx->ev[5]);
+    st.n_rays_shot = c.n_rays_kept; st.n_responses = c.n_responses;
+    return IMRCD_OK;
+}
+
 int imr_frame_run_device(imrcd_ctx* ctx) {
     cudaStream_t s = ctx->stream;
     const uint32_t n = (uint32_t)ctx->n_entries;
@@ -1415,40 +1457,24 @@ int imr_frame_run_device(imrcd_ctx* ctx) {
         { int rc = imr_frame_shoot_device(ctx, ctl, &launches); if (rc != IMRCD_OK) return rc; }
         IMR_CUDA(ctx, cudaEventRecord(ctx->ev[5], s));
         IMR_CUDA(ctx, cudaMemcpyAsync(ctx->p_ctl.p, ctl, sizeof(FrameCtl), cudaMemcpyDeviceToHost, s));
-        IMR_CUDA(ctx, cudaStreamSynchronize(s));
-        IMR_CUDA(ctx, cudaGetLastError());
-        ctx->ctl_host = *ctx->p_ctl.as<FrameCtl>();
-        const FrameCtl& c = ctx->ctl_host;
-        ctx->queue_dirty = std::min<uint64_t>(std::max(c.q_tail, c.q_head), ctx->cap_queue);
-
-        if (c.overflow) {
-            if (c.overflow & OVF_PAIRS) ctx->cap_pairs = std::max<uint64_t>(c.n_pairs + c.n_pairs / 8, ctx->cap_pairs * 2);
-            if (c.overflow & OVF_QUEUE) ctx->cap_queue = std::max<uint64_t>(ctx->cap_queue * 2, ctx->cap_pairs + (1ull << 22));
-            if (ctx->cap_queue < ctx->cap_pairs) ctx->cap_queue = ctx->cap_pairs + (1ull << 22);
-            if (c.overflow & OVF_COMBOS) ctx->cap_combos = std::max<uint64_t>(c.n_combos + c.n_combos / 8, ctx->cap_combos * 2);
-            if (c.overflow & OVF_HITS) ctx->cap_hits = std::max<uint64_t>(c.n_hits + c.n_hits / 8, ctx->cap_hits * 2);
-            if (c.overflow & OVF_RAYS) ctx->cap_rays = std::max<uint64_t>(c.n_rays_kept + c.n_rays_kept / 8, ctx->cap_rays * 2);
-            if (c.overflow & OVF_SCRATCH) ctx->cap_lscratch = std::max<uint64_t>(c.scratch_used + c.scratch_used / 8, ctx->cap_lscratch * 2);
-            if (c.overflow & OVF_RAYSTACK) { ctx->err = "ray stack overflow (tree deeper than the per-thread stack of the response stage)"; return IMRCD_E_CAPACITY; }
-
-            continue;   // re-run the frame with the larger buffers
-        }
-
-        imrcd_frame_stats& st = ctx->stats;
-        st.n_pairs = c.n_pairs; st.n_sat_tests = c.n_sat; st.n_combos = c.n_combos; st.n_tri_tests = c.n_tri_tests;
-        st.n_hits = c.n_hits; st.n_coplanar_hits = c.n_coplanar; st.n_colliding = c.n_colliding;
-        st.n_contact_pairs = c.n_class[0] + c.n_class[16] + c.n_class[32] + c.n_class[48]; st.n_rays = c.n_rays;
-        st.traverse_launches = 1; st.total_launches = launches; st.n_queue_items = c.n_donated; st.n_warp_iterations = c.n_iterations; st.trav_busy_cycles = c.busy_cycles; st.trav_idle_polls = c.idle_polls;
-        cudaEventElapsedTime(&st.ms_total, ctx->ev[0], ctx->ev[5]);
-        cudaEventElapsedTime(&st.ms_broad, ctx->ev[0], ctx->ev[1]);
-        cudaEventElapsedTime(&st.ms_pair_setup, ctx->ev[1], ctx->ev[2]);
-        cudaEventElapsedTime(&st.ms_traverse, ctx->ev[2], ctx->ev[3]);
-        cudaEventElapsedTime(&st.ms_narrow, ctx->ev[3], ctx->ev[4]);
-        cudaEventElapsedTime(&st.ms_reduce, ctx->ev[4], ctx->ev[5]);
-        cudaEventElapsedTime(&st.ms_response, ctx->ev[6], ctx->ev[5]);
-        st.n_rays_shot = c.n_rays_kept; st.n_responses = c.n_responses;
+        if (ctx->enqueue_only) { ctx->pending_launches = launches; return IMRCD_OK; }      // imrcd_frame_run_async: imrcd_frame_finish does the rest
+        bool retry = false;
+        { const int rc = frame_complete(ctx, launches, &retry); if (rc != IMRCD_OK) return rc; }
+        if (retry) continue;
         return IMRCD_OK;
     }
     ctx->err = "frame buffers could not be grown enough (8 attempts)";
     return IMRCD_E_CAPACITY;
+}
+
+// imrcd_frame_finish: 0 = the enqueued frame stands, 1 = a buffer overflowed and the frame was run again (synchronously)
+int imr_frame_finish_device(imrcd_ctx* ctx) {
+    if (ctx->n_entries < 2) return IMRCD_OK;
+    bool retry = false;
+    int rc = frame_complete(ctx, ctx->pending_launches, &retry);
+    if (rc != IMRCD_OK) return rc;
+    if (!retry) return IMRCD_OK;
+    ctx->enqueue_only = false;
+    rc = imr_frame_run_device(ctx);
+    return rc != IMRCD_OK ? rc : 1;
 }

@@ -183,6 +183,8 @@ struct imrcd_ctx {
     bool prev_distinct = false;          // some entry of this frame carries a previous matrix different from its current one
     uint32_t shard_rank = 0, shard_n = 1;
     bool uploaded = false, ran = false, fetched = false;
+    bool enqueue_only = false, async_pending = false;      // imrcd_frame_run_async .. imrcd_frame_finish
+    uint64_t pending_launches = 0;
     // frame, device side
     DevBuf d_cur, d_prev, d_mesh, d_cb, d_entity, d_inv, d_ext, d_keys, d_keys2, d_idx, d_idx2, d_sorted, d_sorted_c, d_flag, d_cpos, d_wlen, d_chunks, d_chunkoff, d_cubtmp;
     DevBuf d_pairs, d_pairrec, d_pairacc, d_queue, d_combos, d_hits, d_epairs, d_ctl;
@@ -213,6 +215,7 @@ int imr_build_mesh_device(imrcd_ctx* ctx, const float* pos, const float* nrm, co
                           uint32_t mode, MeshHost* out);
 int imr_mesh_assemble_device(imrcd_ctx* ctx, uint32_t build_mode, MeshHost* out);      // Triangle::CreateTriangleList on the device, then the build
 int imr_frame_run_device(imrcd_ctx* ctx);
+int imr_frame_finish_device(imrcd_ctx* ctx);
 // response stage: one thread per kept ray (Hermann passes), then one warp per colliding pair that moved (imrcd_rays.cu)
 int imr_frame_shoot_device(imrcd_ctx* ctx, FrameCtl* ctl, uint64_t* launches);
 int imr_test_ray_tree_device(imrcd_ctx* ctx, uint32_t mesh_id, uint64_t n, const float* mats, const float* origins, const float* dirs,

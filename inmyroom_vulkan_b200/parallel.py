@@ -122,6 +122,17 @@ class FrameGather:
         self._cap_alloc = cap_alloc
         return blocks
 
+    def run_and_gather_device(self) -> torch.Tensor:
+        """One frame and its merge with a single host wait: the frame's kernels are enqueued (imrcd_frame_run_async), the collective goes
+        onto the stream right behind them - the block's header row is written on the device, so nothing about the frame has to be
+        known on the host yet - and only then does the host wait (imrcd_frame_finish).  On the rare frame where a buffer overflowed and
+        the library ran the frame again, the collective is repeated on the new block."""
+        self.cd.run_async()
+        blocks = self.gather_device()
+        if self.cd.finish():
+            blocks = self.gather_device()
+        return blocks
+
     def counts(self):
         """Per-rank record counts of the last gather_device(); None when some rank had more records than the capacity (the capacity
         is raised for the next gather, every rank sees the same headers and decides alike)."""

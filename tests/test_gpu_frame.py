@@ -156,3 +156,36 @@ def test_zero_weight_hits_follow_the_combo_rule(gpu_ctx, oracle):
         assert r.n_hits == want_hits and (r.colliding, st["n_colliding"]) == ((want_hits == 2), int(want_hits == 2)), name
         if want_hits == 1:
             assert float(r.hit_seg[0, 6]) == 0.0 and (r.rays_first, r.rays_second) == (0, 0)
+
+
+def test_run_async_finish_equals_run(gpu_ctx):
+    """imrcd_frame_run_async + imrcd_frame_finish is imrcd_frame_run in two halves: same statistics, same records; a fresh context whose
+    first frame overflows its initial buffers reports the re-run through finish()."""
+    from inmyroom_vulkan_b200.collision import Context
+    mesh = scenes.torus(40, 20)
+    scene = scenes.scene_instances(mesh, 300, seed=17)
+    tree = OBBtree(gpu_ctx, mesh.positions, mesh.normals, mesh.vertex_ids)
+    ids = np.full(scene.n_entries, tree.mesh_id, np.uint32)
+    cd = CollisionDetection(ctx=gpu_ctx)
+    cd.Reset(); cd.add_entries(scene.matrices, ids, scene.should_callback, scene.entities); cd.upload(); cd.run(); cd.fetch()
+    a_st = cd.stats(); a_ep, _ = cd.results(want_hits=False)
+    cd.Reset(); cd.add_entries(scene.matrices, ids, scene.should_callback, scene.entities); cd.upload(); cd.run_async()
+    reran = cd.finish(); cd.fetch()
+    b_st = cd.stats(); b_ep, _ = cd.results(want_hits=False)
+    assert not reran
+    for k in ("n_pairs", "n_sat_tests", "n_combos", "n_tri_tests", "n_hits", "n_colliding", "n_rays"):
+        assert a_st[k] == b_st[k], k
+    key = lambda e: np.lexsort((e["entry_second"], e["entry_first"]))
+    same_entity_pairs(a_ep[key(a_ep)], b_ep[key(b_ep)])
+    # a scene with more than 2^20 hits on a fresh context: the first frame overflows the initial hit buffer
+    ctx2 = Context(0)
+    big = scenes.torus(100, 50)
+    sc2 = scenes.scene_instances(big, 3000, seed=3, neighbours=8.0)
+    t2 = OBBtree(ctx2, big.positions, big.normals, big.vertex_ids)
+    cd2 = CollisionDetection(ctx=ctx2)
+    cd2.Reset(); cd2.add_entries(sc2.matrices, np.full(sc2.n_entries, t2.mesh_id, np.uint32), sc2.should_callback, sc2.entities); cd2.upload(); cd2.run_async()
+    reran = cd2.finish()
+    st = cd2.stats()
+    assert st["n_hits"] > (1 << 20) and reran
+    cd2.run_async(); assert not cd2.finish() and cd2.stats()["n_hits"] == st["n_hits"]
+    ctx2.close()
