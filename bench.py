@@ -332,17 +332,17 @@ def run_gpu_arm(args):
         cd.Reset()
         cd.map_entries(scene.n_entries)             # same staging memory: the entries written above are still there
         cd.commit_entries(scene.n_entries, previous_valid=False)
-        cd.ExecuteCollisionDetection()              # H2D + kernels + D2H of the colliding pairs
         if gather is not None:
-            return gather.gather_host()
+            return gather.execute_host()            # H2D + kernels + the collective + D2H of the merged pairs, one host wait
+        cd.ExecuteCollisionDetection()              # H2D + kernels + D2H of the colliding pairs
         return cd.results(want_hits=False)[0]
 
     def e2e_step_pageable():
         cd.Reset()
         cd.add_entries(scene.matrices, mesh_ids, scene.should_callback, scene.entities, scene.previous)
-        cd.ExecuteCollisionDetection()
         if gather is not None:
-            return gather.gather_host()
+            return gather.execute_host()
+        cd.ExecuteCollisionDetection()
         return cd.results(want_hits=False)[0]
 
     def time_e2e(step):
@@ -364,7 +364,8 @@ def run_gpu_arm(args):
     e2e_value = tests_total * args.steps / e2e_s_max
     n_entries = scene.n_entries
     h2d = n_entries * (64 + 4 + 4 + 1 + (64 if scene.previous is not None else 0))   # previous == current is not re-sent
-    d2h = int(len(res)) * 80 + 1280
+    # bytes that cross to the host per step: the pair records (+ the control block), or with N ranks the gathered fixed-capacity blocks
+    d2h = int(len(res)) * 80 + 1280 if gather is None else world * (gather.cap + 1) * 80 + 1280
 
     # ---- response stage: the same scene with every dynamic body moved since the last frame, so that the deltaVector of
     #      every colliding pair is computed (ShootUncollideRays.cpp:14-93); reported beside the headline, not inside it ----

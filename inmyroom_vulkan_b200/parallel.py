@@ -144,6 +144,20 @@ class FrameGather:
         self.last = (self.last[0], counts)
         return counts
 
+    def execute_host(self) -> np.ndarray:
+        """ExecuteCollisionDetection for N ranks, entries already added: upload, the frame, the merge and ONE host wait; returns the
+        merged records of all ranks as a numpy structured array (what gather_host() gives after cd.ExecuteCollisionDetection())."""
+        self.cd.upload()
+        blocks = self.run_and_gather_device()
+        while True:
+            counts = self.counts()
+            if counts is not None:
+                break
+            blocks = self.gather_device()
+        h = blocks.cpu().numpy()
+        parts = [h[r, 1:1 + c].reshape(-1) for r, c in enumerate(counts) if c]
+        return np.concatenate(parts).view(PAIR_DTYPE) if parts else np.zeros(0, PAIR_DTYPE)
+
     def gather_host(self) -> np.ndarray:
         """Call after cd.ExecuteCollisionDetection(): merged records as a numpy structured array."""
         while True:
