@@ -640,8 +640,8 @@ k_tritri(FrameCtl* ctl, const Combo* __restrict__ combos, unsigned long long cap
 // So: (1) k_hit_lists gives every pair with hits a slice of the grouping array (power-of-two sized, one atomic per warp of pairs) and
 // puts it on the list of its size class; (2) k_group_hits drops each hit index into its pair's slice; (3) one block
 // per pair reduces the slice (k_pair_contacts_hash below).  Nothing depends on the order in which the hits were produced.
-// three size classes: S (<= 256 hits: 128 threads), M (<= 1024 hits: 512 threads), both with their tables in shared memory, and
-// L (more: 512 threads, tables in a bump-allocated global scratch)
+// size classes with their tables in shared memory: <= 256 hits (128 threads), <= 512 (512 threads), <= 1024 (1024 threads), and
+// the large pairs (more hits), which go through the grid-wide passes k_large_* with their tables in a global scratch
 #define PC_S_MAX 256u
 #define PC_M1_MAX 512u
 #define PC_M_MAX 1024u
@@ -1411,8 +1411,8 @@ int imr_frame_run_device(imrcd_ctx* ctx) {
             const size_t per_hit = 2 * (sizeof(PcSlot) + 8) + 4 * 8 + 12 + 5 * sizeof(uint16_t);
             const size_t smem_s = PC_S_MAX * per_hit, smem_m1 = PC_M1_MAX * per_hit, smem_m = PC_M_MAX * per_hit;
             if (!ctx->pc_attr_set) {
-                IMR_CUDA(ctx, cudaFuncSetAttribute(k_pair_contacts_hash<256, PC_M1_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m1));
-                IMR_CUDA(ctx, cudaFuncSetAttribute(k_pair_contacts_hash<512, PC_M_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m));
+                IMR_CUDA(ctx, cudaFuncSetAttribute(k_pair_contacts_hash<512, PC_M1_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m1));
+                IMR_CUDA(ctx, cudaFuncSetAttribute(k_pair_contacts_hash<1024, PC_M_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m));
                 ctx->pc_attr_set = true;
             }
             PairAcc* a_acc = ctx->d_pairacc.as<PairAcc>(); const uint32_t* a_grp = ctx->d_grouped.as<uint32_t>();
@@ -1426,7 +1426,7 @@ int imr_frame_run_device(imrcd_ctx* ctx) {
             IMR_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
             IMR_CUDA(ctx, cudaStreamWaitEvent(ctx->stream3, ctx->ev_fork, 0));
             IMR_CUDA(ctx, cudaStreamWaitEvent(ctx->stream4, ctx->ev_fork, 0));
-            k_pair_contacts_hash<512, PC_M_MAX><<<ctx->sm_count, 512, smem_m, ctx->stream2>>>(ctl, l2, 2, a_acc, a_grp, a_hits, a_aux, a_pr, a_tris, a_vid, a_nrm, a_rays, ctx->cap_rays);
+            k_pair_contacts_hash<1024, PC_M_MAX><<<ctx->sm_count, 1024, smem_m, ctx->stream2>>>(ctl, l2, 2, a_acc, a_grp, a_hits, a_aux, a_pr, a_tris, a_vid, a_nrm, a_rays, ctx->cap_rays);
             {   // large pairs: grid-wide passes (k_large_*), on their own side stream
                 cudaStream_t s2 = ctx->stream4;
                 unsigned long long* a_pref = ctx->d_lpref.as<unsigned long long>(); LargeSide* a_sides = ctx->d_lsides.as<LargeSide>();
@@ -1438,7 +1438,7 @@ int imr_frame_run_device(imrcd_ctx* ctx) {
                 k_large_alloc<<<ctx->sm_count, 256, 0, s2>>>(ctl, l3, a_acc, a_sides, ctx->cap_rays);
                 k_large_rays<<<gl, 256, 0, s2>>>(ctl, l3, a_acc, a_pref, a_scr, a_sides, a_pr, a_tris, a_nrm, a_rays);
             }
-            k_pair_contacts_hash<256, PC_M1_MAX><<<ctx->sm_count * 3, 256, smem_m1, ctx->stream3>>>(ctl, l1, 1, a_acc, a_grp, a_hits, a_aux, a_pr, a_tris, a_vid, a_nrm, a_rays, ctx->cap_rays);
+            k_pair_contacts_hash<512, PC_M1_MAX><<<ctx->sm_count * 3, 512, smem_m1, ctx->stream3>>>(ctl, l1, 1, a_acc, a_grp, a_hits, a_aux, a_pr, a_tris, a_vid, a_nrm, a_rays, ctx->cap_rays);
             k_pair_contacts_hash<128, PC_S_MAX><<<ctx->sm_count * 8, 128, smem_s, s>>>(ctl, l0, 0, a_acc, a_grp, a_hits, a_aux, a_pr, a_tris, a_vid, a_nrm, a_rays, ctx->cap_rays);
             IMR_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->stream2));
             IMR_CUDA(ctx, cudaEventRecord(ctx->ev_join3, ctx->stream3));
