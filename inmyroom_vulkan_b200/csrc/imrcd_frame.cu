@@ -739,6 +739,29 @@ __device__ __forceinline__ uint32_t vset_insert_m(unsigned long long* vset, uint
     }
 }
 
+// Set of (own triangle, other LEAF) keys that have a hit with weight != 0: answers "is this combo's weight for this triangle 0?" (:117-127) for
+// the hits whose own weight is 0 in O(1).  (A scan over the pair's hits per such hit looked harmless - they are 0.07 % of the hits on C3 - until
+// the instance-vs-instance scene C2 turned out to have 3 % of them: one scan of a 700-hit pair is 34 us of one warp with the block waiting.)
+__device__ __forceinline__ uint32_t pc_combo_hash(unsigned long long key) { return (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 40); }
+__device__ __forceinline__ void pc_combo_insert(unsigned long long* set, uint32_t mask, unsigned long long key) {
+    uint32_t slot = pc_combo_hash(key) & mask;
+    for (;;) {
+        const unsigned long long old = atomicCAS(&set[slot], ~0ull, key);
+        if (old == ~0ull || old == key) return;
+        slot = (slot + 1u) & mask;
+    }
+}
+template <bool G>
+__device__ __forceinline__ bool pc_combo_contains(const unsigned long long* set, uint32_t mask, unsigned long long key) {
+    uint32_t slot = pc_combo_hash(key) & mask;
+    for (;;) {
+        const unsigned long long v = G ? __ldcg(set + slot) : set[slot];
+        if (v == key) return true;
+        if (v == ~0ull) return false;
+        slot = (slot + 1u) & mask;
+    }
+}
+
 // warp-aggregated append of `v` (for the lanes with `yes`) to list[*count ...]; converged code only
 template <class LT>
 __device__ __forceinline__ void pc_append(bool yes, uint32_t v, LT* list, uint32_t* count, uint32_t lane) {
@@ -789,16 +812,32 @@ k_pair_contacts_hash(FrameCtl* ctl, const uint32_t* __restrict__ list, int cls, 
         const float4* pp = reinterpret_cast<const float4*>(pairrec + p);
         Rel rel; rel.r0 = __ldg(pp); rel.r1 = __ldg(pp + 1); rel.r2 = __ldg(pp + 2);
         const M3 nmat = adjoint_transpose3(rel);                                                     // CreateUncollideRays.cpp:65
+        bool zero_w = false;
         for (uint32_t k = tid; k < n; k += T) {
             const uint32_t h = grp[k];
             const HitAux x = aux[h];
-            s_ta[k] = x.triA; s_tb[k] = x.triB; s_fl[k] = x.flags | (hits[h].weight == 0.f ? 0u : 0x80000000u);
+            const bool nz = !(hits[h].weight == 0.f);
+            zero_w |= !nz;
+            s_ta[k] = x.triA; s_tb[k] = x.triB; s_fl[k] = x.flags | (nz ? 0x80000000u : 0u);
         }
+        const bool any_zero_w = __syncthreads_or(zero_w) != 0;          // block-uniform: does the pair have hits of weight 0 at all?
         for (uint32_t side = 0; side < 2; ++side) {
             for (uint32_t k = tid; k < slots; k += T) { s_key[k] = 0xffffffffu; s_bits[k] = 7u; s_sum[k].w = 0.0; s_sum[k].cx = 0.0; s_sum[k].cy = 0.0; s_sum[k].cz = 0.0; }
             for (uint32_t k = tid; k < vslots; k += T) s_vset[k] = ~0ull;
             if (tid == 0) { s_ncand = 0u; s_nvert = 0u; s_navg = 0u; }
             __syncthreads();
+            if (any_zero_w) {
+                // the vertex table is idle until the candidates are walked: it first holds the set of (own triangle, other leaf) with weight
+                for (uint32_t k = tid; k < n; k += T) {
+                    const uint32_t fl = s_fl[k];
+                    if (fl >> 31) {
+                        const uint32_t own = side ? s_tb[k] : s_ta[k];
+                        const uint32_t leaf = side ? s_ta[k] - ((fl >> 6) & 3u) : s_tb[k] - ((fl >> 8) & 3u);
+                        pc_combo_insert(s_vset, vslots - 1u, ((unsigned long long)own << 32) | leaf);
+                    }
+                }
+                __syncthreads();
+            }
             // ---- one thread per hit: merge into the own triangle's candidate ----
             for (uint32_t k0 = 0; k0 < n; k0 += T) {
                 const uint32_t k = k0 + tid;
@@ -809,14 +848,9 @@ k_pair_contacts_hash(FrameCtl* ctl, const uint32_t* __restrict__ list, int cls, 
                     const uint32_t fl = s_fl[k];
                     const uint32_t own = side ? s_tb[k] : s_ta[k];
                     bool contributes = (fl >> 31) != 0u;
-                    if (!contributes) {                                                  // rare: is the combo's weight for this triangle 0? (:117-127)
+                    if (!contributes) {                                                  // is the combo's weight for this triangle 0? (:117-127)
                         const uint32_t leaf = side ? s_ta[k] - ((fl >> 6) & 3u) : s_tb[k] - ((fl >> 8) & 3u);
-                        for (uint32_t q = 0; q < n && !contributes; ++q) {
-                            const uint32_t fl2 = s_fl[q];
-                            const uint32_t own2 = side ? s_tb[q] : s_ta[q];
-                            const uint32_t leaf2 = side ? s_ta[q] - ((fl2 >> 6) & 3u) : s_tb[q] - ((fl2 >> 8) & 3u);
-                            contributes = own2 == own && leaf2 == leaf && (fl2 >> 31) != 0u;
-                        }
+                        contributes = pc_combo_contains<false>(s_vset, vslots - 1u, ((unsigned long long)own << 32) | leaf);
                     }
                     if (contributes) {
                         const imrcd_tri_hit hh = hits[grp[k]];
@@ -847,6 +881,10 @@ k_pair_contacts_hash(FrameCtl* ctl, const uint32_t* __restrict__ list, int cls, 
                 }
             }
             __syncthreads();
+            if (any_zero_w) {                                                            // the vertex table back to empty
+                for (uint32_t k = tid; k < vslots; k += T) s_vset[k] = ~0ull;
+                __syncthreads();
+            }
             // ---- one thread per candidate: vertex rays into the `emplaced` set, average-point rays onto their list (:139-166) ----
             const uint32_t n_cand = s_ncand;
             for (uint32_t c0 = 0; c0 < n_cand; c0 += T) {
@@ -1002,6 +1040,41 @@ __global__ void k_large_init(const FrameCtl* ctl, const uint32_t* __restrict__ l
     }
 }
 
+// the (own triangle, other leaf) keys with weight, both sides, into the (still idle) vertex tables; k_large_unmark empties them again
+__global__ void __launch_bounds__(256)
+k_large_mark(const FrameCtl* ctl, const uint32_t* __restrict__ list, const PairAcc* __restrict__ acc, const unsigned long long* __restrict__ pref, unsigned char* scratch,
+             const uint32_t* __restrict__ grouped, const imrcd_tri_hit* __restrict__ hits, const HitAux* __restrict__ aux) {
+    const uint32_t n_list = (uint32_t)ctl->n_class[3 * 16];
+    if (ctl->overflow) return;
+    const unsigned long long total = pref[n_list];
+    for (unsigned long long t = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; t < total; t += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint32_t i = pcl_find(pref, n_list, t);
+        const PairAcc& pa = acc[list[i]];
+        const uint32_t n = pa.n_hits, m = pcl_padded(n), k = (uint32_t)(t - pref[i]);
+        if (k >= n) continue;
+        const uint32_t h = grouped[pa.off + k];
+        if (hits[h].weight == 0.f) continue;
+        const HitAux x = aux[h];
+        pc_combo_insert(pcl_tables(scratch, pref[i], m, 0).vset, 4u * m - 1u, ((unsigned long long)x.triA << 32) | (x.triB - ((x.flags >> 8) & 3u)));
+        pc_combo_insert(pcl_tables(scratch, pref[i], m, 1).vset, 4u * m - 1u, ((unsigned long long)x.triB << 32) | (x.triA - ((x.flags >> 6) & 3u)));
+    }
+}
+__global__ void k_large_unmark(const FrameCtl* ctl, const uint32_t* __restrict__ list, const PairAcc* __restrict__ acc, const unsigned long long* __restrict__ pref, unsigned char* scratch) {
+    const uint32_t n_list = (uint32_t)ctl->n_class[3 * 16];
+    if (ctl->overflow) return;
+    const unsigned long long total = pref[n_list];
+    for (unsigned long long t = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; t < total; t += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint32_t i = pcl_find(pref, n_list, t);
+        const uint32_t m = pcl_padded(acc[list[i]].n_hits), u = (uint32_t)(t - pref[i]);
+#pragma unroll
+        for (uint32_t side = 0; side < 2; ++side) {
+            unsigned long long* vs = pcl_tables(scratch, pref[i], m, side).vset;
+#pragma unroll
+            for (uint32_t q = 0; q < 4; ++q) vs[4u * u + q] = ~0ull;
+        }
+    }
+}
+
 // one thread per hit of a large pair, both sides
 __global__ void __launch_bounds__(256)
 k_large_hits(const FrameCtl* ctl, const uint32_t* __restrict__ list, const PairAcc* __restrict__ acc, const unsigned long long* __restrict__ pref, unsigned char* scratch,
@@ -1031,18 +1104,12 @@ k_large_hits(const FrameCtl* ctl, const uint32_t* __restrict__ list, const PairA
             if (have) {
                 const uint32_t own = side ? x.triB : x.triA;
                 bool contributes = !(hh.weight == 0.f);
-                if (!contributes) {                                                      // rare: is the combo's weight for this triangle 0? (:117-127)
+                tb = pcl_tables(scratch, pref[i], m, side);
+                if (!contributes) {                                                      // is the combo's weight for this triangle 0? (:117-127)
                     const uint32_t leaf = side ? x.triA - ((x.flags >> 6) & 3u) : x.triB - ((x.flags >> 8) & 3u);
-                    for (uint32_t q = 0; q < n && !contributes; ++q) {
-                        const uint32_t h2 = grp[q];
-                        const HitAux y = aux[h2];
-                        const uint32_t own2 = side ? y.triB : y.triA;
-                        const uint32_t leaf2 = side ? y.triA - ((y.flags >> 6) & 3u) : y.triB - ((y.flags >> 8) & 3u);
-                        contributes = own2 == own && leaf2 == leaf && !(hits[h2].weight == 0.f);
-                    }
+                    contributes = pc_combo_contains<true>(tb.vset, 4u * m - 1u, ((unsigned long long)own << 32) | leaf);
                 }
                 if (contributes) {
-                    tb = pcl_tables(scratch, pref[i], m, side);
                     bool claimed = false;
                     slot = pc_slot_of(tb.key, 2u * m - 1u, own, claimed);
                     tab = i;
@@ -1433,7 +1500,9 @@ int imr_frame_run_device(imrcd_ctx* ctx) {
                 const unsigned gl = ctx->sm_count * 4;
                 k_large_layout<<<1, 1024, 0, s2>>>(ctl, l3, a_acc, a_pref, a_sides, ctx->cap_lscratch);
                 k_large_init<<<gl, 256, 0, s2>>>(ctl, l3, a_acc, a_pref, a_scr);
+                k_large_mark<<<gl, 256, 0, s2>>>(ctl, l3, a_acc, a_pref, a_scr, a_grp, a_hits, a_aux);
                 k_large_hits<<<gl, 256, 0, s2>>>(ctl, l3, a_acc, a_pref, a_scr, a_grp, a_hits, a_aux);
+                k_large_unmark<<<gl, 256, 0, s2>>>(ctl, l3, a_acc, a_pref, a_scr);
                 k_large_candidates<<<gl, 256, 0, s2>>>(ctl, l3, a_acc, a_pref, a_scr, a_sides, a_vid);
                 k_large_alloc<<<ctx->sm_count, 256, 0, s2>>>(ctl, l3, a_acc, a_sides, ctx->cap_rays);
                 k_large_rays<<<gl, 256, 0, s2>>>(ctl, l3, a_acc, a_pref, a_scr, a_sides, a_pr, a_tris, a_nrm, a_rays);
@@ -1447,7 +1516,7 @@ int imr_frame_run_device(imrcd_ctx* ctx) {
             IMR_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_join3, 0));
             IMR_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_join4, 0));
         }
-        launches += 11;     // lists, group, three per-pair size classes, six passes over the large pairs
+        launches += 13;     // lists, group, three per-pair size classes, eight passes over the large pairs
         k_finalize<<<ctx->sm_count * 4, 256, 0, s>>>(ctl, ctx->cap_pairs, ctx->d_pairs.as<uint2>(), ctx->d_pairacc.as<PairAcc>(),
                                                       ctx->d_entity.as<uint32_t>(), ctx->d_cur.as<float>(), ctx->d_inv.as<float>(),
                                                       ctx->d_epairs.as<imrcd_entity_pair>() + 1, ctx->d_epair_pair.as<uint32_t>());
