@@ -48,6 +48,11 @@ def test_fullsize_sampled_pairs_against_the_oracle(c3, port):
     order = np.argsort(hits["pair"], kind="stable"); hp = hits["pair"][order]
     with_hits = np.unique(hp)
     sample = np.concatenate([rng.choice(with_hits, 120, replace=False), rng.choice(len(bp), 80, replace=False)])
+    # plus every pair of the largest size class (> 1024 hits: the grid-wide passes of the contact reduction), zero-weight hits included
+    per_pair = np.bincount(hp, minlength=len(bp))
+    large = np.nonzero(per_pair > 1024)[0]
+    sample = np.unique(np.concatenate([sample, large[:40]]))
+    zero_w_seen = 0
     ep_by_key = {(int(p["entry_first"]), int(p["entry_second"])): p for p in ep}
     n_checked_hits = 0
     for k in sample.tolist():
@@ -60,11 +65,14 @@ def test_fullsize_sampled_pairs_against_the_oracle(c3, port):
         g_rec = {(int(h["tri_first"]), int(h["tri_second"])): f32_bits(np.concatenate([h["source"], h["target"], [h["weight"]]])).tobytes() for h in gh}
         assert o_rec == g_rec, k
         n_checked_hits += r.n_hits
+        zero_w_seen += int((gh["weight"] == 0).sum())
         p = ep_by_key.get((i, j))
         assert (p is not None) == r.colliding
         if p is not None:
             assert (int(p["n_rays_first"]), int(p["n_rays_second"])) == (r.rays_first, r.rays_second)
     assert n_checked_hits > 5000
+    if scene.n_entries == 4096:          # C2: hits of weight 0 are common (touching triangles) and the largest size class is populated
+        assert zero_w_seen > 100 and len(large) > 10
 
 
 def test_fullsize_shards_add_up_and_runs_agree(c3):
