@@ -200,7 +200,7 @@ struct imrcd_ctx {
     cudaEvent_t ev[8] = {};
     cudaStream_t stream2 = nullptr, stream3 = nullptr, stream4 = nullptr;      // side streams for independent tail work of a frame
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join3 = nullptr, ev_join4 = nullptr;
-    int trav_blocks = 0, narrow_blocks = 0, trav_variant = 0;
+    int trav_blocks = 0, narrow_blocks = 0, trav_variant = 0, shoot_blocks = 0;
     bool pc_attr_set = false;
     uint32_t pc_large_min = 1024;        // contact reduction: pairs with more hits go to the grid-wide passes
     const void* trav_fn = nullptr;

@@ -399,9 +399,12 @@ int imr_frame_shoot_device(imrcd_ctx* ctx, FrameCtl* ctl, uint64_t* launches) {
     cudaStream_t s = ctx->stream;
     // glm::radians(40.f), glm::radians(65.f) -> cos (CollisionDetection.cpp:22-23, ShootUncollideRays.cpp:8-9): smoothstep runs from cos 65 to cos 40
     const float edge_b = cosf(0.01745329251994329576923690768489f * 40.f), edge_a = cosf(0.01745329251994329576923690768489f * 65.f);
-    static int shoot_blocks_per_sm = 0;
-    if (!shoot_blocks_per_sm) { IMR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&shoot_blocks_per_sm, k_shoot, 128, 0)); if (shoot_blocks_per_sm < 1) shoot_blocks_per_sm = 1; }
-    k_shoot<<<ctx->sm_count * shoot_blocks_per_sm, 128, 0, s>>>(ctl, ctx->cap_rays, ctx->d_rays.as<RayRec>(), ctx->d_resp.as<float4>(), ctx->d_pairacc.as<PairAcc>(),
+    if (!ctx->shoot_blocks) {                                             // persistent grid: as many blocks as are co-resident
+        int per_sm = 0;
+        IMR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_shoot, 128, 0));
+        ctx->shoot_blocks = ctx->sm_count * (per_sm < 1 ? 1 : per_sm);
+    }
+    k_shoot<<<ctx->shoot_blocks, 128, 0, s>>>(ctl, ctx->cap_rays, ctx->d_rays.as<RayRec>(), ctx->d_resp.as<float4>(), ctx->d_pairacc.as<PairAcc>(),
                                                ctx->d_pairrec.as<PairRec>(), ctx->d_recs.as<TreeRec>(), ctx->d_tris.as<TriRec>(), ctx->d_tri_nrm.as<float>());
     k_delta<<<ctx->sm_count * 4, 256, 0, s>>>(ctl, ctx->d_epair_pair.as<uint32_t>(), ctx->d_epairs.as<imrcd_entity_pair>() + 1, ctx->d_pairacc.as<PairAcc>(),
                                                ctx->d_resp.as<float4>(), ctx->d_cur.as<float>(), ctx->d_prev.as<float>(), edge_a, edge_b);

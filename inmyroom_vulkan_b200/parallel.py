@@ -60,6 +60,7 @@ class FrameGather:
         self.cap = capacity
         self.last = None
         self._send = None; self._recv = None
+        self._hdr_event = None; self._cap_alloc = capacity
 
     def _local_device_records(self) -> torch.Tensor:
         ctx = self.cd.ctx
@@ -136,6 +137,8 @@ class FrameGather:
     def counts(self):
         """Per-rank record counts of the last gather_device(); None when some rank had more records than the capacity (the capacity
         is raised for the next gather, every rank sees the same headers and decides alike)."""
+        if self._hdr_event is None:
+            raise RuntimeError("FrameGather.counts() before gather_device()")
         self._hdr_event.synchronize()
         counts = self._hdr.view(torch.int64).reshape(-1).tolist()
         if max(counts) > self.cap:
