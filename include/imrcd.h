@@ -111,6 +111,33 @@ int imrcd_mesh_add_primitive(imrcd_ctx* ctx, const float* points, uint64_t n_poi
                              const uint32_t* indices, uint64_t n_indices, uint32_t gltf_mode);
 int imrcd_mesh_end(imrcd_ctx* ctx, uint32_t build_mode, uint32_t* mesh_id);
 
+/* ---- glTF files: .gltf (+ .bin, base64 data URIs) and .glb read on the host, triangles and trees made on the device ----
+ * Replaces the engine's load path for collision geometry: tinygltf + PrimitiveInitializationData (IMR/src/Graphics/Meshes/
+ * PrimitivesOfMeshes.cpp:44-175: float POSITION / NORMAL with y and z negated :83-87,:134-139; u16 / u32 indices :58-70 -- u8 is also taken
+ * here; line loop drawn as line strip :49-55; skinned or morphed primitives give no collision triangles :641,:669) and the per-mesh loop of
+ * MeshesOfNodes.cpp:34-53 (StartRecordOBBtree, the primitives "triangles first", GetOBBtreeAndReset): ONE tree per glTF mesh, mesh_ids[i]
+ * belongs to meshes[i] of the file.  imrcd_gltf_open / _primitive are host-only (no device needed): they expose each mesh's primitives exactly
+ * as they are handed to imrcd_mesh_add_primitive, in the order the reference would record them. */
+typedef struct imrcd_gltf imrcd_gltf;
+typedef struct imrcd_gltf_primitive_view {
+    const float*    points;        /* n_points * 3, glTF -> engine axes (y and z negated) */
+    const float*    normals;       /* n_points * 3 or NULL */
+    const uint32_t* indices;       /* n_indices or NULL */
+    uint64_t        n_points, n_indices;
+    uint32_t        mode;          /* glTF draw mode as recorded (2 has become 3) */
+    uint32_t        skipped;       /* 1 = skinned or morphed: not part of the tree, no arrays */
+    uint32_t        source_index;  /* position in the file's "primitives" array */
+    uint32_t        has_indices;   /* 0 = non-indexed (draws 0 .. n_points-1) */
+} imrcd_gltf_primitive_view;
+int  imrcd_gltf_open(const char* path, imrcd_gltf** out, char* err, uint64_t err_cap);
+void imrcd_gltf_close(imrcd_gltf* g);
+int  imrcd_gltf_mesh_count(const imrcd_gltf* g, uint32_t* n);
+int  imrcd_gltf_primitive_count(const imrcd_gltf* g, uint32_t mesh, uint32_t* n);
+int  imrcd_gltf_primitive(const imrcd_gltf* g, uint32_t mesh, uint32_t k, imrcd_gltf_primitive_view* out);
+int  imrcd_gltf_build_mesh(imrcd_ctx* ctx, const imrcd_gltf* g, uint32_t mesh, uint32_t build_mode, uint32_t* mesh_id);
+/* open + one tree per mesh + close.  mesh_ids == NULL: only count (*n_meshes). */
+int  imrcd_gltf_load(imrcd_ctx* ctx, const char* path, uint32_t build_mode, uint32_t* mesh_ids, uint32_t capacity, uint32_t* n_meshes);
+
 /* Test-only: upload a tree built elsewhere (flat pre-order form, see oracle/imr_oracle.h). */
 int imrcd_mesh_import_tree(imrcd_ctx* ctx, uint64_t n_vertices, const float* boxes, const int32_t* left, const int32_t* right,
                            const uint32_t* tri_off, const uint32_t* tri_cnt, uint64_t n_tri, const float* tri_pos,

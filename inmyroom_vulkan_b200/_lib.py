@@ -50,6 +50,13 @@ _SIGS = [
     ("imrcd_last_error", C.c_char_p, [_P]),
     ("imrcd_version", C.c_char_p, []),
     ("imrcd_mesh_create", C.c_int, [_P, _P, _P, _P, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint32)]),
+    ("imrcd_gltf_open", C.c_int, [C.c_char_p, C.POINTER(_P), C.c_char_p, C.c_uint64]),
+    ("imrcd_gltf_close", None, [_P]),
+    ("imrcd_gltf_mesh_count", C.c_int, [_P, C.POINTER(C.c_uint32)]),
+    ("imrcd_gltf_primitive_count", C.c_int, [_P, C.c_uint32, C.POINTER(C.c_uint32)]),
+    ("imrcd_gltf_primitive", C.c_int, [_P, C.c_uint32, C.c_uint32, _P]),
+    ("imrcd_gltf_build_mesh", C.c_int, [_P, _P, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]),
+    ("imrcd_gltf_load", C.c_int, [_P, C.c_char_p, C.c_uint32, C.POINTER(C.c_uint32), C.c_uint32, C.POINTER(C.c_uint32)]),
     ("imrcd_mesh_begin", C.c_int, [_P]),
     ("imrcd_mesh_add_primitive", C.c_int, [_P, _P, C.c_uint64, C.c_uint32, _P, _P, C.c_uint64, C.c_uint32]),
     ("imrcd_mesh_end", C.c_int, [_P, C.c_uint32, C.POINTER(C.c_uint32)]),

@@ -149,6 +149,13 @@ class OBBtree:
         return ms.value
 
     @classmethod
+    def from_mesh_id(cls, ctx: Context, mesh_id: int):
+        """Wrap a mesh the library already holds (imrcd_gltf_load, imrcd_mesh_end)."""
+        self = cls.__new__(cls)
+        self.ctx = ctx; self.mesh_id = int(mesh_id)
+        return self
+
+    @classmethod
     def from_primitives(cls, ctx: Context, primitives, build_mode: int = IMRCD_BUILD_MORTON):
         """The engine's way in (PrimitivesOfMeshes::StartRecordOBBtree / GetOBBtreeAndReset): `primitives` is a sequence of
         (points (n, 3 or 4), normals or None, indices or None, glTF draw mode); Triangle::CreateTriangleList runs on the device."""

@@ -67,6 +67,16 @@ public:
         return id;
     }
 
+    // A whole .gltf / .glb: one tree per glTF mesh, ids in file order (what MeshesOfNodes::AddMeshesOfModel keeps as
+    // MeshInfo::boundBoxTree, IMR/src/Graphics/Meshes/MeshesOfNodes.cpp:34-53); the file is read by the library, no tinygltf model needed.
+    std::vector<uint32_t> LoadMeshesOfModel(const std::string& path, uint32_t build_mode = IMRCD_BUILD_MORTON) {
+        uint32_t n = 0;
+        check(imrcd_gltf_load(ctx_, path.c_str(), build_mode, nullptr, 0, &n));
+        std::vector<uint32_t> ids(n);
+        if (n) check(imrcd_gltf_load(ctx_, path.c_str(), build_mode, ids.data(), n, &n));
+        return ids;
+    }
+
     void Reset() {                                                       // CollisionDetection.cpp:28
         check(imrcd_frame_reset(ctx_));
         n_ = 0; mapped_ = 0; pending_ = 0; any_previous_ = false;

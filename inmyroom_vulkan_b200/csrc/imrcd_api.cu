@@ -224,6 +224,9 @@ static void recording_clear(imrcd_ctx* ctx) {
     for (auto& r : ctx->recording) { r.points.release(); r.normals.release(); r.indices.release(); }
     ctx->recording.clear(); ctx->recording_open = false;
 }
+// used by imrcd_gltf.cpp, which sees the context only through the ABI
+void imr_ctx_set_error(imrcd_ctx* ctx, const char* msg) { if (ctx) ctx->err = msg ? msg : ""; }
+
 extern "C" int imrcd_mesh_begin(imrcd_ctx* ctx) {
     CHECK_CTX(ctx);
     recording_clear(ctx);

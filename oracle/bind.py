@@ -21,6 +21,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SO = os.path.join(HERE, "_ref", "libimr_ref.so")
+REF_GLTF_SO = os.path.join(HERE, "_ref", "libimr_ref_gltf.so")
 PORT_SO = os.path.join(HERE, "liboracle_port.so")
 
 _f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
@@ -494,6 +495,52 @@ def frame_pairs(orc, mats, trees, pairs, threads: int = 1):
     tot = sum(r[0] for r in res); secs = sum(r[1] for r in res)
     return dict(combos=int(tot[0]), tri_tests=int(tot[1]), colliding=int(tot[2]), with_combos=int(tot[3]), wall_s=wall,
                 mid_s=float(secs[0]), narrow_s=float(secs[1]))
+
+
+class _RefGltfView(C.Structure):
+    _fields_ = [("points", C.POINTER(C.c_float)), ("normals", C.POINTER(C.c_float)), ("indices", C.POINTER(C.c_uint32)),
+                ("n_points", C.c_uint64), ("n_indices", C.c_uint64), ("mode", C.c_uint32), ("skipped", C.c_uint32),
+                ("source_index", C.c_uint32), ("has_indices", C.c_uint32)]
+
+
+class RefGltf:
+    """A .gltf / .glb read by the reference's own reader (tinygltf) and laid out the way the engine hands it to
+    Triangle::CreateTriangleList (ref_gltf_shim.cpp): primitives(mesh) = [(points, normals | None, indices | None, mode, source index)]
+    in the engine's recording order, skinned / morphed primitives left out."""
+
+    def __init__(self, path):
+        self.lib = C.CDLL(REF_GLTF_SO)
+        self.lib.imr_refgltf_open.restype = C.c_void_p; self.lib.imr_refgltf_open.argtypes = [C.c_char_p, C.c_char_p, C.c_uint64]
+        self.lib.imr_refgltf_close.argtypes = [C.c_void_p]
+        self.lib.imr_refgltf_mesh_count.argtypes = [C.c_void_p]; self.lib.imr_refgltf_mesh_count.restype = C.c_uint32
+        self.lib.imr_refgltf_primitive_count.argtypes = [C.c_void_p, C.c_uint32]; self.lib.imr_refgltf_primitive_count.restype = C.c_uint32
+        self.lib.imr_refgltf_primitive.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]; self.lib.imr_refgltf_primitive.restype = None
+        err = C.create_string_buffer(512)
+        self.h = self.lib.imr_refgltf_open(os.fsencode(path), err, len(err))
+        if not self.h:
+            raise ValueError(err.value.decode(errors="replace"))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.imr_refgltf_close(self.h); self.h = None
+
+    @property
+    def n_meshes(self):
+        return int(self.lib.imr_refgltf_mesh_count(self.h))
+
+    def primitives(self, mesh):
+        out = []
+        for k in range(self.lib.imr_refgltf_primitive_count(self.h, mesh)):
+            v = _RefGltfView()
+            self.lib.imr_refgltf_primitive(self.h, mesh, k, C.byref(v))
+            if v.skipped:
+                continue
+            npts, nidx = int(v.n_points), int(v.n_indices)
+            pts = np.ctypeslib.as_array(v.points, (npts, 3)).copy() if npts else np.zeros((0, 3), np.float32)
+            nrm = np.ctypeslib.as_array(v.normals, (npts, 3)).copy() if v.normals else None
+            idx = (np.ctypeslib.as_array(v.indices, (nidx,)).copy() if nidx else np.zeros(0, np.uint32)) if v.has_indices else None
+            out.append((pts, nrm, idx, int(v.mode), int(v.source_index)))
+        return out
 
 
 def load(prefer: str = "reference"):

@@ -107,9 +107,29 @@ def make_primitives(ref):
     print("primitives:", len(names), "cases,", sum(len(out[f"{k}.pos"]) for k in names), "triangles")
 
 
+def make_gltf(ref):
+    """gltf_scene.glb + gltf.npz: a file with every loader situation (tests/gltf_writer.py), read by the reference's own reader (tinygltf) in the
+    engine's primitive order and extraction (oracle/ref_gltf_shim.cpp), through the reference's Triangle::CreateTriangleList."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import gltf_writer
+    path = gltf_writer.write(os.path.join(HERE, "gltf_scene.glb"), gltf_writer.sample_meshes(), "glb")
+    g = bind.RefGltf(path)
+    out = {"n_meshes": np.array([g.n_meshes])}
+    for m in range(g.n_meshes):
+        ps, ns, vs = [np.zeros((0, 9), np.float32)], [np.zeros((0, 9), np.float32)], [np.zeros((0, 3), np.uint32)]
+        for pts, nrm, idx, mode, _ in g.primitives(m):
+            p, n, v = ref.triangle_list(pts, nrm, np.arange(len(pts), dtype=np.uint32) if idx is None else idx, mode)
+            ps.append(p); ns.append(n); vs.append(v)
+        out[f"m{m}.pos"] = np.concatenate(ps); out[f"m{m}.nrm"] = np.concatenate(ns); out[f"m{m}.vid"] = np.concatenate(vs)
+    np.savez_compressed(os.path.join(HERE, "gltf.npz"), **out)
+    print("gltf:", g.n_meshes, "meshes,", [len(out[f"m{m}.pos"]) for m in range(g.n_meshes)], "triangles,", os.path.getsize(path), "bytes")
+
+
 def main():
     bind.build("ref")
     ref = bind.RefOracle()
+    if len(sys.argv) > 1 and sys.argv[1] == "gltf":
+        return make_gltf(ref)
     if len(sys.argv) > 1 and sys.argv[1] == "response":
         return make_response(ref)
     if len(sys.argv) > 1 and sys.argv[1] == "primitives":
