@@ -38,8 +38,12 @@ class CollisionDetection
                 }
                 out.emplace_back(kv.first, std::move(v));
             }
+#ifdef IMRCD_DROP_IN_CALLBACK_SINK
+            IMRCD_DROP_IN_CALLBACK_SINK(out);                   // tests: hand the callbacks to a checker instead of the components
+#else
             for (const auto& id_component : ecs->GetComponentIDtoComponentBaseClassMap())                                       // CollisionDetection.cpp:136-140
                 if (id_component.second != nullptr) id_component.second->CollisionCallback(out);
+#endif
         }
     };
 
