@@ -9,6 +9,8 @@
 //   snake_harness_dropin  tests/cpp/stubs_dropin in front of the include path: ModelCollisionComp.cpp compiles UNCHANGED against the drop-in
 //   snake_harness_shadow  -DIMRCD_SHADOW, tests/cpp/stubs_shadow: BOTH behind one class; the reference drives the game, the drop-in gets the
 //                         same entries every frame and its callbacks are compared with the reference's in lock step ("shadow" lines)
+//   snake_harness_record  -DIMRCD_SHADOW -DIMRCD_RECORD_ONLY: the tee with the reference alone (CPU only); SNAKE_DUMP=<file> writes the meshes,
+//                         every frame's entries and the reference's verdict (tests/golden/make_golden.py snake -> tests/golden/snake_frames.npz)
 // Frames run as Engine::Run does (ECSwrapper::Update, CompleteAddsAndRemoves) on a fixed 1/60 s clock (steady_clock::now is interposed,
 // so both builds see the same delta times and the game's std::rand draws line up).  Every frame prints each snake's position: the loop
 // is closed -- deltaVectors move the snakes (SnakePlayerCompEntity.cpp:223-251), the moved snakes make the next frame's entries.
@@ -79,6 +81,9 @@ void imrcd_shadow_compare() {           // same entries went to both: same recei
         std::fprintf(g_dump, "end\n");
     }
     g_shadow_frame_worst = 0.0; g_shadow_frame_worst_abs = 0.0;
+#ifdef IMRCD_RECORD_ONLY
+    a.clear(); return;
+#endif
     static const bool verbose = std::getenv("SNAKE_SHADOW_VERBOSE") != nullptr;
     size_t i = 0, j = 0;
     while (i < a.size() || j < b.size()) {          // merge by (receiver, family, other)

@@ -10,7 +10,9 @@
 #include "ECS/ECStypes.h"
 #include "ECS/ECSwrapper.h"
 #include "Geometry/OBBtree.h"
+#ifndef IMRCD_RECORD_ONLY
 #include "imrcd_host.hpp"
+#endif
 
 #define CollisionDetection ReferenceCollisionDetection
 #include_next "CollisionDetection/CollisionDetection.h"
@@ -20,29 +22,42 @@ void imrcd_shadow_sink(const std::vector<std::pair<Entity, std::vector<Collision
 void imrcd_shadow_compare();
 void imrcd_shadow_entry(const CollisionDetectionEntry& entry);
 
+#ifndef IMRCD_RECORD_ONLY        // -DIMRCD_RECORD_ONLY: the reference alone behind the tee (CPU only), for writing frame dumps
 namespace imrcd_shadow {
 #define IMRCD_DROP_IN_CALLBACK_SINK(callbacks) ::imrcd_shadow_sink(callbacks)
 #include "CollisionDetection_drop_in.hpp"
 }
+#endif
 
 class CollisionDetection
 {
 public:
+#ifdef IMRCD_RECORD_ONLY
+    CollisionDetection(ECSwrapper* in_ECSwrapper_ptr) : reference(in_ECSwrapper_ptr) {}
+    void Reset() { reference.Reset(); }
+#else
     CollisionDetection(ECSwrapper* in_ECSwrapper_ptr) : reference(in_ECSwrapper_ptr), drop_in(in_ECSwrapper_ptr) {}
     void Reset() { reference.Reset(); drop_in.Reset(); }
+#endif
     void AddCollisionDetectionEntry(const CollisionDetectionEntry in_collisionDetectionEntry)
     {
         imrcd_shadow_entry(in_collisionDetectionEntry);
         reference.AddCollisionDetectionEntry(in_collisionDetectionEntry);
+#ifndef IMRCD_RECORD_ONLY
         drop_in.AddCollisionDetectionEntry(in_collisionDetectionEntry);
+#endif
     }
     void ExecuteCollisionDetection()
     {
+#ifndef IMRCD_RECORD_ONLY
         drop_in.ExecuteCollisionDetection();        // -> imrcd_shadow_sink
+#endif
         reference.ExecuteCollisionDetection();      // -> the ECS components (the game moves by the reference's deltaVectors)
         imrcd_shadow_compare();
     }
 private:
     ReferenceCollisionDetection reference;
+#ifndef IMRCD_RECORD_ONLY
     imrcd_shadow::CollisionDetection drop_in;
+#endif
 };

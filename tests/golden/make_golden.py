@@ -125,9 +125,44 @@ def make_gltf(ref):
     print("gltf:", g.n_meshes, "meshes,", [len(out[f"m{m}.pos"]) for m in range(g.n_meshes)], "triangles,", os.path.getsize(path), "bytes")
 
 
+def make_snake():
+    """snake_frames.npz: frames of the REAL SnakeGame (its game DLL under the reference's ECS, general components and CollisionDetection,
+    oracle/_ref/snake_harness_record, 12 snakes, fixed 1/60 s clock): the scene's meshes, the entries ModelCollisionComp::Update made in
+    a selection of frames, and the engine's verdict on each -- every colliding (entity, other) with the deltaVector it was handed."""
+    import subprocess
+    import tempfile
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import snake_dump
+    subprocess.run(["make", "-s", "-j4", "-C", os.path.join(ROOT, "oracle"), "harness"], check=True)
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    with tempfile.TemporaryDirectory() as d:
+        dump = os.path.join(d, "dump.txt")
+        subprocess.run([os.path.join(ref_dir, "snake_harness_record"), "200", "12", os.path.join(ref_dir, "libsnake_game.so")],
+                       check=True, env=dict(os.environ, SNAKE_DUMP=dump), stdout=subprocess.DEVNULL)
+        meshes, frames = snake_dump.load(dump)
+    busiest = sorted(range(len(frames)), key=lambda f: -len(frames[f]["callbacks"]))[:6]
+    keep = sorted(set([0, 1, 2, 5, 10, 20, 35, 50, 75, 100, 125, 150, 175, 199] + busiest))
+    out = {"n_meshes": np.array([len(meshes)]), "frames": np.array(keep)}
+    for k, (pts, nrm, idx) in enumerate(meshes):
+        out[f"mesh{k}.points"] = pts; out[f"mesh{k}.normals"] = nrm; out[f"mesh{k}.indices"] = idx
+    n_rows = 0
+    for f in keep:
+        fr = frames[f]
+        for key in ("entity", "mesh", "callback", "cur", "prev"):
+            out[f"f{f}.{key}"] = fr[key]
+        rows = fr["callbacks"]
+        out[f"f{f}.pairs"] = np.array([[a, b] for a, b, _ in rows], np.uint32).reshape(-1, 2)
+        out[f"f{f}.deltas"] = np.array([d for _, _, d in rows], np.float32).reshape(-1, 3)
+        n_rows += len(rows)
+    np.savez_compressed(os.path.join(HERE, "snake_frames.npz"), **out)
+    print("snake:", len(keep), "frames,", n_rows, "colliding (entity, other) rows,", os.path.getsize(os.path.join(HERE, "snake_frames.npz")), "bytes")
+
+
 def main():
     bind.build("ref")
     ref = bind.RefOracle()
+    if len(sys.argv) > 1 and sys.argv[1] == "snake":
+        return make_snake()
     if len(sys.argv) > 1 and sys.argv[1] == "gltf":
         return make_gltf(ref)
     if len(sys.argv) > 1 and sys.argv[1] == "response":
