@@ -17,6 +17,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <memory>
 #include <string>
 #include <utility>
@@ -317,8 +318,11 @@ struct Loader {
             default: return fail(std::string("gltf: ") + what + ": bad componentType");
         }
         if (ctype_out) *ctype_out = ctype;
-        out.assign((size_t)count * comps, T(0));
-        if (view < 0) return true;                                            // no bufferView: zeros (glTF 2.0, 5.1.1)
+        if (view < 0) {                                                       // no bufferView: zeros (glTF 2.0, 5.1.1)
+            if (count > (int64_t(1) << 28)) return fail(std::string("gltf: ") + what + ": accessor without a bufferView is too large");
+            out.assign((size_t)count * comps, T(0));
+            return true;
+        }
         const JVal* views = root.get("bufferViews");
         if (!views || views->type != JVal::ARR || (size_t)view >= views->arr.size()) return fail(std::string("gltf: ") + what + ": bad bufferView index");
         const JVal& v = views->arr[(size_t)view];
@@ -330,7 +334,9 @@ struct Loader {
         uint64_t stride = (uint64_t)v.index_or("byteStride", 0);
         if (stride == 0) stride = elem;
         const uint64_t view_end = (uint64_t)v.index_or("byteOffset", 0) + (uint64_t)v.index_or("byteLength", 0);
-        if (count && (offset + stride * (uint64_t)(count - 1) + elem > view_end || view_end > data.size())) return fail(std::string("gltf: ") + what + ": accessor runs past the end of its bufferView");
+        if ((uint64_t)count > data.size() ||                                  // (every element takes at least one byte: no overflow below)
+            (count && (offset + stride * (uint64_t)(count - 1) + elem > view_end || view_end > data.size()))) return fail(std::string("gltf: ") + what + ": accessor runs past the end of its bufferView");
+        out.assign((size_t)count * comps, T(0));
         for (int64_t k = 0; k < count; ++k) {
             const uint8_t* src = data.data() + offset + stride * (uint64_t)k;
             for (int c = 0; c < comps; ++c) {
@@ -423,11 +429,16 @@ void put_err(char* err, uint64_t cap, const std::string& m) {
 extern "C" int imrcd_gltf_open(const char* path, imrcd_gltf** out, char* err, uint64_t err_cap) {
     if (!path || !out) { put_err(err, err_cap, "imrcd_gltf_open: null argument"); return IMRCD_E_ARG; }
     *out = nullptr;
-    Loader ld;
-    std::unique_ptr<imrcd_gltf> g(new imrcd_gltf);
-    if (!ld.parse(path) || !ld.meshes(g->meshes)) { put_err(err, err_cap, ld.err); return IMRCD_E_ARG; }
-    *out = g.release();
-    return IMRCD_OK;
+    try {                                                                     // no exception crosses the ABI
+        Loader ld;
+        std::unique_ptr<imrcd_gltf> g(new imrcd_gltf);
+        if (!ld.parse(path) || !ld.meshes(g->meshes)) { put_err(err, err_cap, ld.err); return IMRCD_E_ARG; }
+        *out = g.release();
+        return IMRCD_OK;
+    } catch (const std::exception& e) {
+        put_err(err, err_cap, std::string("imrcd_gltf_open: ") + e.what());
+        return IMRCD_E_CAPACITY;
+    }
 }
 extern "C" void imrcd_gltf_close(imrcd_gltf* g) { delete g; }
 extern "C" int imrcd_gltf_mesh_count(const imrcd_gltf* g, uint32_t* n) {
