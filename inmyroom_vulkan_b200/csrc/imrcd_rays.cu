@@ -182,7 +182,13 @@ k_shoot(FrameCtl* ctl, unsigned long long cap_rays, const RayRec* __restrict__ r
     if (ctl->overflow) return;
     const unsigned long long n = ctl->n_rays_kept < cap_rays ? ctl->n_rays_kept : cap_rays;
     const uint32_t lane = threadIdx.x & 31u;
-    bool exhausted = false;                                                 // the frame's rays have all been handed out
+    // Lanes per warp that take rays: all 32 when the frame has a ray for every lane of the grid; fewer when it has not, so that a small
+    // frame's rays spread over as many warps as there are (a warp runs its lanes' queries interleaved, one code path at a time: 32 rays in one
+    // warp take ~32/14 times one ray's latency, and a game-sized frame of a few hundred rays used to sit in ten warps while 3500 idled).
+    const unsigned long long total_warps = (unsigned long long)gridDim.x * (blockDim.x >> 5);
+    const unsigned long long per_warp = (n + total_warps - 1ull) / total_warps;
+    const uint32_t quota = per_warp < 1ull ? 1u : (per_warp > 32ull ? 32u : (uint32_t)per_warp);
+    bool exhausted = lane >= quota;                                         // the frame's rays have all been handed out (or: not this lane's to take)
     uint32_t st_node[RAY_STACK]; float st_min[RAY_STACK];
     int sp = 0;
     bool active = false;

@@ -21,6 +21,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <dlfcn.h>
+#include <time.h>
 #include <memory>
 #include <string>
 #include <tuple>
@@ -304,12 +305,16 @@ int main(int argc, char** argv) {
     auto* node_data = static_cast<NodeDataComp*>(ecs.GetComponentByID(ID(componentIDenum::NodeData)));
 
     ecs.RefreshUpdateDeltaTime();                                                                       // Engine.cpp:103
+    auto wall = [] { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; };    // the real clock (steady_clock is the fixed one)
+    double wall_frames = 0.0;
     for (int frame = 0; frame < n_frames; ++frame) {
         g_now_ns += 16'666'667;
         if (g_dump) std::fprintf(g_dump, "frame %d\n", frame);
         const size_t before = counter.n;
+        const double t0 = wall();
         ecs.Update();                                                                                   // Engine.cpp:133-135 (DrawFrame left out)
         ecs.CompleteAddsAndRemoves();
+        if (frame >= 10) wall_frames += wall() - t0;                                                    // the first frames pay for tree uploads / warm-up
         std::printf("frame %d callbacks %zu\n", frame, counter.n - before);
 #ifdef IMRCD_SHADOW
         std::printf("shadow %d compared %zu mismatched %zu worst %.3g abs %.3g over %zu\n", frame, g_shadow_compared, g_shadow_missing, g_shadow_frame_worst, g_shadow_frame_worst_abs, g_shadow_over);
@@ -321,6 +326,7 @@ int main(int argc, char** argv) {
             std::printf("snake %zu %.9g %.9g %.9g\n", s, p.x, p.y, p.z);
         }
     }
+    if (n_frames > 10) std::fprintf(stderr, "wall: %.3f ms per ECS frame over %d frames\n", 1e3 * wall_frames / (n_frames - 10), n_frames - 10);
     if (g_dump) std::fclose(g_dump);
     return 0;
 }
