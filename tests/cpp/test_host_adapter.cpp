@@ -32,7 +32,7 @@ static void translation(float* m, float x, float y, float z, float rot) {
 }
 #define EXPECT(cond) do { if (!(cond)) { printf("FAILED %s:%d: %s\n", __FILE__, __LINE__, #cond); return 1; } } while (0)
 
-int main() {
+int main(int argc, char** argv) {
     ToyEcs ecs;
     // two separate families 1 -> 2 and 3 -> 4, and two siblings 5, 6 under the common parent 7; 8 is far away
     ecs.parent = {{2, 1}, {4, 3}, {5, 7}, {6, 7}};
@@ -89,6 +89,19 @@ int main() {
     const imrcd_entity_pair* pairs; uint64_t n_pairs;
     cd.Results(&pairs, &n_pairs);
     EXPECT(n_pairs == 0);
+    // a whole glTF file through the adapter (F4): one tree per mesh of tests/golden/gltf_scene.glb, triangle counts as the reference's loader gives them
+    if (argc > 1) {
+        const std::vector<uint32_t> ids = cd.LoadMeshesOfModel(argv[1], IMRCD_BUILD_REFERENCE);
+        const uint64_t want[5] = {730, 341, 400, 0, 40};
+        EXPECT(ids.size() == 5);
+        for (size_t m = 0; m < ids.size() && m < 5; ++m) {
+            uint64_t n_tri = 0, n_vert = 0;
+            EXPECT(imrcd_mesh_info(cd.context(), ids[m], &n_tri, &n_vert) == IMRCD_OK && n_tri == want[m]);
+        }
+        bool threw = false;
+        try { cd.LoadMeshesOfModel(std::string(argv[1]) + ".missing"); } catch (const std::runtime_error&) { threw = true; }
+        EXPECT(threw);
+    }
     printf("host adapter ok\n");
     return 0;
 }
