@@ -190,7 +190,7 @@ bool base64(const char* s, size_t n, std::vector<uint8_t>& out) {
 std::string percent_decode(const std::string& s) {
     std::string o;
     for (size_t i = 0; i < s.size(); ++i) {
-        if (s[i] == '%' && i + 2 < s.size() + 0 && std::isxdigit((unsigned char)s[i + 1]) && std::isxdigit((unsigned char)s[i + 2])) {
+        if (s[i] == '%' && i + 2 < s.size() && std::isxdigit((unsigned char)s[i + 1]) && std::isxdigit((unsigned char)s[i + 2])) {
             o += (char)std::strtol(s.substr(i + 1, 2).c_str(), nullptr, 16); i += 2;
         } else o += s[i];
     }
