@@ -60,6 +60,11 @@ public:
 
     void ExecuteCollisionDetection() { impl.ExecuteCollisionDetection(); }
 
+    // Optional: trees that were made on the device (imrcd_gltf_load / LoadMeshesOfModel, imrcd_mesh_end) instead of flattened from the
+    // engine's OBBtree objects.  After UseDeviceTree(&meshInfo.boundBoxTree, id) entries that point at that engine tree use mesh `id`.
+    imrcd::CollisionDetectionT<Entity, EcsPolicy>& Adapter() { return impl; }
+    void UseDeviceTree(const OBBtree* engine_tree, uint32_t mesh_id) { meshes[engine_tree] = mesh_id; }
+
 private:
     struct Flat { std::vector<float> boxes; std::vector<int32_t> left, right; std::vector<uint32_t> off, cnt; size_t n_tri = 0; };
     static int32_t Walk(const OBBtree::OBBtreeTraveler& t, Flat& f)
