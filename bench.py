@@ -238,8 +238,9 @@ def run_gpu_arm(args):
     build_wall = time.perf_counter() - t0
     mesh_ids = np.array([trees[m].mesh_id for m in scene.mesh_index], np.uint32)
     cd = CollisionDetection(ctx=ctx)
-    cd.set_shard(rank, world)
-    gather = parallel.FrameGather(cd, world, rank) if world > 1 else None
+    if world > 1:
+        parallel.init_comm(ctx, rank, world)     # from here on every frame of this context ends with the library's own NCCL all-gather
+    multi = world > 1
     n_tri_total = sum(m.n_tri for m in scene.meshes)
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
@@ -276,16 +277,13 @@ def run_gpu_arm(args):
         with torch.cuda.stream(stream):
             e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            cd.run_async()                          # the frame's kernels; the host does not wait here
-            if gather is not None:
-                gather.gather_device()              # the end-of-frame collective, right behind them on the stream
-            e1.record(stream)
-            if cd.finish() and gather is not None:  # (outside the timed region) a buffer overflowed: the library re-ran the frame
-                gather.gather_device()
+            cd.run_async()                          # the frame's kernels and, with N ranks, the end-of-frame all-gather right behind them
+            e1.record(stream)                       # (both enqueued by the library on this stream); the host does not wait here
+            if cd.finish():
+                raise SystemExit("bench.py: a frame buffer overflowed inside the timed loop (capacities are settled by the warm-up)")
         return e0, e1
 
-    if gather is not None:                               # settle the gather's block capacity before anything is timed
-        cd.run(); gather.gather_host()
+    cd.run()                                              # settle every capacity (frame buffers, gather blocks) before anything is timed
     clocks = ClockSampler(local); clocks.start()          # sampled from the warm-up to the end of the e2e loop
     for _ in range(args.warmup):
         l2_flush(); device_step()
@@ -302,8 +300,6 @@ def run_gpu_arm(args):
     if os.environ.get("IMRCD_BENCH_DEBUG"):               # per-rank stage sums: where a multi-GPU step spends its time
         print(f"[rank {rank}] dev_ms/step {sum(a.elapsed_time(b) for a, b in ev) / args.steps:.3f} stages " +
               " ".join(f"{k}={v / args.steps:.3f}" for k, v in st_acc.items()) + f" pairs={cd.stats()['n_pairs']} hits={cd.stats()['n_hits']}", file=sys.stderr)
-    if gather is not None and gather.counts() is None:
-        raise SystemExit("bench.py: the frame gather outgrew its blocks during the timed loop")
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     st = cd.stats()
     dev_ms_max = global_max(dev_ms)
@@ -312,6 +308,8 @@ def run_gpu_arm(args):
     pairs_total = global_sum(float(st["n_pairs"]))
     hits_total = global_sum(float(st["n_hits"]))
     coll_total = global_sum(float(st["n_colliding"]))
+    if multi and int(coll_total) != int(st["n_merged"]):
+        raise SystemExit(f"bench.py: the merged set has {st['n_merged']} records, the ranks found {int(coll_total)}")
     value = tests_total * args.steps / (dev_ms_max * 1e-3)
 
     # warm-L2 figure (no flush), informational
@@ -332,16 +330,14 @@ def run_gpu_arm(args):
         cd.Reset()
         cd.map_entries(scene.n_entries)             # same staging memory: the entries written above are still there
         cd.commit_entries(scene.n_entries, previous_valid=False)
-        if gather is not None:
-            return gather.execute_host()            # H2D + kernels + the collective + D2H of the merged pairs, one host wait
-        cd.ExecuteCollisionDetection()              # H2D + kernels + D2H of the colliding pairs
+        cd.ExecuteCollisionDetection()              # H2D + kernels (+ the collective) + D2H of the (merged) colliding pairs, one host wait
         return cd.results(want_hits=False)[0]
 
     def e2e_step_pageable():
+        # the headline: the caller's entries live in ordinary host arrays and are WRITTEN into the library's staging inside the timer
+        # (what AddCollisionDetectionEntry's push_back is to the reference); with N ranks each keeps, copies and uploads its share only
         cd.Reset()
         cd.add_entries(scene.matrices, mesh_ids, scene.should_callback, scene.entities, scene.previous)
-        if gather is not None:
-            return gather.execute_host()
         cd.ExecuteCollisionDetection()
         return cd.results(want_hits=False)[0]
 
@@ -358,14 +354,17 @@ def run_gpu_arm(args):
             tot += time.perf_counter() - t0
         return global_max(tot), out
 
-    e2e_s_max, res = time_e2e(e2e_step_pinned)
-    e2e_pageable_s, _ = time_e2e(e2e_step_pageable)
+    e2e_s_max, res = time_e2e(e2e_step_pageable)
+    if len(res) != int(coll_total):
+        raise SystemExit(f"bench.py: the end-to-end step returned {len(res)} records, the device-resident frame {int(coll_total)}")
+    e2e_pinned_s, _ = (time_e2e(e2e_step_pinned) if not multi else (None, None))
     clk = clocks.stop()
     e2e_value = tests_total * args.steps / e2e_s_max
     n_entries = scene.n_entries
-    h2d = n_entries * (64 + 4 + 4 + 1 + (64 if scene.previous is not None else 0))   # previous == current is not re-sent
-    # bytes that cross to the host per step: the pair records (+ the control block), or with N ranks the gathered fixed-capacity blocks
-    d2h = int(len(res)) * 80 + 1280 if gather is None else world * (gather.cap + 1) * 80 + 1280
+    n_local = int(cd.stats()["n_entries_local"])
+    h2d = n_local * (64 + 4 + 4 + 1 + (4 if multi else 0) + (64 if scene.previous is not None else 0))   # this rank's share; previous == current is not re-sent
+    # bytes that cross to the host per step: the control block + the (merged) pair records, copied speculatively with a 25 % margin
+    d2h = int(len(res) * 1.25 + 64) * 80 + 1280
 
     # ---- response stage: the same scene with every dynamic body moved since the last frame, so that the deltaVector of
     #      every colliding pair is computed (ShootUncollideRays.cpp:14-93); reported beside the headline, not inside it ----
@@ -373,6 +372,7 @@ def run_gpu_arm(args):
     prev = scene.matrices.copy()
     prev[ns_static:, 12:15] += (np.random.default_rng(1).normal(size=(scene.n_entries - ns_static, 3)) * 0.02).astype(np.float32)
     cd.Reset(); cd.add_entries(scene.matrices, mesh_ids, scene.should_callback, scene.entities, prev); cd.upload()
+    cd.run()                                              # settle the ray buffers
     for _ in range(args.warmup):
         l2_flush(); device_step()
     barrier()
@@ -402,7 +402,7 @@ def run_gpu_arm(args):
         r["peak_source"] = peaks["source"] if r["bound"] == "hbm" else "derived from sm_max_mhz (" + peaks["source"] + ")"
     dominant, other = (roof_trav, roof_narrow) if ms_trav >= ms_nar else (roof_narrow, roof_trav)
     prof = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(prof):
+    if os.path.exists(prof) and world == 1:          # the ncu capture is of the whole frame on one GPU; a 1/N shard has no measured figure
         try:
             tr = json.load(open(prof))
             for r in (dominant, other):
@@ -417,12 +417,15 @@ def run_gpu_arm(args):
         "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": desc, "entries": n_entries, "triangles_in_trees": n_tri_total, "bodies": args.bodies,
-                   "parallelism": f"broad-phase sweep chunks (entity x window slice) dealt round-robin to {world} GPUs; one end-of-frame NCCL gather" if world > 1 else "1 GPU",
+                   "parallelism": f"frame sharded by entity over {world} GPUs (flagged entries replicated, the others dealt in blocks of 256; each rank uploads, sorts and sweeps its share only); one end-of-frame ncclAllGather inside the library" if world > 1 else "1 GPU",
                    "l2": "flushed between timed steps (256 MiB write); inputs (~35 MB) would otherwise stay L2-resident",
                    "tree_build": "GPU Morton build (IMRCD_BUILD_MORTON)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_s_max / args.steps * 1e3, "inputs": "entries in pinned host memory (imrcd_frame_map_entries / commit_entries)",
-                "from_pageable_numpy": {"value": tests_total * args.steps / e2e_pageable_s, "ms_per_step": e2e_pageable_s / args.steps * 1e3}},
+                "ms_per_step": e2e_s_max / args.steps * 1e3,
+                "inputs": "entries in ordinary (pageable) host arrays; the timer covers writing them into the library's pinned staging (add_entries), H2D, kernels"
+                          + (", the NCCL merge" if multi else "") + " and D2H of the colliding pairs; bytes are per rank",
+                "entries_kept_per_rank": n_local,
+                "from_prefilled_pinned_staging": None if e2e_pinned_s is None else {"value": tests_total * args.steps / e2e_pinned_s, "ms_per_step": e2e_pinned_s / args.steps * 1e3}},
         "gpu_launches": int(launches),
         "clocks": clk,
         "roofline": dominant, "roofline_other": other, "response": response,

@@ -83,6 +83,8 @@ typedef struct {
     uint64_t n_rays_shot;       /* rays of the pairs whose entities moved: each goes through the Hermann passes of ShootUncollideRays.cpp:73-89 */
     uint64_t n_responses;       /* successful Hermann passes (entries of ray_responses, ShootUncollideRays.cpp:43,61) */
     float    ms_response;       /* device time of the response stage (part of ms_reduce) */
+    uint64_t n_merged;          /* colliding entity pairs of ALL ranks after the end-of-frame merge (== n_colliding without a communicator) */
+    uint64_t n_entries_local;   /* entries of the frame this context kept (== n_entries unless the frame is sharded) */
 } imrcd_frame_stats;
 
 /* ---- context ---------------------------------------------------------------------------- */
@@ -92,6 +94,9 @@ int  imrcd_create(int device, void* cuda_stream, imrcd_ctx** out);
 void imrcd_destroy(imrcd_ctx* ctx);
 const char* imrcd_last_error(const imrcd_ctx* ctx);
 const char* imrcd_version(void);
+/* sizeof(imrcd_entity_pair), sizeof(imrcd_tri_hit), sizeof(imrcd_frame_stats), then offsetof every imrcd_frame_stats field in declaration
+ * order, as the library was compiled; returns the number of values (out == NULL or capacity too small: only the count) */
+int imrcd_abi_layout(uint64_t* out, uint64_t capacity);
 
 /* ---- meshes: replaces OBBtree::OBBtree(std::vector<Triangle>&&) (OBBtree.cpp:321) --------- */
 /* positions/normals: n_tri*9 floats (p0,p1,p2 per triangle; normals may be NULL -> face normals,
@@ -173,9 +178,13 @@ int imrcd_frame_add_entries(imrcd_ctx* ctx, uint64_t n, const float* current, co
 int imrcd_frame_map_entries(imrcd_ctx* ctx, uint64_t n, float** current, float** previous, uint32_t** mesh_ids,
                             uint8_t** should_callback, uint32_t** entities);
 int imrcd_frame_commit_entries(imrcd_ctx* ctx, uint64_t n, int previous_valid);
-/* Multi-GPU: this context sweeps only every n_ranks-th chunk of the broad phase (chunk = one entity x 512 consecutive
- * candidates of its U window) and so keeps a disjoint 1/n_ranks slice of the pairs; the slices of ranks 0..n_ranks-1
- * add up to the full pair list.  Default (0,1) = everything. */
+/* Multi-GPU ("the broad-phase pair list sharded by entity"): this context is rank `rank` of `n_ranks` working on the same frame.
+ * Every rank is handed the WHOLE entry list (same calls, same order) and keeps its share: every entry with shouldCallback, and the
+ * entries without it in blocks of 256 caller indices dealt round-robin.  A pair needs the flag on one side (SweepAndPrune.cpp:60), so a
+ * pair with an unflagged entity lives on exactly one rank; a pair of two flagged entities is kept by one rank chosen from the pair.  The
+ * pair lists of ranks 0..n_ranks-1 are disjoint and add up to the unsharded list; entry indices in every result are the caller's.
+ * Only the kept entries are copied, uploaded, sorted and swept.  Takes effect for the next frame (at once when no entry has been added
+ * yet).  Default (0,1) = everything.  imrcd_comm_init sets it. */
 int imrcd_frame_set_shard(imrcd_ctx* ctx, uint32_t rank, uint32_t n_ranks);
 /* ExecuteCollisionDetection() = upload + run + fetch.  The three steps are exposed so that a caller
  * can time the device part with inputs already resident. */
@@ -188,9 +197,13 @@ int imrcd_frame_fetch(imrcd_ctx* ctx);    /* results -> pinned host memory */
  * counters and returns 0, or 1 when a buffer had overflowed and the frame was run again (work enqueued in between saw stale results). */
 int imrcd_frame_run_async(imrcd_ctx* ctx);
 int imrcd_frame_finish(imrcd_ctx* ctx);
-/* Results stay valid until the next imrcd_frame_reset / imrcd_frame_run. */
+/* Results stay valid until the next imrcd_frame_reset / imrcd_frame_run.  With a communicator (imrcd_comm_init, imrcd_group_create)
+ * `pairs` are the merged records of ALL ranks, in rank order; hits, imrcd_frame_pairs / _combos and the counters of the statistics stay
+ * this rank's own. */
 int imrcd_frame_results(imrcd_ctx* ctx, const imrcd_entity_pair** pairs, uint64_t* n_pairs,
                         const imrcd_tri_hit** hits, uint64_t* n_hits);
+/* this rank's own colliding pairs, whatever the communicator merged */
+int imrcd_frame_results_local(imrcd_ctx* ctx, const imrcd_entity_pair** pairs, uint64_t* n_pairs);
 /* Broad-phase pair list of this shard as (first,second) entry indices; host copy made on demand. */
 int imrcd_frame_pairs(imrcd_ctx* ctx, const uint32_t** pairs, uint64_t* n_pairs);
 /* Leaf combos (pair, offA, offB, cntA | cntB<<16) in leaf order; test/diagnostic, host copy on demand. */
@@ -202,6 +215,40 @@ int imrcd_frame_results_device(imrcd_ctx* ctx, void** d_pairs, uint64_t* n_pairs
 /* The same records as one contiguous device block for a fixed-capacity collective: row 0 (80 B) starts with the u64 record count, the
  * records follow from row 1; `capacity` = rows allocated after the header (rows past the count hold stale data). */
 int imrcd_frame_results_block(imrcd_ctx* ctx, void** d_block, uint64_t* n_pairs, uint64_t* capacity);
+
+/* ---- multi-GPU: the end-of-frame merge inside the library ----------------------------------------------------------------
+ * The reference is one host thread (CollisionDetection.cpp:44-129); its contract is that after ExecuteCollisionDetection the caller sees
+ * the whole colliding set.  Here N contexts (one per GPU) each work on their shard of the frame and ONE ncclAllGather of fixed-capacity
+ * blocks (header row = record count + overflow bits, then the 80-B records, as they lie in HBM) runs on the frame's own stream right
+ * behind its kernels, so imrcd_frame_run / _run_async + _finish / _execute return the merged set with a single host wait.  Whether a
+ * frame has to be run again (a buffer overflowed somewhere, or the blocks were too small) is decided from the gathered headers, i.e.
+ * identically on every rank.  NCCL is bound at run time (dlopen libnccl.so.2): without it these calls return IMRCD_E_NODEVICE and
+ * everything else works.
+ *   one process per GPU : rank 0 calls imrcd_comm_unique_id and hands the 128 bytes to the others (any transport), every rank calls
+ *                         imrcd_comm_init (collective);
+ *   one process, N GPUs : imrcd_group_create (what SURVEY 8b sketches as imrcd_create(device_ids[], n)): the engine is a single process. */
+#define IMRCD_COMM_ID_BYTES 128
+int imrcd_comm_unique_id(void* id_out /* IMRCD_COMM_ID_BYTES */);
+int imrcd_comm_init(imrcd_ctx* ctx, const void* id, uint32_t rank, uint32_t n_ranks);
+int imrcd_comm_destroy(imrcd_ctx* ctx);
+
+typedef struct imrcd_group imrcd_group;
+int         imrcd_group_create(const int* device_ids, uint32_t n, imrcd_group** out);
+void        imrcd_group_destroy(imrcd_group* g);
+uint32_t    imrcd_group_size(const imrcd_group* g);
+imrcd_ctx*  imrcd_group_ctx(imrcd_group* g, uint32_t i);           /* for per-context calls (statistics, tree export, ...) */
+const char* imrcd_group_last_error(const imrcd_group* g);
+/* meshes are replicated: the same id on every context of the group */
+int imrcd_group_mesh_create(imrcd_group* g, const float* positions, const float* normals, const uint32_t* vertex_ids, uint64_t n_tri,
+                            uint32_t build_mode, uint32_t* mesh_id);
+int imrcd_group_gltf_load(imrcd_group* g, const char* path, uint32_t build_mode, uint32_t* mesh_ids, uint32_t capacity, uint32_t* n_meshes);
+/* Reset / AddCollisionDetectionEntry / ExecuteCollisionDetection over all GPUs of the group; results = the merged colliding pairs */
+int imrcd_group_frame_reset(imrcd_group* g);
+int imrcd_group_frame_add_entry(imrcd_group* g, const float current[16], const float previous[16], uint32_t mesh_id, uint8_t should_callback, uint32_t entity);
+int imrcd_group_frame_add_entries(imrcd_group* g, uint64_t n, const float* current, const float* previous, const uint32_t* mesh_ids,
+                                  const uint8_t* should_callback, const uint32_t* entities);
+int imrcd_group_frame_execute(imrcd_group* g);
+int imrcd_group_frame_results(imrcd_group* g, const imrcd_entity_pair** pairs, uint64_t* n_pairs);
 
 /* ---- unit-level entry points used by the parity tests (device kernels on flat arrays) ---- */
 int imrcd_test_sat(imrcd_ctx* ctx, uint64_t n, const float* boxes_a, const float* boxes_b, const float* mats /* n*16 or NULL */,

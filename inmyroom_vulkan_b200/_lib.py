@@ -36,7 +36,8 @@ class FrameStats(C.Structure):
                 ("traverse_launches", C.c_uint64), ("total_launches", C.c_uint64), ("n_queue_items", C.c_uint64), ("n_warp_iterations", C.c_uint64), ("trav_busy_cycles", C.c_uint64), ("trav_idle_polls", C.c_uint64), ("ms_total", C.c_float), ("ms_broad", C.c_float),
                 ("ms_pair_setup", C.c_float), ("ms_traverse", C.c_float), ("ms_narrow", C.c_float), ("ms_reduce", C.c_float),
                 ("n_contact_pairs", C.c_uint64), ("n_rays", C.c_uint64),
-                ("n_rays_shot", C.c_uint64), ("n_responses", C.c_uint64), ("ms_response", C.c_float)]
+                ("n_rays_shot", C.c_uint64), ("n_responses", C.c_uint64), ("ms_response", C.c_float),
+                ("n_merged", C.c_uint64), ("n_entries_local", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -49,6 +50,7 @@ _SIGS = [
     ("imrcd_destroy", None, [_P]),
     ("imrcd_last_error", C.c_char_p, [_P]),
     ("imrcd_version", C.c_char_p, []),
+    ("imrcd_abi_layout", C.c_int, [C.POINTER(C.c_uint64), C.c_uint64]),
     ("imrcd_mesh_create", C.c_int, [_P, _P, _P, _P, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint32)]),
     ("imrcd_gltf_open", C.c_int, [C.c_char_p, C.POINTER(_P), C.c_char_p, C.c_uint64]),
     ("imrcd_gltf_close", None, [_P]),
@@ -85,6 +87,22 @@ _SIGS = [
     ("imrcd_frame_get_stats", C.c_int, [_P, C.POINTER(FrameStats)]),
     ("imrcd_frame_results_device", C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_uint64), C.POINTER(_P), C.POINTER(C.c_uint64)]),
     ("imrcd_frame_results_block", C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    ("imrcd_frame_results_local", C.c_int, [_P, C.POINTER(C.POINTER(EntityPair)), C.POINTER(C.c_uint64)]),
+    ("imrcd_comm_unique_id", C.c_int, [_P]),
+    ("imrcd_comm_init", C.c_int, [_P, _P, C.c_uint32, C.c_uint32]),
+    ("imrcd_comm_destroy", C.c_int, [_P]),
+    ("imrcd_group_create", C.c_int, [C.POINTER(C.c_int), C.c_uint32, C.POINTER(_P)]),
+    ("imrcd_group_destroy", None, [_P]),
+    ("imrcd_group_size", C.c_uint32, [_P]),
+    ("imrcd_group_ctx", _P, [_P, C.c_uint32]),
+    ("imrcd_group_last_error", C.c_char_p, [_P]),
+    ("imrcd_group_mesh_create", C.c_int, [_P, _P, _P, _P, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint32)]),
+    ("imrcd_group_gltf_load", C.c_int, [_P, C.c_char_p, C.c_uint32, C.POINTER(C.c_uint32), C.c_uint32, C.POINTER(C.c_uint32)]),
+    ("imrcd_group_frame_reset", C.c_int, [_P]),
+    ("imrcd_group_frame_add_entry", C.c_int, [_P, _P, _P, C.c_uint32, C.c_uint8, C.c_uint32]),
+    ("imrcd_group_frame_add_entries", C.c_int, [_P, C.c_uint64, _P, _P, _P, _P, _P]),
+    ("imrcd_group_frame_execute", C.c_int, [_P]),
+    ("imrcd_group_frame_results", C.c_int, [_P, C.POINTER(C.POINTER(EntityPair)), C.POINTER(C.c_uint64)]),
     ("imrcd_test_sat", C.c_int, [_P, C.c_uint64, _P, _P, _P, _P, _P, _P]),
     ("imrcd_test_tri_tri", C.c_int, [_P, C.c_uint64, _P, _P, _P, _P, _P]),
     ("imrcd_test_pair_matrix", C.c_int, [_P, C.c_uint64, _P, _P, _P]),

@@ -61,6 +61,20 @@ class Context:
             msg = self.lib.imrcd_last_error(self.h)
             raise ImrcdError(f"{_lib.ERRORS.get(rc, rc)}: {msg.decode() if msg else ''}")
 
+    # ---- multi-GPU: the end-of-frame merge lives in the library (imrcd_comm_*) ----------
+    def comm_unique_id(self) -> bytes:
+        buf = (C.c_uint8 * 128)()
+        self.check(self.lib.imrcd_comm_unique_id(buf))
+        return bytes(buf)
+
+    def comm_init(self, uid: bytes, rank: int, n_ranks: int):
+        """Collective over the ranks that share `uid` (one context per GPU); sets the frame shard to (rank, n_ranks)."""
+        raw = (C.c_uint8 * 128).from_buffer_copy(uid)
+        self.check(self.lib.imrcd_comm_init(self.h, raw, rank, n_ranks))
+
+    def comm_destroy(self):
+        self.check(self.lib.imrcd_comm_destroy(self.h))
+
     # ---- unit-level hooks ---------------------------------------------------------------
     def test_sat(self, boxes_a, boxes_b, mats=None):
         a = _c(boxes_a, np.float32).reshape(-1, 12); b = _c(boxes_b, np.float32).reshape(-1, 12)
@@ -315,6 +329,14 @@ class CollisionDetection:
             hits = np.zeros(0, HIT_DTYPE)
         return pairs, hits
 
+    def results_local(self) -> np.ndarray:
+        """This rank's own colliding pairs (results() gives the merged records of all ranks when the context has a communicator)."""
+        pp = C.POINTER(EntityPair)(); np_ = C.c_uint64()
+        self.ctx.check(self.lib.imrcd_frame_results_local(self.ctx.h, C.byref(pp), C.byref(np_)))
+        if not np_.value:
+            return np.zeros(0, PAIR_DTYPE)
+        return np.ctypeslib.as_array(C.cast(pp, C.POINTER(C.c_uint8)), shape=(np_.value * C.sizeof(EntityPair),)).copy().view(PAIR_DTYPE)
+
     def broad_pairs(self) -> np.ndarray:
         pp = C.POINTER(C.c_uint32)(); n = C.c_uint64()
         self.ctx.check(self.lib.imrcd_frame_pairs(self.ctx.h, C.byref(pp), C.byref(n)))
@@ -358,3 +380,63 @@ PAIR_DTYPE = np.dtype([("entry_first", "<u4"), ("entry_second", "<u4"), ("entity
 HIT_DTYPE = np.dtype([("pair", "<u4"), ("tri_first", "<u4"), ("tri_second", "<u4"), ("source", "<f4", 3), ("target", "<f4", 3),
                       ("weight", "<f4")])
 assert PAIR_DTYPE.itemsize == 80 and HIT_DTYPE.itemsize == 40
+
+
+class Group:
+    """One process, several GPUs (imrcd_group_*): meshes replicated, every frame sharded over the devices and merged by the library's
+    own NCCL all-gather; the calls mirror CollisionDetection's."""
+
+    def __init__(self, device_ids: Sequence[int]):
+        self.lib = _lib.load()
+        ids = (C.c_int * len(device_ids))(*[int(d) for d in device_ids])
+        h = C.c_void_p()
+        rc = self.lib.imrcd_group_create(ids, len(device_ids), C.byref(h))
+        if rc != 0:
+            raise ImrcdError(f"imrcd_group_create({list(device_ids)}) failed: {_lib.ERRORS.get(rc, rc)}")
+        self.h = h
+        self.n = len(device_ids)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.imrcd_group_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc: int):
+        if rc != 0:
+            msg = self.lib.imrcd_group_last_error(self.h)
+            raise ImrcdError(f"{_lib.ERRORS.get(rc, rc)}: {msg.decode() if msg else ''}")
+
+    def mesh_create(self, positions, normals=None, vertex_ids=None, build_mode: int = IMRCD_BUILD_MORTON) -> int:
+        pos = _c(positions, np.float32).reshape(-1, 9)
+        nrm = None if normals is None else _c(normals, np.float32).reshape(-1, 9)
+        vid = None if vertex_ids is None else _c(vertex_ids, np.uint32).reshape(-1, 3)
+        mid = C.c_uint32()
+        self.check(self.lib.imrcd_group_mesh_create(self.h, _ptr(pos), _ptr(nrm), _ptr(vid), pos.shape[0], build_mode, C.byref(mid)))
+        return mid.value
+
+    def Reset(self):
+        self.check(self.lib.imrcd_group_frame_reset(self.h))
+
+    def add_entries(self, matrices, mesh_ids, should_callback=None, entities=None, previous=None):
+        m = _c(matrices, np.float32).reshape(-1, 16); n = m.shape[0]
+        p = None if previous is None else _c(previous, np.float32).reshape(-1, 16)
+        mid = _c(mesh_ids, np.uint32).reshape(n)
+        cb = None if should_callback is None else _c(should_callback, np.uint8).reshape(n)
+        ent = None if entities is None else _c(entities, np.uint32).reshape(n)
+        self.check(self.lib.imrcd_group_frame_add_entries(self.h, n, _ptr(m), _ptr(p), _ptr(mid), _ptr(cb), _ptr(ent)))
+
+    def ExecuteCollisionDetection(self):
+        self.check(self.lib.imrcd_group_frame_execute(self.h))
+
+    def results(self) -> np.ndarray:
+        pp = C.POINTER(EntityPair)(); np_ = C.c_uint64()
+        self.check(self.lib.imrcd_group_frame_results(self.h, C.byref(pp), C.byref(np_)))
+        if not np_.value:
+            return np.zeros(0, PAIR_DTYPE)
+        return np.ctypeslib.as_array(C.cast(pp, C.POINTER(C.c_uint8)), shape=(np_.value * C.sizeof(EntityPair),)).copy().view(PAIR_DTYPE)

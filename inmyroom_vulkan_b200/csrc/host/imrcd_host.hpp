@@ -40,7 +40,14 @@ public:
         const int rc = imrcd_create(device, cuda_stream, &ctx_);
         if (rc != IMRCD_OK) throw std::runtime_error("imrcd_create failed (" + std::to_string(rc) + "): there is no CPU fallback");
     }
-    ~CollisionDetectionT() { imrcd_destroy(ctx_); }
+    // several GPUs of this process (imrcd_group_*): meshes replicated, every frame sharded by entity over the devices, the colliding
+    // pairs merged by the library's end-of-frame NCCL all-gather; the interface stays the engine's
+    CollisionDetectionT(EcsPolicy* ecs, const std::vector<int>& devices) : ecs_(ecs) {
+        const int rc = imrcd_group_create(devices.data(), static_cast<uint32_t>(devices.size()), &group_);
+        if (rc != IMRCD_OK) throw std::runtime_error("imrcd_group_create failed (" + std::to_string(rc) + "): there is no CPU fallback");
+        ctx_ = imrcd_group_ctx(group_, 0);
+    }
+    ~CollisionDetectionT() { if (group_) imrcd_group_destroy(group_); else imrcd_destroy(ctx_); }
     CollisionDetectionT(const CollisionDetectionT&) = delete;
     CollisionDetectionT& operator=(const CollisionDetectionT&) = delete;
 
@@ -50,20 +57,21 @@ public:
     uint32_t CreateOBBtree(const float* positions, const float* normals, const uint32_t* vertex_ids, uint64_t n_tri,
                            uint32_t build_mode = IMRCD_BUILD_MORTON) {
         uint32_t id = 0;
-        check(imrcd_mesh_create(ctx_, positions, normals, vertex_ids, n_tri, build_mode, &id));
+        if (group_) gcheck(imrcd_group_mesh_create(group_, positions, normals, vertex_ids, n_tri, build_mode, &id));
+        else check(imrcd_mesh_create(ctx_, positions, normals, vertex_ids, n_tri, build_mode, &id));
         return id;
     }
 
     // the engine's own route, PrimitivesOfMeshes::StartRecordOBBtree / one PrimitiveOBBtreeData per primitive / GetOBBtreeAndReset
     // (IMR/src/Graphics/Meshes/PrimitivesOfMeshes.cpp:637-671,835-863): Triangle::CreateTriangleList runs on the device.
     // points / normals: n_points * stride floats (stride 4 = the engine's vec4 arrays), indices may be null, draw_mode = glTFmode.
-    void StartRecordOBBtree() { check(imrcd_mesh_begin(ctx_)); }
+    void StartRecordOBBtree() { for (uint32_t i = 0; i < n_ctx(); ++i) check_on(ctx_at(i), imrcd_mesh_begin(ctx_at(i))); }
     void RecordPrimitive(const float* points, uint64_t n_points, uint32_t stride, const float* normals, const uint32_t* indices, uint64_t n_indices, uint32_t draw_mode) {
-        check(imrcd_mesh_add_primitive(ctx_, points, n_points, stride, normals, indices, n_indices, draw_mode));
+        for (uint32_t i = 0; i < n_ctx(); ++i) check_on(ctx_at(i), imrcd_mesh_add_primitive(ctx_at(i), points, n_points, stride, normals, indices, n_indices, draw_mode));
     }
     uint32_t GetOBBtreeAndReset(uint32_t build_mode = IMRCD_BUILD_MORTON) {
         uint32_t id = 0;
-        check(imrcd_mesh_end(ctx_, build_mode, &id));
+        for (uint32_t i = 0; i < n_ctx(); ++i) check_on(ctx_at(i), imrcd_mesh_end(ctx_at(i), build_mode, &id));      // the same id on every GPU
         return id;
     }
 
@@ -73,12 +81,13 @@ public:
         uint32_t n = 0;
         check(imrcd_gltf_load(ctx_, path.c_str(), build_mode, nullptr, 0, &n));
         std::vector<uint32_t> ids(n);
-        if (n) check(imrcd_gltf_load(ctx_, path.c_str(), build_mode, ids.data(), n, &n));
+        if (n && group_) gcheck(imrcd_group_gltf_load(group_, path.c_str(), build_mode, ids.data(), n, &n));
+        else if (n) check(imrcd_gltf_load(ctx_, path.c_str(), build_mode, ids.data(), n, &n));
         return ids;
     }
 
     void Reset() {                                                       // CollisionDetection.cpp:28
-        check(imrcd_frame_reset(ctx_));
+        if (group_) gcheck(imrcd_group_frame_reset(group_)); else check(imrcd_frame_reset(ctx_));
         n_ = 0; mapped_ = 0; pending_ = 0; any_previous_ = false;
     }
 
@@ -98,9 +107,9 @@ public:
     void ExecuteCollisionDetection() {                                   // CollisionDetection.cpp:38-129
         if (n_ < 2) return;                                              // :40
         commit();
-        check(imrcd_frame_execute(ctx_));
+        if (group_) gcheck(imrcd_group_frame_execute(group_)); else check(imrcd_frame_execute(ctx_));
         const imrcd_entity_pair* pairs = nullptr; uint64_t n_pairs = 0;
-        check(imrcd_frame_results(ctx_, &pairs, &n_pairs, nullptr, nullptr));
+        check(imrcd_frame_results(ctx_, &pairs, &n_pairs, nullptr, nullptr));          // with a group: the merged pairs of all GPUs
         if (!ecs_) return;
         std::unordered_map<EntityT, std::vector<Callback>> to_make;
         for (uint64_t k = 0; k < n_pairs; ++k) {
@@ -129,18 +138,29 @@ private:
     static constexpr uint64_t kBatch = 4096;       // entries mapped at a time (each batch's DMA starts at its commit)
 
     void check(int rc) { if (rc != IMRCD_OK) throw std::runtime_error(std::string("imrcd: ") + imrcd_last_error(ctx_)); }
+    void check_on(imrcd_ctx* c, int rc) { if (rc != IMRCD_OK) throw std::runtime_error(std::string("imrcd: ") + imrcd_last_error(c)); }
+    void gcheck(int rc) { if (rc != IMRCD_OK) throw std::runtime_error(std::string("imrcd: ") + imrcd_group_last_error(group_)); }
+    uint32_t n_ctx() const { return group_ ? imrcd_group_size(group_) : 1u; }
+    imrcd_ctx* ctx_at(uint32_t i) const { return group_ ? imrcd_group_ctx(group_, i) : ctx_; }
     void commit() {
-        if (pending_) { check(imrcd_frame_commit_entries(ctx_, pending_, any_previous_ ? 1 : 0)); }
+        if (pending_ && group_)        // every GPU of the group is handed the batch and keeps its share
+            gcheck(imrcd_group_frame_add_entries(group_, pending_, cur_, any_previous_ ? prev_ : nullptr, mesh_, cb_, ent_));
+        else if (pending_) check(imrcd_frame_commit_entries(ctx_, pending_, any_previous_ ? 1 : 0));
         pending_ = 0; mapped_ = 0; any_previous_ = false;
     }
     void flush_and_map() {
         commit();
-        check(imrcd_frame_map_entries(ctx_, kBatch, &cur_, &prev_, &mesh_, &cb_, &ent_));
+        if (group_) {
+            g_cur_.resize(16 * kBatch); g_prev_.resize(16 * kBatch); g_mesh_.resize(kBatch); g_cb_.resize(kBatch); g_ent_.resize(kBatch);
+            cur_ = g_cur_.data(); prev_ = g_prev_.data(); mesh_ = g_mesh_.data(); cb_ = g_cb_.data(); ent_ = g_ent_.data();
+        } else check(imrcd_frame_map_entries(ctx_, kBatch, &cur_, &prev_, &mesh_, &cb_, &ent_));
         mapped_ = kBatch;
     }
 
     EcsPolicy* ecs_ = nullptr;
     imrcd_ctx* ctx_ = nullptr;
+    imrcd_group* group_ = nullptr;
+    std::vector<float> g_cur_, g_prev_; std::vector<uint32_t> g_mesh_, g_ent_; std::vector<uint8_t> g_cb_;      // group mode: the batch being written
     uint64_t n_ = 0, mapped_ = 0, pending_ = 0;
     bool any_previous_ = false;
     float* cur_ = nullptr; float* prev_ = nullptr; uint32_t* mesh_ = nullptr; uint8_t* cb_ = nullptr; uint32_t* ent_ = nullptr;

@@ -2,6 +2,7 @@
 // mesh arena (import / export), frame entry list, upload / run / fetch, and the unit-level test hooks.
 #include "imrcd_internal.cuh"
 #include <algorithm>
+#include <cstddef>
 #include <cstring>
 #include <deque>
 
@@ -12,6 +13,23 @@ static_assert(sizeof(TreeRec) == 64 && sizeof(TriRec) == 64 && sizeof(PairRec) =
 #define CHECK_CTX(ctx) do { if (!(ctx)) return IMRCD_E_ARG; } while (0)
 
 extern "C" const char* imrcd_version(void) { return "imrcd 0.1 (sm_100a, fmad=false)"; }
+
+// sizes and offsets of the ABI's structs as this library was compiled: a binding checks its own mirror against them (tests/test_abi.py)
+extern "C" int imrcd_abi_layout(uint64_t* out, uint64_t capacity) {
+    const uint64_t v[] = { sizeof(imrcd_entity_pair), sizeof(imrcd_tri_hit), sizeof(imrcd_frame_stats),
+                           offsetof(imrcd_frame_stats, n_entries), offsetof(imrcd_frame_stats, n_pairs), offsetof(imrcd_frame_stats, n_sat_tests), offsetof(imrcd_frame_stats, n_combos),
+                           offsetof(imrcd_frame_stats, n_tri_tests), offsetof(imrcd_frame_stats, n_hits), offsetof(imrcd_frame_stats, n_coplanar_hits), offsetof(imrcd_frame_stats, n_colliding),
+                           offsetof(imrcd_frame_stats, traverse_launches), offsetof(imrcd_frame_stats, total_launches), offsetof(imrcd_frame_stats, n_queue_items),
+                           offsetof(imrcd_frame_stats, n_warp_iterations), offsetof(imrcd_frame_stats, trav_busy_cycles), offsetof(imrcd_frame_stats, trav_idle_polls),
+                           offsetof(imrcd_frame_stats, ms_total), offsetof(imrcd_frame_stats, ms_broad), offsetof(imrcd_frame_stats, ms_pair_setup), offsetof(imrcd_frame_stats, ms_traverse),
+                           offsetof(imrcd_frame_stats, ms_narrow), offsetof(imrcd_frame_stats, ms_reduce), offsetof(imrcd_frame_stats, n_contact_pairs), offsetof(imrcd_frame_stats, n_rays),
+                           offsetof(imrcd_frame_stats, n_rays_shot), offsetof(imrcd_frame_stats, n_responses), offsetof(imrcd_frame_stats, ms_response), offsetof(imrcd_frame_stats, n_merged),
+                           offsetof(imrcd_frame_stats, n_entries_local) };
+    const uint64_t n = sizeof(v) / sizeof(v[0]);
+    if (!out || capacity < n) return (int)n;
+    for (uint64_t i = 0; i < n; ++i) out[i] = v[i];
+    return (int)n;
+}
 
 extern "C" const char* imrcd_last_error(const imrcd_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
@@ -40,16 +58,17 @@ extern "C" int imrcd_create(int device, void* cuda_stream, imrcd_ctx** out) {
 
 static void recording_clear(imrcd_ctx* ctx);
 extern "C" void imrcd_destroy(imrcd_ctx* ctx) {
-    if (ctx) recording_clear(ctx);
     if (!ctx) return;
+    recording_clear(ctx);
+    imrcd_comm_destroy(ctx);
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = { &ctx->d_recs, &ctx->d_tris, &ctx->d_tri_nrm, &ctx->d_tri_vid, &ctx->d_meshes, &ctx->d_rf_stage, &ctx->d_rf_segs, &ctx->d_rf_scratch, &ctx->d_cur, &ctx->d_prev, &ctx->d_mesh,
                        &ctx->d_cb, &ctx->d_entity, &ctx->d_inv, &ctx->d_ext, &ctx->d_keys, &ctx->d_keys2, &ctx->d_idx, &ctx->d_idx2,
                        &ctx->d_sorted, &ctx->d_sorted_c, &ctx->d_flag, &ctx->d_cpos, &ctx->d_wlen, &ctx->d_chunks, &ctx->d_chunkoff, &ctx->d_cubtmp, &ctx->d_pairs, &ctx->d_pairrec, &ctx->d_pairacc, &ctx->d_queue, &ctx->d_combos,
-                       &ctx->d_hits, &ctx->d_epairs, &ctx->d_ctl, &ctx->d_aux, &ctx->d_grouped, &ctx->d_lscratch, &ctx->d_lpref, &ctx->d_lsides, &ctx->d_rays, &ctx->d_resp, &ctx->d_epair_pair, &ctx->d_padded, &ctx->d_padoff, &ctx->d_lsmall, &ctx->d_lmid, &ctx->d_llarge };
+                       &ctx->d_hits, &ctx->d_epairs, &ctx->d_ctl, &ctx->d_aux, &ctx->d_grouped, &ctx->d_lscratch, &ctx->d_lpref, &ctx->d_lsides, &ctx->d_rays, &ctx->d_resp, &ctx->d_epair_pair, &ctx->d_gidx, &ctx->d_gather, &ctx->d_padded, &ctx->d_padoff, &ctx->d_lsmall, &ctx->d_lmid, &ctx->d_llarge };
     for (DevBuf* b : bufs) b->release();
-    PinBuf* pins[] = { &ctx->p_cur, &ctx->p_prev, &ctx->p_mesh, &ctx->p_entity, &ctx->p_cb, &ctx->p_ctl, &ctx->p_epairs, &ctx->p_hits, &ctx->p_pairs, &ctx->p_combos };
+    PinBuf* pins[] = { &ctx->p_gidx, &ctx->p_gather, &ctx->p_cur, &ctx->p_prev, &ctx->p_mesh, &ctx->p_entity, &ctx->p_cb, &ctx->p_ctl, &ctx->p_epairs, &ctx->p_hits, &ctx->p_pairs, &ctx->p_combos };
     for (PinBuf* b : pins) b->release();
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
@@ -359,11 +378,20 @@ extern "C" int imrcd_mesh_export_tree(imrcd_ctx* ctx, uint32_t mesh_id, float* b
 extern "C" int imrcd_frame_reset(imrcd_ctx* ctx) {
     CHECK_CTX(ctx);
     ctx->n_entries = 0; ctx->n_sent = 0; ctx->prev_distinct = false;
-    ctx->uploaded = ctx->ran = ctx->fetched = false;
+    ctx->n_entries_global = 0; ctx->n_flagged_global = 0;
+    ctx->shard_rank = ctx->shard_rank_next; ctx->shard_n = ctx->shard_n_next;
+    ctx->uploaded = ctx->ran = ctx->fetched = false; ctx->merged_valid = false;
     return IMRCD_OK;
 }
 
 #define ENTRY_CHUNK 16384u     // entries per H2D chunk of the pipelined upload (1 MiB of matrices)
+#define SHARD_BLOCK 256u       // sharded frames: entries without shouldCallback are dealt to the ranks in blocks of this many caller indices
+
+// Sharded frames (imrcd_frame_set_shard, SURVEY 8e "sharded by entity").  A pair needs shouldCallback on one side at least
+// (SweepAndPrune.cpp:60), so entries WITH the flag go to every rank and entries WITHOUT it to exactly one: a pair with an unflagged entity is
+// found by the rank that owns that entity, a pair of two flagged entities by one rank picked from the pair itself (k_sweep).  Every rank is
+// handed the whole entry list and keeps its share, in the caller's order, with the caller's index of every kept entry (gidx).
+static inline bool shard_owns(const imrcd_ctx* ctx, uint64_t g) { return (g / SHARD_BLOCK) % ctx->shard_n == ctx->shard_rank; }
 
 // enqueue the H2D copies of entries [n_sent, upto)
 static int entries_send(imrcd_ctx* ctx, uint64_t upto) {
@@ -375,50 +403,8 @@ static int entries_send(imrcd_ctx* ctx, uint64_t upto) {
     IMR_CUDA(ctx, cudaMemcpyAsync(ctx->d_mesh.as<char>() + 4 * a, ctx->p_mesh.as<char>() + 4 * a, 4 * k, cudaMemcpyHostToDevice, s));
     IMR_CUDA(ctx, cudaMemcpyAsync(ctx->d_entity.as<char>() + 4 * a, ctx->p_entity.as<char>() + 4 * a, 4 * k, cudaMemcpyHostToDevice, s));
     IMR_CUDA(ctx, cudaMemcpyAsync(ctx->d_cb.as<char>() + a, ctx->p_cb.as<char>() + a, k, cudaMemcpyHostToDevice, s));
+    if (ctx->shard_n > 1) IMR_CUDA(ctx, cudaMemcpyAsync(ctx->d_gidx.as<char>() + 4 * a, ctx->p_gidx.as<char>() + 4 * a, 4 * k, cudaMemcpyHostToDevice, s));
     ctx->n_sent = upto;
-    return IMRCD_OK;
-}
-
-extern "C" int imrcd_frame_add_entries(imrcd_ctx* ctx, uint64_t n, const float* current, const float* previous,
-                                       const uint32_t* mesh_ids, const uint8_t* should_callback, const uint32_t* entities) {
-    CHECK_CTX(ctx);
-    if (n && (!current || !mesh_ids)) { ctx->err = "imrcd_frame_add_entries: bad argument"; return IMRCD_E_ARG; }
-    const uint32_t n_meshes = (uint32_t)ctx->meshes.size();
-    const uint64_t base = ctx->n_entries, total = base + n;
-    if (total >= (1ull << 32) - 1) { ctx->err = "too many entries"; return IMRCD_E_ARG; }
-    if (n == 0) return IMRCD_OK;
-    cudaSetDevice(ctx->device);
-    cudaStream_t s = ctx->stream;
-    IMR_CUDA(ctx, ctx->p_cur.reserve(64 * total, 64 * base, s));
-    IMR_CUDA(ctx, ctx->p_prev.reserve(64 * total, 64 * base, s));
-    IMR_CUDA(ctx, ctx->p_mesh.reserve(4 * total, 4 * base, s));
-    IMR_CUDA(ctx, ctx->p_entity.reserve(4 * total, 4 * base, s));
-    IMR_CUDA(ctx, ctx->p_cb.reserve(total, base, s));
-    const bool bulk = n >= ENTRY_CHUNK / 4;      // single entries (the reference's call pattern) are sent by imrcd_frame_upload
-    if (bulk) {
-        IMR_CUDA(ctx, ctx->d_cur.reserve(64 * total, 64 * ctx->n_sent, s));
-        IMR_CUDA(ctx, ctx->d_mesh.reserve(4 * total, 4 * ctx->n_sent, s));
-        IMR_CUDA(ctx, ctx->d_entity.reserve(4 * total, 4 * ctx->n_sent, s));
-        IMR_CUDA(ctx, ctx->d_cb.reserve(total, ctx->n_sent, s));
-    }
-    float* pc = ctx->p_cur.as<float>(); float* pp = ctx->p_prev.as<float>();
-    uint32_t* pm = ctx->p_mesh.as<uint32_t>(); uint32_t* pe = ctx->p_entity.as<uint32_t>(); uint8_t* pb = ctx->p_cb.as<uint8_t>();
-    for (uint64_t c0 = 0; c0 < n; c0 += ENTRY_CHUNK) {
-        const uint64_t c1 = std::min<uint64_t>(n, c0 + ENTRY_CHUNK), k = c1 - c0, at = base + c0;
-        for (uint64_t i = c0; i < c1; ++i) if (mesh_ids[i] >= n_meshes) { ctx->err = "imrcd_frame_add_entries: unknown mesh id"; return IMRCD_E_ARG; }
-        memcpy(pc + 16 * at, current + 16 * c0, 64 * k);
-        if (previous && previous != current) {
-            if (!ctx->prev_distinct && at) memcpy(pp, pc, 64 * at);      // earlier entries of this frame had previous == current
-            memcpy(pp + 16 * at, previous + 16 * c0, 64 * k); ctx->prev_distinct = true;
-        }
-        else if (ctx->prev_distinct) memcpy(pp + 16 * at, current + 16 * c0, 64 * k);
-        memcpy(pm + at, mesh_ids + c0, 4 * k);
-        if (entities) memcpy(pe + at, entities + c0, 4 * k); else for (uint64_t i = 0; i < k; ++i) pe[at + i] = (uint32_t)(at + i);
-        if (should_callback) for (uint64_t i = 0; i < k; ++i) pb[at + i] = should_callback[c0 + i] ? 1 : 0; else memset(pb + at, 1, k);
-        ctx->n_entries = at + k;
-        if (bulk) { int rc = entries_send(ctx, ctx->n_entries); if (rc) return rc; }
-    }
-    ctx->uploaded = ctx->ran = ctx->fetched = false;
     return IMRCD_OK;
 }
 
@@ -430,12 +416,88 @@ static int entries_reserve(imrcd_ctx* ctx, uint64_t total, bool device_too) {
     IMR_CUDA(ctx, ctx->p_mesh.reserve(4 * total, 4 * base, s));
     IMR_CUDA(ctx, ctx->p_entity.reserve(4 * total, 4 * base, s));
     IMR_CUDA(ctx, ctx->p_cb.reserve(total, base, s));
+    if (ctx->shard_n > 1) IMR_CUDA(ctx, ctx->p_gidx.reserve(4 * total, 4 * base, s));
     if (device_too) {
         IMR_CUDA(ctx, ctx->d_cur.reserve(64 * total, 64 * ctx->n_sent, s));
         IMR_CUDA(ctx, ctx->d_mesh.reserve(4 * total, 4 * ctx->n_sent, s));
         IMR_CUDA(ctx, ctx->d_entity.reserve(4 * total, 4 * ctx->n_sent, s));
         IMR_CUDA(ctx, ctx->d_cb.reserve(total, ctx->n_sent, s));
+        if (ctx->shard_n > 1) IMR_CUDA(ctx, ctx->d_gidx.reserve(4 * total, 4 * ctx->n_sent, s));
     }
+    return IMRCD_OK;
+}
+
+// copy k consecutive caller entries, starting at i of the call's arrays (caller index g0 + i), behind the entries kept so far
+static void entries_append_run(imrcd_ctx* ctx, uint64_t i, uint64_t k, uint64_t g0, const float* current, const float* previous,
+                               const uint32_t* mesh_ids, const uint8_t* should_callback, const uint32_t* entities) {
+    float* pc = ctx->p_cur.as<float>(); float* pp = ctx->p_prev.as<float>();
+    uint32_t* pm = ctx->p_mesh.as<uint32_t>(); uint32_t* pe = ctx->p_entity.as<uint32_t>(); uint8_t* pb = ctx->p_cb.as<uint8_t>();
+    const uint64_t at = ctx->n_entries;
+    memcpy(pc + 16 * at, current + 16 * i, 64 * k);
+    if (previous && previous != current) {
+        if (!ctx->prev_distinct && at) memcpy(pp, pc, 64 * at);      // earlier entries of this frame had previous == current
+        memcpy(pp + 16 * at, previous + 16 * i, 64 * k); ctx->prev_distinct = true;
+    }
+    else if (ctx->prev_distinct) memcpy(pp + 16 * at, current + 16 * i, 64 * k);
+    memcpy(pm + at, mesh_ids + i, 4 * k);
+    if (entities) memcpy(pe + at, entities + i, 4 * k); else for (uint64_t q = 0; q < k; ++q) pe[at + q] = (uint32_t)(g0 + i + q);
+    if (should_callback) for (uint64_t q = 0; q < k; ++q) pb[at + q] = should_callback[i + q] ? 1 : 0; else memset(pb + at, 1, k);
+    if (ctx->shard_n > 1) { uint32_t* pg = ctx->p_gidx.as<uint32_t>(); for (uint64_t q = 0; q < k; ++q) pg[at + q] = (uint32_t)(g0 + i + q); }
+    ctx->n_entries = at + k;
+}
+
+extern "C" int imrcd_frame_add_entries(imrcd_ctx* ctx, uint64_t n, const float* current, const float* previous,
+                                       const uint32_t* mesh_ids, const uint8_t* should_callback, const uint32_t* entities) {
+    CHECK_CTX(ctx);
+    if (n && (!current || !mesh_ids)) { ctx->err = "imrcd_frame_add_entries: bad argument"; return IMRCD_E_ARG; }
+    const uint32_t n_meshes = (uint32_t)ctx->meshes.size();
+    const uint64_t g0 = ctx->n_entries_global;
+    if (g0 + n >= (1ull << 32) - 1) { ctx->err = "too many entries"; return IMRCD_E_ARG; }
+    if (n == 0) return IMRCD_OK;
+    for (uint64_t i = 0; i < n; ++i) if (mesh_ids[i] >= n_meshes) { ctx->err = "imrcd_frame_add_entries: unknown mesh id"; return IMRCD_E_ARG; }
+    cudaSetDevice(ctx->device);
+    const bool sharded = ctx->shard_n > 1;
+    const bool bulk = n >= ENTRY_CHUNK / 4;      // single entries (the reference's call pattern) are sent by imrcd_frame_upload
+    uint64_t n_flagged = 0;
+    if (!sharded) {
+        int rc = entries_reserve(ctx, ctx->n_entries + n, bulk);
+        if (rc) return rc;
+        for (uint64_t c0 = 0; c0 < n; c0 += ENTRY_CHUNK) {       // chunks: the DMA of one runs while the next is being written
+            const uint64_t k = std::min<uint64_t>(n, c0 + ENTRY_CHUNK) - c0;
+            entries_append_run(ctx, c0, k, g0, current, previous, mesh_ids, should_callback, entities);
+            if (bulk) { rc = entries_send(ctx, ctx->n_entries); if (rc) return rc; }
+        }
+        if (should_callback) for (uint64_t i = 0; i < n; ++i) n_flagged += should_callback[i] ? 1 : 0; else n_flagged = n;
+    } else {
+        // count what this rank keeps, reserve once, then copy run by run: whole blocks it owns, and the flagged entries of the other blocks
+        uint64_t keep = 0;
+        for (uint64_t i = 0; i < n; ) {
+            const uint64_t g = g0 + i, blk_end = std::min<uint64_t>(n, i + (SHARD_BLOCK - g % SHARD_BLOCK));
+            uint64_t f = 0;
+            if (should_callback) for (uint64_t q = i; q < blk_end; ++q) f += should_callback[q] ? 1 : 0; else f = blk_end - i;
+            n_flagged += f;
+            keep += shard_owns(ctx, g) ? blk_end - i : f;
+            i = blk_end;
+        }
+        int rc = entries_reserve(ctx, ctx->n_entries + keep, bulk);
+        if (rc) return rc;
+        for (uint64_t i = 0; i < n; ) {
+            const uint64_t g = g0 + i, blk_end = std::min<uint64_t>(n, i + (SHARD_BLOCK - g % SHARD_BLOCK));
+            if (shard_owns(ctx, g)) entries_append_run(ctx, i, blk_end - i, g0, current, previous, mesh_ids, should_callback, entities);
+            else for (uint64_t q = i; q < blk_end; ++q) {
+                if (should_callback && !should_callback[q]) continue;
+                uint64_t r = q + 1;
+                while (r < blk_end && (!should_callback || should_callback[r])) ++r;
+                entries_append_run(ctx, q, r - q, g0, current, previous, mesh_ids, should_callback, entities);
+                q = r - 1;
+            }
+            i = blk_end;
+            if (bulk && ctx->n_entries - ctx->n_sent >= ENTRY_CHUNK) { rc = entries_send(ctx, ctx->n_entries); if (rc) return rc; }
+        }
+        if (bulk) { rc = entries_send(ctx, ctx->n_entries); if (rc) return rc; }
+    }
+    ctx->n_entries_global = g0 + n; ctx->n_flagged_global += n_flagged;
+    ctx->uploaded = ctx->ran = ctx->fetched = false;
     return IMRCD_OK;
 }
 
@@ -443,7 +505,7 @@ extern "C" int imrcd_frame_map_entries(imrcd_ctx* ctx, uint64_t n, float** curre
                                        uint8_t** should_callback, uint32_t** entities) {
     CHECK_CTX(ctx);
     const uint64_t base = ctx->n_entries, total = base + n;
-    if (total >= (1ull << 32) - 1) { ctx->err = "too many entries"; return IMRCD_E_ARG; }
+    if (ctx->n_entries_global + n >= (1ull << 32) - 1) { ctx->err = "too many entries"; return IMRCD_E_ARG; }
     cudaSetDevice(ctx->device);
     int rc = entries_reserve(ctx, total ? total : 1, false);
     if (rc) return rc;
@@ -457,22 +519,37 @@ extern "C" int imrcd_frame_map_entries(imrcd_ctx* ctx, uint64_t n, float** curre
 
 extern "C" int imrcd_frame_commit_entries(imrcd_ctx* ctx, uint64_t n, int previous_valid) {
     CHECK_CTX(ctx);
-    const uint64_t base = ctx->n_entries, total = base + n;
-    if (64 * total > ctx->p_cur.cap) { ctx->err = "imrcd_frame_commit_entries: more entries than were mapped"; return IMRCD_E_STATE; }
+    const uint64_t base = ctx->n_entries, g0 = ctx->n_entries_global;
+    if (64 * (base + n) > ctx->p_cur.cap) { ctx->err = "imrcd_frame_commit_entries: more entries than were mapped"; return IMRCD_E_STATE; }
     if (n == 0) return IMRCD_OK;
     cudaSetDevice(ctx->device);
     const uint32_t n_meshes = (uint32_t)ctx->meshes.size();
-    const uint32_t* pm = ctx->p_mesh.as<uint32_t>();
-    for (uint64_t i = base; i < total; ++i) if (pm[i] >= n_meshes) { ctx->err = "imrcd_frame_commit_entries: unknown mesh id"; return IMRCD_E_ARG; }
+    uint32_t* pm = ctx->p_mesh.as<uint32_t>(); uint8_t* pb = ctx->p_cb.as<uint8_t>();
+    for (uint64_t i = base; i < base + n; ++i) if (pm[i] >= n_meshes) { ctx->err = "imrcd_frame_commit_entries: unknown mesh id"; return IMRCD_E_ARG; }
     if (previous_valid) {
         if (!ctx->prev_distinct && base) memcpy(ctx->p_prev.p, ctx->p_cur.p, 64 * base);
         ctx->prev_distinct = true;
     } else if (ctx->prev_distinct) memcpy(ctx->p_prev.as<char>() + 64 * base, ctx->p_cur.as<char>() + 64 * base, 64 * n);
-    int rc = entries_reserve(ctx, total, true);
+    uint64_t n_flagged = 0, kept = n;
+    for (uint64_t i = base; i < base + n; ++i) n_flagged += pb[i] ? 1 : 0;
+    if (ctx->shard_n > 1) {
+        // the caller wrote all n entries; keep this rank's share by compacting the staging in place (destinations never pass sources)
+        char* pc = ctx->p_cur.as<char>(); char* pp = ctx->p_prev.as<char>(); uint32_t* pe = ctx->p_entity.as<uint32_t>(); uint32_t* pg = ctx->p_gidx.as<uint32_t>();
+        uint64_t w = base;
+        for (uint64_t i = 0; i < n; ++i) {
+            const uint64_t r = base + i;
+            if (!(pb[r] || shard_owns(ctx, g0 + i))) continue;
+            if (w != r) { memmove(pc + 64 * w, pc + 64 * r, 64); if (ctx->prev_distinct) memmove(pp + 64 * w, pp + 64 * r, 64); pm[w] = pm[r]; pe[w] = pe[r]; pb[w] = pb[r]; }
+            pg[w] = (uint32_t)(g0 + i);
+            ++w;
+        }
+        kept = w - base;
+    }
+    int rc = entries_reserve(ctx, base + kept, true);
     if (rc) return rc;
-    ctx->n_entries = total;
+    ctx->n_entries = base + kept; ctx->n_entries_global = g0 + n; ctx->n_flagged_global += n_flagged;
     ctx->uploaded = ctx->ran = ctx->fetched = false;
-    return entries_send(ctx, total);          // the DMA starts now; imrcd_frame_upload has nothing left to copy
+    return entries_send(ctx, ctx->n_entries);          // the DMA starts now; imrcd_frame_upload has nothing left to copy
 }
 
 extern "C" int imrcd_frame_add_entry(imrcd_ctx* ctx, const float current[16], const float previous[16], uint32_t mesh_id,
@@ -483,7 +560,9 @@ extern "C" int imrcd_frame_add_entry(imrcd_ctx* ctx, const float current[16], co
 extern "C" int imrcd_frame_set_shard(imrcd_ctx* ctx, uint32_t rank, uint32_t n_ranks) {
     CHECK_CTX(ctx);
     if (n_ranks == 0 || rank >= n_ranks) { ctx->err = "imrcd_frame_set_shard: bad rank"; return IMRCD_E_ARG; }
-    ctx->shard_rank = rank; ctx->shard_n = n_ranks;
+    if (ctx->comm && (n_ranks != ctx->comm_n || rank != ctx->comm_rank)) { ctx->err = "imrcd_frame_set_shard: the context's communicator fixes the shard"; return IMRCD_E_STATE; }
+    ctx->shard_rank_next = rank; ctx->shard_n_next = n_ranks;
+    if (ctx->n_entries_global == 0) { ctx->shard_rank = rank; ctx->shard_n = n_ranks; }      // else: from the next imrcd_frame_reset on
     return IMRCD_OK;
 }
 
@@ -499,6 +578,7 @@ extern "C" int imrcd_frame_upload(imrcd_ctx* ctx) {
         IMR_CUDA(ctx, ctx->d_mesh.reserve(4 * n, 4 * ctx->n_sent, s));
         IMR_CUDA(ctx, ctx->d_entity.reserve(4 * n, 4 * ctx->n_sent, s));
         IMR_CUDA(ctx, ctx->d_cb.reserve(n, ctx->n_sent, s));
+        if (ctx->shard_n > 1) IMR_CUDA(ctx, ctx->d_gidx.reserve(4 * n, 4 * ctx->n_sent, s));
         rc = entries_send(ctx, n);
         if (rc) return rc;
         // previous matrices feed only the response stage (CollisionDetection.cpp:80-98); an entry added with previous == NULL
@@ -544,15 +624,20 @@ extern "C" int imrcd_frame_finish(imrcd_ctx* ctx) {
     return rc;                                            // 1: the frame was re-run with larger buffers (anything enqueued behind it saw stale results)
 }
 
+const imrcd_entity_pair* imr_comm_merged(const imrcd_ctx* ctx);
+const imrcd_entity_pair* imr_comm_merged_device(const imrcd_ctx* ctx);
+
 extern "C" int imrcd_frame_fetch(imrcd_ctx* ctx) {
     CHECK_CTX(ctx);
     if (!ctx->ran) { ctx->err = "imrcd_frame_fetch before imrcd_frame_run"; return IMRCD_E_STATE; }
     cudaSetDevice(ctx->device);
     const uint64_t nc = ctx->ctl_host.n_colliding;
-    if (nc) {
-        IMR_CUDA(ctx, ctx->p_epairs.reserve(sizeof(imrcd_entity_pair) * nc));
-        IMR_CUDA(ctx, cudaMemcpyAsync(ctx->p_epairs.p, ctx->d_epairs.as<imrcd_entity_pair>() + 1, sizeof(imrcd_entity_pair) * nc, cudaMemcpyDeviceToHost, ctx->stream));
+    if (!ctx->comm && nc > ctx->spec_rows_sent) {        // more records than the speculative copy behind the frame brought: the rest
+        const uint64_t have = ctx->spec_rows_sent;
+        IMR_CUDA(ctx, ctx->p_epairs.reserve(sizeof(imrcd_entity_pair) * nc, sizeof(imrcd_entity_pair) * have, ctx->stream));
+        IMR_CUDA(ctx, cudaMemcpyAsync(ctx->p_epairs.as<imrcd_entity_pair>() + have, ctx->d_epairs.as<imrcd_entity_pair>() + 1 + have, sizeof(imrcd_entity_pair) * (nc - have), cudaMemcpyDeviceToHost, ctx->stream));
         IMR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->spec_rows_sent = nc;
     }
     ctx->fetched = true;
     return IMRCD_OK;
@@ -568,8 +653,9 @@ extern "C" int imrcd_frame_results(imrcd_ctx* ctx, const imrcd_entity_pair** pai
                                    const imrcd_tri_hit** hits, uint64_t* n_hits) {
     CHECK_CTX(ctx);
     if (!ctx->fetched) { ctx->err = "imrcd_frame_results before imrcd_frame_fetch/execute"; return IMRCD_E_STATE; }
-    if (pairs) *pairs = ctx->p_epairs.as<imrcd_entity_pair>();
-    if (n_pairs) *n_pairs = ctx->ctl_host.n_colliding;
+    // with a communicator: the merged records of ALL ranks (in rank order); hits stay this rank's own
+    if (pairs) *pairs = ctx->comm ? (ctx->n_merged ? imr_comm_merged(ctx) : nullptr) : ctx->p_epairs.as<imrcd_entity_pair>();
+    if (n_pairs) *n_pairs = ctx->comm ? ctx->n_merged : ctx->ctl_host.n_colliding;
     if (hits) {   // the hit list is an intermediate of the contact reduction; copied to the host only on demand
         const uint64_t nh = ctx->ctl_host.n_hits;
         if (!ctx->hits_fetched && nh) {
@@ -585,6 +671,21 @@ extern "C" int imrcd_frame_results(imrcd_ctx* ctx, const imrcd_entity_pair** pai
     return IMRCD_OK;
 }
 
+extern "C" int imrcd_frame_results_local(imrcd_ctx* ctx, const imrcd_entity_pair** pairs, uint64_t* n_pairs) {
+    CHECK_CTX(ctx);
+    if (!ctx->ran) { ctx->err = "imrcd_frame_results_local before imrcd_frame_run"; return IMRCD_E_STATE; }
+    cudaSetDevice(ctx->device);
+    const uint64_t nc = ctx->ctl_host.n_colliding;
+    if (ctx->comm && nc) {        // the speculative copy of a frame with a communicator carries the merged records, not the local ones
+        IMR_CUDA(ctx, ctx->p_epairs.reserve(sizeof(imrcd_entity_pair) * nc));
+        IMR_CUDA(ctx, cudaMemcpyAsync(ctx->p_epairs.p, ctx->d_epairs.as<imrcd_entity_pair>() + 1, sizeof(imrcd_entity_pair) * nc, cudaMemcpyDeviceToHost, ctx->stream));
+        IMR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    } else if (!ctx->comm) { const int rc = imrcd_frame_fetch(ctx); if (rc) return rc; }
+    if (pairs) *pairs = ctx->p_epairs.as<imrcd_entity_pair>();
+    if (n_pairs) *n_pairs = nc;
+    return IMRCD_OK;
+}
+
 extern "C" int imrcd_frame_pairs(imrcd_ctx* ctx, const uint32_t** pairs, uint64_t* n_pairs) {
     CHECK_CTX(ctx);
     if (!ctx->ran) { ctx->err = "imrcd_frame_pairs before imrcd_frame_run"; return IMRCD_E_STATE; }
@@ -594,6 +695,10 @@ extern "C" int imrcd_frame_pairs(imrcd_ctx* ctx, const uint32_t** pairs, uint64_
         IMR_CUDA(ctx, ctx->p_pairs.reserve(8 * n));
         IMR_CUDA(ctx, cudaMemcpyAsync(ctx->p_pairs.p, ctx->d_pairs.p, 8 * n, cudaMemcpyDeviceToHost, ctx->stream));
         IMR_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->shard_n > 1) {                            // entry slots of this shard -> the caller's entry indices
+            uint32_t* q = ctx->p_pairs.as<uint32_t>(); const uint32_t* g = ctx->p_gidx.as<uint32_t>();
+            for (uint64_t i = 0; i < 2 * n; ++i) q[i] = g[q[i]];
+        }
     }
     if (pairs) *pairs = ctx->p_pairs.as<uint32_t>();
     if (n_pairs) *n_pairs = n;
@@ -625,8 +730,8 @@ extern "C" int imrcd_frame_get_stats(imrcd_ctx* ctx, imrcd_frame_stats* out) {
 extern "C" int imrcd_frame_results_device(imrcd_ctx* ctx, void** d_pairs, uint64_t* n_pairs, void** d_hits, uint64_t* n_hits) {
     CHECK_CTX(ctx);
     if (!ctx->ran) { ctx->err = "imrcd_frame_results_device before imrcd_frame_run"; return IMRCD_E_STATE; }
-    if (d_pairs) *d_pairs = ctx->d_epairs.as<imrcd_entity_pair>() + 1;
-    if (n_pairs) *n_pairs = ctx->ctl_host.n_colliding;
+    if (d_pairs) *d_pairs = ctx->comm ? (void*)imr_comm_merged_device(ctx) : (void*)(ctx->d_epairs.as<imrcd_entity_pair>() + 1);      // merged records of all ranks when the context has a communicator
+    if (n_pairs) *n_pairs = ctx->comm ? ctx->n_merged : ctx->ctl_host.n_colliding;
     if (d_hits) *d_hits = ctx->d_hits.p;
     if (n_hits) *n_hits = ctx->ctl_host.n_hits;
     return IMRCD_OK;

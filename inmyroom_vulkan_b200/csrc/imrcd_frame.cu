@@ -25,10 +25,13 @@ __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 // ------------------------------------------------------------------------------------------
 // One thread per entry: world-space root box (SweepAndPrune.cpp:23), its extents on the three fixed
 // sweep axes (Paralgram.cpp:175-190), the sort key, and inverse(M) for the pair stage.
+// With `frecs` (the few-flagged-entries path, see k_pairs_few_flagged) the entries WITH shouldCallback are also appended, in no particular
+// order, to a dense list of sweep records whose last word carries the caller's entry index.
 __global__ void k_entry_prep(uint32_t n, const float* __restrict__ cur, const uint32_t* __restrict__ mesh_id,
                              const MeshDev* __restrict__ meshes, const TreeRec* __restrict__ recs,
                              float* __restrict__ inv_out, float* __restrict__ ext_out,
-                             uint32_t* __restrict__ keys, uint32_t* __restrict__ idx) {
+                             uint32_t* __restrict__ keys, uint32_t* __restrict__ idx,
+                             const uint8_t* __restrict__ cb, const uint32_t* __restrict__ gidx, SweepRec* __restrict__ frecs, FrameCtl* ctl) {
     uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
     float m[16];
@@ -40,11 +43,13 @@ __global__ void k_entry_prep(uint32_t n, const float* __restrict__ cur, const ui
     V3 U, V, W; sweep_axes(U, V, W);
     float mn, mx;
     float* eo = ext_out + 6 * (size_t)e;
-    box_minmax(b, U, mn, mx); eo[0] = mn; eo[1] = mx;
-    keys[e] = float_orderable(mn + 0.0f);   // -0 -> +0 so equal floats get equal keys; ties then keep entry order (stable sort)
-    idx[e] = e;
-    box_minmax(b, V, mn, mx); eo[2] = mn; eo[3] = mx;
-    box_minmax(b, W, mn, mx); eo[4] = mn; eo[5] = mx;
+    SweepRec sr;
+    box_minmax(b, U, mn, mx); eo[0] = mn; eo[1] = mx; sr.umin = mn; sr.umax = mx;
+    if (keys) { keys[e] = float_orderable(mn + 0.0f);   // -0 -> +0 so equal floats get equal keys; ties then keep entry order (stable sort)
+                idx[e] = e; }
+    box_minmax(b, V, mn, mx); eo[2] = mn; eo[3] = mx; sr.vmin = mn; sr.vmax = mx;
+    box_minmax(b, W, mn, mx); eo[4] = mn; eo[5] = mx; sr.wmin = mn; sr.wmax = mx;
+    if (frecs && cb[e]) { sr.idx = e; sr.cb = gidx ? gidx[e] : e; frecs[atomicAdd(&ctl->n_flagged, 1ull)] = sr; }
     float inv[16];
     mat4_inverse(m, inv);
     float4* ip = reinterpret_cast<float4*>(inv_out + 16 * (size_t)e);
@@ -120,17 +125,20 @@ __device__ __forceinline__ uint32_t warp_find_owner(const uint32_t* __restrict__
 
 // Load-balanced sweep: one warp per chunk of SWEEP_CHUNK candidates, so that the few entries with very long windows
 // (a floor spanning the whole scene) are spread over the machine.  Orientation = U order (:63).
+// Multi-GPU (n_ranks > 1): the lists hold this rank's share of the frame (every flagged entry + the unflagged entries it owns, see
+// imrcd_frame_add_entries), so a pair with an unflagged entity exists on exactly one rank and is always kept; a pair of two flagged
+// entities is seen by every rank and kept by rank (gidx_a + gidx_e) % n_ranks.  When NO entry of the frame is unflagged the lists are the
+// same on all ranks and the sweep itself is dealt out instead: rank r looks only at the chunks c with c % n_ranks == r.
 __global__ void __launch_bounds__(256)
 k_sweep(uint32_t n, const SweepRec* __restrict__ sorted, const SweepRec* __restrict__ sorted_c, const uint32_t* __restrict__ cpos,
         const uint32_t* __restrict__ wlen, const uint32_t* __restrict__ chunk_off, uint2* __restrict__ pairs, unsigned long long cap,
-        FrameCtl* ctl, uint32_t rank, uint32_t n_ranks) {
+        FrameCtl* ctl, uint32_t rank, uint32_t n_ranks, const uint32_t* __restrict__ gidx, uint32_t deal_chunks) {
     const uint32_t lane = lane_id();
     const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
     const uint32_t total = chunk_off[n];
-    // Multi-GPU: rank r sweeps the chunks c with c % n_ranks == r, so the sweep itself is sharded and every pair is found by
-    // exactly one rank.  A chunk is (one entity) x (512 consecutive candidates of its window): entities with short windows
-    // (the dynamic bodies) land whole on one rank, the long windows of large static parts are dealt round-robin.
-    for (uint32_t c = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * n_ranks + rank; c < total; c += warps_total * n_ranks) {
+    const uint32_t c_first = deal_chunks ? rank : 0u, c_step = deal_chunks ? n_ranks : 1u;
+    const bool by_pair = n_ranks > 1u && !deal_chunks;
+    for (uint32_t c = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * c_step + c_first; c < total; c += warps_total * c_step) {
         const uint32_t p = warp_find_owner(chunk_off, n, c, lane);
         const SweepRec a = sorted[p];
         const SweepRec* list = a.cb ? sorted : sorted_c;
@@ -148,6 +156,7 @@ k_sweep(uint32_t n, const SweepRec* __restrict__ sorted, const SweepRec* __restr
                     const bool v_ok = (a.vmin <= e.vmin) ? !(a.vmax < e.vmin) : !(e.vmax < a.vmin);
                     const bool w_ok = (a.wmin <= e.wmin) ? !(a.wmax < e.wmin) : !(e.wmax < a.wmin);
                     emit = v_ok && w_ok;
+                    if (emit && by_pair && a.cb && e.cb) emit = (gidx[a.idx] + gidx[e.idx]) % n_ranks == rank;
                 }
             }
             const uint32_t m = __ballot_sync(FULL_MASK, emit);
@@ -158,6 +167,61 @@ k_sweep(uint32_t n, const SweepRec* __restrict__ sorted, const SweepRec* __restr
                 if (emit) {
                     const unsigned long long slot = base + __popc(m & ((1u << lane) - 1));
                     if (slot < cap) pairs[slot] = make_uint2(a.idx, e.idx);
+                    else atomicOr(&ctl->overflow, (unsigned)OVF_PAIRS);
+                }
+            }
+        }
+    }
+}
+
+// Frames with few flagged entries (a static scene of some hundred parts against any number of bodies that only collide with it, BASELINE
+// config 3; or a game-sized frame): no sort at all.  A pair needs shouldCallback on one side (SweepAndPrune.cpp:60), so every pair has a
+// flagged member: each entry walks the dense list of the flagged ones (k_entry_prep) from shared memory and applies the sweep's own
+// predicate - closed overlap on U, V and W, orientation by U-min with the lower entry index first on ties (:42-63) - to every candidate.
+// An unflagged entry reports all its pairs, a flagged one those with flagged entries of lower index (each pair once); with n_ranks > 1 a
+// pair of two flagged entries belongs to rank (gidx_a + gidx_b) % n_ranks, every other pair to the one rank that holds the unflagged entry.
+#define FEW_FLAGGED_MAX 2048u
+__global__ void __launch_bounds__(256)
+k_pairs_few_flagged(uint32_t n, const float* __restrict__ ext, const uint8_t* __restrict__ cb, const uint32_t* __restrict__ gidx,
+                    const SweepRec* __restrict__ frecs, uint2* __restrict__ pairs, unsigned long long cap, FrameCtl* ctl, uint32_t rank, uint32_t n_ranks) {
+    __shared__ SweepRec tile[256];
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x, lane = lane_id();
+    const bool valid = e < n;
+    SweepRec me; me.umin = me.umax = me.vmin = me.vmax = me.wmin = me.wmax = 0.f; me.idx = e; me.cb = 0u;
+    uint32_t ge = e;
+    if (valid) {
+        const float* eo = ext + 6 * (size_t)e;
+        me.umin = eo[0]; me.umax = eo[1]; me.vmin = eo[2]; me.vmax = eo[3]; me.wmin = eo[4]; me.wmax = eo[5]; me.cb = cb[e];
+        ge = gidx ? gidx[e] : e;
+    }
+    const uint32_t nf = (uint32_t)ctl->n_flagged;
+    for (uint32_t t0 = 0; t0 < nf; t0 += 256u) {
+        __syncthreads();
+        if (t0 + threadIdx.x < nf) tile[threadIdx.x] = frecs[t0 + threadIdx.x];
+        __syncthreads();
+        const uint32_t tn = nf - t0 < 256u ? nf - t0 : 256u;
+        for (uint32_t k = 0; k < tn; ++k) {
+            const SweepRec f = tile[k];                       // every lane reads the same record: a broadcast
+            const uint32_t gf = f.cb;                         // the flagged entry's caller index (k_entry_prep)
+            bool emit = valid && (me.cb ? gf < ge : true);
+            bool me_first = false;
+            if (emit) {
+                me_first = (me.umin < f.umin) || (me.umin == f.umin && ge < gf);
+                const SweepRec& a = me_first ? me : f; const SweepRec& b = me_first ? f : me;      // a before b on U
+                const bool u_ok = !(a.umax < b.umin);                                               // expiry is strict (:58)
+                const bool v_ok = (a.vmin <= b.vmin) ? !(a.vmax < b.vmin) : !(b.vmax < a.vmin);
+                const bool w_ok = (a.wmin <= b.wmin) ? !(a.wmax < b.wmin) : !(b.wmax < a.wmin);
+                emit = u_ok && v_ok && w_ok;
+                if (emit && me.cb && n_ranks > 1u) emit = (ge + gf) % n_ranks == rank;
+            }
+            const uint32_t m = __ballot_sync(FULL_MASK, emit);
+            if (m) {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(&ctl->n_pairs, (unsigned long long)__popc(m));
+                base = __shfl_sync(FULL_MASK, base, 0);
+                if (emit) {
+                    const unsigned long long slot = base + __popc(m & ((1u << lane) - 1));
+                    if (slot < cap) pairs[slot] = me_first ? make_uint2(e, f.idx) : make_uint2(f.idx, e);
                     else atomicOr(&ctl->overflow, (unsigned)OVF_PAIRS);
                 }
             }
@@ -1243,17 +1307,18 @@ k_large_rays(const FrameCtl* ctl, const uint32_t* __restrict__ list, PairAcc* ac
     }
 }
 
-// row 0 of the result block: the number of records that follow (what a fixed-capacity all-gather of the block needs to carry)
+// row 0 of the result block: the number of records that follow and the frame's overflow bits (what a fixed-capacity all-gather of the
+// block needs to carry: every rank learns from the gathered headers whether any rank has to run its frame again)
 __global__ void k_epairs_header(const FrameCtl* ctl, imrcd_entity_pair* block) {
     imrcd_entity_pair h; memset(&h, 0, sizeof(h));
     const unsigned long long n = ctl->n_colliding;
-    h.entry_first = (uint32_t)n; h.entry_second = (uint32_t)(n >> 32);
+    h.entry_first = (uint32_t)n; h.entry_second = (uint32_t)(n >> 32); h.entity_first = ctl->overflow;
     block[0] = h;
 }
 
 __global__ void k_finalize(FrameCtl* ctl, unsigned long long cap_pairs, const uint2* __restrict__ pairs, const PairAcc* __restrict__ acc,
                            const uint32_t* __restrict__ entity, const float* __restrict__ cur, const float* __restrict__ inv,
-                           imrcd_entity_pair* __restrict__ out, uint32_t* __restrict__ out_pair) {
+                           imrcd_entity_pair* __restrict__ out, uint32_t* __restrict__ out_pair, const uint32_t* __restrict__ gidx) {
     unsigned long long n = ctl->n_pairs < cap_pairs ? ctl->n_pairs : cap_pairs;
     for (unsigned long long p = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; p < n; p += (unsigned long long)gridDim.x * blockDim.x) {
         if (!(acc[p].flags & 1u)) continue;
@@ -1262,7 +1327,7 @@ __global__ void k_finalize(FrameCtl* ctl, unsigned long long cap_pairs, const ui
         uint2 pr = pairs[p];
         imrcd_entity_pair o;
         memset(&o, 0, sizeof(o));
-        o.entry_first = pr.x; o.entry_second = pr.y;
+        o.entry_first = gidx ? gidx[pr.x] : pr.x; o.entry_second = gidx ? gidx[pr.y] : pr.y;      // the caller's entry indices
         o.entity_first = entity[pr.x]; o.entity_second = entity[pr.y];
         o.n_hits = a.n_hits; o.flags = 1u;
         o.n_rays_first = a.rays_a; o.n_rays_second = a.rays_b;
@@ -1287,10 +1352,19 @@ __global__ void k_finalize(FrameCtl* ctl, unsigned long long cap_pairs, const ui
 // ------------------------------------------------------------------------------------------
 static inline unsigned blocks_for(unsigned long long n, unsigned bs) { return (unsigned)((n + bs - 1) / bs); }
 
+int imr_comm_allgather(imrcd_ctx* ctx);
+int imr_comm_after_gather(imrcd_ctx* ctx, uint64_t spec_rows);
+int imr_comm_decide(imrcd_ctx* ctx, uint64_t spec_rows, bool* retry, bool* fatal);
+
+// rows of the result that travel to the host speculatively, right behind the frame's kernels (the count is not known on the host yet):
+// what the last frame had plus a margin.  A frame with more records pays one extra copy after the wait.
+uint64_t imr_frame_spec_rows(const imrcd_ctx* ctx) { return std::max<uint64_t>(256, ctx->spec_hint + ctx->spec_hint / 4 + 64); }
+
 // Second half of a frame: wait for the stream, read the control block back, grow whatever overflowed (the caller re-runs the frame) or
-// fill in the statistics.  Split from the enqueue half so that a caller can put more work (the end-of-frame collective) on the stream
-// before the host looks at the frame (imrcd_frame_run_async / imrcd_frame_finish).
-static int frame_complete(imrcd_ctx* ctx, uint64_t launches, bool* retry) {
+// fill in the statistics.  Split from the enqueue half so that a caller can put more work on the stream before the host looks at the frame
+// (imrcd_frame_run_async / imrcd_frame_finish).  With a communicator the re-run decision is taken from the GATHERED headers, so every rank
+// takes the same one and issues the same number of collectives.
+int imr_frame_complete(imrcd_ctx* ctx, bool* retry) {
     cudaStream_t s = ctx->stream;
     *retry = false;
     IMR_CUDA(ctx, cudaStreamSynchronize(s));
@@ -1298,6 +1372,10 @@ static int frame_complete(imrcd_ctx* ctx, uint64_t launches, bool* retry) {
     ctx->ctl_host = *ctx->p_ctl.as<FrameCtl>();
     const FrameCtl& c = ctx->ctl_host;
     ctx->queue_dirty = std::min<uint64_t>(std::max(c.q_tail, c.q_head), ctx->cap_queue);
+    bool fatal = (c.overflow & OVF_RAYSTACK) != 0;
+    if (ctx->comm) { const int rc = imr_comm_decide(ctx, ctx->spec_rows_sent, retry, &fatal); if (rc) return rc; }
+    else *retry = c.overflow != 0;
+    if (fatal) { ctx->err = "ray stack overflow (tree deeper than the per-thread stack of the response stage)"; return IMRCD_E_CAPACITY; }
 
     if (c.overflow) {
         if (c.overflow & OVF_PAIRS) ctx->cap_pairs = std::max<uint64_t>(c.n_pairs + c.n_pairs / 8, ctx->cap_pairs * 2);
@@ -1307,17 +1385,15 @@ static int frame_complete(imrcd_ctx* ctx, uint64_t launches, bool* retry) {
         if (c.overflow & OVF_HITS) ctx->cap_hits = std::max<uint64_t>(c.n_hits + c.n_hits / 8, ctx->cap_hits * 2);
         if (c.overflow & OVF_RAYS) ctx->cap_rays = std::max<uint64_t>(c.n_rays_kept + c.n_rays_kept / 8, ctx->cap_rays * 2);
         if (c.overflow & OVF_SCRATCH) ctx->cap_lscratch = std::max<uint64_t>(c.scratch_used + c.scratch_used / 8, ctx->cap_lscratch * 2);
-        if (c.overflow & OVF_RAYSTACK) { ctx->err = "ray stack overflow (tree deeper than the per-thread stack of the response stage)"; return IMRCD_E_CAPACITY; }
-
-        *retry = true;   // re-run the frame with the larger buffers
-        return IMRCD_OK;
     }
+    if (*retry) return IMRCD_OK;   // re-run the frame (with the larger buffers)
 
+    ctx->spec_hint = ctx->comm ? ctx->n_merged : c.n_colliding;
     imrcd_frame_stats& st = ctx->stats;
     st.n_pairs = c.n_pairs; st.n_sat_tests = c.n_sat; st.n_combos = c.n_combos; st.n_tri_tests = c.n_tri_tests;
     st.n_hits = c.n_hits; st.n_coplanar_hits = c.n_coplanar; st.n_colliding = c.n_colliding;
     st.n_contact_pairs = c.n_class[0] + c.n_class[16] + c.n_class[32] + c.n_class[48]; st.n_rays = c.n_rays;
-    st.traverse_launches = 1; st.total_launches = launches; st.n_queue_items = c.n_donated; st.n_warp_iterations = c.n_iterations; st.trav_busy_cycles = c.busy_cycles; st.trav_idle_polls = c.idle_polls;
+    st.traverse_launches = 1; st.total_launches = ctx->pending_launches; st.n_queue_items = c.n_donated; st.n_warp_iterations = c.n_iterations; st.trav_busy_cycles = c.busy_cycles; st.trav_idle_polls = c.idle_polls;
     cudaEventElapsedTime(&st.ms_total, ctx->ev[0], ctx->ev[5]);
     cudaEventElapsedTime(&st.ms_broad, ctx->ev[0], ctx->ev[1]);
     cudaEventElapsedTime(&st.ms_pair_setup, ctx->ev[1], ctx->ev[2]);
@@ -1326,20 +1402,13 @@ static int frame_complete(imrcd_ctx* ctx, uint64_t launches, bool* retry) {
     cudaEventElapsedTime(&st.ms_reduce, ctx->ev[4], ctx->ev[5]);
     cudaEventElapsedTime(&st.ms_response, ctx->ev[6], ctx->ev[5]);
     st.n_rays_shot = c.n_rays_kept; st.n_responses = c.n_responses;
+    st.n_merged = ctx->comm ? ctx->n_merged : c.n_colliding;
     return IMRCD_OK;
 }
 
-int imr_frame_run_device(imrcd_ctx* ctx) {
-    cudaStream_t s = ctx->stream;
-    const uint32_t n = (uint32_t)ctx->n_entries;
-    memset(&ctx->stats, 0, sizeof(ctx->stats));
-    memset(&ctx->ctl_host, 0, sizeof(ctx->ctl_host));
-    ctx->stats.n_entries = n;
-    ctx->hits_fetched = false;
-    if (n < 2) return IMRCD_OK;                                   // CollisionDetection.cpp:40
-
-    // capacities (persist across frames; grown on overflow)
-    if (ctx->cap_pairs == 0) ctx->cap_pairs = std::max<uint64_t>(1u << 16, 4ull * n);      // grown (and the frame re-run) when a frame has more pairs
+// once per context: kernel attributes, persistent grid sizes, initial capacities (all persist across frames; capacities grow on overflow)
+static int frame_prepare(imrcd_ctx* ctx) {
+    if (ctx->cap_pairs == 0) ctx->cap_pairs = std::max<uint64_t>(1u << 16, 4ull * ctx->n_entries);      // grown (and the frame re-run) when a frame has more pairs
     if (ctx->cap_queue == 0) ctx->cap_queue = ctx->cap_pairs + (1ull << 22);
     if (ctx->cap_combos == 0) ctx->cap_combos = 1ull << 22;
     if (ctx->cap_hits == 0) ctx->cap_hits = 1ull << 20;
@@ -1349,32 +1418,10 @@ int imr_frame_run_device(imrcd_ctx* ctx) {
         const char* ev = getenv("IMRCD_PC_LARGE_MIN");                 // pairs with more hits than this take the grid-wide passes (tuning knob)
         if (ev) ctx->pc_large_min = std::min<uint32_t>((uint32_t)atoi(ev), PC_M_MAX);
     }
-
-    IMR_CUDA(ctx, ctx->d_inv.reserve(64ull * n, 0, s));
-    IMR_CUDA(ctx, ctx->d_ext.reserve(24ull * n, 0, s));
-    IMR_CUDA(ctx, ctx->d_keys.reserve(4ull * n, 0, s));
-    IMR_CUDA(ctx, ctx->d_keys2.reserve(4ull * n, 0, s));
-    IMR_CUDA(ctx, ctx->d_idx.reserve(4ull * n, 0, s));
-    IMR_CUDA(ctx, ctx->d_idx2.reserve(4ull * n, 0, s));
-    IMR_CUDA(ctx, ctx->d_sorted.reserve(sizeof(SweepRec) * (size_t)n, 0, s));
-    IMR_CUDA(ctx, ctx->d_sorted_c.reserve(sizeof(SweepRec) * (size_t)n, 0, s));
-    IMR_CUDA(ctx, ctx->d_flag.reserve(4ull * (n + 1), 0, s));
-    IMR_CUDA(ctx, ctx->d_cpos.reserve(4ull * (n + 1), 0, s));
-    IMR_CUDA(ctx, ctx->d_wlen.reserve(4ull * (n + 1), 0, s));
-    IMR_CUDA(ctx, ctx->d_chunks.reserve(4ull * (n + 1), 0, s));
-    IMR_CUDA(ctx, ctx->d_chunkoff.reserve(4ull * (n + 1), 0, s));
-    IMR_CUDA(ctx, ctx->d_ctl.reserve(sizeof(FrameCtl), 0, s));
-    IMR_CUDA(ctx, ctx->p_ctl.reserve(sizeof(FrameCtl)));
-    size_t cub_bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, ctx->d_keys.as<uint32_t>(), ctx->d_keys2.as<uint32_t>(),
-                                    ctx->d_idx.as<uint32_t>(), ctx->d_idx2.as<uint32_t>(), (int)n, 0, 32, s);
-    {
-        size_t scan_bytes = 0;
-        cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, ctx->d_flag.as<uint32_t>(), ctx->d_cpos.as<uint32_t>(), (int)(n + 1), s);
-        cub_bytes = std::max(cub_bytes, scan_bytes);
+    if (ctx->few_flagged_max == 0xffffffffu) {
+        const char* ev = getenv("IMRCD_FEW_FLAGGED_MAX");              // 0 = always the sort-and-sweep broad phase (tests run both)
+        ctx->few_flagged_max = ev ? std::min<uint32_t>((uint32_t)atoi(ev), FEW_FLAGGED_MAX) : FEW_FLAGGED_MAX;
     }
-    IMR_CUDA(ctx, ctx->d_cubtmp.reserve(cub_bytes, 0, s));
-
     if (ctx->narrow_blocks == 0) {
         const int smem = (int)(NT_WARPS * sizeof(NarrowWarp));
         IMR_CUDA(ctx, cudaFuncSetAttribute(k_tritri, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -1401,12 +1448,62 @@ int imr_frame_run_device(imrcd_ctx* ctx) {
         if (per_sm < 1) per_sm = 1;
         ctx->trav_blocks = per_sm * ctx->sm_count;
     }
+    if (!ctx->pc_attr_set) {
+        const size_t per_hit = 2 * (sizeof(PcSlot) + 8) + 4 * 8 + 12 + 5 * sizeof(uint16_t);
+        IMR_CUDA(ctx, cudaFuncSetAttribute(k_pair_contacts_hash<512, PC_M1_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PC_M1_MAX * per_hit)));
+        IMR_CUDA(ctx, cudaFuncSetAttribute(k_pair_contacts_hash<1024, PC_M_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PC_M_MAX * per_hit)));
+        ctx->pc_attr_set = true;
+    }
+    return IMRCD_OK;
+}
 
-    for (int attempt = 0; attempt < 8; ++attempt) {
+// First half of a frame: every kernel of it, the control block's way back to the host and a speculative copy of the result rows, all on the
+// context's stream; nothing here waits for the device.
+int imr_frame_enqueue(imrcd_ctx* ctx) {
+    cudaStream_t s = ctx->stream;
+    const uint32_t n = (uint32_t)ctx->n_entries;
+    { const int rc = frame_prepare(ctx); if (rc) return rc; }
+    IMR_CUDA(ctx, ctx->d_ctl.reserve(sizeof(FrameCtl), 0, s));
+    IMR_CUDA(ctx, ctx->p_ctl.reserve(sizeof(FrameCtl)));
+    IMR_CUDA(ctx, ctx->d_epairs.reserve(sizeof(imrcd_entity_pair) * (std::max<uint64_t>(ctx->cap_pairs, ctx->gcap) + 1), 0, s));      // row 0 = header (record count), see imrcd_frame_results_block
+    FrameCtl* ctl = ctx->d_ctl.as<FrameCtl>();
+    uint64_t launches = 0;
+    IMR_CUDA(ctx, cudaEventRecord(ctx->ev[0], s));
+    IMR_CUDA(ctx, cudaMemsetAsync(ctl, 0, sizeof(FrameCtl), s));
+    if (n < 2) {
+        // a shard can be left with fewer than two entries of a frame that has more: it has no pairs, but it still answers the collective
+        for (int k = 1; k <= 6; ++k) IMR_CUDA(ctx, cudaEventRecord(ctx->ev[k], s));
+        IMR_CUDA(ctx, cudaMemsetAsync(ctx->d_epairs.p, 0, sizeof(imrcd_entity_pair), s));
+        IMR_CUDA(ctx, cudaMemcpyAsync(ctx->p_ctl.p, ctl, sizeof(FrameCtl), cudaMemcpyDeviceToHost, s));
+        ctx->pending_launches = 0; ctx->spec_rows_sent = 0;
+        return IMRCD_OK;
+    }
+    IMR_CUDA(ctx, ctx->d_inv.reserve(64ull * n, 0, s));
+    IMR_CUDA(ctx, ctx->d_ext.reserve(24ull * n, 0, s));
+    IMR_CUDA(ctx, ctx->d_keys.reserve(4ull * n, 0, s));
+    IMR_CUDA(ctx, ctx->d_keys2.reserve(4ull * n, 0, s));
+    IMR_CUDA(ctx, ctx->d_idx.reserve(4ull * n, 0, s));
+    IMR_CUDA(ctx, ctx->d_idx2.reserve(4ull * n, 0, s));
+    IMR_CUDA(ctx, ctx->d_sorted.reserve(sizeof(SweepRec) * (size_t)n, 0, s));
+    IMR_CUDA(ctx, ctx->d_sorted_c.reserve(sizeof(SweepRec) * (size_t)n, 0, s));
+    IMR_CUDA(ctx, ctx->d_flag.reserve(4ull * (n + 1), 0, s));
+    IMR_CUDA(ctx, ctx->d_cpos.reserve(4ull * (n + 1), 0, s));
+    IMR_CUDA(ctx, ctx->d_wlen.reserve(4ull * (n + 1), 0, s));
+    IMR_CUDA(ctx, ctx->d_chunks.reserve(4ull * (n + 1), 0, s));
+    IMR_CUDA(ctx, ctx->d_chunkoff.reserve(4ull * (n + 1), 0, s));
+    size_t cub_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, ctx->d_keys.as<uint32_t>(), ctx->d_keys2.as<uint32_t>(),
+                                    ctx->d_idx.as<uint32_t>(), ctx->d_idx2.as<uint32_t>(), (int)n, 0, 32, s);
+    {
+        size_t scan_bytes = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, ctx->d_flag.as<uint32_t>(), ctx->d_cpos.as<uint32_t>(), (int)(n + 1), s);
+        cub_bytes = std::max(cub_bytes, scan_bytes);
+    }
+    IMR_CUDA(ctx, ctx->d_cubtmp.reserve(cub_bytes, 0, s));
+    {
         IMR_CUDA(ctx, ctx->d_pairs.reserve(8ull * ctx->cap_pairs, 0, s));
         IMR_CUDA(ctx, ctx->d_pairrec.reserve(sizeof(PairRec) * ctx->cap_pairs, 0, s));
         IMR_CUDA(ctx, ctx->d_pairacc.reserve(sizeof(PairAcc) * ctx->cap_pairs, 0, s));
-        IMR_CUDA(ctx, ctx->d_epairs.reserve(sizeof(imrcd_entity_pair) * (ctx->cap_pairs + 1), 0, s));      // row 0 = header (record count), see imrcd_frame_results_block
         if (16ull * ctx->cap_queue > ctx->d_queue.cap) { IMR_CUDA(ctx, ctx->d_queue.reserve(16ull * ctx->cap_queue, 0, s)); ctx->queue_dirty = ctx->cap_queue; }
         IMR_CUDA(ctx, ctx->d_combos.reserve(16ull * ctx->cap_combos, 0, s));
         IMR_CUDA(ctx, ctx->d_hits.reserve(sizeof(imrcd_tri_hit) * ctx->cap_hits, 0, s));
@@ -1422,18 +1519,25 @@ int imr_frame_run_device(imrcd_ctx* ctx) {
             IMR_CUDA(ctx, ctx->d_resp.reserve(32ull * ctx->cap_rays, 0, s));
         }
         IMR_CUDA(ctx, ctx->d_lsmall.reserve(4ull * PC_CLASSES * ctx->cap_pairs, 0, s));      // the size-class lists, cap_pairs entries each
-        FrameCtl* ctl = ctx->d_ctl.as<FrameCtl>();
-        uint64_t launches = 0;
-        IMR_CUDA(ctx, cudaEventRecord(ctx->ev[0], s));
-        IMR_CUDA(ctx, cudaMemsetAsync(ctl, 0, sizeof(FrameCtl), s));
         if (ctx->queue_dirty) {                       // clear publication flags left by the previous frame
             uint64_t nclr = std::min<uint64_t>(ctx->queue_dirty, ctx->cap_queue);
             IMR_CUDA(ctx, cudaMemsetAsync(ctx->d_queue.p, 0, 16ull * nclr, s));
         }
         // ---- broad ----
+        const uint32_t* a_gidx = ctx->shard_n > 1 ? ctx->d_gidx.as<uint32_t>() : nullptr;
+        if (ctx->n_flagged_global <= ctx->few_flagged_max) {
+            // few flagged entries: every entry against the dense list of the flagged ones, no sort (k_pairs_few_flagged)
+            IMR_CUDA(ctx, ctx->d_sorted_c.reserve(sizeof(SweepRec) * (size_t)FEW_FLAGGED_MAX, 0, s));
+            k_entry_prep<<<blocks_for(n, 128), 128, 0, s>>>(n, ctx->d_cur.as<float>(), ctx->d_mesh.as<uint32_t>(), ctx->d_meshes.as<MeshDev>(),
+                                                             ctx->d_recs.as<TreeRec>(), ctx->d_inv.as<float>(), ctx->d_ext.as<float>(), nullptr, nullptr,
+                                                             ctx->d_cb.as<uint8_t>(), a_gidx, ctx->d_sorted_c.as<SweepRec>(), ctl);
+            k_pairs_few_flagged<<<blocks_for(n, 256), 256, 0, s>>>(n, ctx->d_ext.as<float>(), ctx->d_cb.as<uint8_t>(), a_gidx, ctx->d_sorted_c.as<SweepRec>(),
+                                                                    ctx->d_pairs.as<uint2>(), ctx->cap_pairs, ctl, ctx->shard_rank, ctx->shard_n);
+            launches += 2;
+        } else {
         k_entry_prep<<<blocks_for(n, 128), 128, 0, s>>>(n, ctx->d_cur.as<float>(), ctx->d_mesh.as<uint32_t>(), ctx->d_meshes.as<MeshDev>(),
                                                          ctx->d_recs.as<TreeRec>(), ctx->d_inv.as<float>(), ctx->d_ext.as<float>(),
-                                                         ctx->d_keys.as<uint32_t>(), ctx->d_idx.as<uint32_t>());
+                                                         ctx->d_keys.as<uint32_t>(), ctx->d_idx.as<uint32_t>(), nullptr, nullptr, nullptr, ctl);
         cub::DeviceRadixSort::SortPairs(ctx->d_cubtmp.p, cub_bytes, ctx->d_keys.as<uint32_t>(), ctx->d_keys2.as<uint32_t>(),
                                         ctx->d_idx.as<uint32_t>(), ctx->d_idx2.as<uint32_t>(), (int)n, 0, 32, s);
         k_gather_sorted<<<blocks_for(n, 256), 256, 0, s>>>(n, ctx->d_idx2.as<uint32_t>(), ctx->d_ext.as<float>(), ctx->d_cb.as<uint8_t>(),
@@ -1445,8 +1549,10 @@ int imr_frame_run_device(imrcd_ctx* ctx) {
         cub::DeviceScan::ExclusiveSum(ctx->d_cubtmp.p, cub_bytes, ctx->d_chunks.as<uint32_t>(), ctx->d_chunkoff.as<uint32_t>(), (int)(n + 1), s);
         k_sweep<<<ctx->sm_count * 8, 256, 0, s>>>(n, ctx->d_sorted.as<SweepRec>(), ctx->d_sorted_c.as<SweepRec>(), ctx->d_cpos.as<uint32_t>(),
                                                    ctx->d_wlen.as<uint32_t>(), ctx->d_chunkoff.as<uint32_t>(), ctx->d_pairs.as<uint2>(), ctx->cap_pairs,
-                                                   ctl, ctx->shard_rank, ctx->shard_n);
+                                                   ctl, ctx->shard_rank, ctx->shard_n, a_gidx,
+                                                   (ctx->shard_n > 1 && ctx->n_flagged_global == ctx->n_entries_global) ? 1u : 0u);
         launches += 6 + 4 + 2 * 2;   // + radix sort (histogram + onesweep passes, counted as 4) + two decoupled-look-back scans (init + scan)
+        }
         IMR_CUDA(ctx, cudaEventRecord(ctx->ev[1], s));
         // ---- pair setup ----
         k_queue_init<<<1, 1, 0, s>>>(ctl, ctx->cap_pairs, ctx->cap_queue);
@@ -1477,11 +1583,6 @@ int imr_frame_run_device(imrcd_ctx* ctx) {
         {
             const size_t per_hit = 2 * (sizeof(PcSlot) + 8) + 4 * 8 + 12 + 5 * sizeof(uint16_t);
             const size_t smem_s = PC_S_MAX * per_hit, smem_m1 = PC_M1_MAX * per_hit, smem_m = PC_M_MAX * per_hit;
-            if (!ctx->pc_attr_set) {
-                IMR_CUDA(ctx, cudaFuncSetAttribute(k_pair_contacts_hash<512, PC_M1_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m1));
-                IMR_CUDA(ctx, cudaFuncSetAttribute(k_pair_contacts_hash<1024, PC_M_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m));
-                ctx->pc_attr_set = true;
-            }
             PairAcc* a_acc = ctx->d_pairacc.as<PairAcc>(); const uint32_t* a_grp = ctx->d_grouped.as<uint32_t>();
             const imrcd_tri_hit* a_hits = ctx->d_hits.as<imrcd_tri_hit>(); const HitAux* a_aux = ctx->d_aux.as<HitAux>();
             const PairRec* a_pr = ctx->d_pairrec.as<PairRec>(); const TriRec* a_tris = ctx->d_tris.as<TriRec>(); const uint32_t* a_vid = ctx->d_tri_vid.as<uint32_t>();
@@ -1519,28 +1620,70 @@ int imr_frame_run_device(imrcd_ctx* ctx) {
         launches += 13;     // lists, group, three per-pair size classes, eight passes over the large pairs
         k_finalize<<<ctx->sm_count * 4, 256, 0, s>>>(ctl, ctx->cap_pairs, ctx->d_pairs.as<uint2>(), ctx->d_pairacc.as<PairAcc>(),
                                                       ctx->d_entity.as<uint32_t>(), ctx->d_cur.as<float>(), ctx->d_inv.as<float>(),
-                                                      ctx->d_epairs.as<imrcd_entity_pair>() + 1, ctx->d_epair_pair.as<uint32_t>());
-        k_epairs_header<<<1, 1, 0, s>>>(ctl, ctx->d_epairs.as<imrcd_entity_pair>());
+                                                      ctx->d_epairs.as<imrcd_entity_pair>() + 1, ctx->d_epair_pair.as<uint32_t>(),
+                                                      ctx->shard_n > 1 ? ctx->d_gidx.as<uint32_t>() : nullptr);
         launches += 2;
         IMR_CUDA(ctx, cudaEventRecord(ctx->ev[6], s));
         { int rc = imr_frame_shoot_device(ctx, ctl, &launches); if (rc != IMRCD_OK) return rc; }
+        k_epairs_header<<<1, 1, 0, s>>>(ctl, ctx->d_epairs.as<imrcd_entity_pair>());      // after the last kernel that can raise an overflow bit
         IMR_CUDA(ctx, cudaEventRecord(ctx->ev[5], s));
         IMR_CUDA(ctx, cudaMemcpyAsync(ctx->p_ctl.p, ctl, sizeof(FrameCtl), cudaMemcpyDeviceToHost, s));
-        if (ctx->enqueue_only) { ctx->pending_launches = launches; return IMRCD_OK; }      // imrcd_frame_run_async: imrcd_frame_finish does the rest
-        bool retry = false;
-        { const int rc = frame_complete(ctx, launches, &retry); if (rc != IMRCD_OK) return rc; }
-        if (retry) continue;
+        ctx->pending_launches = launches;
+        ctx->spec_rows_sent = 0;
+        if (!ctx->comm) {            // the records themselves, speculatively (imrcd_frame_fetch copies the rest when the frame has more)
+            const uint64_t rows = std::min<uint64_t>(imr_frame_spec_rows(ctx), ctx->cap_pairs);
+            IMR_CUDA(ctx, ctx->p_epairs.reserve(sizeof(imrcd_entity_pair) * rows));
+            IMR_CUDA(ctx, cudaMemcpyAsync(ctx->p_epairs.p, ctx->d_epairs.as<imrcd_entity_pair>() + 1, sizeof(imrcd_entity_pair) * rows, cudaMemcpyDeviceToHost, s));
+            ctx->spec_rows_sent = rows;
+        }
+    }
+    return IMRCD_OK;
+}
+
+static int frame_enqueue_all(imrcd_ctx* ctx) {
+    int rc = imr_frame_enqueue(ctx);
+    if (rc) return rc;
+    if (ctx->comm) {
+        rc = imr_comm_allgather(ctx); if (rc) return rc;
+        ctx->spec_rows_sent = imr_frame_spec_rows(ctx);
+        rc = imr_comm_after_gather(ctx, ctx->spec_rows_sent); if (rc) return rc;
+    }
+    return IMRCD_OK;
+}
+
+void imr_frame_begin(imrcd_ctx* ctx) {
+    memset(&ctx->stats, 0, sizeof(ctx->stats));
+    memset(&ctx->ctl_host, 0, sizeof(ctx->ctl_host));
+    ctx->stats.n_entries = ctx->n_entries_global; ctx->stats.n_entries_local = ctx->n_entries;
+    ctx->hits_fetched = false; ctx->merged_valid = false; ctx->n_merged = 0; ctx->spec_rows_sent = 0;
+}
+
+int imr_frame_run_device(imrcd_ctx* ctx) {
+    imr_frame_begin(ctx);
+    if (ctx->n_entries_global < 2) {                              // CollisionDetection.cpp:40 (every rank of a sharded frame sees the same count)
+        if (ctx->d_epairs.p) IMR_CUDA(ctx, cudaMemsetAsync(ctx->d_epairs.p, 0, sizeof(imrcd_entity_pair), ctx->stream));      // the result block says "no records"
+        ctx->merged_valid = true;
         return IMRCD_OK;
     }
-    ctx->err = "frame buffers could not be grown enough (8 attempts)";
+    for (int attempt = 0; attempt < 10; ++attempt) {
+        int rc = frame_enqueue_all(ctx);
+        if (rc) return rc;
+        if (ctx->enqueue_only) return IMRCD_OK;                   // imrcd_frame_run_async: imrcd_frame_finish does the rest
+        bool retry = false;
+        rc = imr_frame_complete(ctx, &retry);
+        if (rc) return rc;
+        if (!retry) return IMRCD_OK;
+    }
+    ctx->err = "frame buffers could not be grown enough (10 attempts)";
     return IMRCD_E_CAPACITY;
 }
 
-// imrcd_frame_finish: 0 = the enqueued frame stands, 1 = a buffer overflowed and the frame was run again (synchronously)
+// imrcd_frame_finish: 0 = the enqueued frame stands, 1 = a buffer overflowed (on this rank or, with a communicator, on any) and the frame
+// was run again, synchronously
 int imr_frame_finish_device(imrcd_ctx* ctx) {
-    if (ctx->n_entries < 2) return IMRCD_OK;
+    if (ctx->n_entries_global < 2) return IMRCD_OK;
     bool retry = false;
-    int rc = frame_complete(ctx, ctx->pending_launches, &retry);
+    int rc = imr_frame_complete(ctx, &retry);
     if (rc != IMRCD_OK) return rc;
     if (!retry) return IMRCD_OK;
     ctx->enqueue_only = false;

@@ -82,6 +82,7 @@ struct __align__(128) FrameCtl {
     unsigned long long scratch_used;       // bytes of the large-pair scratch handed out (bump allocator)
     unsigned long long n_responses;        // successful Hermann passes of the frame
     unsigned long long grouped_used;       // slots of the hit-grouping array handed out (contact reduction)
+    unsigned long long n_flagged;          // entries with shouldCallback appended by k_entry_prep (few-flagged broad phase)
     unsigned long long ray_cursor;         // next ray to hand out (k_shoot fetches dynamically: ray costs differ by two orders of magnitude)
     unsigned int overflow;                 // bit0 pairs, bit1 queue, bit2 combos, bit3 hits, bit4 rays, bit5 large-pair scratch, bit6 ray stack
     unsigned int pad;
@@ -178,7 +179,11 @@ struct imrcd_ctx {
     // frame, host side: the entry table is written straight into pinned memory (one host copy per entry) and goes to
     // HBM in chunks while the caller is still adding entries
     PinBuf p_cur, p_prev, p_mesh, p_entity, p_cb;
-    uint64_t n_entries = 0;              // entries added this frame
+    uint64_t n_entries = 0;              // entries of this frame KEPT by this context (all of them unless the frame is sharded)
+    uint64_t n_entries_global = 0;       // entries added this frame by the caller (every rank of a sharded frame is handed the whole list)
+    uint64_t n_flagged_global = 0;       // ... of which shouldCallback
+    PinBuf p_gidx; DevBuf d_gidx;        // sharded frames: caller's index of every kept entry (ascending); unsharded: unused (identity)
+    uint32_t shard_rank_next = 0, shard_n_next = 1;     // imrcd_frame_set_shard takes effect at the next frame
     uint64_t n_sent = 0;                 // entries whose H2D copy has been enqueued
     bool prev_distinct = false;          // some entry of this frame carries a previous matrix different from its current one
     uint32_t shard_rank = 0, shard_n = 1;
@@ -201,7 +206,15 @@ struct imrcd_ctx {
     cudaStream_t stream2 = nullptr, stream3 = nullptr, stream4 = nullptr;      // side streams for independent tail work of a frame
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join3 = nullptr, ev_join4 = nullptr;
     int trav_blocks = 0, narrow_blocks = 0, trav_variant = 0, shoot_blocks = 0;
+    // end-of-frame merge over NCCL (imrcd_comm.cu): one all-gather of fixed-capacity blocks on the frame's stream
+    void* comm = nullptr;                // ncclComm_t
+    uint32_t comm_rank = 0, comm_n = 1;
+    uint64_t gcap = 0;                   // rows per rank in the gathered blocks (after the header row); the same on every rank
+    DevBuf d_gather; PinBuf p_gather;    // comm_n x (gcap + 1) x 80 B
+    uint64_t n_merged = 0; bool merged_valid = false;
+    uint64_t spec_hint = 0, spec_rows_sent = 0;      // speculative D2H of the result rows (imr_frame_spec_rows)
     bool pc_attr_set = false;
+    uint32_t few_flagged_max = 0xffffffffu;      // frames with at most this many flagged entries take the sort-free broad phase
     uint32_t pc_large_min = 1024;        // contact reduction: pairs with more hits go to the grid-wide passes
     const void* trav_fn = nullptr;
 };

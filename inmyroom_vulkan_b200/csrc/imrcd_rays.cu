@@ -347,7 +347,8 @@ k_shoot(FrameCtl* ctl, unsigned long long cap_rays, const RayRec* __restrict__ r
 // and its split between the two entities by how far each moved at its contact point (CollisionDetection.cpp:85-96,143-150).
 __global__ void __launch_bounds__(256)
 k_delta(FrameCtl* ctl, const uint32_t* __restrict__ epair_pair, imrcd_entity_pair* __restrict__ out, const PairAcc* __restrict__ acc,
-        const float4* __restrict__ resp, const float* __restrict__ cur, const float* __restrict__ prev, float edge_a, float edge_b) {
+        const float4* __restrict__ resp, const float* __restrict__ cur, const float* __restrict__ prev, float edge_a, float edge_b,
+        const uint2* __restrict__ pairs) {
     if (ctl->overflow) return;
     const unsigned long long n = ctl->n_colliding;
     const uint32_t lane = threadIdx.x & 31u;
@@ -383,8 +384,9 @@ k_delta(FrameCtl* ctl, const uint32_t* __restrict__ epair_pair, imrcd_entity_pai
         }
         if (lane == 0) {
             imrcd_entity_pair o = out[e];
-            const float* m1 = cur + 16 * (size_t)o.entry_first; const float* m2 = cur + 16 * (size_t)o.entry_second;
-            const float* q1 = prev + 16 * (size_t)o.entry_first; const float* q2 = prev + 16 * (size_t)o.entry_second;
+            const uint2 pr = pairs[p];                                      // this context's entry slots (o.entry_* are the caller's indices)
+            const float* m1 = cur + 16 * (size_t)pr.x; const float* m2 = cur + 16 * (size_t)pr.y;
+            const float* q1 = prev + 16 * (size_t)pr.x; const float* q2 = prev + 16 * (size_t)pr.y;
             const V3 delta = rel_mul(rel_from_mat(m1), local, 0.f);         // first.current * vec4(localspace_response, 0)
             const V3 pa = mk3(o.avg_first[0], o.avg_first[1], o.avg_first[2]), pb = mk3(o.avg_second[0], o.avg_second[1], o.avg_second[2]);
             const float mv1 = length3(sub3(rel_mul(rel_from_mat(m1), pa, 1.f), rel_mul(rel_from_mat(q1), pa, 1.f)));
@@ -413,7 +415,7 @@ int imr_frame_shoot_device(imrcd_ctx* ctx, FrameCtl* ctl, uint64_t* launches) {
     k_shoot<<<ctx->shoot_blocks, 128, 0, s>>>(ctl, ctx->cap_rays, ctx->d_rays.as<RayRec>(), ctx->d_resp.as<float4>(), ctx->d_pairacc.as<PairAcc>(),
                                                ctx->d_pairrec.as<PairRec>(), ctx->d_recs.as<TreeRec>(), ctx->d_tris.as<TriRec>(), ctx->d_tri_nrm.as<float>());
     k_delta<<<ctx->sm_count * 4, 256, 0, s>>>(ctl, ctx->d_epair_pair.as<uint32_t>(), ctx->d_epairs.as<imrcd_entity_pair>() + 1, ctx->d_pairacc.as<PairAcc>(),
-                                               ctx->d_resp.as<float4>(), ctx->d_cur.as<float>(), ctx->d_prev.as<float>(), edge_a, edge_b);
+                                               ctx->d_resp.as<float4>(), ctx->d_cur.as<float>(), ctx->d_prev.as<float>(), edge_a, edge_b, ctx->d_pairs.as<uint2>());
     *launches += 2;
     return IMRCD_OK;
 }

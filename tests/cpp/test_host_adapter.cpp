@@ -3,6 +3,7 @@
 // Built and run by tests/test_gpu_host_adapter.py.  Exit code 0 = pass.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <map>
 #include <set>
 #include "imrcd_host.hpp"
@@ -32,11 +33,30 @@ static void translation(float* m, float x, float y, float z, float rot) {
 }
 #define EXPECT(cond) do { if (!(cond)) { printf("FAILED %s:%d: %s\n", __FILE__, __LINE__, #cond); return 1; } } while (0)
 
+using CD = imrcd::CollisionDetectionT<Entity, ToyEcs>;
+static int run_all(CD& cd, ToyEcs& ecs, int argc, char** argv);
+
 int main(int argc, char** argv) {
-    ToyEcs ecs;
     // two separate families 1 -> 2 and 3 -> 4, and two siblings 5, 6 under the common parent 7; 8 is far away
-    ecs.parent = {{2, 1}, {4, 3}, {5, 7}, {6, 7}};
-    imrcd::CollisionDetectionT<Entity, ToyEcs> cd(&ecs, 0);
+    {
+        ToyEcs ecs; ecs.parent = {{2, 1}, {4, 3}, {5, 7}, {6, 7}};
+        CD cd(&ecs, 0);
+        if (run_all(cd, ecs, argc, argv)) return 1;
+    }
+    // the same through N GPUs of this process (argv[2] = N): frames sharded by entity, merged by the library's NCCL all-gather
+    const int n_gpus = argc > 2 ? atoi(argv[2]) : 1;
+    if (n_gpus > 1) {
+        ToyEcs ecs; ecs.parent = {{2, 1}, {4, 3}, {5, 7}, {6, 7}};
+        std::vector<int> devs; for (int d = 0; d < n_gpus; ++d) devs.push_back(d);
+        CD cd(&ecs, devs);
+        if (run_all(cd, ecs, argc, argv)) return 1;
+        printf("host adapter ok on %d gpus\n", n_gpus);
+    }
+    printf("host adapter ok\n");
+    return 0;
+}
+
+static int run_all(CD& cd, ToyEcs& ecs, int argc, char** argv) {
     std::vector<float> pos; std::vector<uint32_t> vid;
     box_mesh(pos, vid);
     const uint32_t mesh = cd.CreateOBBtree(pos.data(), nullptr, vid.data(), 12);
@@ -102,6 +122,5 @@ int main(int argc, char** argv) {
         try { cd.LoadMeshesOfModel(std::string(argv[1]) + ".missing"); } catch (const std::runtime_error&) { threw = true; }
         EXPECT(threw);
     }
-    printf("host adapter ok\n");
     return 0;
 }

@@ -37,6 +37,21 @@ def test_struct_layouts_match_header():
         assert name == f and getattr(_lib.EntityPair, name).offset == PAIR_DTYPE.fields[f][1]
 
 
+def test_frame_stats_layout_matches_the_library():
+    """The ctypes mirror of imrcd_frame_stats against sizeof / offsetof as libimrcd.so was compiled (imrcd_abi_layout)."""
+    from inmyroom_vulkan_b200 import _lib
+    lib = _lib.load()
+    n = lib.imrcd_abi_layout(None, 0)
+    out = (C.c_uint64 * n)()
+    assert lib.imrcd_abi_layout(out, n) == n
+    v = list(out)
+    assert v[0] == C.sizeof(_lib.EntityPair) and v[1] == C.sizeof(_lib.TriHit) and v[2] == C.sizeof(_lib.FrameStats)
+    fields = [name for name, _ in _lib.FrameStats._fields_]
+    assert len(fields) == n - 3, "imrcd_frame_stats has a field the binding does not know (or the other way round)"
+    for name, off in zip(fields, v[3:]):
+        assert getattr(_lib.FrameStats, name).offset == off, name
+
+
 def test_no_cpu_fallback():
     import torch
     if torch.cuda.is_available():

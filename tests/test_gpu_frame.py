@@ -189,3 +189,38 @@ def test_run_async_finish_equals_run(gpu_ctx):
     assert st["n_hits"] > (1 << 20) and reran
     cd2.run_async(); assert not cd2.finish() and cd2.stats()["n_hits"] == st["n_hits"]
     ctx2.close()
+
+
+def test_broad_phase_paths_agree(gpu_ctx, port, monkeypatch):
+    """The sort-free broad phase (frames with few flagged entries: every entry against the dense list of the flagged ones) and the
+    sort-and-sweep one give the same ordered pair set, unsharded and sharded, and both equal the port of SweepAndPrune.cpp:15-88."""
+    from inmyroom_vulkan_b200.collision import Context
+    monkeypatch.setenv("IMRCD_FEW_FLAGGED_MAX", "0")
+    swept = Context(0)                                          # reads the knob at its first frame
+    static = scenes.atrium_static(detail=1)
+    keep = list(range(0, 8)) + list(range(60, 70))
+    static = ([static[0][i] for i in keep], static[1][keep])
+    sc_a = scenes.scene_static_vs_bodies(scenes.uv_sphere(12, 9), 3000, seed=21, body_scale=(0.5, 1.5), static=static)
+    sc_b = scenes.scene_instances(scenes.torus(16, 8), 700, seed=22, neighbours=8.0)
+    sc_c = scenes.scene_instances(scenes.torus(16, 8), 500, seed=23, neighbours=8.0)
+    sc_c.should_callback[::3] = 0                               # a mix: two thirds flagged
+    for sc in (sc_a, sc_b, sc_c):
+        got = {}
+        for name, ctx in (("few", gpu_ctx), ("sweep", swept)):
+            trees = [OBBtree(ctx, m.positions, m.normals, m.vertex_ids) for m in sc.meshes]
+            cd = CollisionDetection(ctx=ctx)
+            _, bp, _, _ = gpu_frame(cd, sc, trees)
+            got[name] = set(map(tuple, bp.tolist()))
+            assert len(got[name]) == len(bp)
+            for world in (2, 5):
+                parts = []
+                for r in range(world):
+                    cd.set_shard(r, world)
+                    parts.append(set(map(tuple, gpu_frame(cd, sc, trees)[1].tolist())))
+                cd.set_shard(0, 1)
+                assert sum(len(x) for x in parts) == len(set().union(*parts)) and set().union(*parts) == got[name], (name, world)
+        assert got["few"] == got["sweep"] and len(got["few"]) > 100
+        ptrees = [port.tree_import(OBBtree(gpu_ctx, m.positions, m.normals, m.vertex_ids).export()) for m in sc.meshes]
+        want, _ = port.broad(sc.matrices, [ptrees[m] for m in sc.mesh_index], sc.should_callback)
+        assert got["few"] == set(map(tuple, want.tolist()))
+    swept.close()

@@ -16,8 +16,12 @@ def test_cpp_host_adapter(tmp_path, gpu_ctx):
     lib = os.path.join(ROOT, "inmyroom_vulkan_b200")
     subprocess.run(["g++", "-std=c++17", "-O1", "-I", HOST, os.path.join(ROOT, "tests", "cpp", "test_host_adapter.cpp"), "-o", exe,
                     "-L", lib, "-limrcd", f"-Wl,-rpath,{lib}", "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64"], check=True)
-    r = subprocess.run([exe, os.path.join(ROOT, "tests", "golden", "gltf_scene.glb")], capture_output=True, text=True, timeout=120)
+    import torch
+    n_gpus = min(torch.cuda.device_count(), 2)          # with two GPUs also the group constructor (one process, N GPUs, in-library NCCL merge)
+    r = subprocess.run([exe, os.path.join(ROOT, "tests", "golden", "gltf_scene.glb"), str(n_gpus)], capture_output=True, text=True, timeout=180)
     assert r.returncode == 0 and "host adapter ok" in r.stdout, r.stdout + r.stderr
+    if n_gpus > 1:
+        assert f"host adapter ok on {n_gpus} gpus" in r.stdout
 
 
 def test_drop_in_compiles_against_the_reference_headers():
