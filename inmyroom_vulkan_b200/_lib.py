@@ -114,6 +114,21 @@ EXPORTED_SYMBOLS = [s[0] for s in _SIGS]
 _lib = None
 
 
+def preload_nccl():
+    """The library binds NCCL at run time by soname (dlopen "libnccl.so.2").  A process that will also import torch must end up with ONE
+    NCCL: load torch's bundled copy first (when there is one) so that the soname resolves to it, whichever of the two is used first."""
+    import glob
+    import site
+    for sp in site.getsitepackages():
+        for path in glob.glob(os.path.join(sp, "nvidia", "nccl", "lib", "libnccl.so.2")):
+            try:
+                C.CDLL(path, mode=C.RTLD_GLOBAL)
+                return path
+            except OSError:
+                pass
+    return None
+
+
 def load() -> C.CDLL:
     """dlopen libimrcd.so and bind every declared symbol.  Never touches the GPU by itself."""
     global _lib

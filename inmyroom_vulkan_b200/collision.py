@@ -63,12 +63,14 @@ class Context:
 
     # ---- multi-GPU: the end-of-frame merge lives in the library (imrcd_comm_*) ----------
     def comm_unique_id(self) -> bytes:
+        _lib.preload_nccl()
         buf = (C.c_uint8 * 128)()
         self.check(self.lib.imrcd_comm_unique_id(buf))
         return bytes(buf)
 
     def comm_init(self, uid: bytes, rank: int, n_ranks: int):
         """Collective over the ranks that share `uid` (one context per GPU); sets the frame shard to (rank, n_ranks)."""
+        _lib.preload_nccl()
         raw = (C.c_uint8 * 128).from_buffer_copy(uid)
         self.check(self.lib.imrcd_comm_init(self.h, raw, rank, n_ranks))
 
@@ -388,6 +390,7 @@ class Group:
 
     def __init__(self, device_ids: Sequence[int]):
         self.lib = _lib.load()
+        _lib.preload_nccl()
         ids = (C.c_int * len(device_ids))(*[int(d) for d in device_ids])
         h = C.c_void_p()
         rc = self.lib.imrcd_group_create(ids, len(device_ids), C.byref(h))

@@ -245,10 +245,16 @@ IMR_D PlaneN plane_from_tri(V3 p0, V3 p1, V3 p2) {
 IMR_D bool plane_outside(const PlaneN& pl, V3 p) { return dot3(p, pl.n) + pl.d > 0.f; }     // Plane.cpp:23-29
 
 
-__global__ void k_queue_init(FrameCtl* ctl, unsigned long long cap_pairs, unsigned long long cap_queue) {
+// The roots are dealt evenly: warp w of the traversal starts on slots [w * k, w * k + k), k = ceil(roots / warps) <= 32 (its first "ticket"
+// needs no atomic); later tickets come from q_head, which therefore starts behind the fixed ones.
+__device__ __forceinline__ uint32_t trav_first_ticket(unsigned long long n_roots, uint32_t n_warps) {
+    const unsigned long long k = (n_roots + n_warps - 1) / n_warps;
+    return k > 32ull ? 32u : (k < 1ull ? 1u : (uint32_t)k);
+}
+__global__ void k_queue_init(FrameCtl* ctl, unsigned long long cap_pairs, unsigned long long cap_queue, uint32_t trav_warps) {
     unsigned long long n = ctl->n_pairs < cap_pairs ? ctl->n_pairs : cap_pairs;
     if (n > cap_queue) { n = cap_queue; atomicOr(&ctl->overflow, (unsigned)OVF_QUEUE); }
-    ctl->q_head = 0; ctl->q_tail = n; ctl->pending = (long long)n;
+    ctl->q_head = (unsigned long long)trav_first_ticket(n, trav_warps) * trav_warps; ctl->q_tail = n; ctl->pending = (long long)n; ctl->n_roots = n;
 }
 
 // One thread per pair: rel = glm::inverse(first.M) * second.M (OBBtreesCollision.cpp:15), the bases of the
@@ -286,7 +292,7 @@ __global__ void k_pair_setup(const FrameCtl* ctl, unsigned long long cap_pairs, 
             if (moved) z.flags = PAIR_MOVED;
         }
         acc[p] = z;
-        if (p < cap_queue) queue[p] = make_uint4((uint32_t)p, 0u, 0u, 1u);
+        if (p < cap_queue) queue[p] = make_uint4((uint32_t)p, ma.rec_base, mb.rec_base, 1u);      // arena indices of the two roots
     }
 }
 
@@ -345,25 +351,26 @@ __device__ __forceinline__ void trav_donate(TravStack& st, uint32_t warp, uint32
 template <int STRAIGHT, int MIN_BLOCKS>
 __global__ void __launch_bounds__(TRAV_WARPS * 32, MIN_BLOCKS)
 k_traverse(FrameCtl* ctl, const PairRec* __restrict__ pairrec, const TreeRec* __restrict__ recs,
-           WorkItem* queue, unsigned long long cap_queue, Combo* __restrict__ combos, unsigned long long cap_combos) {
+           WorkItem* queue, unsigned long long cap_queue, Combo* __restrict__ combos, unsigned long long cap_combos,
+           uint32_t keep_items, uint32_t backoff_max, uint4* __restrict__ trace, uint32_t trace_cap, uint32_t coop) {
     __shared__ TravStack st;
     const uint32_t lane = lane_id();
     const uint32_t warp = threadIdx.x >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    uint32_t top = 0, bot = 0;          // deque: items live in [bot, top)
+    const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    uint32_t top = 0, bot = 0;          // deque: items live in [bot, top); a and b are ARENA record indices (no base to wait for)
     int delta = 0;                      // alive-item change not yet added to ctl->pending
-    unsigned long long own_base = 0;    // ticket: this warp consumes global slots own_base + lane for set bits of own_mask
-    uint32_t own_mask = 0;
+    // ticket: this warp consumes global slots own_base + lane for set bits of own_mask.  The first one is fixed by the warp's id.
+    const uint32_t k_first = trav_first_ticket(ctl->n_roots, n_warps);
+    unsigned long long own_base = (unsigned long long)gwarp * k_first;
+    uint32_t own_mask = k_first >= 32u ? FULL_MASK : ((1u << k_first) - 1u);
     unsigned long long my_sat = 0, my_tri = 0, my_iter = 0, my_busy = 0, my_polls = 0;
     bool finished = false;
 
     while (!finished) {
         uint32_t cnt = top - bot;
-        bool have = false;
-        uint32_t ip = 0, ia = 0, ib = 0;
-
         if (cnt == 0) {
-            // ---- refill: wait on this warp's own global slots ----
+            // ---- refill: wait on this warp's own global slots; what arrives goes on the deque ----
             if (lane == 0 && delta != 0) atomicAdd((unsigned long long*)&ctl->pending, (unsigned long long)(long long)delta);
             delta = 0;
             uint32_t backoff = 32;
@@ -382,9 +389,12 @@ k_traverse(FrameCtl* ctl, const PairRec* __restrict__ pairrec, const TreeRec* __
                     if (f) {
                         __threadfence();
                         const uint4 it = __ldcg(&queue[slot]);
-                        ip = it.x; ia = it.y; ib = it.z; have = true;
+                        const uint32_t s = (top + (uint32_t)__popc(ready & lt_mask)) & STK_MASK;
+                        st.pair[warp][s] = it.x; st.a[warp][s] = it.y; st.b[warp][s] = it.z;
                     }
+                    top += (uint32_t)__popc(ready);
                     own_mask &= ~ready;
+                    __syncwarp();
                     break;
                 }
                 int done = 0;
@@ -393,47 +403,69 @@ k_traverse(FrameCtl* ctl, const PairRec* __restrict__ pairrec, const TreeRec* __
                 if (done) { finished = true; break; }
                 ++my_polls;
                 __nanosleep(backoff);
-                if (backoff < 1024) backoff <<= 1;
+                if (backoff < backoff_max) backoff <<= 1;
             }
             if (finished) break;
-        } else {
-            const uint32_t take = cnt < 32u ? cnt : 32u;
-            if (lane < take) {
-                const uint32_t s = (top - 1u - lane) & STK_MASK;
-                ip = st.pair[warp][s]; ia = st.a[warp][s]; ib = st.b[warp][s]; have = true;
-            }
-            top -= take;
-            __syncwarp();
+            cnt = top - bot;
         }
-        ++my_iter;
-        const long long t_begin = clock64();
-
-        // ---- one SAT visit per lane (IntersectOBBtreesRecursive, OBBtree.cpp:414-477) ----
-        bool push = false, emit = false;
-        uint32_t c0a = 0, c0b = 0, c1a = 0, c1b = 0;
-        Combo cmb = make_uint4(0, 0, 0, 0);
+        // ---- this iteration's node pairs: the newest ones (depth first).  A warp with fewer pairs than lanes deals the 15 axes of each
+        //      to a group of g lanes (box_sat_part): the visit's latency, which is what a ramp or a tail of the frame waits for, drops ----
+        const uint32_t take = cnt < 32u ? cnt : 32u;
+        const uint32_t g_log = coop ? (take > 16u ? 0u : (take > 8u ? 1u : (take > 4u ? 2u : (take > 2u ? 3u : 4u)))) : 0u;
+        const uint32_t item = lane >> g_log, sub = lane & ((1u << g_log) - 1u);
+        const bool have = item < take, leader = have && sub == 0u;
+        uint32_t ip = 0, ia = 0, ib = 0;
         if (have) {
+            const uint32_t s = (top - 1u - item) & STK_MASK;
+            ip = st.pair[warp][s]; ia = st.a[warp][s]; ib = st.b[warp][s];
+        }
+        top -= take;
+        __syncwarp();
+        const long long t_begin = clock64();
+        uint32_t trace_t0 = 0;
+        if (trace) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); trace_t0 = (uint32_t)t; }
+        const uint32_t trace_slot = (uint32_t)my_iter;
+        ++my_iter;
+
+        // ---- one SAT visit per lane group (IntersectOBBtreesRecursive, OBBtree.cpp:414-477) ----
+        bool push = false, emit = false, ok = false, leafA = false, leafB = false;
+        uint32_t c0a = 0, c0b = 0, c1a = 0, c1b = 0, childA = 0, childB = 0, cnt_ab = 0;
+        float surf_a = 0.f, surf_b = 0.f;
+        if (have) {
+            // the three records are independent loads (the item carries arena indices): one memory latency per visit, not two
             const float4* pp = reinterpret_cast<const float4*>(pairrec + ip);
+            const float4* ra = reinterpret_cast<const float4*>(recs + ia);
+            const float4* rb = reinterpret_cast<const float4*>(recs + ib);
             Rel rel; rel.r0 = __ldg(pp); rel.r1 = __ldg(pp + 1); rel.r2 = __ldg(pp + 2);
-            const uint4 bases = __ldg(reinterpret_cast<const uint4*>(pp + 3));
-            const float4* ra = reinterpret_cast<const float4*>(recs + bases.x + ia);
-            const float4* rb = reinterpret_cast<const float4*>(recs + bases.y + ib);
             const float4 a0 = __ldg(ra), a1 = __ldg(ra + 1), a2 = __ldg(ra + 2), a3 = __ldg(ra + 3);
             const float4 b0 = __ldg(rb), b1 = __ldg(rb + 1), b2 = __ldg(rb + 2), b3 = __ldg(rb + 3);
+            const uint2 bases = __ldg(reinterpret_cast<const uint2*>(pp + 3));
+            leafA = __float_as_uint(a3.w) != 0u; leafB = __float_as_uint(b3.w) != 0u;
+            childA = __float_as_uint(a3.y); childB = __float_as_uint(b3.y);
+            cnt_ab = __float_as_uint(a3.z) | (__float_as_uint(b3.z) << 16);
+            surf_a = a3.x;
             const Box first = unpack_box(a0, a1, a2);
             const Box second = box_transform(rel, unpack_box(b0, b1, b2));        // :420
+            if (g_log == 0u) ok = box_sat_t<STRAIGHT>(first, second);             // :422
+            else ok = box_sat_part(first, second, (int)sub, 1 << g_log);
+            if (!leafA && !leafB) surf_b = box_surface(second);                   // for :426
+            if (!leafA) childA += bases.x;                                        // arena indices of the children
+            if (!leafB) childB += bases.y;
+        }
+        if (g_log != 0u) {                                                        // the verdict of a group: every lane's axes overlap
+            const uint32_t okm = __ballot_sync(FULL_MASK, ok);
+            const uint32_t gm = ((1u << (1u << g_log)) - 1u) << (item << g_log);
+            ok = have && (okm & gm) == gm;
+        }
+        if (leader) {
             ++my_sat;
-            if (box_sat_t<STRAIGHT>(first, second)) {                              // :422
-                const bool leafA = __float_as_uint(a3.w) != 0u, leafB = __float_as_uint(b3.w) != 0u;
-                const uint32_t childA = __float_as_uint(a3.y), childB = __float_as_uint(b3.y);
+            if (ok) {
                 if (leafA && leafB) {
-                    const uint32_t cntA = __float_as_uint(a3.z), cntB = __float_as_uint(b3.z);
-                    emit = true;
-                    cmb = make_uint4(ip, childA, childB, cntA | (cntB << 16));     // :473
-                    my_tri += (unsigned long long)cntA * cntB;
+                    emit = true;                                                   // :473
+                    my_tri += (unsigned long long)(cnt_ab & 0xffffu) * (cnt_ab >> 16);
                 } else {
                     bool descend_first;
-                    if (!leafA && !leafB) descend_first = a3.x >= box_surface(second);   // :426 (a3.x caches first.GetSurface())
+                    if (!leafA && !leafB) descend_first = surf_a >= surf_b;        // :426 (TreeRec caches first.GetSurface())
                     else descend_first = !leafA;
                     push = true;
                     if (descend_first) { c0a = childA; c1a = childA + 1u; c0b = ib; c1b = ib; }
@@ -441,23 +473,15 @@ k_traverse(FrameCtl* ctl, const PairRec* __restrict__ pairrec, const TreeRec* __
                 }
             }
         }
-        const uint32_t have_m = __ballot_sync(FULL_MASK, have);
+        const uint32_t have_m = __ballot_sync(FULL_MASK, leader);
         const uint32_t push_m = __ballot_sync(FULL_MASK, push);
         const uint32_t emit_m = __ballot_sync(FULL_MASK, emit);
         const uint32_t total = 2u * (uint32_t)__popc(push_m);
         delta += (int)total - (int)__popc(have_m);
 
-        // ---- leaf combos: warp-aggregated append ----
-        if (emit_m) {
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(&ctl->n_combos, (unsigned long long)__popc(emit_m));
-            base = __shfl_sync(FULL_MASK, base, 0);
-            if (emit) {
-                const unsigned long long slot = base + __popc(emit_m & lt_mask);
-                if (slot < cap_combos) combos[slot] = cmb;
-                else atomicOr(&ctl->overflow, (unsigned)OVF_COMBOS);
-            }
-        }
+        // ---- leaf combos: warp-aggregated append; the atomic goes out now, its result is used after the deque work ----
+        unsigned long long combo_base = 0;
+        if (emit_m && lane == 0) combo_base = atomicAdd(&ctl->n_combos, (unsigned long long)__popc(emit_m));
 
         // ---- make room, then push the children on the warp's deque ----
         cnt = top - bot;
@@ -478,17 +502,29 @@ k_traverse(FrameCtl* ctl, const PairRec* __restrict__ pairrec, const TreeRec* __
         // ---- feed waiting warps with what this warp cannot start on in its next iteration ----
         cnt = top - bot;
         uint32_t give = 0;
-        if (cnt > 32u && lane == 0) {           // only a warp with a surplus looks at the shared control words
+        if (cnt > keep_items && lane == 0) {           // only a warp with a surplus looks at the shared control words
             const unsigned long long qh = ld_volatile_u64(&ctl->q_head), qt = ld_volatile_u64(&ctl->q_tail);
             if (qh > qt) {
                 const unsigned long long want = qh - qt;
-                give = cnt - 32u;
+                give = cnt - keep_items;
                 if (give > 64u) give = 64u;
                 if ((unsigned long long)give > want) give = (uint32_t)want;
             }
         }
         give = __shfl_sync(FULL_MASK, give, 0);
+        if (emit_m) {
+            combo_base = __shfl_sync(FULL_MASK, combo_base, 0);
+            if (emit) {
+                const unsigned long long slot = combo_base + __popc(emit_m & lt_mask);
+                if (slot < cap_combos) combos[slot] = make_uint4(ip, childA, childB, cnt_ab);
+                else atomicOr(&ctl->overflow, (unsigned)OVF_COMBOS);
+            }
+        }
         my_busy += (unsigned long long)(clock64() - t_begin);
+        if (trace && lane == 0 && trace_slot < trace_cap) {            // diagnostic timeline (IMRCD_TRAV_TRACE): begin, end (ns), lanes with an item, deque size after
+            unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            trace[(size_t)gwarp * trace_cap + trace_slot] = make_uint4(trace_t0, (uint32_t)t1, (uint32_t)__popc(have_m), cnt);
+        }
         if (give) {
             if (lane == 0 && delta != 0) atomicAdd((unsigned long long*)&ctl->pending, (unsigned long long)(long long)delta);
             delta = 0;
@@ -1555,7 +1591,7 @@ int imr_frame_enqueue(imrcd_ctx* ctx) {
         }
         IMR_CUDA(ctx, cudaEventRecord(ctx->ev[1], s));
         // ---- pair setup ----
-        k_queue_init<<<1, 1, 0, s>>>(ctl, ctx->cap_pairs, ctx->cap_queue);
+        k_queue_init<<<1, 1, 0, s>>>(ctl, ctx->cap_pairs, ctx->cap_queue, (uint32_t)(ctx->trav_blocks * TRAV_WARPS));
         k_pair_setup<<<ctx->sm_count * 8, 128, 0, s>>>(ctl, ctx->cap_pairs, ctx->d_pairs.as<uint2>(), ctx->d_cur.as<float>(), ctx->prev_distinct ? ctx->d_prev.as<float>() : nullptr, ctx->d_inv.as<float>(),
                                                         ctx->d_mesh.as<uint32_t>(), ctx->d_meshes.as<MeshDev>(), ctx->d_pairrec.as<PairRec>(),
                                                         ctx->d_pairacc.as<PairAcc>(), ctx->d_queue.as<WorkItem>(), ctx->cap_queue);
@@ -1565,7 +1601,17 @@ int imr_frame_enqueue(imrcd_ctx* ctx) {
         {
             const PairRec* a_pairrec = ctx->d_pairrec.as<PairRec>(); const TreeRec* a_recs = ctx->d_recs.as<TreeRec>();
             WorkItem* a_queue = ctx->d_queue.as<WorkItem>(); Combo* a_combos = ctx->d_combos.as<Combo>();
-            void* targs[] = { &ctl, &a_pairrec, &a_recs, &a_queue, &ctx->cap_queue, &a_combos, &ctx->cap_combos };
+            static uint32_t keep_items = getenv("IMRCD_TRAV_KEEP") ? (uint32_t)atoi(getenv("IMRCD_TRAV_KEEP")) : 32u;
+            static uint32_t backoff_max = getenv("IMRCD_TRAV_BACKOFF") ? (uint32_t)atoi(getenv("IMRCD_TRAV_BACKOFF")) : 1024u;
+            uint4* a_trace = nullptr; uint32_t trace_cap = 0;
+            if (getenv("IMRCD_TRAV_TRACE")) {                            // diagnostic: per-warp iteration timeline, dumped by imrcd_debug_trav_trace
+                trace_cap = 256;
+                IMR_CUDA(ctx, ctx->d_trace.reserve(16ull * trace_cap * ctx->trav_blocks * TRAV_WARPS, 0, s));
+                IMR_CUDA(ctx, cudaMemsetAsync(ctx->d_trace.p, 0, 16ull * trace_cap * ctx->trav_blocks * TRAV_WARPS, s));
+                a_trace = ctx->d_trace.as<uint4>();
+            }
+            static uint32_t coop = getenv("IMRCD_TRAV_COOP") ? (uint32_t)atoi(getenv("IMRCD_TRAV_COOP")) : 1u;
+            void* targs[] = { &ctl, &a_pairrec, &a_recs, &a_queue, &ctx->cap_queue, &a_combos, &ctx->cap_combos, &keep_items, &backoff_max, &a_trace, &trace_cap, &coop };
             IMR_CUDA(ctx, cudaLaunchKernel(ctx->trav_fn, dim3(ctx->trav_blocks), dim3(TRAV_WARPS * 32), targs, 0, s));
             launches += 1;
         }
@@ -1648,6 +1694,17 @@ static int frame_enqueue_all(imrcd_ctx* ctx) {
         ctx->spec_rows_sent = imr_frame_spec_rows(ctx);
         rc = imr_comm_after_gather(ctx, ctx->spec_rows_sent); if (rc) return rc;
     }
+    return IMRCD_OK;
+}
+
+// diagnostic (IMRCD_TRAV_TRACE=1): the traversal's per-warp iteration timeline of the last frame, 256 x uint4 per warp
+extern "C" int imrcd_debug_trav_trace(imrcd_ctx* ctx, uint32_t* out, uint64_t cap_u32, uint32_t* n_warps) {
+    if (!ctx || !n_warps) return IMRCD_E_ARG;
+    *n_warps = (uint32_t)(ctx->trav_blocks * TRAV_WARPS);
+    const uint64_t need = 4ull * 256 * *n_warps;
+    if (!out || cap_u32 < need || !ctx->d_trace.p) return IMRCD_OK;
+    cudaSetDevice(ctx->device);
+    IMR_CUDA(ctx, cudaMemcpy(out, ctx->d_trace.p, 4 * need, cudaMemcpyDeviceToHost));
     return IMRCD_OK;
 }
 

@@ -82,6 +82,7 @@ struct __align__(128) FrameCtl {
     unsigned long long scratch_used;       // bytes of the large-pair scratch handed out (bump allocator)
     unsigned long long n_responses;        // successful Hermann passes of the frame
     unsigned long long grouped_used;       // slots of the hit-grouping array handed out (contact reduction)
+    unsigned long long n_roots;            // root items of the traversal (k_queue_init)
     unsigned long long n_flagged;          // entries with shouldCallback appended by k_entry_prep (few-flagged broad phase)
     unsigned long long ray_cursor;         // next ray to hand out (k_shoot fetches dynamically: ray costs differ by two orders of magnitude)
     unsigned int overflow;                 // bit0 pairs, bit1 queue, bit2 combos, bit3 hits, bit4 rays, bit5 large-pair scratch, bit6 ray stack
@@ -194,6 +195,7 @@ struct imrcd_ctx {
     DevBuf d_cur, d_prev, d_mesh, d_cb, d_entity, d_inv, d_ext, d_keys, d_keys2, d_idx, d_idx2, d_sorted, d_sorted_c, d_flag, d_cpos, d_wlen, d_chunks, d_chunkoff, d_cubtmp;
     DevBuf d_pairs, d_pairrec, d_pairacc, d_queue, d_combos, d_hits, d_epairs, d_ctl;
     DevBuf d_aux, d_grouped, d_lscratch, d_lpref, d_lsides, d_padded, d_padoff, d_lsmall, d_lmid, d_llarge;      // contact reduction scratch (imrcd_frame.cu)
+    DevBuf d_trace;                                                                        // diagnostic timeline of k_traverse (IMRCD_TRAV_TRACE)
     DevBuf d_rays, d_resp, d_epair_pair;                                                    // response stage (imrcd_rays.cu)
     uint64_t cap_pairs = 0, cap_queue = 0, cap_combos = 0, cap_hits = 0, cap_rays = 0, cap_lscratch = 0;
     uint64_t queue_dirty = 0;            // slots whose ready flag may still be set

@@ -51,14 +51,11 @@ def init_comm(ctx, rank: int, world: int, group=None):
     execute of this context end with the in-library all-gather and imrcd_frame_results returns the merged records of all ranks."""
     uid = torch.zeros(128, dtype=torch.uint8)
     if rank == 0:
-        buf = (C.c_uint8 * 128)()
-        ctx.check(ctx.lib.imrcd_comm_unique_id(buf))
-        uid = torch.frombuffer(bytearray(buf), dtype=torch.uint8).clone()
+        uid = torch.frombuffer(bytearray(ctx.comm_unique_id()), dtype=torch.uint8).clone()
     dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
     uid = uid.to(dev)
     dist.broadcast(uid, src=0, group=group)
-    raw = (C.c_uint8 * 128).from_buffer_copy(uid.cpu().numpy().tobytes())
-    ctx.check(ctx.lib.imrcd_comm_init(ctx.h, raw, rank, world))
+    ctx.comm_init(uid.cpu().numpy().tobytes(), rank, world)
 
 
 class FrameGather:
