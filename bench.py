@@ -273,9 +273,14 @@ def run_gpu_arm(args):
     # ---- device-resident loop: upload once, then K x run (+ gather) ----
     cd.Reset(); cd.add_entries(scene.matrices, mesh_ids, scene.should_callback, scene.entities); cd.upload()
 
+    align = torch.zeros(1, device="cuda") if multi else None
+
     def device_step():
         with torch.cuda.stream(stream):
             e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            if multi:
+                dist.all_reduce(align)              # not part of the frame: the ranks leave their L2 flushes at different times, and a step timed
+                                                    # from an early rank's start would count its wait for the latest one inside the frame's collective
             e0.record(stream)
             cd.run_async()                          # the frame's kernels and, with N ranks, the end-of-frame all-gather right behind them
             e1.record(stream)                       # (both enqueued by the library on this stream); the host does not wait here

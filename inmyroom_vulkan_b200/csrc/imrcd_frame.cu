@@ -411,7 +411,7 @@ k_traverse(FrameCtl* ctl, const PairRec* __restrict__ pairrec, const TreeRec* __
         // ---- this iteration's node pairs: the newest ones (depth first).  A warp with fewer pairs than lanes deals the 15 axes of each
         //      to a group of g lanes (box_sat_part): the visit's latency, which is what a ramp or a tail of the frame waits for, drops ----
         const uint32_t take = cnt < 32u ? cnt : 32u;
-        const uint32_t g_log = coop ? (take > 16u ? 0u : (take > 8u ? 1u : (take > 4u ? 2u : (take > 2u ? 3u : 4u)))) : 0u;
+        const uint32_t g_log = (coop && take <= 4u) ? (take > 2u ? 3u : 4u) : 0u;       // measured: groups of 2 or 4 lanes do not pay (the indexed axis costs more than it saves)
         const uint32_t item = lane >> g_log, sub = lane & ((1u << g_log) - 1u);
         const bool have = item < take, leader = have && sub == 0u;
         uint32_t ip = 0, ia = 0, ib = 0;

@@ -497,6 +497,42 @@ def frame_pairs(orc, mats, trees, pairs, threads: int = 1):
                 mid_s=float(secs[0]), narrow_s=float(secs[1]))
 
 
+def hit_fingerprint(tri_first, tri_second) -> int:
+    """The order-free fingerprint of a hit set that imr_ref_frame_pairs_detail computes (sum of a 64-bit mix of the two ORIGINAL triangle
+    indices, modulo 2^64), for hit lists that come from somewhere else (the device)."""
+    x = (np.asarray(tri_first, np.uint64) << np.uint64(32)) | np.asarray(tri_second, np.uint64)
+    with np.errstate(over="ignore"):
+        x ^= x >> np.uint64(33); x *= np.uint64(0xff51afd7ed558ccd); x ^= x >> np.uint64(33); x *= np.uint64(0xc4ceb9fe1a85ec53); x ^= x >> np.uint64(33)
+    return x
+
+
+def frame_pairs_detail(orc, mats, trees, pairs, threads: int = 1) -> np.ndarray:
+    """Per pair of `pairs`: (non-coplanar hits, coplanar hits, colliding, fingerprint of the hit set) from the unmodified reference
+    (imr_ref_frame_pairs_detail), the pair loop split over `threads` host threads.  Returns (k, 3) u32 and (k,) u64."""
+    from concurrent.futures import ThreadPoolExecutor
+    assert orc.kind == "reference"
+    mats = _c(mats, np.float32).reshape(-1, 16)
+    pairs = _c(pairs, np.uint32).reshape(-1, 2)
+    handles = (C.c_void_p * mats.shape[0])(*[t.h for t in trees])
+    f = orc.lib.imr_ref_frame_pairs_detail
+    f.restype = None; f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+    out = np.zeros((len(pairs), 5), np.uint32)
+    threads = max(1, int(threads))
+
+    def run(t):
+        chunk = np.ascontiguousarray(pairs[t::threads]); o = np.zeros((len(chunk), 5), np.uint32)
+        if len(chunk):
+            f(mats.ctypes.data, handles, chunk.ctypes.data, len(chunk), o.ctypes.data)
+        out[t::threads] = o
+
+    if threads == 1:
+        run(0)
+    else:
+        with ThreadPoolExecutor(threads) as ex:
+            list(ex.map(run, range(threads)))
+    return out[:, :3].copy(), out[:, 3].astype(np.uint64) | (out[:, 4].astype(np.uint64) << np.uint64(32))
+
+
 class _RefGltfView(C.Structure):
     _fields_ = [("points", C.POINTER(C.c_float)), ("normals", C.POINTER(C.c_float)), ("indices", C.POINTER(C.c_uint32)),
                 ("n_points", C.c_uint64), ("n_indices", C.c_uint64), ("mode", C.c_uint32), ("skipped", C.c_uint32),

@@ -419,6 +419,43 @@ void imr_ref_frame_pairs(const float* mats, void* const* trees, const uint32_t* 
     if (seconds) { seconds[0] = s_mid; seconds[1] = s_narrow; }
 }
 
+// The same loop with a per-pair verdict: out[5 * k ..] = { non-coplanar hits, coplanar hits, colliding (>= 1 ray, CollisionDetection.cpp:63),
+// an order-free 64-bit fingerprint of the pair's hit set over ORIGINAL triangle indices (low word, high word) }.  Lets a test compare a whole
+// full-size frame (every pair of the sweep) with the device pair by pair and ask for the hit lists (imr_ref_pair) only where they differ.
+static inline uint64_t hit_mix(uint64_t a, uint64_t b) {
+    uint64_t x = (a << 32) | b;
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+    return x;
+}
+void imr_ref_frame_pairs_detail(const float* mats, void* const* trees, const uint32_t* pairs, uint64_t n_pairs, uint32_t* out) {
+    OBBtreesCollision mid;
+    CreateUncollideRays narrow;
+    for (uint64_t k = 0; k < n_pairs; ++k) {
+        const uint32_t ia = pairs[2 * k], ib = pairs[2 * k + 1];
+        RefTree* a = static_cast<RefTree*>(trees[ia]); RefTree* b = static_cast<RefTree*>(trees[ib]);
+        auto pr = std::make_pair(make_entry(mats + 16 * uint64_t(ia), nullptr, a, true, 1), make_entry(mats + 16 * uint64_t(ib), nullptr, b, true, 2));
+        uint32_t* o = out + 5 * k;
+        o[0] = o[1] = o[2] = o[3] = o[4] = 0;
+        CDentriesPairTrianglesPairs m = mid.ExecuteOBBtreesCollision(pr);
+        const auto& cc = m.OBBtreesIntersectInfoObj.candidateTriangleRangeCombinations;
+        if (cc.empty()) continue;
+        CDentriesUncollideRays rays = narrow.ExecuteCreateUncollideRays(m);
+        o[2] = (rays.rays_from_first_to_second.size() || rays.rays_from_second_to_first.size()) ? 1u : 0u;
+        const glm::mat4 rel = glm::inverse(pr.first.currentGlobalMatrix) * pr.second.currentGlobalMatrix;      // CreateUncollideRays.cpp:62
+        uint64_t fp = 0;
+        for (auto& c : cc)
+            for (size_t i = 0; i != c.first_obbtree_count; ++i)
+                for (size_t j = 0; j != c.second_obbtree_count; ++j) {
+                    TrianglePosition ta = a->tree.GetTrianglePosition(i + c.first_obbtree_offset);
+                    TrianglePosition tb = rel * b->tree.GetTrianglePosition(j + c.second_obbtree_offset);
+                    TrianglesIntersectionInfo info = Triangle::IntersectTriangles(ta, tb);
+                    if (info.doIntersept && info.areCoplanar) ++o[1];
+                    if (info.doIntersept && !info.areCoplanar) { ++o[0]; fp += hit_mix(a->orig_index[i + c.first_obbtree_offset], b->orig_index[j + c.second_obbtree_offset]); }
+                }
+        o[3] = uint32_t(fp); o[4] = uint32_t(fp >> 32);
+    }
+}
+
 // ---- response rays --------------------------------------------------------------
 // Ray::IntersectOBBtree (Ray.cpp:136-161) on one ray.  out3 = distanceFromOrigin, baryPosition; tri = leaf-order triangle index.
 int imr_ref_ray_tree(void* tree, const float* m16, const float* origin3, const float* dir3, float* out3, uint32_t* tri, int* back) {

@@ -44,3 +44,12 @@ for lo in bins:
     print(f"  t={lo:6.0f} us  warps busy {int(inside.any(1).sum()):5d}  iterations {int(inside.sum()):6d}  mean lanes {buf[:, :, 2][inside].mean() if inside.any() else 0:5.1f}  mean deque {buf[:, :, 3][inside].mean() if inside.any() else 0:6.1f}")
 iters = used.sum(1)
 print("iterations per warp: min %d median %d max %d; warps that never worked: %d" % (iters.min(), np.median(iters), iters.max(), int((iters == 0).sum())))
+# iteration length by number of node pairs in the iteration (a warp with few pairs deals their axes to several lanes)
+ln = buf[:, :, 2]
+dur = (e - b)
+for lo, hi in ((1, 2), (3, 4), (5, 8), (9, 16), (17, 24), (25, 32)):
+    m = used & (ln >= lo) & (ln <= hi)
+    if m.any():
+        late = m & (b > 0.6 * end)
+        print(f"pairs {lo:2d}-{hi:2d}: {int(m.sum()):7d} iterations, median {np.median(dur[m]):.2f} us, p10 {np.percentile(dur[m], 10):.2f}, p90 {np.percentile(dur[m], 90):.2f}"
+              + (f"; in the last 40 % of the kernel: {int(late.sum())} iterations, median {np.median(dur[late]):.2f} us" if late.any() else ""))
