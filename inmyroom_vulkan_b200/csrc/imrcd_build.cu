@@ -411,6 +411,13 @@ k_extents(uint32_t n, const TriRec* __restrict__ tris, const RecDesc* __restrict
 }
 
 // ---- 8. boxes -------------------------------------------------------------------------------------
+// Outward padding of a box whose centre has components up to cmax and whose largest half extent is hmax.  It has to cover (a) the FP32
+// rounding of the centre and of the side vectors and (b) the rounding of the 15-axis SAT itself (Paralgram.cpp:17-173 runs in FP32 on
+// coordinates of this size): two tight boxes around triangles that cross with a penetration depth of a few ulp would otherwise be called
+// separated and the hit lost (measured on BASELINE config 2: ~1e-4 of the hits with 4 ulp; the reference's own pad is 2 * FLT_EPSILON
+// absolute, OBB.cpp:123, but its boxes are loose).  32 ulp of the box's scale, plus the reference's absolute pad.
+__device__ __forceinline__ double box_pad(double cmax, double hmax) { return 32.0 * 5.9604644775390625e-8 * (cmax + hmax) + (double)FLT_EPSILON; }
+
 __global__ void k_finalize_boxes(uint32_t n_rec, const RecDesc* __restrict__ desc, const double* __restrict__ axes,
                                  const unsigned long long* __restrict__ ext, TreeRec* __restrict__ recs) {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -432,7 +439,7 @@ __global__ void k_finalize_boxes(uint32_t n_rec, const RecDesc* __restrict__ des
     // outward padding: covers the FP32 rounding of the centre and of the side vectors, plus the reference's own pad
     const double cmax = fmax(fabs(c[0]), fmax(fabs(c[1]), fabs(c[2])));
     const double hmax = fmax(half[0], fmax(half[1], half[2]));
-    const double pad = 4.0 * 5.9604644775390625e-8 * (cmax + hmax) + (double)FLT_EPSILON;
+    const double pad = box_pad(cmax, hmax);
     float s[9];
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
@@ -675,7 +682,7 @@ __global__ void k_rf_boxes(uint32_t total_rec, const RefitSeg* __restrict__ segs
     const float cf[3] = { (float)c[0], (float)c[1], (float)c[2] };
     const double cmax = fmax(fabs(c[0]), fmax(fabs(c[1]), fabs(c[2])));
     const double hmax = fmax(half[0], fmax(half[1], half[2]));
-    const double pad = 4.0 * 5.9604644775390625e-8 * (cmax + hmax) + (double)FLT_EPSILON;     // same outward rounding as k_finalize_boxes
+    const double pad = box_pad(cmax, hmax);     // same outward rounding as k_finalize_boxes
     float s[9];
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
