@@ -1,0 +1,580 @@
+// imrcd_fit.cu -- the OBB fit of a whole tree (or of many trees at once), shared by the Morton build and by the refit of re-posed meshes:
+// the replacement for OBB::CreateOBBfromPoints / CreateAABBfromPoints (IMR/src/Geometry/OBB.cpp:33-166) applied to every node of a tree
+// whose topology is given (OBBtree.cpp:8-108 builds boxes and topology together, top-down, re-walking a node's points ~11 times per level).
+//
+// A node's box needs (a) the covariance of its points -> axes (OBB.cpp:52-87) and (b) the extents of its points along those axes
+// (OBB.cpp:105-166).  (a) is a bottom-up sum of raw moments; (b) is not: every node projects all of its triangles on its OWN axes, so a
+// triangle is projected once per ancestor.  The tree is cut into TREELETS - maximal subtrees of at most FIT_T triangles, a contiguous
+// slice of the leaf-ordered triangle array:
+//   k_fit_treelets  one block per treelet: its triangles go to shared memory once; FP64 moments of every node bottom-up (leaf sums, then
+//                   child + child), covariance -> closed-form symmetric 3x3 eigen-solve -> axes, every triangle walks treelet root -> leaf
+//                   projecting on each node's axes (shared-memory min / max), boxes written; the treelet root's moments go to HBM
+//   k_fit_climb     the nodes ABOVE the treelets (1 in ~FIT_T/2 of all nodes): moments by child + child with one ticket per node
+//   k_fit_axes      ... their axes
+//   k_fit_upper     one block per treelet again: its triangles against every ancestor above it, one warp-reduced min / max per block
+//                   and ancestor, merged by atomics that are issued only when they would change the value
+//   k_fit_boxes     ... their boxes
+// Triangles are read twice (48 of their 64 bytes), node records written once: the pass is bandwidth-shaped, not atomic-shaped (round 1
+// walked every triangle root -> leaf through FP64 atomics: 0.03 of the HBM roofline).
+// Covariance sums are FP64 with explicit FMAs; projections are FP32 (explicit FMAs) of (point - node mean) on the FP32-rounded axes, and
+// the box is built from those same axes in FP64 and padded outward (box_pad) so that the FP32 box contains its triangles - unlike the
+// reference's, whose 2 * FLT_EPSILON pad (OBB.cpp:123) does not guarantee that.  Boxes use true PCA axes (the reference uses the ROWS of
+// eig3's V, SURVEY finding 3), so this is not the reference's tree: parity for it is asserted on tree-independent outputs.
+#include "imrcd_internal.cuh"
+#include "imrcd_fit.cuh"
+#include <algorithm>
+#include <cfloat>
+
+#define FULL_MASK 0xffffffffu
+
+__device__ __forceinline__ uint32_t f32_ord(float f) { uint32_t u = __float_as_uint(f); return (u >> 31) ? ~u : (u | 0x80000000u); }
+__device__ __forceinline__ float f32_unord(uint32_t u) { u = (u >> 31) ? (u & 0x7fffffffu) : ~u; return __uint_as_float(u); }
+
+// ---- closed-form symmetric 3x3 eigenvectors (trigonometric eigenvalues; eigenvector of the best separated eigenvalue from cross products of
+//      rows, the other two from the 2x2 problem in its orthogonal complement).  Replaces eig3's iterative tred2 / tql2 (eig3.cpp:21-254). ----
+__device__ __forceinline__ void cross_d(const double a[3], const double b[3], double o[3]) {
+    o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0];
+}
+__device__ __forceinline__ double dot_d(const double a[3], const double b[3]) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+
+__device__ void sym_eig3_axes(double a00, double a11, double a22, double a01, double a02, double a12, double ax[9]) {
+    ax[0] = 1; ax[1] = 0; ax[2] = 0; ax[3] = 0; ax[4] = 1; ax[5] = 0; ax[6] = 0; ax[7] = 0; ax[8] = 1;          // default: coordinate axes
+    const double mxabs = fmax(fmax(fabs(a00), fabs(a11)), fmax(fabs(a22), fmax(fabs(a01), fmax(fabs(a02), fabs(a12)))));
+    if (!(mxabs > 0.0) || !isfinite(mxabs)) return;
+    const double inv = 1.0 / mxabs;                  // scale to [-1,1] for robustness
+    a00 *= inv; a11 *= inv; a22 *= inv; a01 *= inv; a02 *= inv; a12 *= inv;
+    const double p1 = a01 * a01 + a02 * a02 + a12 * a12;
+    if (p1 < 1e-30) return;                          // already diagonal
+    const double q = (a00 + a11 + a22) / 3.0;
+    const double b00 = a00 - q, b11 = a11 - q, b22 = a22 - q;
+    const double p = sqrt((b00 * b00 + b11 * b11 + b22 * b22 + 2.0 * p1) / 6.0);
+    const double ip = 1.0 / p;
+    const double c00 = b00 * ip, c11 = b11 * ip, c22 = b22 * ip, c01 = a01 * ip, c02 = a02 * ip, c12 = a12 * ip;
+    double hd = 0.5 * (c00 * (c11 * c22 - c12 * c12) - c01 * (c01 * c22 - c12 * c02) + c02 * (c01 * c12 - c11 * c02));
+    hd = fmin(1.0, fmax(-1.0, hd));
+    const double ang = acos(hd) / 3.0;
+    const double e_hi = q + 2.0 * p * cos(ang);
+    const double e_lo = q + 2.0 * p * cos(ang + 2.0943951023931954923);
+    const double e_mid = 3.0 * q - e_hi - e_lo;
+    const bool use_hi = (e_hi - e_mid) >= (e_mid - e_lo);      // eigenvector of the best separated eigenvalue
+    const double ev = use_hi ? e_hi : e_lo;
+    const double r0[3] = { a00 - ev, a01, a02 }, r1[3] = { a01, a11 - ev, a12 }, r2[3] = { a02, a12, a22 - ev };
+    double c0[3], c1[3], c2[3];
+    cross_d(r0, r1, c0); cross_d(r0, r2, c1); cross_d(r1, r2, c2);
+    const double d0 = dot_d(c0, c0), d1 = dot_d(c1, c1), d2 = dot_d(c2, c2);
+    double w[3]; double dmax = d0; w[0] = c0[0]; w[1] = c0[1]; w[2] = c0[2];
+    if (d1 > dmax) { dmax = d1; w[0] = c1[0]; w[1] = c1[1]; w[2] = c1[2]; }
+    if (d2 > dmax) { dmax = d2; w[0] = c2[0]; w[1] = c2[1]; w[2] = c2[2]; }
+    if (!(dmax > 1e-60)) return;
+    const double iw = 1.0 / sqrt(dmax);
+    w[0] *= iw; w[1] *= iw; w[2] *= iw;
+    double u[3], v[3];                               // orthonormal complement (u, v) of w
+    if (fabs(w[0]) > fabs(w[1])) { const double il = 1.0 / sqrt(w[0] * w[0] + w[2] * w[2]); u[0] = -w[2] * il; u[1] = 0.0; u[2] = w[0] * il; }
+    else { const double il = 1.0 / sqrt(w[1] * w[1] + w[2] * w[2]); u[0] = 0.0; u[1] = w[2] * il; u[2] = -w[1] * il; }
+    cross_d(w, u, v);
+    const double Au[3] = { a00 * u[0] + a01 * u[1] + a02 * u[2], a01 * u[0] + a11 * u[1] + a12 * u[2], a02 * u[0] + a12 * u[1] + a22 * u[2] };
+    const double Av[3] = { a00 * v[0] + a01 * v[1] + a02 * v[2], a01 * v[0] + a11 * v[1] + a12 * v[2], a02 * v[0] + a12 * v[1] + a22 * v[2] };
+    const double m00 = dot_d(u, Au), m01 = dot_d(u, Av), m11 = dot_d(v, Av);      // 2x2 problem of A restricted to span(u, v)
+    const double th = 0.5 * atan2(2.0 * m01, m00 - m11);
+    const double cs = cos(th), sn = sin(th);
+    double e1[3] = { cs * u[0] + sn * v[0], cs * u[1] + sn * v[1], cs * u[2] + sn * v[2] };
+    double e2[3];
+    cross_d(w, e1, e2);
+    ax[0] = w[0]; ax[1] = w[1]; ax[2] = w[2]; ax[3] = e1[0]; ax[4] = e1[1]; ax[5] = e1[2]; ax[6] = e2[0]; ax[7] = e2[1]; ax[8] = e2[2];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) if (!isfinite(ax[k])) { ax[0] = 1; ax[1] = 0; ax[2] = 0; ax[3] = 0; ax[4] = 1; ax[5] = 0; ax[6] = 0; ax[7] = 0; ax[8] = 1; break; }
+}
+
+// ---- shared pieces --------------------------------------------------------------------------------------------------------------------
+// raw moments of a node relative to the call's origin: m[0..2] = sum(p - o), m[3..8] = sum of (xx, yy, zz, xy, xz, yz), m[9] = points
+__device__ __forceinline__ void mom_add_point(double m[10], double x, double y, double z) {
+    m[0] += x; m[1] += y; m[2] += z;
+    m[3] = __fma_rn(x, x, m[3]); m[4] = __fma_rn(y, y, m[4]); m[5] = __fma_rn(z, z, m[5]);
+    m[6] = __fma_rn(x, y, m[6]); m[7] = __fma_rn(x, z, m[7]); m[8] = __fma_rn(y, z, m[8]);
+    m[9] += 1.0;
+}
+
+// moments -> the node's frame: 12 floats = mean (the origin of the projections) + three unit axes, all rounded to FP32 once; every later
+// step (projections, the box itself) uses exactly these values
+__device__ __forceinline__ void frame_from_moments(const double m[10], const double o[3], float fr[12]) {
+    double ax[9] = { 1, 0, 0, 0, 1, 0, 0, 0, 1 };
+    double mean[3] = { o[0], o[1], o[2] };
+    if (m[9] > 0.0) {
+        const double in = 1.0 / m[9];
+        const double mx = m[0] * in, my = m[1] * in, mz = m[2] * in;
+        mean[0] += mx; mean[1] += my; mean[2] += mz;
+        sym_eig3_axes(m[3] * in - mx * mx, m[4] * in - my * my, m[5] * in - mz * mz, m[6] * in - mx * my, m[7] * in - mx * mz, m[8] * in - my * mz, ax);
+    }
+    fr[0] = (float)mean[0]; fr[1] = (float)mean[1]; fr[2] = (float)mean[2];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) fr[3 + k] = (float)ax[k];
+}
+
+// a triangle's three points on the three axes of a frame: min / max per axis as orderable integers (for integer min / max reductions)
+struct Ext6 { uint32_t v[6]; };
+__device__ __forceinline__ Ext6 project_tri(const float fr[12], const float p[9]) {
+    Ext6 e;
+    float mn[3] = { INFINITY, INFINITY, INFINITY }, mx[3] = { -INFINITY, -INFINITY, -INFINITY };
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float x = p[3 * k] - fr[0], y = p[3 * k + 1] - fr[1], z = p[3 * k + 2] - fr[2];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float pr = __fmaf_rn(fr[3 + 3 * a + 2], z, __fmaf_rn(fr[3 + 3 * a + 1], y, fr[3 + 3 * a] * x));
+            mn[a] = fminf(mn[a], pr); mx[a] = fmaxf(mx[a], pr);
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { e.v[2 * a] = f32_ord(mn[a]); e.v[2 * a + 1] = f32_ord(mx[a]); }
+    return e;
+}
+
+// Outward padding of a box whose centre has components up to cmax and whose largest half extent is hmax.  It covers the FP32 rounding of
+// the projections, of the centre and of the side vectors, and the rounding of the 15-axis SAT itself (Paralgram.cpp:17-173 runs in FP32 on
+// coordinates of this size).  32 ulp of the box's scale, plus the reference's own absolute pad (OBB.cpp:123).
+__device__ __forceinline__ double box_pad(double cmax, double hmax) { return 32.0 * 5.9604644775390625e-8 * (cmax + hmax) + (double)FLT_EPSILON; }
+
+// frame + extents -> the box (centre + three half-extent vectors, Paralgram.h:29-35) rounded to FP32 outward, with its surface
+__device__ __forceinline__ void box_from_frame(const float fr[12], const uint32_t ext[6], float4& q0, float4& q1, float4& q2, float& surface) {
+    double c[3] = { (double)fr[0], (double)fr[1], (double)fr[2] }, half[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const double mn = (double)f32_unord(ext[2 * a]), mx = (double)f32_unord(ext[2 * a + 1]);
+        const double mid = 0.5 * (mx + mn);
+        half[a] = 0.5 * (mx - mn);
+        c[0] = __fma_rn(mid, (double)fr[3 + 3 * a], c[0]); c[1] = __fma_rn(mid, (double)fr[3 + 3 * a + 1], c[1]); c[2] = __fma_rn(mid, (double)fr[3 + 3 * a + 2], c[2]);
+    }
+    const float cf[3] = { (float)c[0], (float)c[1], (float)c[2] };
+    const double cmax = fmax(fabs(c[0]), fmax(fabs(c[1]), fabs(c[2])));
+    const double hmax = fmax(half[0], fmax(half[1], half[2]));
+    const double pad = box_pad(cmax, hmax);
+    float s[9];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const double h = half[a] * (1.0 + 2.384185791015625e-7) + pad;
+        s[3 * a] = (float)(h * (double)fr[3 + 3 * a]); s[3 * a + 1] = (float)(h * (double)fr[3 + 3 * a + 1]); s[3 * a + 2] = (float)(h * (double)fr[3 + 3 * a + 2]);
+    }
+    q0 = make_float4(cf[0], cf[1], cf[2], s[0]); q1 = make_float4(s[1], s[2], s[3], s[4]); q2 = make_float4(s[5], s[6], s[7], s[8]);
+    Box b; b.c = mk3(cf[0], cf[1], cf[2]); b.u = mk3(s[0], s[1], s[2]); b.v = mk3(s[3], s[4], s[5]); b.w = mk3(s[6], s[7], s[8]);
+    surface = box_surface(b);
+}
+
+__device__ __forceinline__ void store_rec(TreeRec* recs, uint32_t rec, const FitRec& f, const FitSeg& sg, const float4& q0, const float4& q1, const float4& q2, float surface, bool write_links) {
+    TreeRec* out = recs + rec;
+    out->q0 = q0; out->q1 = q1; out->q2 = q2;
+    if (!write_links) { out->q3.x = surface; return; }                  // refit: links and leaf ranges are topology, unchanged
+    if (f.kind == 1u) out->q3 = make_float4(surface, __uint_as_float(f.first - sg.tri_base), __uint_as_float(f.last - f.first + 1u), __uint_as_float(1u));
+    else out->q3 = make_float4(surface, __uint_as_float(f.child - sg.rec_base), __uint_as_float(0u), __uint_as_float(0u));
+}
+
+// ---- classify the records of the call: above the treelets / treelet root / inside a treelet ------------------------------------------
+__device__ __forceinline__ uint32_t seg_locate(const uint32_t* __restrict__ prefix, uint32_t n_seg, uint32_t g) {   // last s with prefix[s] <= g
+    uint32_t lo = 0, hi = n_seg;
+    while (hi - lo > 1u) { const uint32_t mid = (lo + hi) >> 1; if (prefix[mid] <= g) lo = mid; else hi = mid; }
+    return lo;
+}
+
+__global__ void k_fit_collect(uint32_t total_rec, const FitSeg* __restrict__ segs, const uint32_t* __restrict__ rec_prefix, uint32_t n_seg,
+                              const FitRec* __restrict__ fit, uint32_t* __restrict__ slot_of, uint2* __restrict__ troots, uint32_t* __restrict__ uppers,
+                              FitCounters* cnt, TreeRec* recs, int write_links, const uint32_t* __restrict__ n_inner_dev) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n_inner_dev) total_rec = 2u + 2u * *n_inner_dev;                // a tree being built: its record count is known on the device only
+    if (g >= total_rec) return;
+    const uint32_t s = seg_locate(rec_prefix, n_seg, g);
+    const uint32_t rec = segs[s].rec_base + (g - rec_prefix[s]);
+    const FitRec f = fit[rec];
+    if (f.kind == 2u) {                                                  // the padding record beside the root
+        if (write_links) { TreeRec z; z.q0 = z.q1 = z.q2 = z.q3 = make_float4(0.f, 0.f, 0.f, 0.f); z.q3.w = __uint_as_float(1u); recs[rec] = z; }
+        return;
+    }
+    const uint32_t n = f.last - f.first + 1u;
+    if (n > FIT_T) { const uint32_t sl = atomicAdd(&cnt->n_slots, 1u); slot_of[rec] = sl; uppers[atomicAdd(&cnt->n_upper, 1u)] = rec; return; }
+    bool root = f.parent == 0xffffffffu;
+    if (!root) { const FitRec p = fit[f.parent]; root = p.last - p.first + 1u > FIT_T; }
+    if (root) { const uint32_t sl = atomicAdd(&cnt->n_slots, 1u); slot_of[rec] = sl; troots[atomicAdd(&cnt->n_troot, 1u)] = make_uint2(rec, s); }
+}
+
+// ---- the treelets ---------------------------------------------------------------------------------------------------------------------
+struct FitSmem {
+    float p[FIT_T][9];                      // the treelet's triangles (stride 9: conflict-free for consecutive threads)
+    double mom[FIT_R][10];
+    float fr[FIT_R][12];
+    uint32_t ext[FIT_R][6];
+    uint32_t rec[FIT_R], first[FIT_R], last[FIT_R], split[FIT_R], lchild[FIT_R], kind[FIT_R];
+    uint32_t lvl[FIT_T + 2];
+    uint32_t n_loc;
+};
+
+__global__ void __launch_bounds__(FIT_T)
+k_fit_treelets(const FitCounters* __restrict__ cnt, const uint2* __restrict__ troots, const FitSeg* __restrict__ segs, const FitRec* __restrict__ fit,
+               const TriRec* __restrict__ tris, const uint32_t* __restrict__ slot_of, double* __restrict__ mom_out, TreeRec* __restrict__ recs, int write_links) {
+    extern __shared__ __align__(16) unsigned char fit_smem[];
+    FitSmem& sm = *reinterpret_cast<FitSmem*>(fit_smem);
+    const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    for (uint32_t b = blockIdx.x; b < cnt->n_troot; b += gridDim.x) {
+        const uint2 tr = troots[b];
+        const FitSeg sg = segs[tr.y];
+        const FitRec root = fit[tr.x];
+        const uint32_t n = root.last - root.first + 1u;
+        __syncthreads();                                                 // the previous treelet's tables are no longer read
+        float p[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+        if (tid < n) {
+            const float4* tp = reinterpret_cast<const float4*>(tris + root.first + tid);
+            const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
+            p[0] = t0.x; p[1] = t0.y; p[2] = t0.z; p[3] = t1.x; p[4] = t1.y; p[5] = t1.z; p[6] = t2.x; p[7] = t2.y; p[8] = t2.z;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) sm.p[tid][k] = p[k];
+        }
+        if (tid == 0) { sm.rec[0] = tr.x; sm.n_loc = 1u; sm.lvl[0] = 0u; }
+        __syncthreads();
+        // -- the treelet's records, level by level (children of a node sit side by side) --
+        uint32_t begin = 0, end = 1, n_lvl = 0;
+        while (begin < end) {
+            for (uint32_t i = begin + tid; i < end; i += FIT_T) {
+                const FitRec f = fit[sm.rec[i]];
+                sm.first[i] = f.first; sm.last[i] = f.last; sm.split[i] = f.split; sm.kind[i] = f.kind;
+                uint32_t lc = 0xffffffffu;
+                if (f.kind == 0u) { lc = atomicAdd(&sm.n_loc, 2u); sm.rec[lc] = f.child; sm.rec[lc + 1u] = f.child + 1u; }
+                sm.lchild[i] = lc;
+            }
+            __syncthreads();
+            begin = end; end = sm.n_loc; sm.lvl[++n_lvl] = begin;        // every thread writes the same value
+            __syncthreads();
+        }
+        const uint32_t n_loc = end;
+        // -- FP64 moments bottom-up: leaves sum their points, inner nodes their two children (left + right: a fixed order) --
+        for (int l = (int)n_lvl - 1; l >= 0; --l) {
+            for (uint32_t i = sm.lvl[l] + tid; i < sm.lvl[l + 1]; i += FIT_T) {
+                double m[10];
+                if (sm.kind[i] == 1u) {
+#pragma unroll
+                    for (int k = 0; k < 10; ++k) m[k] = 0.0;
+                    for (uint32_t t = sm.first[i] - root.first; t <= sm.last[i] - root.first; ++t)
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) mom_add_point(m, (double)sm.p[t][3 * k] - sg.origin[0], (double)sm.p[t][3 * k + 1] - sg.origin[1], (double)sm.p[t][3 * k + 2] - sg.origin[2]);
+                } else {
+                    const uint32_t c = sm.lchild[i];
+#pragma unroll
+                    for (int k = 0; k < 10; ++k) m[k] = sm.mom[c][k] + sm.mom[c + 1u][k];
+                }
+#pragma unroll
+                for (int k = 0; k < 10; ++k) sm.mom[i][k] = m[k];
+            }
+            __syncthreads();
+        }
+        // -- frames (mean + PCA axes), extents reset; the root's moments travel up --
+        for (uint32_t i = tid; i < n_loc; i += FIT_T) {
+            double m[10];
+#pragma unroll
+            for (int k = 0; k < 10; ++k) m[k] = sm.mom[i][k];
+            float fr[12];
+            frame_from_moments(m, sg.origin, fr);
+#pragma unroll
+            for (int k = 0; k < 12; ++k) sm.fr[i][k] = fr[k];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { sm.ext[i][2 * k] = 0xffffffffu; sm.ext[i][2 * k + 1] = 0u; }
+            if (i == 0u) { double* mo = mom_out + 10ull * slot_of[tr.x];
+#pragma unroll
+                for (int k = 0; k < 10; ++k) mo[k] = m[k]; }
+        }
+        __syncthreads();
+        // -- extents: every triangle walks treelet root -> leaf; lanes of a warp that sit in the same node reduce among themselves first --
+        {
+            bool active = tid < n;
+            uint32_t node = 0;
+            const uint32_t my_tri = root.first + tid;
+            while (__any_sync(FULL_MASK, active)) {
+                Ext6 e;
+#pragma unroll
+                for (int q = 0; q < 6; ++q) e.v[q] = (q & 1) ? 0u : 0xffffffffu;
+                if (active) e = project_tri(sm.fr[node], p);
+                const uint32_t lead_node = __shfl_sync(FULL_MASK, node, __ffs(__ballot_sync(FULL_MASK, active)) - 1);
+                const bool uniform = __all_sync(FULL_MASK, !active || node == lead_node);
+                if (uniform) {
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) e.v[q] = (q & 1) ? __reduce_max_sync(FULL_MASK, e.v[q]) : __reduce_min_sync(FULL_MASK, e.v[q]);
+                    if (lane == 0) {
+#pragma unroll
+                        for (int q = 0; q < 6; ++q) { if (q & 1) atomicMax(&sm.ext[lead_node][q], e.v[q]); else atomicMin(&sm.ext[lead_node][q], e.v[q]); }
+                    }
+                } else if (active) {
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) { if (q & 1) atomicMax(&sm.ext[node][q], e.v[q]); else atomicMin(&sm.ext[node][q], e.v[q]); }
+                }
+                if (active) {
+                    if (sm.kind[node] == 1u) active = false;
+                    else node = sm.lchild[node] + (my_tri > sm.split[node] ? 1u : 0u);
+                }
+            }
+        }
+        __syncthreads();
+        // -- boxes --
+        for (uint32_t i = tid; i < n_loc; i += FIT_T) {
+            float4 q0, q1, q2; float surface;
+            box_from_frame(sm.fr[i], sm.ext[i], q0, q1, q2, surface);
+            FitRec f; f.first = sm.first[i]; f.last = sm.last[i]; f.kind = sm.kind[i]; f.child = sm.kind[i] == 0u ? sm.rec[sm.lchild[i]] : 0u;
+            store_rec(recs, sm.rec[i], f, sg, q0, q1, q2, surface, write_links != 0);
+        }
+    }
+}
+
+// ---- above the treelets -----------------------------------------------------------------------------------------------------------------
+// one thread per treelet root climbs: the second child to arrive at a node adds its sibling's moments and goes on
+__global__ void k_fit_climb(const FitCounters* __restrict__ cnt, const uint2* __restrict__ troots, const FitRec* __restrict__ fit,
+                            const uint32_t* __restrict__ slot_of, double* mom, uint32_t* ticket) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= cnt->n_troot) return;
+    uint32_t cur = troots[t].x;
+    double m[10];
+    { const double* mo = mom + 10ull * slot_of[cur];
+#pragma unroll
+      for (int k = 0; k < 10; ++k) m[k] = __ldcg(mo + k); }
+    for (;;) {
+        const uint32_t par = fit[cur].parent;
+        if (par == 0xffffffffu) return;
+        const uint32_t ps = slot_of[par];
+        __threadfence();                                                 // my subtree's total is visible before I take the ticket
+        if (atomicAdd(&ticket[ps], 1u) == 0u) return;                    // the sibling's subtree is not finished: it will go on from here
+        const uint32_t child = fit[par].child;
+        const uint32_t sib = (cur == child) ? child + 1u : child;
+        const double* so = mom + 10ull * slot_of[sib];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) m[k] += __ldcg(so + k);
+        double* po = mom + 10ull * ps;
+#pragma unroll
+        for (int k = 0; k < 10; ++k) __stcg(po + k, m[k]);
+        cur = par;
+    }
+}
+
+__global__ void k_fit_axes(const FitCounters* __restrict__ cnt, const uint32_t* __restrict__ uppers, const FitSeg* __restrict__ segs, const uint32_t* __restrict__ seg_of_upper,
+                           const uint32_t* __restrict__ slot_of, const double* __restrict__ mom, float* __restrict__ frames, uint32_t* __restrict__ ext) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= cnt->n_upper) return;
+    const uint32_t rec = uppers[t], sl = slot_of[rec];
+    double m[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) m[k] = mom[10ull * sl + k];
+    float fr[12];
+    frame_from_moments(m, segs[seg_of_upper[t]].origin, fr);
+#pragma unroll
+    for (int k = 0; k < 12; ++k) frames[12ull * sl + k] = fr[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { ext[6ull * sl + 2 * k] = 0xffffffffu; ext[6ull * sl + 2 * k + 1] = 0u; }
+}
+
+// one block per treelet: its triangles against every ancestor above the treelet.  One min / max per block and ancestor (hardware warp
+// reductions on orderable integers, then across the warps), merged by an atomic only when it would change the stored value: the top of
+// the tree hears from every treelet, and almost none of them moves its extents.
+__global__ void __launch_bounds__(FIT_T)
+k_fit_upper(const FitCounters* __restrict__ cnt, const uint2* __restrict__ troots, const FitRec* __restrict__ fit, const TriRec* __restrict__ tris,
+            const uint32_t* __restrict__ slot_of, const float* __restrict__ frames, uint32_t* ext) {
+    __shared__ uint32_t s_part[FIT_T / 32][6];
+    __shared__ float s_fr[12];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    for (uint32_t b = blockIdx.x; b < cnt->n_troot; b += gridDim.x) {
+        const FitRec root = fit[troots[b].x];
+        const uint32_t n = root.last - root.first + 1u;
+        float p[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+        if (tid < n) {
+            const float4* tp = reinterpret_cast<const float4*>(tris + root.first + tid);
+            const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
+            p[0] = t0.x; p[1] = t0.y; p[2] = t0.z; p[3] = t1.x; p[4] = t1.y; p[5] = t1.z; p[6] = t2.x; p[7] = t2.y; p[8] = t2.z;
+        }
+        for (uint32_t a = root.parent; a != 0xffffffffu; a = fit[a].parent) {
+            const uint32_t sl = slot_of[a];
+            __syncthreads();                                             // s_fr / s_part of the previous ancestor are no longer read
+            if (tid < 12) s_fr[tid] = frames[12ull * sl + tid];
+            __syncthreads();
+            Ext6 e;
+#pragma unroll
+            for (int q = 0; q < 6; ++q) e.v[q] = (q & 1) ? 0u : 0xffffffffu;
+            if (tid < n) e = project_tri(s_fr, p);
+#pragma unroll
+            for (int q = 0; q < 6; ++q) e.v[q] = (q & 1) ? __reduce_max_sync(FULL_MASK, e.v[q]) : __reduce_min_sync(FULL_MASK, e.v[q]);
+            if (lane == 0) {
+#pragma unroll
+                for (int q = 0; q < 6; ++q) s_part[warp][q] = e.v[q];
+            }
+            __syncthreads();
+            if (tid < 6) {
+                uint32_t v = s_part[0][tid];
+#pragma unroll
+                for (int w = 1; w < FIT_T / 32; ++w) v = (tid & 1) ? max(v, s_part[w][tid]) : min(v, s_part[w][tid]);
+                uint32_t* dst = ext + 6ull * sl + tid;
+                const uint32_t seen = *((volatile uint32_t*)dst);       // a stale value only costs an atomic that changes nothing
+                if (tid & 1) { if (v > seen) atomicMax(dst, v); } else { if (v < seen) atomicMin(dst, v); }
+            }
+        }
+    }
+}
+
+__global__ void k_fit_boxes(const FitCounters* __restrict__ cnt, const uint32_t* __restrict__ uppers, const FitSeg* __restrict__ segs, const uint32_t* __restrict__ seg_of_upper,
+                            const FitRec* __restrict__ fit, const uint32_t* __restrict__ slot_of, const float* __restrict__ frames, const uint32_t* __restrict__ ext,
+                            TreeRec* __restrict__ recs, int write_links) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= cnt->n_upper) return;
+    const uint32_t rec = uppers[t], sl = slot_of[rec];
+    float fr[12]; uint32_t ex[6];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) fr[k] = frames[12ull * sl + k];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) ex[k] = ext[6ull * sl + k];
+    float4 q0, q1, q2; float surface;
+    box_from_frame(fr, ex, q0, q1, q2, surface);
+    store_rec(recs, rec, fit[rec], segs[seg_of_upper[t]], q0, q1, q2, surface, write_links != 0);
+}
+
+// uppers were collected without their segment: look it up once (the list is short)
+__global__ void k_fit_upper_segs(const FitCounters* __restrict__ cnt, const uint32_t* __restrict__ uppers, const FitSeg* __restrict__ segs, uint32_t n_seg, uint32_t* __restrict__ seg_of_upper) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= cnt->n_upper) return;
+    const uint32_t rec = uppers[t];
+    uint32_t lo = 0, hi = n_seg;                                          // segments are sorted by rec_base (arena order)
+    while (hi - lo > 1u) { const uint32_t mid = (lo + hi) >> 1; if (segs[mid].rec_base <= rec) lo = mid; else hi = mid; }
+    seg_of_upper[t] = lo;
+}
+
+// ---- FitRec of a tree that was not built here (imported, reference mode): from the records' links ---------------------------------------
+__global__ void k_plan_links(uint32_t n_rec, uint32_t rec_base, uint32_t tri_base, const TreeRec* __restrict__ recs, FitRec* fit, uint32_t* ticket) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rec) return;
+    ticket[r] = 0u;
+    FitRec& f = fit[rec_base + r];
+    if (r == 0u) f.parent = 0xffffffffu;
+    if (r == 1u) { f.first = f.last = f.split = f.child = 0u; f.parent = 0xffffffffu; f.kind = 2u; return; }
+    const float4 q3 = recs[rec_base + r].q3;
+    if (__float_as_uint(q3.w) == 0u) {
+        const uint32_t c = rec_base + __float_as_uint(q3.y);
+        f.child = c; f.kind = 0u;
+        fit[c].parent = rec_base + r; fit[c + 1u].parent = rec_base + r;
+    } else {
+        const uint32_t cntt = __float_as_uint(q3.z);
+        f.first = tri_base + __float_as_uint(q3.y); f.last = cntt ? f.first + cntt - 1u : f.first; f.split = f.last; f.child = 0u; f.kind = 1u;
+    }
+}
+__global__ void k_plan_ranges(uint32_t n_rec, uint32_t rec_base, FitRec* fit, uint32_t* ticket) {
+    const uint32_t r0 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r0 >= n_rec || r0 == 1u) return;
+    uint32_t cur = rec_base + r0;
+    if (fit[cur].kind != 1u) return;                                     // leaves start; the second child to arrive finishes the parent
+    for (;;) {
+        const uint32_t par = fit[cur].parent;
+        if (par == 0xffffffffu) return;
+        __threadfence();
+        if (atomicAdd(&ticket[par - rec_base], 1u) == 0u) return;
+        const uint32_t child = fit[par].child;
+        const FitRec l = fit[child], r = fit[child + 1u];
+        volatile FitRec* p = fit + par;
+        p->first = min(l.first, r.first); p->last = max(l.last, r.last); p->split = l.last;
+        cur = par;
+    }
+}
+
+// ---- host -------------------------------------------------------------------------------------------------------------------------------
+static inline unsigned nb(uint64_t n, unsigned bs) { return (unsigned)((n + bs - 1) / bs); }
+
+int imr_fit_reserve(imrcd_ctx* ctx, uint64_t n_rec_total) {
+    IMR_CUDA(ctx, ctx->d_fit.reserve(sizeof(FitRec) * n_rec_total, std::min<uint64_t>(ctx->d_fit.cap, sizeof(FitRec) * n_rec_total), ctx->stream));
+    return IMRCD_OK;
+}
+
+int imr_fit_plan_from_records(imrcd_ctx* ctx, const MeshDev& md) {
+    cudaStream_t s = ctx->stream;
+    int rc = imr_fit_reserve(ctx, ctx->n_rec_total); if (rc) return rc;
+    IMR_CUDA(ctx, ctx->d_fit_ticket.reserve(4ull * md.n_rec, 0, s));
+    k_plan_links<<<nb(md.n_rec, 256), 256, 0, s>>>(md.n_rec, md.rec_base, md.tri_base, ctx->d_recs.as<TreeRec>(), ctx->d_fit.as<FitRec>(), ctx->d_fit_ticket.as<uint32_t>());
+    k_plan_ranges<<<nb(md.n_rec, 256), 256, 0, s>>>(md.n_rec, md.rec_base, ctx->d_fit.as<FitRec>(), ctx->d_fit_ticket.as<uint32_t>());
+    IMR_CUDA(ctx, cudaGetLastError());
+    return IMRCD_OK;
+}
+
+// origin of the raw moments of a segment: the centre of the mesh's bounds (build) or of its old root box (refit), taken on the device
+__global__ void k_fit_origin_bounds(FitSeg* seg, const uint32_t* __restrict__ bounds) {
+    for (int a = 0; a < 3; ++a) seg->origin[a] = 0.5 * ((double)f32_unord(bounds[a]) + (double)f32_unord(bounds[3 + a]));
+}
+__global__ void k_fit_origin_roots(uint32_t n_seg, FitSeg* segs, const TreeRec* __restrict__ recs) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_seg) return;
+    const float4 q = recs[segs[s].rec_base].q0;
+    segs[s].origin[0] = (double)q.x; segs[s].origin[1] = (double)q.y; segs[s].origin[2] = (double)q.z;
+}
+
+struct FitLayout { FitCounters* cnt; FitSeg* segs; uint32_t* prefix; double* mom; uint2* troots; float* frames; uint32_t* ext; uint32_t* uppers; uint32_t* seg_of_upper; uint32_t* ticket; };
+static FitLayout fit_layout(imrcd_ctx* ctx) {
+    FitLayout L;
+    char* sb = ctx->d_fit_segs.as<char>();
+    L.cnt = reinterpret_cast<FitCounters*>(sb);
+    L.segs = reinterpret_cast<FitSeg*>(sb + 64);
+    L.prefix = reinterpret_cast<uint32_t*>(L.segs + ctx->fit_ns);
+    char* b = ctx->d_fit_scratch.as<char>();
+    L.mom = reinterpret_cast<double*>(b); b += 80 * ctx->fit_max_slots;
+    L.troots = reinterpret_cast<uint2*>(b); b += 8 * ctx->fit_max_troot;
+    L.frames = reinterpret_cast<float*>(b); b += 48 * ctx->fit_max_slots;
+    L.ext = reinterpret_cast<uint32_t*>(b); b += 24 * ctx->fit_max_slots;
+    L.uppers = reinterpret_cast<uint32_t*>(b); b += 4 * ctx->fit_max_slots;
+    L.seg_of_upper = reinterpret_cast<uint32_t*>(b); b += 4 * ctx->fit_max_slots;
+    L.ticket = reinterpret_cast<uint32_t*>(b);
+    return L;
+}
+
+// First half of a fit: buffers and the segment table (segments in arena order; their origins are filled in on the device by the caller's
+// k_fit_origin_* launch).  Waits for the stream once (the pinned staging block may still feed the previous call's copy): call it before a
+// timed region.
+int imr_fit_prepare(imrcd_ctx* ctx, const std::vector<FitSeg>& segs) {
+    cudaStream_t s = ctx->stream;
+    const uint32_t ns = (uint32_t)segs.size();
+    std::vector<uint32_t> prefix(ns);
+    uint64_t tot_rec = 0, tot_tri = 0;
+    for (uint32_t k = 0; k < ns; ++k) { prefix[k] = (uint32_t)tot_rec; tot_rec += segs[k].n_rec; tot_tri += segs[k].n_tri; }
+    if (tot_rec >= (1ull << 32)) { ctx->err = "fit: too many records in one call"; return IMRCD_E_CAPACITY; }
+    // every treelet root has more than FIT_T / 2 triangles or is a whole tree; the nodes above the treelets are fewer than the treelets
+    ctx->fit_ns = ns; ctx->fit_tot_rec = tot_rec;
+    ctx->fit_max_troot = 2 * (tot_tri / (FIT_T / 2 + 1)) + ns + 16; ctx->fit_max_slots = 2 * ctx->fit_max_troot + 16;
+    IMR_CUDA(ctx, ctx->d_fit_segs.reserve(sizeof(FitSeg) * ns + 4ull * ns + 64, 0, s));
+    IMR_CUDA(ctx, ctx->p_fit_segs.reserve(sizeof(FitSeg) * ns + 4ull * ns, 0, s));
+    IMR_CUDA(ctx, ctx->d_fit_slot.reserve(4ull * (ctx->d_recs.cap / sizeof(TreeRec)) + 64, 0, s));
+    IMR_CUDA(ctx, ctx->d_fit_scratch.reserve(8ull * ctx->fit_max_troot + (80 + 48 + 24 + 4 + 4 + 4) * ctx->fit_max_slots + 256, 0, s));
+    IMR_CUDA(ctx, cudaStreamSynchronize(s));
+    memcpy(ctx->p_fit_segs.p, segs.data(), sizeof(FitSeg) * ns);
+    memcpy(ctx->p_fit_segs.as<char>() + sizeof(FitSeg) * ns, prefix.data(), 4ull * ns);
+    const FitLayout L = fit_layout(ctx);
+    IMR_CUDA(ctx, cudaMemcpyAsync(L.segs, ctx->p_fit_segs.p, sizeof(FitSeg) * ns + 4ull * ns, cudaMemcpyHostToDevice, s));
+    if (!ctx->fit_attr_set) {
+        IMR_CUDA(ctx, cudaFuncSetAttribute(k_fit_treelets, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FitSmem)));
+        int per_sm = 0;
+        IMR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fit_treelets, FIT_T, sizeof(FitSmem)));
+        ctx->fit_blocks = ctx->sm_count * std::max(per_sm, 1);
+        ctx->fit_attr_set = true;
+    }
+    return IMRCD_OK;
+}
+
+// Second half: every kernel of the fit, enqueued on the context's stream; nothing waits.  `bounds` (build: the mesh's centroid bounds, still on
+// the device) or the old root boxes (refit) give the origins; n_inner_dev, when given, is the device-side count of kept inner nodes of the ONE
+// tree being built (its record count is not known on the host yet).
+int imr_fit_launch(imrcd_ctx* ctx, bool write_links, const uint32_t* bounds, const uint32_t* n_inner_dev) {
+    cudaStream_t s = ctx->stream;
+    const FitLayout L = fit_layout(ctx);
+    const uint32_t ns = ctx->fit_ns;
+    const uint64_t max_troot = ctx->fit_max_troot, max_slots = ctx->fit_max_slots;
+    IMR_CUDA(ctx, cudaMemsetAsync(L.cnt, 0, sizeof(FitCounters), s));
+    IMR_CUDA(ctx, cudaMemsetAsync(L.ticket, 0, 4 * max_slots, s));
+    if (bounds) k_fit_origin_bounds<<<1, 1, 0, s>>>(L.segs, bounds);
+    else k_fit_origin_roots<<<nb(ns, 128), 128, 0, s>>>(ns, L.segs, ctx->d_recs.as<TreeRec>());
+    const FitRec* fit = ctx->d_fit.as<FitRec>();
+    uint32_t* slot_of = ctx->d_fit_slot.as<uint32_t>();
+    TreeRec* recs = ctx->d_recs.as<TreeRec>();
+    const TriRec* tris = ctx->d_tris.as<TriRec>();
+    const int wl = write_links ? 1 : 0;
+    k_fit_collect<<<nb(ctx->fit_tot_rec, 256), 256, 0, s>>>((uint32_t)ctx->fit_tot_rec, L.segs, L.prefix, ns, fit, slot_of, L.troots, L.uppers, L.cnt, recs, wl, n_inner_dev);
+    const unsigned g_troot = (unsigned)std::min<uint64_t>(max_troot, 1u << 30);
+    k_fit_treelets<<<std::min<unsigned>(g_troot, ctx->fit_blocks), FIT_T, sizeof(FitSmem), s>>>(L.cnt, L.troots, L.segs, fit, tris, slot_of, L.mom, recs, wl);
+    k_fit_climb<<<nb(max_troot, 128), 128, 0, s>>>(L.cnt, L.troots, fit, slot_of, L.mom, L.ticket);
+    k_fit_upper_segs<<<nb(max_slots, 256), 256, 0, s>>>(L.cnt, L.uppers, L.segs, ns, L.seg_of_upper);
+    k_fit_axes<<<nb(max_slots, 128), 128, 0, s>>>(L.cnt, L.uppers, L.segs, L.seg_of_upper, slot_of, L.mom, L.frames, L.ext);
+    k_fit_upper<<<std::min<unsigned>(g_troot, ctx->sm_count * 16), FIT_T, 0, s>>>(L.cnt, L.troots, fit, tris, slot_of, L.frames, L.ext);
+    k_fit_boxes<<<nb(max_slots, 128), 128, 0, s>>>(L.cnt, L.uppers, L.segs, L.seg_of_upper, fit, slot_of, L.frames, L.ext, recs, wl);
+    IMR_CUDA(ctx, cudaGetLastError());
+    return IMRCD_OK;
+}

@@ -154,6 +154,7 @@ struct MeshHost {
     float root_box[12];
     float build_ms = 0.f;
     bool needs_refit = false;            // positions were updated since the last refit
+    bool fit_plan = false;               // d_fit holds this mesh's FitRecs (Morton builds leave them; other trees get them at their first refit)
 };
 
 struct imrcd_ctx {
@@ -166,7 +167,9 @@ struct imrcd_ctx {
     // mesh arena
     std::vector<MeshHost> meshes;
     DevBuf d_recs, d_tris, d_tri_nrm, d_tri_vid, d_meshes;
-    DevBuf d_rf_stage, d_rf_segs, d_rf_scratch;      // refit staging / segment table / scratch (imrcd_build.cu)
+    DevBuf d_rf_stage;                               // re-posed positions on their way into the arena (imrcd_build.cu)
+    DevBuf d_fit, d_fit_slot, d_fit_segs, d_fit_scratch, d_fit_ticket; PinBuf p_fit_segs;      // the tree fit (imrcd_fit.cu): FitRec per arena record, per-call tables
+    uint32_t fit_ns = 0; uint64_t fit_tot_rec = 0, fit_max_troot = 0, fit_max_slots = 0; bool fit_attr_set = false; int fit_blocks = 0;
     float last_refit_ms = 0.f;
     uint64_t n_rec_total = 0, n_tri_total = 0;
     bool meshes_dirty = false;

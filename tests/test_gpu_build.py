@@ -65,6 +65,38 @@ def test_morton_tree_structure_and_containment(gpu_ctx, mesh):
     check_boxes_contain(flat, lo, hi)
 
 
+def test_morton_build_two_million_triangles(gpu_ctx):
+    """Structure and containment at a size where the tree has thousands of treelets and ~20 levels above them (BASELINE config 4 is the same
+    mesh at 10 M triangles: scripts / bench.py --workload c4 check it the same way)."""
+    mesh = scenes.grid_sheet(1450, 725, 1500.0, 750.0, bump=40.0)
+    assert mesh.n_tri > 2_000_000
+    t = OBBtree(gpu_ctx, mesh.positions, mesh.normals, mesh.vertex_ids)
+    flat = t.export()
+    lo, hi = check_tree_structure(flat, mesh)
+    check_boxes_contain(flat, lo, hi, sample=600)
+    # every box on the path from the root to a few leaves, the largest ones included
+    leaf_v = np.nonzero(flat.left < 0)[0]
+    parent = np.full(flat.nv, -1, np.int64)
+    inner = np.nonzero(flat.left >= 0)[0]
+    parent[flat.left[inner]] = inner; parent[flat.right[inner]] = inner
+    for v in leaf_v[:: max(1, len(leaf_v) // 7)][:7].tolist():
+        chain = []
+        while v >= 0:
+            chain.append(v); v = int(parent[v])
+        sub = type("F", (), {})()
+        check_boxes_contain_list(flat, lo, hi, chain)
+
+
+def check_boxes_contain_list(flat, lo, hi, vs):
+    for v in vs:
+        b = flat.boxes[v].astype(np.float64)
+        c, sides = b[:3], b[3:].reshape(3, 3)
+        pts = flat.tri_pos[lo[v]:hi[v]].reshape(-1, 3).astype(np.float64) - c
+        for a in range(3):
+            h = np.linalg.norm(sides[a])
+            assert np.abs(pts @ (sides[a] / h)).max() <= h, v
+
+
 def test_morton_build_tiny_and_empty(gpu_ctx):
     m = scenes.box_mesh(1, 1, 1, sub=1)
     for k in (1, 2, 3, 4, 5):
