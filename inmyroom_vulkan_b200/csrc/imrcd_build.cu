@@ -166,39 +166,79 @@ __global__ void k_flag_inner(int n_int, const uint32_t* __restrict__ first, cons
 }
 
 // The kept nodes become records (FitRec, imrcd_fit.cuh: arena indices): an inner node writes its own record and those of its children that
-// are leaves (collapsed subtrees or single triangles); record 0 is the root, record 1 the padding beside it.
-__global__ void k_assign(int n_int, const int* __restrict__ left, const int* __restrict__ right, const int* __restrict__ parent_int,
-                         const uint32_t* __restrict__ first, const uint32_t* __restrict__ last, const uint32_t* __restrict__ flag,
-                         const uint32_t* __restrict__ slot, FitRec* __restrict__ fit, uint32_t rec_base, uint32_t tri_base) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) { FitRec pad; pad.first = pad.last = pad.split = pad.child = 0u; pad.parent = 0xffffffffu; pad.kind = 2u; pad.pad0 = pad.pad1 = 0u; fit[rec_base + 1u] = pad; }
-    if (i >= n_int || !flag[i]) return;
-    // my own record: root -> 0, else the slot my parent reserved for its children
-    uint32_t myrec = 0, mypar = 0xffffffffu;
-    if (i != 0) { const int p = parent_int[i]; myrec = 2u + 2u * slot[p] + (left[p] == i ? 0u : 1u); mypar = rec_base + (p == 0 ? 0u : 2u + 2u * slot[parent_int[p]] + (left[parent_int[p]] == p ? 0u : 1u)); }
-    const uint32_t child_base = 2u + 2u * slot[i];
-    const int lc = left[i], rc = right[i];
-    FitRec me; me.first = tri_base + first[i]; me.last = tri_base + last[i]; me.child = rec_base + child_base; me.kind = 0u; me.parent = mypar; me.pad0 = me.pad1 = 0u;
-    me.split = tri_base + ((lc >= 0) ? last[lc] : (uint32_t)(~lc));
-    fit[rec_base + myrec] = me;
-#pragma unroll
-    for (int side = 0; side < 2; ++side) {
-        const int c = side ? rc : lc;
-        if (c >= 0 && flag[c]) continue;               // a kept inner node writes its own record
-        FitRec d;
-        if (c >= 0) { d.first = tri_base + first[c]; d.last = tri_base + last[c]; }
-        else { d.first = d.last = tri_base + (uint32_t)(~c); }
-        d.split = d.last; d.child = 0u; d.kind = 1u; d.parent = rec_base + myrec; d.pad0 = d.pad1 = 0u;
-        fit[rec_base + child_base + side] = d;
+// are leaves (collapsed subtrees or single triangles); record 0 is the root, record 1 the padding beside it.  The same thread puts the
+// node on the fit's lists: "upper" when its subtree is too large for one block (more than FIT_T triangles or FIT_R records), and each
+// child whose subtree is small enough under such a node as a treelet root.  The inner nodes of a subtree over leaves [l, r] are consecutive in
+// the radix tree's numbering - [l, r - 1] when its root is numbered l (a right child, or the root), [l + 1, r] when it is numbered r (a left
+// child) - so the records of their children are consecutive in the arena: slots [slot[lo], slot[lo + r - l]).
+// append `rec` (for the lanes with `yes`) to a list: one atomic per warp for the list position and one for the slots; converged code only
+__device__ __forceinline__ void fit_list_append(bool yes, uint32_t rec, uint32_t* counter, uint32_t* n_slots, uint32_t* slot_of, uint2* troots, uint32_t* uppers) {
+    const uint32_t m = __ballot_sync(0xffffffffu, yes);
+    if (m == 0u) return;
+    const uint32_t lane = threadIdx.x & 31u, leader = (uint32_t)__ffs(m) - 1u, k = (uint32_t)__popc(m);
+    uint32_t base = 0, sbase = 0;
+    if (lane == leader) { base = atomicAdd(counter, k); sbase = atomicAdd(n_slots, k); }
+    base = __shfl_sync(0xffffffffu, base, leader); sbase = __shfl_sync(0xffffffffu, sbase, leader);
+    if (yes) {
+        const uint32_t off = (uint32_t)__popc(m & ((1u << lane) - 1u));
+        slot_of[rec] = sbase + off;
+        if (troots) troots[base + off] = make_uint2(rec, 0u); else uppers[base + off] = rec;
     }
 }
 
+__global__ void k_assign(int n_int, const int* __restrict__ left, const int* __restrict__ right, const int* __restrict__ parent_int,
+                         const uint32_t* __restrict__ first, const uint32_t* __restrict__ last, const uint32_t* __restrict__ flag,
+                         const uint32_t* __restrict__ slot, FitRec* __restrict__ fit, uint32_t rec_base, uint32_t tri_base, FitLists L) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) { FitRec pad; pad.first = pad.last = pad.split = pad.child = 0u; pad.parent = 0xffffffffu; pad.kind = 2u; pad.desc = 0xffffffffu; pad.n_sub = 1u; fit[rec_base + 1u] = pad; }
+    const bool kept_me = i < n_int && flag[i];
+    bool me_upper = false, me_troot = false, c_troot[2] = { false, false };
+    uint32_t myrec = 0, child_base = 0;
+    if (kept_me) {
+        // my own record: root -> 0, else the slot my parent reserved for its children
+        uint32_t mypar = 0xffffffffu;
+        if (i != 0) { const int p = parent_int[i]; myrec = 2u + 2u * slot[p] + (left[p] == i ? 0u : 1u); mypar = rec_base + (p == 0 ? 0u : 2u + 2u * slot[parent_int[p]] + (left[parent_int[p]] == p ? 0u : 1u)); }
+        child_base = 2u + 2u * slot[i];
+        const int lc = left[i], rc = right[i];
+        const uint32_t my_tris = last[i] - first[i] + 1u;
+        const uint32_t my_lo = ((uint32_t)i == first[i]) ? first[i] : first[i] + 1u, my_sub = 2u * (slot[my_lo + last[i] - first[i]] - slot[my_lo]) + 1u;
+        FitRec me; me.first = tri_base + first[i]; me.last = tri_base + last[i]; me.child = rec_base + child_base; me.kind = 0u; me.parent = mypar;
+        me.split = tri_base + ((lc >= 0) ? last[lc] : (uint32_t)(~lc));
+        me.desc = rec_base + 2u + 2u * slot[my_lo]; me.n_sub = my_sub;
+        fit[rec_base + myrec] = me;
+        const bool me_small = FIT_SMALL(my_tris, my_sub);
+        me_upper = !me_small; me_troot = me_small && i == 0;
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+            const int c = side ? rc : lc;
+            const bool kept = c >= 0 && flag[c];
+            if (!kept) {                               // a leaf record (a kept inner node writes its own)
+                FitRec d;
+                if (c >= 0) { d.first = tri_base + first[c]; d.last = tri_base + last[c]; }
+                else { d.first = d.last = tri_base + (uint32_t)(~c); }
+                d.split = d.last; d.child = 0u; d.kind = 1u; d.parent = rec_base + myrec; d.desc = 0xffffffffu; d.n_sub = 1u;
+                fit[rec_base + child_base + side] = d;
+            }
+            if (!me_small) {                           // a child with a small subtree under a large one: a treelet root
+                bool c_small = true;
+                if (kept) { const uint32_t c_lo = ((uint32_t)c == first[c]) ? first[c] : first[c] + 1u; c_small = FIT_SMALL(last[c] - first[c] + 1u, 2u * (slot[c_lo + last[c] - first[c]] - slot[c_lo]) + 1u); }
+                c_troot[side] = c_small;
+            }
+        }
+    }
+    fit_list_append(me_upper, rec_base + myrec, &L.cnt->n_upper, &L.cnt->n_slots, L.slot_of, nullptr, L.uppers);
+    fit_list_append(me_troot, rec_base + myrec, &L.cnt->n_troot, &L.cnt->n_slots, L.slot_of, L.troots, nullptr);
+    fit_list_append(c_troot[0], rec_base + child_base, &L.cnt->n_troot, &L.cnt->n_slots, L.slot_of, L.troots, nullptr);
+    fit_list_append(c_troot[1], rec_base + child_base + 1u, &L.cnt->n_troot, &L.cnt->n_slots, L.slot_of, L.troots, nullptr);
+}
+
 // single-leaf meshes (<= 4 triangles): OBBtree.cpp:346-356
-__global__ void k_assign_single_leaf(FitRec* fit, uint32_t rec_base, uint32_t tri_base, uint32_t n, uint32_t* n_inner) {
-    FitRec d; d.first = tri_base; d.last = tri_base + (n ? n - 1u : 0u); d.split = d.last; d.child = 0u; d.parent = 0xffffffffu; d.kind = 1u; d.pad0 = d.pad1 = 0u;
+__global__ void k_assign_single_leaf(FitRec* fit, uint32_t rec_base, uint32_t tri_base, uint32_t n, uint32_t* n_inner, FitLists L) {
+    FitRec d; d.first = tri_base; d.last = tri_base + (n ? n - 1u : 0u); d.split = d.last; d.child = 0u; d.parent = 0xffffffffu; d.kind = 1u; d.desc = 0xffffffffu; d.n_sub = 1u;
     fit[rec_base] = d;
     d.first = d.last = d.split = 0u; d.kind = 2u; fit[rec_base + 1u] = d;
     *n_inner = 0u;
+    L.slot_of[rec_base] = 0u; L.troots[0] = make_uint2(rec_base, 0u); L.cnt->n_slots = 1u; L.cnt->n_troot = 1u; L.cnt->n_upper = 0u;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -273,8 +313,9 @@ static int build_morton(imrcd_ctx* ctx, const float* h_pos, const float* h_nrm, 
     std::vector<FitSeg> segs(1);
     segs[0].rec_base = mh->dev.rec_base; segs[0].n_rec = (uint32_t)n_rec_max; segs[0].tri_base = mh->dev.tri_base; segs[0].n_tri = n;
     segs[0].origin[0] = segs[0].origin[1] = segs[0].origin[2] = 0.0;
-    rc = imr_fit_prepare(ctx, segs);
+    rc = imr_fit_prepare(ctx, segs, 0);
     if (rc) { free_all(); return rc; }
+    const FitLists lists = imr_fit_lists(ctx);
     TriRec* tris = ctx->d_tris.as<TriRec>() + mh->dev.tri_base;
     TreeRec* recs = ctx->d_recs.as<TreeRec>() + mh->dev.rec_base;
     FitRec* fit = ctx->d_fit.as<FitRec>();
@@ -297,11 +338,13 @@ static int build_morton(imrcd_ctx* ctx, const float* h_pos, const float* h_nrm, 
         k_flag_inner<<<nb(n_int + 1, 256), 256, 0, s>>>((int)n_int, d_first.as<uint32_t>(), d_last.as<uint32_t>(), d_flag.as<uint32_t>());
         cub::DeviceScan::ExclusiveSum(d_tmp.p, scan_bytes, d_flag.as<uint32_t>(), d_slot.as<uint32_t>(), (int)(n_int + 1), s);
         k_assign<<<nb(n_int, 128), 128, 0, s>>>((int)n_int, d_left.as<int>(), d_right.as<int>(), d_pint.as<int>(), d_first.as<uint32_t>(), d_last.as<uint32_t>(),
-                                                d_flag.as<uint32_t>(), d_slot.as<uint32_t>(), fit, mh->dev.rec_base, mh->dev.tri_base);
-    } else k_assign_single_leaf<<<1, 1, 0, s>>>(fit, mh->dev.rec_base, mh->dev.tri_base, n, n_inner_dev);
+                                                d_flag.as<uint32_t>(), d_slot.as<uint32_t>(), fit, mh->dev.rec_base, mh->dev.tri_base, lists);
+    } else k_assign_single_leaf<<<1, 1, 0, s>>>(fit, mh->dev.rec_base, mh->dev.tri_base, n, n_inner_dev, lists);
     // 5. the fit
-    rc = imr_fit_launch(ctx, true, d_bounds.as<uint32_t>(), n_inner_dev);
+    rc = imr_fit_launch(ctx, true, d_bounds.as<uint32_t>(), true);
     if (rc) { free_all(); return rc; }
+    { TreeRec z; memset(&z, 0, sizeof(z)); uint32_t one = 1u; memcpy(&z.q3.w, &one, 4);      // the padding record beside the root
+      BUILD_CUDA(cudaMemcpyAsync(recs + 1, &z, sizeof(z), cudaMemcpyHostToDevice, s)); }
     BUILD_CUDA(cudaEventRecord(e1, s));
     TreeRec root; uint32_t n_inner = 0;
     BUILD_CUDA(cudaMemcpyAsync(&root, recs, sizeof(TreeRec), cudaMemcpyDeviceToHost, s));
@@ -366,11 +409,13 @@ int imr_meshes_refit_device(imrcd_ctx* ctx, const uint32_t* ids, uint64_t n_ids,
     }
     if (segs.empty()) { if (ms_out) *ms_out = 0.f; return IMRCD_OK; }
     cudaStream_t s = ctx->stream;
-    int rc = imr_fit_prepare(ctx, segs);
+    uint64_t key = 0xcbf29ce484222325ull;               // the same trees as the last call (the arena is append-only: base + size name a tree)
+    for (const FitSeg& g : segs) { key = (key ^ g.rec_base) * 0x100000001b3ull; key = (key ^ g.n_rec) * 0x100000001b3ull; key = (key ^ g.n_tri) * 0x100000001b3ull; }
+    int rc = imr_fit_prepare(ctx, segs, key | 1ull);
     if (rc) return rc;
     cudaEvent_t e0 = ctx->ev[6], e1 = ctx->ev[7];
     IMR_CUDA(ctx, cudaEventRecord(e0, s));
-    rc = imr_fit_launch(ctx, false, nullptr, nullptr);      // origins: the old root boxes' centres
+    rc = imr_fit_launch(ctx, false, nullptr, false);      // origins: the old root boxes' centres
     if (rc) return rc;
     IMR_CUDA(ctx, cudaEventRecord(e1, s));
     IMR_CUDA(ctx, cudaStreamSynchronize(s));

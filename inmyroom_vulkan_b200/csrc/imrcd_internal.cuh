@@ -170,6 +170,7 @@ struct imrcd_ctx {
     DevBuf d_rf_stage;                               // re-posed positions on their way into the arena (imrcd_build.cu)
     DevBuf d_fit, d_fit_slot, d_fit_segs, d_fit_scratch, d_fit_ticket; PinBuf p_fit_segs;      // the tree fit (imrcd_fit.cu): FitRec per arena record, per-call tables
     uint32_t fit_ns = 0; uint64_t fit_tot_rec = 0, fit_max_troot = 0, fit_max_slots = 0; bool fit_attr_set = false; int fit_blocks = 0;
+    uint64_t fit_key = 0; bool fit_lists_valid = false;      // the last fit call's trees (a hash of their ids and sizes): its lists can be used again
     float last_refit_ms = 0.f;
     uint64_t n_rec_total = 0, n_tri_total = 0;
     bool meshes_dirty = false;
