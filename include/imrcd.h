@@ -160,6 +160,24 @@ int imrcd_mesh_export_tree(imrcd_ctx* ctx, uint32_t mesh_id, float* boxes, int32
 int imrcd_mesh_update_positions(imrcd_ctx* ctx, uint32_t mesh_id, const float* positions, const float* normals);
 int imrcd_mesh_refit(imrcd_ctx* ctx, const uint32_t* mesh_ids, uint64_t n);
 int imrcd_mesh_last_refit_ms(imrcd_ctx* ctx, float* ms);
+/* Re-posing on the device (BASELINE config 5): the arithmetic of the engine's dynamic-mesh compute pass for the position stream
+ * (IMR/shaders/dynamicMeshShader_glsl.comp:99-145, DynamicMeshes::RecordTransformations, IMR/src/Graphics/DynamicMeshes.cpp:672-790):
+ *     morphed = V[x (T + 1)] + sum_i w_i V[x (T + 1) + i + 1]
+ *     result  = morphed (no joints)  or  sum_groups sum_c weights.c * (M[joints.c] * InvBind[joints.c] * morphed)
+ * A skin is what that pass reads per vertex: `vertices` = n_vertices * (n_morph_targets + 1) vec4 (the base vertex, then its morph
+ * targets, as the engine lays them out), and per vertex `joints_groups` groups of 4 u16 joint indices and 4 float weights (0 groups: a
+ * morph-only mesh).  imrcd_mesh_bind_skin ties a mesh to a skin: the corners of its triangles are the skin's vertices named by the
+ * mesh's vertex ids (TriangleIndices, Triangle.cpp:242-250).  imrcd_meshes_repose re-poses any number of bound meshes in one batched
+ * pass - morph_weights: the skins' n_morph_targets floats per mesh, concatenated; joint_matrices / inverse_bind: n_joints[k] mat4 per
+ * mesh, concatenated (modelMatrices[matrixOffset + 1 + j].positionMatrix and inverseModelMatrices[inverseMatricesOffset + j] of the
+ * shader) - and rewrites the triangles of their trees; imrcd_mesh_refit (NULL) then refits exactly those meshes.  Normals are not
+ * re-posed (imrcd_mesh_update_positions takes new ones). */
+int imrcd_skin_create(imrcd_ctx* ctx, uint64_t n_vertices, uint32_t n_morph_targets, const float* vertices, uint32_t joints_groups,
+                      const uint16_t* joints, const float* weights, uint32_t* skin_id);
+int imrcd_mesh_bind_skin(imrcd_ctx* ctx, uint32_t mesh_id, uint32_t skin_id);
+int imrcd_meshes_repose(imrcd_ctx* ctx, uint64_t n, const uint32_t* mesh_ids, const float* morph_weights, const float* joint_matrices,
+                        const float* inverse_bind, const uint32_t* n_joints);
+int imrcd_mesh_last_repose_ms(imrcd_ctx* ctx, float* ms);
 /* device time of the last imrcd_mesh_create in ms */
 int imrcd_mesh_last_build_ms(imrcd_ctx* ctx, float* ms);
 
@@ -257,6 +275,8 @@ int imrcd_test_tri_tri(imrcd_ctx* ctx, uint64_t n, const float* tris_a, const fl
                        uint8_t* flags, float* seg /* n*6 */);
 int imrcd_test_pair_matrix(imrcd_ctx* ctx, uint64_t n, const float* a, const float* b, float* out /* n*16 */);
 int imrcd_test_obb_fit(imrcd_ctx* ctx, uint64_t n_points, const float* points, float* out12);
+/* the re-posed vertices (vec4 each) of the last imrcd_meshes_repose call, in the call's order */
+int imrcd_test_reposed_vertices(imrcd_ctx* ctx, float* out, uint64_t n_vertices);
 /* Ray::IntersectOBBtree (Ray.cpp:136-236) on n rays against one mesh: mats n*16 (tree -> ray space), origins / directions n*3;
  * flags bit0 doIntersect, bit1 itBackfaces; out3 = distanceFromOrigin, baryPosition.x, .y; tri = LEAF-ORDER triangle index (0xffffffff: none) */
 int imrcd_test_ray_tree(imrcd_ctx* ctx, uint32_t mesh_id, uint64_t n, const float* mats, const float* origins, const float* directions,

@@ -69,6 +69,11 @@ _SIGS = [
     ("imrcd_mesh_update_positions", C.c_int, [_P, C.c_uint32, _P, _P]),
     ("imrcd_mesh_refit", C.c_int, [_P, _P, C.c_uint64]),
     ("imrcd_mesh_last_refit_ms", C.c_int, [_P, C.POINTER(C.c_float)]),
+    ("imrcd_skin_create", C.c_int, [_P, C.c_uint64, C.c_uint32, _P, C.c_uint32, _P, _P, C.POINTER(C.c_uint32)]),
+    ("imrcd_mesh_bind_skin", C.c_int, [_P, C.c_uint32, C.c_uint32]),
+    ("imrcd_meshes_repose", C.c_int, [_P, C.c_uint64, _P, _P, _P, _P, _P]),
+    ("imrcd_mesh_last_repose_ms", C.c_int, [_P, C.POINTER(C.c_float)]),
+    ("imrcd_test_reposed_vertices", C.c_int, [_P, _P, C.c_uint64]),
     ("imrcd_frame_reset", C.c_int, [_P]),
     ("imrcd_frame_add_entry", C.c_int, [_P, _P, _P, C.c_uint32, C.c_uint8, C.c_uint32]),
     ("imrcd_frame_add_entries", C.c_int, [_P, C.c_uint64, _P, _P, _P, _P, _P]),

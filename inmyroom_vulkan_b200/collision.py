@@ -115,6 +115,45 @@ class Context:
         return (flags & 1).astype(bool), (flags & 2).astype(bool), out[:, 0].copy(), out[:, 1:3].copy(), tri
 
 
+class Skin:
+    """What the engine's dynamic-mesh pass reads per vertex (imrcd_skin_create): vertices (n, T + 1, 4) = base + morph targets,
+    joints (n, G, 4) u16 and weights (n, G, 4) f32 (None: morph only)."""
+
+    def __init__(self, ctx: "Context", vertices, joints=None, weights=None):
+        v = _c(vertices, np.float32)
+        assert v.ndim == 3 and v.shape[2] == 4
+        self.ctx = ctx; self.n_vertices = v.shape[0]; self.n_targets = v.shape[1] - 1
+        jn = None if joints is None else _c(joints, np.uint16).reshape(self.n_vertices, -1, 4)
+        w = None if weights is None else _c(weights, np.float32).reshape(self.n_vertices, -1, 4)
+        self.n_groups = 0 if jn is None else jn.shape[1]
+        sid = C.c_uint32()
+        ctx.check(ctx.lib.imrcd_skin_create(ctx.h, self.n_vertices, self.n_targets, _ptr(v), self.n_groups, _ptr(jn), _ptr(w), C.byref(sid)))
+        self.skin_id = sid.value
+
+
+def repose_meshes(ctx: "Context", trees, morph_weights=None, joint_matrices=None, inverse_bind=None) -> None:
+    """imrcd_meshes_repose: one batched pass over `trees` (each bound to a Skin).  morph_weights: (len(trees), T) or None;
+    joint_matrices / inverse_bind: (len(trees), J, 16) or None.  Follow with refit_meshes(ctx)."""
+    ids = np.array([t.mesh_id for t in trees], np.uint32)
+    mw = None if morph_weights is None else _c(morph_weights, np.float32)
+    jm = None if joint_matrices is None else _c(joint_matrices, np.float32).reshape(len(trees), -1, 16)
+    ib = None if inverse_bind is None else _c(inverse_bind, np.float32).reshape(len(trees), -1, 16)
+    nj = None if jm is None else np.full(len(trees), jm.shape[1], np.uint32)
+    ctx.check(ctx.lib.imrcd_meshes_repose(ctx.h, len(ids), _ptr(ids), _ptr(mw), _ptr(jm), _ptr(ib), _ptr(nj)))
+
+
+def last_repose_ms(ctx: "Context") -> float:
+    ms = C.c_float()
+    ctx.check(ctx.lib.imrcd_mesh_last_repose_ms(ctx.h, C.byref(ms)))
+    return ms.value
+
+
+def reposed_vertices(ctx: "Context", n_vertices: int) -> np.ndarray:
+    out = np.zeros((n_vertices, 4), np.float32)
+    ctx.check(ctx.lib.imrcd_test_reposed_vertices(ctx.h, _ptr(out), n_vertices))
+    return out
+
+
 def refit_meshes(ctx: "Context", trees=None) -> float:
     """Batched refit of `trees` (None = every mesh updated since its last refit); returns the device time in ms."""
     if trees is None:
@@ -188,6 +227,9 @@ class OBBtree:
         self = cls.__new__(cls)
         self.ctx = ctx; self.mesh_id = mid.value
         return self
+
+    def bind_skin(self, skin: "Skin"):
+        self.ctx.check(self.ctx.lib.imrcd_mesh_bind_skin(self.ctx.h, self.mesh_id, skin.skin_id))
 
     def update_positions(self, positions, normals=None):
         """New triangle positions (original input order); call refit() / refit_meshes() before the next frame."""

@@ -61,14 +61,15 @@ extern "C" void imrcd_destroy(imrcd_ctx* ctx) {
     if (!ctx) return;
     recording_clear(ctx);
     imrcd_comm_destroy(ctx);
+    imr_skins_release(ctx);
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf* bufs[] = { &ctx->d_recs, &ctx->d_tris, &ctx->d_tri_nrm, &ctx->d_tri_vid, &ctx->d_meshes, &ctx->d_rf_stage, &ctx->d_fit, &ctx->d_fit_slot, &ctx->d_fit_segs, &ctx->d_fit_scratch, &ctx->d_fit_ticket, &ctx->d_cur, &ctx->d_prev, &ctx->d_mesh,
+    DevBuf* bufs[] = { &ctx->d_recs, &ctx->d_tris, &ctx->d_tri_nrm, &ctx->d_tri_vid, &ctx->d_meshes, &ctx->d_rf_stage, &ctx->d_repose_in, &ctx->d_repose_prod, &ctx->d_repose_vtx, &ctx->d_scalar, &ctx->d_fit, &ctx->d_fit_slot, &ctx->d_fit_segs, &ctx->d_fit_scratch, &ctx->d_fit_ticket, &ctx->d_cur, &ctx->d_prev, &ctx->d_mesh,
                        &ctx->d_cb, &ctx->d_entity, &ctx->d_inv, &ctx->d_ext, &ctx->d_keys, &ctx->d_keys2, &ctx->d_idx, &ctx->d_idx2,
                        &ctx->d_sorted, &ctx->d_sorted_c, &ctx->d_flag, &ctx->d_cpos, &ctx->d_wlen, &ctx->d_chunks, &ctx->d_chunkoff, &ctx->d_cubtmp, &ctx->d_pairs, &ctx->d_pairrec, &ctx->d_pairacc, &ctx->d_queue, &ctx->d_combos,
                        &ctx->d_hits, &ctx->d_epairs, &ctx->d_ctl, &ctx->d_aux, &ctx->d_grouped, &ctx->d_lscratch, &ctx->d_lpref, &ctx->d_lsides, &ctx->d_rays, &ctx->d_resp, &ctx->d_epair_pair, &ctx->d_trace, &ctx->d_gidx, &ctx->d_gather, &ctx->d_padded, &ctx->d_padoff, &ctx->d_lsmall, &ctx->d_lmid, &ctx->d_llarge };
     for (DevBuf* b : bufs) b->release();
-    PinBuf* pins[] = { &ctx->p_fit_segs, &ctx->p_gidx, &ctx->p_gather, &ctx->p_cur, &ctx->p_prev, &ctx->p_mesh, &ctx->p_entity, &ctx->p_cb, &ctx->p_ctl, &ctx->p_epairs, &ctx->p_hits, &ctx->p_pairs, &ctx->p_combos };
+    PinBuf* pins[] = { &ctx->p_repose, &ctx->p_fit_segs, &ctx->p_gidx, &ctx->p_gather, &ctx->p_cur, &ctx->p_prev, &ctx->p_mesh, &ctx->p_entity, &ctx->p_cb, &ctx->p_ctl, &ctx->p_epairs, &ctx->p_hits, &ctx->p_pairs, &ctx->p_combos };
     for (PinBuf* b : pins) b->release();
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
@@ -257,6 +258,7 @@ extern "C" int imrcd_mesh_add_primitive(imrcd_ctx* ctx, const float* points, uin
     CHECK_CTX(ctx);
     if (!ctx->recording_open) { ctx->err = "imrcd_mesh_add_primitive before imrcd_mesh_begin"; return IMRCD_E_STATE; }
     if ((n_points && !points) || (stride_floats != 3 && stride_floats != 4) || gltf_mode > 6) { ctx->err = "imrcd_mesh_add_primitive: bad argument"; return IMRCD_E_ARG; }
+    if (n_points == 0 && indices && n_indices) { ctx->err = "imrcd_mesh_add_primitive: indices without points"; return IMRCD_E_ARG; }
     cudaSetDevice(ctx->device);
     cudaStream_t s = ctx->stream;
     ctx->recording.emplace_back();
@@ -272,6 +274,15 @@ extern "C" int imrcd_mesh_add_primitive(imrcd_ctx* ctx, const float* points, uin
     }
     if (indices && n_indices) { IMR_CUDA(ctx, r.indices.reserve(4ull * n_indices, 0, s)); IMR_CUDA(ctx, cudaMemcpyAsync(r.indices.p, indices, 4ull * n_indices, cudaMemcpyDefault, s)); }
     IMR_CUDA(ctx, cudaStreamSynchronize(s));                            // the caller may reuse its buffers
+    if (indices && n_indices) {       // the engine forwards raw glTF index buffers: an index past the points would read outside the primitive
+        uint32_t mx = 0;
+        const int rc = imr_device_max_u32(ctx, r.indices.as<uint32_t>(), n_indices, &mx);
+        if (rc) { ctx->recording.back().points.release(); ctx->recording.back().normals.release(); ctx->recording.back().indices.release(); ctx->recording.pop_back(); return rc; }
+        if (mx >= n_points) {
+            ctx->recording.back().points.release(); ctx->recording.back().normals.release(); ctx->recording.back().indices.release(); ctx->recording.pop_back();
+            ctx->err = "imrcd_mesh_add_primitive: an index exceeds the number of points"; return IMRCD_E_ARG;
+        }
+    }
     return IMRCD_OK;
 }
 extern "C" int imrcd_mesh_end(imrcd_ctx* ctx, uint32_t build_mode, uint32_t* mesh_id) {

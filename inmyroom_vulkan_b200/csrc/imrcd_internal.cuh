@@ -154,6 +154,7 @@ struct MeshHost {
     float root_box[12];
     float build_ms = 0.f;
     bool needs_refit = false;            // positions were updated since the last refit
+    int skin = -1;                       // imrcd_mesh_bind_skin
     bool fit_plan = false;               // d_fit holds this mesh's FitRecs (Morton builds leave them; other trees get them at their first refit)
 };
 
@@ -167,6 +168,8 @@ struct imrcd_ctx {
     // mesh arena
     std::vector<MeshHost> meshes;
     DevBuf d_recs, d_tris, d_tri_nrm, d_tri_vid, d_meshes;
+    void* skins = nullptr; std::vector<uint32_t> skin_max_joint;                       // re-posing (imrcd_repose.cu)
+    PinBuf p_repose; DevBuf d_repose_in, d_repose_prod, d_repose_vtx, d_scalar; bool repose_pending = false; float last_repose_ms = 0.f;
     DevBuf d_rf_stage;                               // re-posed positions on their way into the arena (imrcd_build.cu)
     DevBuf d_fit, d_fit_slot, d_fit_segs, d_fit_scratch, d_fit_ticket; PinBuf p_fit_segs;      // the tree fit (imrcd_fit.cu): FitRec per arena record, per-call tables
     uint32_t fit_ns = 0; uint64_t fit_tot_rec = 0, fit_max_troot = 0, fit_max_slots = 0; bool fit_attr_set = false; int fit_blocks = 0;
@@ -208,7 +211,7 @@ struct imrcd_ctx {
     FrameCtl ctl_host;
     imrcd_frame_stats stats;
     bool hits_fetched = false;
-    cudaEvent_t ev[8] = {};
+    cudaEvent_t ev[10] = {};            // [0..6] frame stages, [6..7] build / refit, [8..9] re-pose
     cudaStream_t stream2 = nullptr, stream3 = nullptr, stream4 = nullptr;      // side streams for independent tail work of a frame
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join3 = nullptr, ev_join4 = nullptr;
     int trav_blocks = 0, narrow_blocks = 0, trav_variant = 0, shoot_blocks = 0;
@@ -241,3 +244,5 @@ int imr_test_ray_tree_device(imrcd_ctx* ctx, uint32_t mesh_id, uint64_t n, const
                              uint8_t* flags, float* out3, uint32_t* tri);
 int imr_mesh_update_positions_device(imrcd_ctx* ctx, uint32_t mesh_id, const float* pos, const float* nrm);
 int imr_meshes_refit_device(imrcd_ctx* ctx, const uint32_t* ids, uint64_t n_ids, float* ms_out);
+void imr_skins_release(imrcd_ctx* ctx);
+int imr_device_max_u32(imrcd_ctx* ctx, const uint32_t* d_values, uint64_t n, uint32_t* out);

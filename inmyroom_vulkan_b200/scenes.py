@@ -268,3 +268,55 @@ def scene_static_vs_bodies(body: Mesh, n_bodies: int, seed: int = 2026, body_sca
     ents = np.arange(1, ns + n_bodies + 1, dtype=np.uint32)
     return Scene(st_meshes + [body], mesh_index, np.ascontiguousarray(mats), cb, ents,
                  name=f"static{ns}+{n_bodies}x{body.name}", meta=dict(seed=seed))
+
+
+# ---- BASELINE config 5: a skinned / morphed character (a ring of joints along a torus) --------------------------------------------------
+@dataclass
+class Character:
+    mesh: Mesh                  # the bind pose as a triangle mesh (vertex_ids index `vertices`)
+    vertices: np.ndarray        # (n_vertices, T + 1, 4) f32: base vertex (w = 1), then its morph targets (deltas, w = 0): the engine's layout
+    joints: np.ndarray          # (n_vertices, G, 4) u16
+    weights: np.ndarray         # (n_vertices, G, 4) f32, rows sum to 1
+    inverse_bind: np.ndarray    # (J, 16) f32 column-major
+    joint_centres: np.ndarray   # (J, 3) f64
+
+    @property
+    def n_joints(self) -> int:
+        return int(self.inverse_bind.shape[0])
+
+    def pose(self, phase: float, amplitude: float = 0.35):
+        """Joint matrices (J, 16) and morph weights (T,) of one frame of a seeded animation: every joint turns about the ring's tangent by
+        an angle that travels round the ring (modelMatrices[j].positionMatrix of the shader: bind translation x rotation)."""
+        J = self.n_joints
+        ang = amplitude * np.sin(phase + 4.0 * np.pi * np.arange(J) / J)
+        t = 2 * np.pi * np.arange(J) / J
+        tangent = np.stack([-np.sin(t), np.cos(t), np.zeros(J)], 1)
+        q = np.concatenate([tangent * np.sin(ang / 2)[:, None], np.cos(ang / 2)[:, None]], 1)
+        mats = trs_matrices(self.joint_centres, q, np.ones((J, 3)))
+        T = self.vertices.shape[1] - 1
+        mw = (0.5 + 0.5 * np.sin(phase * 1.7 + np.arange(T))).astype(np.float32)
+        return mats, mw
+
+
+def character(nu: int = 142, nv: int = 71, n_joints: int = 64, n_targets: int = 2, R: float = 1.0, r: float = 0.35) -> Character:
+    """A nu x nv torus (142 x 71 = 20,164 triangles, 10,082 vertices) skinned to a ring of joints: 4 joints per vertex (the two nearest on
+    either side, smooth weights), `n_targets` morph targets (radial bulges)."""
+    mesh = torus(nu, nv, R, r)
+    u = np.arange(nu) * (2 * np.pi / nu); v = np.arange(nv) * (2 * np.pi / nv)
+    uu, vv = np.meshgrid(u, v, indexing="ij")
+    verts = np.stack([(R + r * np.cos(vv)) * np.cos(uu), (R + r * np.cos(vv)) * np.sin(uu), r * np.sin(vv)], -1).reshape(-1, 3)
+    n = verts.shape[0]
+    V = np.zeros((n, n_targets + 1, 4), np.float32)
+    V[:, 0, :3] = verts; V[:, 0, 3] = 1.0
+    rad = np.stack([np.cos(vv) * np.cos(uu), np.cos(vv) * np.sin(uu), np.sin(vv)], -1).reshape(-1, 3)
+    for k in range(n_targets):
+        V[:, k + 1, :3] = (0.08 * np.cos((k + 2) * uu + k).reshape(-1, 1) * rad)
+    pos = uu.reshape(-1) / (2 * np.pi) * n_joints                     # position along the ring in joint units
+    j0 = np.floor(pos).astype(np.int64)
+    f = pos - j0
+    idx = np.stack([(j0 - 1) % n_joints, j0 % n_joints, (j0 + 1) % n_joints, (j0 + 2) % n_joints], 1)
+    w = np.stack([(1 - f) ** 3, 3 * f ** 3 - 6 * f ** 2 + 4, -3 * f ** 3 + 3 * f ** 2 + 3 * f + 1, f ** 3], 1) / 6.0      # cubic B-spline: smooth, sums to 1
+    t = 2 * np.pi * np.arange(n_joints) / n_joints
+    centres = np.stack([R * np.cos(t), R * np.sin(t), np.zeros(n_joints)], 1)
+    inv_bind = trs_matrices(-centres, np.tile([0.0, 0.0, 0.0, 1.0], (n_joints, 1)), np.ones((n_joints, 3)))
+    return Character(mesh, V, idx.astype(np.uint16).reshape(n, 1, 4), w.astype(np.float32).reshape(n, 1, 4), inv_bind, centres)

@@ -349,6 +349,21 @@ class PortOracle(_Base):
     def _sig(self):
         pass
 
+    def repose(self, vertices, n_targets, joints, weights, morph_weights, joint_matrices, inverse_bind):
+        """dynamicMeshShader_glsl.comp:99-145, position stream: vertices (n, T + 1, 4) f32, joints (n, G, 4) u16 / weights (n, G, 4) f32 or
+        None, morph_weights (T,), matrices (J, 16) each -> (n, 4) f32."""
+        v = _c(vertices, np.float32).reshape(-1, n_targets + 1, 4); n = v.shape[0]
+        g = 0 if joints is None else _c(joints, np.uint16).reshape(n, -1, 4).shape[1]
+        jn = None if joints is None else _c(joints, np.uint16); w = None if weights is None else _c(weights, np.float32)
+        mw = _c(morph_weights if n_targets else np.zeros(1), np.float32)
+        jm = None if joint_matrices is None else _c(joint_matrices, np.float32).reshape(-1, 16)
+        ib = None if inverse_bind is None else _c(inverse_bind, np.float32).reshape(-1, 16)
+        out = np.zeros((n, 4), np.float32)
+        f = self.lib.imro_repose; f.restype = None
+        f.argtypes = [C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+        f(n, n_targets, v.ctypes.data, g, _opt(jn), _opt(w), mw.ctypes.data, 0 if jm is None else jm.shape[0], _opt(jm), _opt(ib), out.ctypes.data)
+        return out
+
     def eig3(self, A):
         A = _c(A, np.float64).reshape(9)
         V = np.empty(9, np.float64); d = np.empty(3, np.float64)

@@ -1339,3 +1339,45 @@ void imro_frame_pairs(const float* mats, const imro_tree* const* trees, const ui
     }
     totals[0] = combos; totals[1] = tests; totals[2] = colliding; totals[3] = with_combos;
 }
+
+
+/* ---- re-posing (BASELINE config 5; parity = this port, the reference runs it as GLSL) --------------------------------------
+ * IMR/shaders/dynamicMeshShader_glsl.comp:99-145 for the position stream (VEC = vec4, no NORMALIZE / ZERO_W / USE_NORMAL_MATRIX):
+ *   :105-111  morphed = V[x (T + 1)];  for i < T: morphed += morph_weights[i] * V[x (T + 1) + i + 1]
+ *   :121-123  result = morphed when jointsGroupsCount == 0
+ *   :124-132  result = sum over groups, components c: weights.c * CalucateSkinJoint(joints.c + matrixOffset + 1, joints.c + inverseMatricesOffset, morphed)
+ *   :79-84    CalucateSkinJoint = modelMatrices[m].positionMatrix * inverseModelMatrices[i].positionMatrix * vertex
+ * GLSL does not fix the order of the sums inside a matrix product; taken here as (M * InvBind) * v in glm's order
+ * (type_mat4x4.inl:630-648 for mat4 * mat4, :561-572 for mat4 * vec4), no contraction -- the order the device uses.
+ * vertices: n_vertices * (n_targets + 1) * 4 floats; joints / weights: n_vertices * n_groups * 4; matrices: n_joints * 16 each (already
+ * offset: joint j is modelMatrices[matrixOffset + 1 + j] / inverseModelMatrices[inverseMatricesOffset + j]); out: n_vertices * 4. */
+static void mat4_mul_vec4(const float* m, const float* v, float* r) {
+    for (int k = 0; k < 4; ++k) r[k] = (m[k] * v[0] + m[4 + k] * v[1]) + (m[8 + k] * v[2] + m[12 + k] * v[3]);
+}
+void imro_repose(uint64_t n_vertices, uint32_t n_targets, const float* vertices, uint32_t n_groups, const uint16_t* joints, const float* weights,
+                 const float* morph_weights, uint32_t n_joints, const float* joint_matrices, const float* inverse_bind, float* out) {
+    float* prod = n_joints ? (float*)malloc(64ull * n_joints) : NULL;
+    for (uint32_t j = 0; j < n_joints; ++j) mat4_mul(joint_matrices + 16ull * j, inverse_bind + 16ull * j, prod + 16ull * j);
+    for (uint64_t x = 0; x < n_vertices; ++x) {
+        const float* V = vertices + 4ull * (n_targets + 1ull) * x;
+        float m[4] = { V[0], V[1], V[2], V[3] };
+        for (uint32_t i = 0; i < n_targets; ++i) {
+            const float* t = V + 4ull * (i + 1u); const float w = morph_weights[i];
+            for (int k = 0; k < 4; ++k) m[k] += w * t[k];
+        }
+        float r[4] = { m[0], m[1], m[2], m[3] };
+        if (n_groups) {
+            r[0] = r[1] = r[2] = r[3] = 0.f;
+            for (uint32_t g = 0; g < n_groups; ++g) {
+                const float* w = weights + 4ull * (x * n_groups + g); const uint16_t* jn = joints + 4ull * (x * n_groups + g);
+                for (int c = 0; c < 4; ++c) {
+                    float v[4];
+                    mat4_mul_vec4(prod + 16ull * jn[c], m, v);
+                    for (int k = 0; k < 4; ++k) r[k] += w[c] * v[k];
+                }
+            }
+        }
+        for (int k = 0; k < 4; ++k) out[4 * x + k] = r[k];
+    }
+    free(prod);
+}
