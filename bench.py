@@ -591,8 +591,10 @@ def run_gpu_arm(args):
                                            f"{r['tri_tests']} tri-pair tests; broad {r['broad_s']:.2f} s + mid {r['mid_s']:.2f} s + narrow {r['narrow_s']:.2f} s, "
                                            f"single thread of {host_cores()} host cores")}
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
+        torch.cuda.synchronize()
+        ctx.comm_destroy()                       # the library's communicator goes first (every rank), then torch's
         dist.barrier()
         dist.destroy_process_group()
     return 0

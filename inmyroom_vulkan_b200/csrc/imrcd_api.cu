@@ -71,6 +71,7 @@ extern "C" void imrcd_destroy(imrcd_ctx* ctx) {
     for (DevBuf* b : bufs) b->release();
     PinBuf* pins[] = { &ctx->p_repose, &ctx->p_fit_segs, &ctx->p_gidx, &ctx->p_gather, &ctx->p_cur, &ctx->p_prev, &ctx->p_mesh, &ctx->p_entity, &ctx->p_cb, &ctx->p_ctl, &ctx->p_epairs, &ctx->p_hits, &ctx->p_pairs, &ctx->p_combos };
     for (PinBuf* b : pins) b->release();
+    if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
@@ -160,15 +161,18 @@ extern "C" int imrcd_mesh_import_tree(imrcd_ctx* ctx, uint64_t nv, const float* 
     if (!boxes || !left || !right || !tri_off || !tri_cnt || !mesh_id || nv == 0 || (n_tri && !tri_pos)) { ctx->err = "imrcd_mesh_import_tree: bad argument"; return IMRCD_E_ARG; }
     cudaSetDevice(ctx->device);
     // flat pre-order -> sibling-adjacent records: root at 0, slot 1 padding, children pairs from 2 on (BFS order)
-    std::vector<uint32_t> rec_of(nv, 0xffffffffu);
+    std::vector<uint32_t> rec_of(nv, 0xffffffffu), depth_of(nv, 0u);
     std::deque<uint32_t> bfs;
     uint64_t next = 2;
     rec_of[0] = 0; bfs.push_back(0);
     while (!bfs.empty()) {
         uint32_t v = bfs.front(); bfs.pop_front();
+        if (depth_of[v] >= 120u) { ctx->err = "imrcd_mesh_import_tree: the tree is deeper than 120 levels (the ray descent of the response stage keeps one stack entry per level)"; return IMRCD_E_ARG; }
         if (left[v] >= 0) {
             if ((uint64_t)left[v] >= nv || (uint64_t)right[v] >= nv || right[v] < 0) { ctx->err = "imrcd_mesh_import_tree: child index out of range"; return IMRCD_E_ARG; }
+            if (rec_of[left[v]] != 0xffffffffu || rec_of[right[v]] != 0xffffffffu || left[v] == right[v]) { ctx->err = "imrcd_mesh_import_tree: a vertex has two parents"; return IMRCD_E_ARG; }
             rec_of[left[v]] = (uint32_t)next; rec_of[right[v]] = (uint32_t)(next + 1); next += 2;
+            depth_of[left[v]] = depth_of[right[v]] = depth_of[v] + 1u;
             bfs.push_back((uint32_t)left[v]); bfs.push_back((uint32_t)right[v]);
         }
     }

@@ -78,6 +78,9 @@ extern "C" int imrcd_comm_destroy(imrcd_ctx* ctx) {
     NcclApi* api = nccl_api();
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    // a captured frame holds the communicator's collective as a graph node, and NCCL waits for such graphs to be gone before it lets a
+    // communicator go: the graph first
+    if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; ctx->graph_key = 0; ctx->graph_seen_key = 0; }
     if (api) api->CommDestroy(static_cast<ncclComm_t>(ctx->comm));
     ctx->comm = nullptr; ctx->comm_n = 1; ctx->comm_rank = 0;
     ctx->shard_rank_next = 0; ctx->shard_n_next = 1;
@@ -114,11 +117,16 @@ static int gather_reserve(imrcd_ctx* ctx) {
     return IMRCD_OK;
 }
 
+int imr_comm_reserve(imrcd_ctx* ctx) {
+    int rc = gather_reserve(ctx); if (rc) return rc;
+    IMR_CUDA(ctx, ctx->p_gather.reserve((hdr_rows(ctx->comm_n) + (uint64_t)ctx->comm_n * ctx->gcap) * sizeof(imrcd_entity_pair)));
+    return IMRCD_OK;
+}
+
 // part 1: the collective itself (the send block is the library's own result block: header row + records, as it lies in HBM)
 int imr_comm_allgather(imrcd_ctx* ctx) {
     NcclApi* api = nccl_api();
     if (!api || !ctx->comm) { ctx->err = "no communicator"; return IMRCD_E_STATE; }
-    int rc = gather_reserve(ctx); if (rc) return rc;
     if (ctx->d_epairs.cap < sizeof(imrcd_entity_pair) * (ctx->gcap + 1)) { ctx->err = "result block smaller than the gather capacity"; return IMRCD_E_STATE; }      // imr_frame_enqueue sizes it
     IMR_NCCL(ctx, api, api->AllGather(ctx->d_epairs.p, ctx->d_gather.p, (ctx->gcap + 1) * sizeof(imrcd_entity_pair), ncclUint8, static_cast<ncclComm_t>(ctx->comm), ctx->stream));
     return IMRCD_OK;
@@ -134,7 +142,6 @@ int imr_comm_after_gather(imrcd_ctx* ctx, uint64_t spec_rows) {
     IMR_CUDA(ctx, cudaGetLastError());
     const uint64_t max_rows = (uint64_t)ctx->comm_n * ctx->gcap;
     spec_rows = std::min<uint64_t>(spec_rows, max_rows);
-    IMR_CUDA(ctx, ctx->p_gather.reserve((hr + max_rows) * sizeof(imrcd_entity_pair)));
     IMR_CUDA(ctx, cudaMemcpyAsync(ctx->p_gather.p, base + blocks_rows, (hr + spec_rows) * sizeof(imrcd_entity_pair), cudaMemcpyDeviceToHost, s));
     return IMRCD_OK;
 }
@@ -172,6 +179,7 @@ const imrcd_entity_pair* imr_comm_merged_device(const imrcd_ctx* ctx) {
 
 // ---- one process, several GPUs (the engine is a single process: SURVEY 8b "imrcd_create(device_ids[], n)") ---------------------------
 int imr_frame_enqueue(imrcd_ctx* ctx);
+int imr_frame_reserve(imrcd_ctx* ctx);
 void imr_frame_begin(imrcd_ctx* ctx);
 int imr_frame_complete(imrcd_ctx* ctx, bool* retry);
 uint64_t imr_frame_spec_rows(const imrcd_ctx* ctx);
@@ -247,6 +255,7 @@ extern "C" int imrcd_group_frame_execute(imrcd_group* g) {
     for (imrcd_ctx* c : g->ctx) imr_frame_begin(c);
     if (g->ctx[0]->n_entries_global < 2) { for (imrcd_ctx* c : g->ctx) { c->ran = true; c->fetched = true; c->merged_valid = true; c->n_merged = 0; } return IMRCD_OK; }
     for (int attempt = 0; attempt < 10; ++attempt) {
+        GROUP_EACH(g, (cudaSetDevice(c->device), imr_frame_reserve(c)));
         GROUP_EACH(g, (cudaSetDevice(c->device), imr_frame_enqueue(c)));
         if (api->GroupStart() != ncclSuccess) { g->err = "ncclGroupStart"; return IMRCD_E_CUDA; }
         GROUP_EACH(g, (cudaSetDevice(c->device), imr_comm_allgather(c)));

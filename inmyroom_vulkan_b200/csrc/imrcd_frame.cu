@@ -1388,13 +1388,18 @@ __global__ void k_finalize(FrameCtl* ctl, unsigned long long cap_pairs, const ui
 // ------------------------------------------------------------------------------------------
 static inline unsigned blocks_for(unsigned long long n, unsigned bs) { return (unsigned)((n + bs - 1) / bs); }
 
+int imr_comm_reserve(imrcd_ctx* ctx);
 int imr_comm_allgather(imrcd_ctx* ctx);
 int imr_comm_after_gather(imrcd_ctx* ctx, uint64_t spec_rows);
 int imr_comm_decide(imrcd_ctx* ctx, uint64_t spec_rows, bool* retry, bool* fatal);
 
 // rows of the result that travel to the host speculatively, right behind the frame's kernels (the count is not known on the host yet):
 // what the last frame had plus a margin.  A frame with more records pays one extra copy after the wait.
-uint64_t imr_frame_spec_rows(const imrcd_ctx* ctx) { return std::max<uint64_t>(256, ctx->spec_hint + ctx->spec_hint / 4 + 64); }
+uint64_t imr_frame_spec_rows(const imrcd_ctx* ctx) {
+    uint64_t want = std::max<uint64_t>(256, ctx->spec_hint + ctx->spec_hint / 4 + 64), r = 256;
+    while (r < want) r <<= 1;                        // a power of two: the copy's size is part of what a captured frame is made of
+    return r;
+}
 
 // Second half of a frame: wait for the stream, read the control block back, grow whatever overflowed (the caller re-runs the frame) or
 // fill in the statistics.  Split from the enqueue half so that a caller can put more work on the stream before the host looks at the frame
@@ -1493,27 +1498,23 @@ static int frame_prepare(imrcd_ctx* ctx) {
     return IMRCD_OK;
 }
 
-// First half of a frame: every kernel of it, the control block's way back to the host and a speculative copy of the result rows, all on the
-// context's stream; nothing here waits for the device.
-int imr_frame_enqueue(imrcd_ctx* ctx) {
+// Every buffer a frame of the current size and capacities needs.  Separate from the enqueue half so that the latter makes no allocation
+// and can run under stream capture (imr_frame_enqueue_all replays the captured frame while nothing that shapes it has changed).
+int imr_frame_reserve(imrcd_ctx* ctx) {
     cudaStream_t s = ctx->stream;
     const uint32_t n = (uint32_t)ctx->n_entries;
     { const int rc = frame_prepare(ctx); if (rc) return rc; }
+    size_t cub_bytes = 0;
+    if (n >= 2) {
+        cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, ctx->d_keys.as<uint32_t>(), ctx->d_keys2.as<uint32_t>(),
+                                        ctx->d_idx.as<uint32_t>(), ctx->d_idx2.as<uint32_t>(), (int)n, 0, 32, s);
+        size_t scan_bytes = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, ctx->d_flag.as<uint32_t>(), ctx->d_cpos.as<uint32_t>(), (int)(n + 1), s);
+        cub_bytes = std::max(cub_bytes, scan_bytes);
+    }
     IMR_CUDA(ctx, ctx->d_ctl.reserve(sizeof(FrameCtl), 0, s));
     IMR_CUDA(ctx, ctx->p_ctl.reserve(sizeof(FrameCtl)));
     IMR_CUDA(ctx, ctx->d_epairs.reserve(sizeof(imrcd_entity_pair) * (std::max<uint64_t>(ctx->cap_pairs, ctx->gcap) + 1), 0, s));      // row 0 = header (record count), see imrcd_frame_results_block
-    FrameCtl* ctl = ctx->d_ctl.as<FrameCtl>();
-    uint64_t launches = 0;
-    IMR_CUDA(ctx, cudaEventRecord(ctx->ev[0], s));
-    IMR_CUDA(ctx, cudaMemsetAsync(ctl, 0, sizeof(FrameCtl), s));
-    if (n < 2) {
-        // a shard can be left with fewer than two entries of a frame that has more: it has no pairs, but it still answers the collective
-        for (int k = 1; k <= 6; ++k) IMR_CUDA(ctx, cudaEventRecord(ctx->ev[k], s));
-        IMR_CUDA(ctx, cudaMemsetAsync(ctx->d_epairs.p, 0, sizeof(imrcd_entity_pair), s));
-        IMR_CUDA(ctx, cudaMemcpyAsync(ctx->p_ctl.p, ctl, sizeof(FrameCtl), cudaMemcpyDeviceToHost, s));
-        ctx->pending_launches = 0; ctx->spec_rows_sent = 0;
-        return IMRCD_OK;
-    }
     IMR_CUDA(ctx, ctx->d_inv.reserve(64ull * n, 0, s));
     IMR_CUDA(ctx, ctx->d_ext.reserve(24ull * n, 0, s));
     IMR_CUDA(ctx, ctx->d_keys.reserve(4ull * n, 0, s));
@@ -1521,12 +1522,62 @@ int imr_frame_enqueue(imrcd_ctx* ctx) {
     IMR_CUDA(ctx, ctx->d_idx.reserve(4ull * n, 0, s));
     IMR_CUDA(ctx, ctx->d_idx2.reserve(4ull * n, 0, s));
     IMR_CUDA(ctx, ctx->d_sorted.reserve(sizeof(SweepRec) * (size_t)n, 0, s));
-    IMR_CUDA(ctx, ctx->d_sorted_c.reserve(sizeof(SweepRec) * (size_t)n, 0, s));
+    IMR_CUDA(ctx, ctx->d_sorted_c.reserve(sizeof(SweepRec) * (size_t)std::max<uint32_t>(n, FEW_FLAGGED_MAX), 0, s));
     IMR_CUDA(ctx, ctx->d_flag.reserve(4ull * (n + 1), 0, s));
     IMR_CUDA(ctx, ctx->d_cpos.reserve(4ull * (n + 1), 0, s));
     IMR_CUDA(ctx, ctx->d_wlen.reserve(4ull * (n + 1), 0, s));
     IMR_CUDA(ctx, ctx->d_chunks.reserve(4ull * (n + 1), 0, s));
     IMR_CUDA(ctx, ctx->d_chunkoff.reserve(4ull * (n + 1), 0, s));
+    IMR_CUDA(ctx, ctx->d_cubtmp.reserve(cub_bytes, 0, s));
+    IMR_CUDA(ctx, ctx->d_pairs.reserve(8ull * ctx->cap_pairs, 0, s));
+    IMR_CUDA(ctx, ctx->d_pairrec.reserve(sizeof(PairRec) * ctx->cap_pairs, 0, s));
+    IMR_CUDA(ctx, ctx->d_pairacc.reserve(sizeof(PairAcc) * ctx->cap_pairs, 0, s));
+    if (16ull * ctx->cap_queue > ctx->d_queue.cap) { IMR_CUDA(ctx, ctx->d_queue.reserve(16ull * ctx->cap_queue, 0, s)); ctx->queue_dirty = ctx->cap_queue; }
+    IMR_CUDA(ctx, ctx->d_combos.reserve(16ull * ctx->cap_combos, 0, s));
+    IMR_CUDA(ctx, ctx->d_hits.reserve(sizeof(imrcd_tri_hit) * ctx->cap_hits, 0, s));
+    IMR_CUDA(ctx, ctx->d_aux.reserve(sizeof(HitAux) * ctx->cap_hits, 0, s));
+    IMR_CUDA(ctx, ctx->d_grouped.reserve(4ull * 2 * ctx->cap_hits, 0, s));
+    IMR_CUDA(ctx, ctx->d_lscratch.reserve(ctx->cap_lscratch, 0, s));
+    IMR_CUDA(ctx, ctx->d_lpref.reserve(8ull * (ctx->cap_pairs + 1), 0, s));
+    IMR_CUDA(ctx, ctx->d_lsides.reserve(sizeof(LargeSide) * 2ull * ctx->cap_pairs, 0, s));
+    IMR_CUDA(ctx, ctx->d_epair_pair.reserve(4ull * ctx->cap_pairs, 0, s));
+    if (ctx->prev_distinct) IMR_CUDA(ctx, ctx->d_rays.reserve(sizeof(RayRec) * ctx->cap_rays, 0, s));
+    if (ctx->prev_distinct) IMR_CUDA(ctx, ctx->d_resp.reserve(32ull * ctx->cap_rays, 0, s));
+    IMR_CUDA(ctx, ctx->d_lsmall.reserve(4ull * PC_CLASSES * ctx->cap_pairs, 0, s));      // the size-class lists, cap_pairs entries each
+    IMR_CUDA(ctx, ctx->p_epairs.reserve(sizeof(imrcd_entity_pair) * std::min<uint64_t>(imr_frame_spec_rows(ctx), ctx->cap_pairs), 0, s));
+    if (ctx->comm) { const int rc = imr_comm_reserve(ctx); if (rc) return rc; }
+    return IMRCD_OK;
+}
+
+static inline uint64_t queue_clear_slots(const imrcd_ctx* ctx) {
+    uint64_t r = 1ull << 16;
+    while (r < ctx->queue_dirty) r <<= 1;
+    return std::min<uint64_t>(r, ctx->cap_queue);
+}
+
+// a stage-boundary event: inside a stream capture it has to be recorded as an external node to stay usable for cudaEventElapsedTime
+static inline cudaError_t frame_event(imrcd_ctx* ctx, cudaEvent_t ev, cudaStream_t s) {
+    return ctx->capturing ? cudaEventRecordWithFlags(ev, s, cudaEventRecordExternal) : cudaEventRecord(ev, s);
+}
+
+// First half of a frame: every kernel of it, the control block's way back to the host and a speculative copy of the result rows, all on the
+// context's stream; nothing here waits for the device.
+int imr_frame_enqueue(imrcd_ctx* ctx) {
+    cudaStream_t s = ctx->stream;
+    const uint32_t n = (uint32_t)ctx->n_entries;
+    { const int rc = frame_prepare(ctx); if (rc) return rc; }
+    FrameCtl* ctl = ctx->d_ctl.as<FrameCtl>();
+    uint64_t launches = 0;
+    IMR_CUDA(ctx, frame_event(ctx, ctx->ev[0], s));
+    IMR_CUDA(ctx, cudaMemsetAsync(ctl, 0, sizeof(FrameCtl), s));
+    if (n < 2) {
+        // a shard can be left with fewer than two entries of a frame that has more: it has no pairs, but it still answers the collective
+        for (int k = 1; k <= 6; ++k) IMR_CUDA(ctx, frame_event(ctx, ctx->ev[k], s));
+        IMR_CUDA(ctx, cudaMemsetAsync(ctx->d_epairs.p, 0, sizeof(imrcd_entity_pair), s));
+        IMR_CUDA(ctx, cudaMemcpyAsync(ctx->p_ctl.p, ctl, sizeof(FrameCtl), cudaMemcpyDeviceToHost, s));
+        ctx->pending_launches = 0; ctx->spec_rows_sent = 0;
+        return IMRCD_OK;
+    }
     size_t cub_bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, ctx->d_keys.as<uint32_t>(), ctx->d_keys2.as<uint32_t>(),
                                     ctx->d_idx.as<uint32_t>(), ctx->d_idx2.as<uint32_t>(), (int)n, 0, 32, s);
@@ -1535,35 +1586,17 @@ int imr_frame_enqueue(imrcd_ctx* ctx) {
         cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, ctx->d_flag.as<uint32_t>(), ctx->d_cpos.as<uint32_t>(), (int)(n + 1), s);
         cub_bytes = std::max(cub_bytes, scan_bytes);
     }
-    IMR_CUDA(ctx, ctx->d_cubtmp.reserve(cub_bytes, 0, s));
     {
-        IMR_CUDA(ctx, ctx->d_pairs.reserve(8ull * ctx->cap_pairs, 0, s));
-        IMR_CUDA(ctx, ctx->d_pairrec.reserve(sizeof(PairRec) * ctx->cap_pairs, 0, s));
-        IMR_CUDA(ctx, ctx->d_pairacc.reserve(sizeof(PairAcc) * ctx->cap_pairs, 0, s));
-        if (16ull * ctx->cap_queue > ctx->d_queue.cap) { IMR_CUDA(ctx, ctx->d_queue.reserve(16ull * ctx->cap_queue, 0, s)); ctx->queue_dirty = ctx->cap_queue; }
-        IMR_CUDA(ctx, ctx->d_combos.reserve(16ull * ctx->cap_combos, 0, s));
-        IMR_CUDA(ctx, ctx->d_hits.reserve(sizeof(imrcd_tri_hit) * ctx->cap_hits, 0, s));
         // contact reduction scratch: per-pair slices are power-of-two padded, so at most 2 x hits slots in total
-        IMR_CUDA(ctx, ctx->d_aux.reserve(sizeof(HitAux) * ctx->cap_hits, 0, s));
-        IMR_CUDA(ctx, ctx->d_grouped.reserve(4ull * 2 * ctx->cap_hits, 0, s));
-        IMR_CUDA(ctx, ctx->d_lscratch.reserve(ctx->cap_lscratch, 0, s));
-        IMR_CUDA(ctx, ctx->d_lpref.reserve(8ull * (ctx->cap_pairs + 1), 0, s));
-        IMR_CUDA(ctx, ctx->d_lsides.reserve(sizeof(LargeSide) * 2ull * ctx->cap_pairs, 0, s));
-        IMR_CUDA(ctx, ctx->d_epair_pair.reserve(4ull * ctx->cap_pairs, 0, s));
         if (ctx->prev_distinct) {
-            IMR_CUDA(ctx, ctx->d_rays.reserve(sizeof(RayRec) * ctx->cap_rays, 0, s));
-            IMR_CUDA(ctx, ctx->d_resp.reserve(32ull * ctx->cap_rays, 0, s));
         }
-        IMR_CUDA(ctx, ctx->d_lsmall.reserve(4ull * PC_CLASSES * ctx->cap_pairs, 0, s));      // the size-class lists, cap_pairs entries each
-        if (ctx->queue_dirty) {                       // clear publication flags left by the previous frame
-            uint64_t nclr = std::min<uint64_t>(ctx->queue_dirty, ctx->cap_queue);
-            IMR_CUDA(ctx, cudaMemsetAsync(ctx->d_queue.p, 0, 16ull * nclr, s));
+        if (ctx->queue_dirty) {                       // clear publication flags left by the previous frame (a power-of-two many: see frame_key)
+            IMR_CUDA(ctx, cudaMemsetAsync(ctx->d_queue.p, 0, 16ull * queue_clear_slots(ctx), s));
         }
         // ---- broad ----
         const uint32_t* a_gidx = ctx->shard_n > 1 ? ctx->d_gidx.as<uint32_t>() : nullptr;
         if (ctx->n_flagged_global <= ctx->few_flagged_max) {
             // few flagged entries: every entry against the dense list of the flagged ones, no sort (k_pairs_few_flagged)
-            IMR_CUDA(ctx, ctx->d_sorted_c.reserve(sizeof(SweepRec) * (size_t)FEW_FLAGGED_MAX, 0, s));
             k_entry_prep<<<blocks_for(n, 128), 128, 0, s>>>(n, ctx->d_cur.as<float>(), ctx->d_mesh.as<uint32_t>(), ctx->d_meshes.as<MeshDev>(),
                                                              ctx->d_recs.as<TreeRec>(), ctx->d_inv.as<float>(), ctx->d_ext.as<float>(), nullptr, nullptr,
                                                              ctx->d_cb.as<uint8_t>(), a_gidx, ctx->d_sorted_c.as<SweepRec>(), ctl);
@@ -1589,14 +1622,14 @@ int imr_frame_enqueue(imrcd_ctx* ctx) {
                                                    (ctx->shard_n > 1 && ctx->n_flagged_global == ctx->n_entries_global) ? 1u : 0u);
         launches += 6 + 4 + 2 * 2;   // + radix sort (histogram + onesweep passes, counted as 4) + two decoupled-look-back scans (init + scan)
         }
-        IMR_CUDA(ctx, cudaEventRecord(ctx->ev[1], s));
+        IMR_CUDA(ctx, frame_event(ctx, ctx->ev[1], s));
         // ---- pair setup ----
         k_queue_init<<<1, 1, 0, s>>>(ctl, ctx->cap_pairs, ctx->cap_queue, (uint32_t)(ctx->trav_blocks * TRAV_WARPS));
         k_pair_setup<<<ctx->sm_count * 8, 128, 0, s>>>(ctl, ctx->cap_pairs, ctx->d_pairs.as<uint2>(), ctx->d_cur.as<float>(), ctx->prev_distinct ? ctx->d_prev.as<float>() : nullptr, ctx->d_inv.as<float>(),
                                                         ctx->d_mesh.as<uint32_t>(), ctx->d_meshes.as<MeshDev>(), ctx->d_pairrec.as<PairRec>(),
                                                         ctx->d_pairacc.as<PairAcc>(), ctx->d_queue.as<WorkItem>(), ctx->cap_queue);
         launches += 2;
-        IMR_CUDA(ctx, cudaEventRecord(ctx->ev[2], s));
+        IMR_CUDA(ctx, frame_event(ctx, ctx->ev[2], s));
         // ---- mid ----
         {
             const PairRec* a_pairrec = ctx->d_pairrec.as<PairRec>(); const TreeRec* a_recs = ctx->d_recs.as<TreeRec>();
@@ -1615,13 +1648,13 @@ int imr_frame_enqueue(imrcd_ctx* ctx) {
             IMR_CUDA(ctx, cudaLaunchKernel(ctx->trav_fn, dim3(ctx->trav_blocks), dim3(TRAV_WARPS * 32), targs, 0, s));
             launches += 1;
         }
-        IMR_CUDA(ctx, cudaEventRecord(ctx->ev[3], s));
+        IMR_CUDA(ctx, frame_event(ctx, ctx->ev[3], s));
         // ---- narrow ----
         k_tritri<<<ctx->narrow_blocks, NT_WARPS * 32, NT_WARPS * sizeof(NarrowWarp), s>>>(ctl, ctx->d_combos.as<Combo>(), ctx->cap_combos, ctx->d_pairrec.as<PairRec>(),
                                                     ctx->d_tris.as<TriRec>(), ctx->d_hits.as<imrcd_tri_hit>(), ctx->cap_hits,
                                                     ctx->d_pairacc.as<PairAcc>(), ctx->d_aux.as<HitAux>());
         launches += 1;
-        IMR_CUDA(ctx, cudaEventRecord(ctx->ev[4], s));
+        IMR_CUDA(ctx, frame_event(ctx, ctx->ev[4], s));
         // ---- reduce ----
         k_hit_lists<<<ctx->sm_count * 4, 256, 0, s>>>(ctl, ctx->cap_pairs, ctx->d_pairacc.as<PairAcc>(),
                                                        ctx->d_lsmall.as<uint32_t>(), ctx->pc_large_min);
@@ -1669,16 +1702,15 @@ int imr_frame_enqueue(imrcd_ctx* ctx) {
                                                       ctx->d_epairs.as<imrcd_entity_pair>() + 1, ctx->d_epair_pair.as<uint32_t>(),
                                                       ctx->shard_n > 1 ? ctx->d_gidx.as<uint32_t>() : nullptr);
         launches += 2;
-        IMR_CUDA(ctx, cudaEventRecord(ctx->ev[6], s));
+        IMR_CUDA(ctx, frame_event(ctx, ctx->ev[6], s));
         { int rc = imr_frame_shoot_device(ctx, ctl, &launches); if (rc != IMRCD_OK) return rc; }
         k_epairs_header<<<1, 1, 0, s>>>(ctl, ctx->d_epairs.as<imrcd_entity_pair>());      // after the last kernel that can raise an overflow bit
-        IMR_CUDA(ctx, cudaEventRecord(ctx->ev[5], s));
+        IMR_CUDA(ctx, frame_event(ctx, ctx->ev[5], s));
         IMR_CUDA(ctx, cudaMemcpyAsync(ctx->p_ctl.p, ctl, sizeof(FrameCtl), cudaMemcpyDeviceToHost, s));
         ctx->pending_launches = launches;
         ctx->spec_rows_sent = 0;
         if (!ctx->comm) {            // the records themselves, speculatively (imrcd_frame_fetch copies the rest when the frame has more)
             const uint64_t rows = std::min<uint64_t>(imr_frame_spec_rows(ctx), ctx->cap_pairs);
-            IMR_CUDA(ctx, ctx->p_epairs.reserve(sizeof(imrcd_entity_pair) * rows));
             IMR_CUDA(ctx, cudaMemcpyAsync(ctx->p_epairs.p, ctx->d_epairs.as<imrcd_entity_pair>() + 1, sizeof(imrcd_entity_pair) * rows, cudaMemcpyDeviceToHost, s));
             ctx->spec_rows_sent = rows;
         }
@@ -1686,7 +1718,25 @@ int imr_frame_enqueue(imrcd_ctx* ctx) {
     return IMRCD_OK;
 }
 
-static int frame_enqueue_all(imrcd_ctx* ctx) {
+// everything that shapes the frame's launches: sizes, capacities, the buffers' addresses
+static uint64_t frame_key(imrcd_ctx* ctx) {
+    uint64_t h = 0xcbf29ce484222325ull;
+    auto mix = [&](uint64_t v) { h = (h ^ v) * 0x100000001b3ull; };
+    mix(ctx->n_entries); mix(ctx->n_entries_global); mix(ctx->n_flagged_global <= ctx->few_flagged_max); mix(ctx->n_flagged_global == ctx->n_entries_global);
+    mix(ctx->prev_distinct); mix(ctx->shard_rank); mix(ctx->shard_n); mix(ctx->cap_pairs); mix(ctx->cap_queue); mix(ctx->cap_combos); mix(ctx->cap_hits);
+    mix(ctx->cap_rays); mix(ctx->cap_lscratch); mix(ctx->pc_large_min); mix(ctx->queue_dirty ? queue_clear_slots(ctx) : 0); mix(imr_frame_spec_rows(ctx));
+    mix(ctx->gcap); mix((uint64_t)ctx->comm); mix(ctx->meshes.size());
+    const DevBuf* bufs[] = { &ctx->d_recs, &ctx->d_tris, &ctx->d_tri_nrm, &ctx->d_tri_vid, &ctx->d_meshes, &ctx->d_cur, &ctx->d_prev, &ctx->d_mesh, &ctx->d_cb, &ctx->d_entity, &ctx->d_gidx,
+                             &ctx->d_inv, &ctx->d_ext, &ctx->d_keys, &ctx->d_keys2, &ctx->d_idx, &ctx->d_idx2, &ctx->d_sorted, &ctx->d_sorted_c, &ctx->d_flag, &ctx->d_cpos, &ctx->d_wlen,
+                             &ctx->d_chunks, &ctx->d_chunkoff, &ctx->d_cubtmp, &ctx->d_pairs, &ctx->d_pairrec, &ctx->d_pairacc, &ctx->d_queue, &ctx->d_combos, &ctx->d_hits, &ctx->d_epairs,
+                             &ctx->d_ctl, &ctx->d_aux, &ctx->d_grouped, &ctx->d_lscratch, &ctx->d_lpref, &ctx->d_lsides, &ctx->d_lsmall, &ctx->d_rays, &ctx->d_resp, &ctx->d_epair_pair,
+                             &ctx->d_gather };
+    for (const DevBuf* b : bufs) mix((uint64_t)b->p);
+    mix((uint64_t)ctx->p_ctl.p); mix((uint64_t)ctx->p_epairs.p); mix((uint64_t)ctx->p_gather.p);
+    return h | 1ull;
+}
+
+static int frame_enqueue_body(imrcd_ctx* ctx) {
     int rc = imr_frame_enqueue(ctx);
     if (rc) return rc;
     if (ctx->comm) {
@@ -1694,6 +1744,42 @@ static int frame_enqueue_all(imrcd_ctx* ctx) {
         ctx->spec_rows_sent = imr_frame_spec_rows(ctx);
         rc = imr_comm_after_gather(ctx, ctx->spec_rows_sent); if (rc) return rc;
     }
+    return IMRCD_OK;
+}
+
+// The whole frame (and, with a communicator, its end-of-frame merge) goes onto the stream.  The ~25 launches, memsets and copies of a frame
+// are recorded once as a CUDA graph and replayed while nothing that shapes them changes (entry count, capacities, buffer addresses): on a
+// frame of a millisecond the host's launch calls are a tenth of the end-to-end time, and with eight ranks a fifth.  IMRCD_GRAPH=0 turns
+// it off; the traversal's diagnostic trace runs eagerly.
+static int frame_enqueue_all(imrcd_ctx* ctx) {
+    int rc = imr_frame_reserve(ctx);
+    if (rc) return rc;
+    if (ctx->use_graph < 0) { const char* ev = getenv("IMRCD_GRAPH"); ctx->use_graph = (ev && atoi(ev) == 0) ? 0 : 1; if (getenv("IMRCD_TRAV_TRACE")) ctx->use_graph = 0; }
+    if (!ctx->use_graph) return frame_enqueue_body(ctx);
+    cudaStream_t s = ctx->stream;
+    const uint64_t key = frame_key(ctx);
+    if (ctx->graph_exec && key == ctx->graph_key) {
+        IMR_CUDA(ctx, cudaGraphLaunch(ctx->graph_exec, s));
+        ctx->pending_launches = ctx->graph_launches; ctx->spec_rows_sent = ctx->graph_spec_rows;
+        return IMRCD_OK;
+    }
+    // a frame shape is captured the second time in a row it is seen: one-off frames are not worth a capture, and the first collective on a
+    // communicator must run eagerly (NCCL sets its connections up inside it, which a capture cannot hold)
+    if (key != ctx->graph_seen_key) { ctx->graph_seen_key = key; return frame_enqueue_body(ctx); }
+    if (ctx->graph_exec) { cudaGraphExecDestroy(ctx->graph_exec); ctx->graph_exec = nullptr; ctx->graph_key = 0; }
+    IMR_CUDA(ctx, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    ctx->capturing = true;
+    rc = frame_enqueue_body(ctx);
+    ctx->capturing = false;
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(s, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return rc; }
+    if (e != cudaSuccess || !graph) { ctx->err = std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e); cudaGetLastError(); return IMRCD_E_CUDA; }
+    const cudaError_t ei = cudaGraphInstantiate(&ctx->graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ei != cudaSuccess) { ctx->graph_exec = nullptr; ctx->err = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ei); return IMRCD_E_CUDA; }
+    ctx->graph_key = key; ctx->graph_launches = ctx->pending_launches; ctx->graph_spec_rows = ctx->spec_rows_sent;
+    IMR_CUDA(ctx, cudaGraphLaunch(ctx->graph_exec, s));
     return IMRCD_OK;
 }
 

@@ -221,6 +221,7 @@ struct imrcd_ctx {
     uint64_t gcap = 0;                   // rows per rank in the gathered blocks (after the header row); the same on every rank
     DevBuf d_gather; PinBuf p_gather;    // comm_n x (gcap + 1) x 80 B
     uint64_t n_merged = 0; bool merged_valid = false;
+    cudaGraphExec_t graph_exec = nullptr; uint64_t graph_key = 0, graph_seen_key = 0, graph_launches = 0, graph_spec_rows = 0; bool capturing = false; int use_graph = -1;      // the frame as a CUDA graph
     uint64_t spec_hint = 0, spec_rows_sent = 0;      // speculative D2H of the result rows (imr_frame_spec_rows)
     bool pc_attr_set = false;
     uint32_t few_flagged_max = 0xffffffffu;      // frames with at most this many flagged entries take the sort-free broad phase

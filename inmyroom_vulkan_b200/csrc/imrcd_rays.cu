@@ -13,7 +13,9 @@
 #include <algorithm>
 
 #define FULL_MASK 0xffffffffu
-#define RAY_STACK 64
+#define RAY_STACK 128        // per-lane stack of the ray descent: one entry per level (the far child waits while the near one is walked).
+                             // The Morton build's trees are at most ~70 deep (54 key bits + duplicates); imported trees deeper than this are
+                             // refused at import (imrcd_mesh_import_tree), so a frame never meets a tree it cannot walk
 
 struct RayHit { bool hit, back; float dist; uint32_t tri; float bx, by; };      // RayOBBtreeIntersectInfo, Ray.h:17-24
 

@@ -224,3 +224,29 @@ def test_broad_phase_paths_agree(gpu_ctx, port, monkeypatch):
         want, _ = port.broad(sc.matrices, [ptrees[m] for m in sc.mesh_index], sc.should_callback)
         assert got["few"] == set(map(tuple, want.tolist()))
     swept.close()
+
+
+def test_frame_with_coplanar_and_zero_area_triangles(gpu_ctx, port):
+    """Frame-level coverage of the path DESIGN section 8 documents: coincident faces (intersecting AND coplanar pairs, dropped by
+    CreateUncollideRays.cpp:88) and zero-area triangles (their normal is 0, everything is "coplanar" to them, and
+    tri_tri_intersect_with_isectline reads its segment uninitialised, Triangle.cpp:956-960).  There the reference's answer depends on
+    stack contents; the library and the port define the unread values as zeros.  So the checker of this scene is the port, on the same
+    (reference-identical) trees: counters, hit sets and segments bit for bit, n_coplanar_hits > 0."""
+    box = scenes.box_mesh(1.0, 1.0, 1.0, sub=2)
+    # a mesh with zero-area triangles: every fourth triangle of the box collapsed onto an edge (two equal corners)
+    deg = scenes.Mesh(box.positions.copy(), box.normals.copy(), box.vertex_ids.copy(), "degenerate")
+    deg.positions[::4, 6:9] = deg.positions[::4, 3:6]
+    meshes = [box, deg]
+    t = np.array([[0, 0, 0], [0.5, 0.25, 0.0], [2.0, 0, 0], [2.0, 0.5, 0.0], [0.25, 0.25, 2.0], [4.0, 4.0, 4.0], [4.5, 4.0, 4.25], [0.0, 0.0, 2.0]], np.float64)
+    n = len(t)
+    q = np.tile([0.0, 0.0, 0.0, 1.0], (n, 1))              # axis-aligned: faces of neighbouring boxes lie exactly in common planes
+    mats = scenes.trs_matrices(t, q, np.ones((n, 3)))
+    scene = scenes.Scene(meshes, np.array([0, 0, 0, 1, 0, 1, 1, 1], np.uint32), mats, np.ones(n, np.uint8), np.arange(1, n + 1, dtype=np.uint32))
+    p_trees = [port.tree_build(m.positions, m.normals, m.vertex_ids) for m in meshes]
+    g_trees = [OBBtree.from_flat(gpu_ctx, tr.flat) for tr in p_trees]
+    cd = CollisionDetection(ctx=gpu_ctx)
+    st, bp, ep, hits = gpu_frame(cd, scene, g_trees)
+    ores = oracle_frame(port, scene, p_trees, port=port)
+    assert ores["totals"]["coplanar"] > 20 and ores["totals"]["hits"] > 20
+    compare_frame(ores, st, bp, ep, hits, rel_of=lambda k: port.pair_matrix(scene.matrices[k[0]], scene.matrices[k[1]]))
+    assert st["n_coplanar_hits"] == ores["totals"]["coplanar"] > 0
