@@ -57,11 +57,13 @@ extern "C" int imrcd_create(int device, void* cuda_stream, imrcd_ctx** out) {
 }
 
 static void recording_clear(imrcd_ctx* ctx);
+void imr_copy_pool_release(imrcd_ctx* ctx);
 extern "C" void imrcd_destroy(imrcd_ctx* ctx) {
     if (!ctx) return;
     recording_clear(ctx);
     imrcd_comm_destroy(ctx);
     imr_skins_release(ctx);
+    imr_copy_pool_release(ctx);
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = { &ctx->d_recs, &ctx->d_tris, &ctx->d_tri_nrm, &ctx->d_tri_vid, &ctx->d_meshes, &ctx->d_rf_stage, &ctx->d_repose_in, &ctx->d_repose_prod, &ctx->d_repose_vtx, &ctx->d_scalar, &ctx->d_fit, &ctx->d_fit_slot, &ctx->d_fit_segs, &ctx->d_fit_scratch, &ctx->d_fit_ticket, &ctx->d_cur, &ctx->d_prev, &ctx->d_mesh,
@@ -442,18 +444,64 @@ static int entries_reserve(imrcd_ctx* ctx, uint64_t total, bool device_too) {
     return IMRCD_OK;
 }
 
+// ---- the staging copy of a large submission on a few host threads -----------------------------------------------------------------------
+// Writing 100,000 entries into the pinned staging is 6.4 MB of memcpy: ~0.65 ms on one host thread, a third of the end-to-end frame.  A small
+// persistent pool (created at the first large submission) copies a chunk in slices while the previous chunk's DMA runs.
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+struct CopyPool {
+    std::vector<std::thread> workers;
+    std::mutex m; std::condition_variable cv_go, cv_done;
+    char* dst = nullptr; const char* src = nullptr; size_t bytes = 0; uint64_t epoch = 0; int pending = 0; bool quit = false;
+    explicit CopyPool(int n) {
+        for (int w = 0; w < n; ++w) workers.emplace_back([this, w, n]() {
+            uint64_t seen = 0;
+            for (;;) {
+                char* d; const char* sp; size_t b;
+                { std::unique_lock<std::mutex> lk(m); cv_go.wait(lk, [&] { return quit || epoch != seen; }); if (quit) return; seen = epoch; d = dst; sp = src; b = bytes; }
+                const size_t per = ((b / (size_t)(n + 1)) + 63) & ~size_t(63), lo = std::min(b, per * (size_t)(w + 1)), hi = std::min(b, lo + per);
+                if (hi > lo) memcpy(d + lo, sp + lo, hi - lo);
+                { std::lock_guard<std::mutex> lk(m); if (--pending == 0) cv_done.notify_one(); }
+            }
+        });
+    }
+    void copy(void* d, const void* sp, size_t b) {
+        const int n = (int)workers.size();
+        { std::lock_guard<std::mutex> lk(m); dst = (char*)d; src = (const char*)sp; bytes = b; pending = n; ++epoch; }
+        cv_go.notify_all();
+        const size_t per = ((b / (size_t)(n + 1)) + 63) & ~size_t(63);
+        memcpy(d, sp, std::min(b, per));                                  // the caller's own slice, then whatever the slices of the workers left over
+        if (per * (size_t)(n + 1) < b) memcpy((char*)d + per * (size_t)(n + 1), (const char*)sp + per * (size_t)(n + 1), b - per * (size_t)(n + 1));
+        std::unique_lock<std::mutex> lk(m); cv_done.wait(lk, [&] { return pending == 0; });
+    }
+    ~CopyPool() { { std::lock_guard<std::mutex> lk(m); quit = true; } cv_go.notify_all(); for (auto& t : workers) t.join(); }
+};
+void imr_copy_pool_release(imrcd_ctx* ctx) { delete static_cast<CopyPool*>(ctx->copy_pool); ctx->copy_pool = nullptr; }
+static inline void staging_copy(imrcd_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (bytes < (512u << 10)) { memcpy(dst, src, bytes); return; }
+    if (!ctx->copy_pool) {
+        const unsigned hw = std::thread::hardware_concurrency();
+        const char* ev = getenv("IMRCD_COPY_THREADS");
+        const int n = ev ? atoi(ev) : (hw >= 8 ? 3 : (hw >= 4 ? 1 : 0));
+        ctx->copy_pool = new CopyPool(n < 0 ? 0 : n);
+    }
+    static_cast<CopyPool*>(ctx->copy_pool)->copy(dst, src, bytes);
+}
+
 // copy k consecutive caller entries, starting at i of the call's arrays (caller index g0 + i), behind the entries kept so far
 static void entries_append_run(imrcd_ctx* ctx, uint64_t i, uint64_t k, uint64_t g0, const float* current, const float* previous,
                                const uint32_t* mesh_ids, const uint8_t* should_callback, const uint32_t* entities) {
     float* pc = ctx->p_cur.as<float>(); float* pp = ctx->p_prev.as<float>();
     uint32_t* pm = ctx->p_mesh.as<uint32_t>(); uint32_t* pe = ctx->p_entity.as<uint32_t>(); uint8_t* pb = ctx->p_cb.as<uint8_t>();
     const uint64_t at = ctx->n_entries;
-    memcpy(pc + 16 * at, current + 16 * i, 64 * k);
+    staging_copy(ctx, pc + 16 * at, current + 16 * i, 64 * k);
     if (previous && previous != current) {
         if (!ctx->prev_distinct && at) memcpy(pp, pc, 64 * at);      // earlier entries of this frame had previous == current
-        memcpy(pp + 16 * at, previous + 16 * i, 64 * k); ctx->prev_distinct = true;
+        staging_copy(ctx, pp + 16 * at, previous + 16 * i, 64 * k); ctx->prev_distinct = true;
     }
-    else if (ctx->prev_distinct) memcpy(pp + 16 * at, current + 16 * i, 64 * k);
+    else if (ctx->prev_distinct) staging_copy(ctx, pp + 16 * at, current + 16 * i, 64 * k);
     memcpy(pm + at, mesh_ids + i, 4 * k);
     if (entities) memcpy(pe + at, entities + i, 4 * k); else for (uint64_t q = 0; q < k; ++q) pe[at + q] = (uint32_t)(g0 + i + q);
     if (should_callback) for (uint64_t q = 0; q < k; ++q) pb[at + q] = should_callback[i + q] ? 1 : 0; else memset(pb + at, 1, k);

@@ -1396,8 +1396,10 @@ int imr_comm_decide(imrcd_ctx* ctx, uint64_t spec_rows, bool* retry, bool* fatal
 // rows of the result that travel to the host speculatively, right behind the frame's kernels (the count is not known on the host yet):
 // what the last frame had plus a margin.  A frame with more records pays one extra copy after the wait.
 uint64_t imr_frame_spec_rows(const imrcd_ctx* ctx) {
-    uint64_t want = std::max<uint64_t>(256, ctx->spec_hint + ctx->spec_hint / 4 + 64), r = 256;
-    while (r < want) r <<= 1;                        // a power of two: the copy's size is part of what a captured frame is made of
+    const uint64_t want = std::max<uint64_t>(256, ctx->spec_hint + ctx->spec_hint / 4 + 64);
+    if (want >= 2048) return (want + 1023) & ~1023ull;      // coarse steps: the copy's size is part of what a captured frame is made of
+    uint64_t r = 256;
+    while (r < want) r <<= 1;
     return r;
 }
 

@@ -168,6 +168,7 @@ struct imrcd_ctx {
     // mesh arena
     std::vector<MeshHost> meshes;
     DevBuf d_recs, d_tris, d_tri_nrm, d_tri_vid, d_meshes;
+    void* copy_pool = nullptr;           // host threads for the staging copy of large submissions (imrcd_api.cu)
     void* skins = nullptr; std::vector<uint32_t> skin_max_joint;                       // re-posing (imrcd_repose.cu)
     PinBuf p_repose; DevBuf d_repose_in, d_repose_prod, d_repose_vtx, d_scalar; bool repose_pending = false; float last_repose_ms = 0.f;
     DevBuf d_rf_stage;                               // re-posed positions on their way into the arena (imrcd_build.cu)
