@@ -239,6 +239,10 @@ int imr_build_mesh_device(imrcd_ctx* ctx, const float* pos, const float* nrm, co
                           uint32_t mode, MeshHost* out);
 int imr_mesh_assemble_device(imrcd_ctx* ctx, uint32_t build_mode, MeshHost* out);      // Triangle::CreateTriangleList on the device, then the build
 int imr_frame_run_device(imrcd_ctx* ctx);
+struct FrameCtl;
+int imr_traverse_prepare(imrcd_ctx* ctx);                                   // mid phase (imrcd_traverse.cu)
+int imr_traverse_queue_init(imrcd_ctx* ctx, FrameCtl* ctl);
+int imr_traverse_launch(imrcd_ctx* ctx, FrameCtl* ctl);
 int imr_frame_finish_device(imrcd_ctx* ctx);
 // response stage: one thread per kept ray (Hermann passes), then one warp per colliding pair that moved (imrcd_rays.cu)
 int imr_frame_shoot_device(imrcd_ctx* ctx, FrameCtl* ctl, uint64_t* launches);

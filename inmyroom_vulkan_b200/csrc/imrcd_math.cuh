@@ -149,21 +149,31 @@ IMR_HD V3 sat_axis(const Box& l, const Box& r, int k) {
 // (each axis test is a pure function of the two boxes), so the device evaluates all 15 and ANDs.
 // MODE 0: lane-level early exit after every axis (branches); 1: straight-line, all 15 axes; 2: the six face-normal axes straight-line,
 // one exit, then the nine edge-edge axes straight-line (most separated pairs are caught by a face normal).
+// the two halves of the verdict: the six face-normal axes (Paralgram.cpp:21-81) and the nine edge-edge axes (:83-163)
+IMR_HD bool box_sat_faces(const Box& l, const Box& r) {
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) ok = ok & axis_overlap(l, r, sat_axis(l, r, k));
+    return ok;
+}
+IMR_HD bool box_sat_edges(const Box& l, const Box& r) {
+    bool ok = true;
+#pragma unroll
+    for (int k = 6; k < 15; ++k) ok = ok & axis_overlap(l, r, sat_axis(l, r, k));
+    return ok;
+}
 template <int MODE>
 IMR_HD bool box_sat_t(const Box& l, const Box& r) {
     bool ok = true;
     if (MODE == 2) {
+        ok = box_sat_faces(l, r);
+        if (ok) ok = box_sat_edges(l, r);
+    } else {
 #pragma unroll
-        for (int k = 0; k < 6; ++k) ok = ok & axis_overlap(l, r, sat_axis(l, r, k));
-        if (!ok) return false;
-#pragma unroll
-        for (int k = 6; k < 15; ++k) ok = ok & axis_overlap(l, r, sat_axis(l, r, k));
-        return ok;
-    }
-#pragma unroll
-    for (int k = 0; k < 15; ++k) {
-        if (MODE == 1) ok = ok & axis_overlap(l, r, sat_axis(l, r, k));     // straight-line: no per-axis branches
-        else ok = ok && axis_overlap(l, r, sat_axis(l, r, k));             // lane-level early exit (branches)
+        for (int k = 0; k < 15; ++k) {
+            if (MODE == 1) ok = ok & axis_overlap(l, r, sat_axis(l, r, k));     // straight-line: no per-axis branches
+            else ok = ok && axis_overlap(l, r, sat_axis(l, r, k));             // lane-level early exit (branches)
+        }
     }
     return ok;
 }
