@@ -314,7 +314,7 @@ struct NarrowWarp {
                                           // survivors of the rejection tests into its front (in place: writes trail reads)
 };
 
-__global__ void __launch_bounds__(NT_WARPS * 32)
+__global__ void __launch_bounds__(NT_WARPS * 32, 3)
 k_tritri(FrameCtl* ctl, const Combo* __restrict__ combos, unsigned long long cap_combos, const PairRec* __restrict__ pairrec,
          const TriRec* __restrict__ tris, imrcd_tri_hit* __restrict__ hits, unsigned long long cap_hits, PairAcc* acc, HitAux* __restrict__ aux) {
     extern __shared__ __align__(16) unsigned char nt_smem[];
@@ -422,23 +422,32 @@ k_tritri(FrameCtl* ctl, const Combo* __restrict__ combos, unsigned long long cap
                 const int f = tt_segment(V0, V1, V2, U0, U1, U2, N1, N2, du0, du1, du2, du0du1, du0du2, dv0, dv1, dv2, dv0dv1, dv0dv2, src, tgt);   // :86
                 hit = (f == 1);                                                        // doIntersept && !areCoplanar (:88)
                 if (f == 3) ++my_cop;
-                if (hit) {
-                    hpair = cm.x; triA = cm.y + i; triB = sm.absB[slot]; origA = __float_as_uint(a0.w);
-                    // each vertex against the other triangle's plane (:102-112)
-                    const PlaneN pa = plane_from_tri(V0, V1, V2), pb = plane_from_tri(U0, U1, U2);
-                    if (plane_outside(pb, V0)) bits_a &= ~1u; if (plane_outside(pb, V1)) bits_a &= ~2u; if (plane_outside(pb, V2)) bits_a &= ~4u;
-                    if (plane_outside(pa, U0)) bits_b &= ~1u; if (plane_outside(pa, U1)) bits_b &= ~2u; if (plane_outside(pa, U2)) bits_b &= ~4u;
-                }
             }
             const uint32_t hm = __ballot_sync(FULL_MASK, hit);
             if (hm == 0u) continue;
+            // the slots of this iteration's hits: the atomic goes out first, the per-hit work below runs while it is on its way through L2
             unsigned long long base = 0;
             if (lane == 0) base = atomicAdd(&ctl->n_hits, (unsigned long long)__popc(hm));
-            base = __shfl_sync(FULL_MASK, base, 0);
             float weight = 0.f;
             bool zero_w = false;
             if (hit) {
+                const uint32_t c = code & 31u, i = (code >> 5) & 3u, slot = 4u * c + (code >> 7);
+                const uint4 cm = sm.cmb[c];
+                const float4* ta = reinterpret_cast<const float4*>(tris + cm.y + i);
+                const float4 a0 = __ldg(ta), a1 = __ldg(ta + 1), a2 = __ldg(ta + 2);
+                const V3 V0 = mk3(a0.x, a0.y, a0.z), V1 = mk3(a1.x, a1.y, a1.z), V2 = mk3(a2.x, a2.y, a2.z);
+                const V3 U0 = mk3(sm.ux[0][slot], sm.uy[0][slot], sm.uz[0][slot]);
+                const V3 U1 = mk3(sm.ux[1][slot], sm.uy[1][slot], sm.uz[1][slot]);
+                const V3 U2 = mk3(sm.ux[2][slot], sm.uy[2][slot], sm.uz[2][slot]);
+                hpair = cm.x; triA = cm.y + i; triB = sm.absB[slot]; origA = __float_as_uint(a0.w);
+                // each vertex against the other triangle's plane (:102-112)
+                const PlaneN pa = plane_from_tri(V0, V1, V2), pb = plane_from_tri(U0, U1, U2);
+                if (plane_outside(pb, V0)) bits_a &= ~1u; if (plane_outside(pb, V1)) bits_a &= ~2u; if (plane_outside(pb, V2)) bits_a &= ~4u;
+                if (plane_outside(pa, U0)) bits_b &= ~1u; if (plane_outside(pa, U1)) bits_b &= ~2u; if (plane_outside(pa, U2)) bits_b &= ~4u;
                 weight = length3(sub3(src, tgt));                                      // :93
+            }
+            base = __shfl_sync(FULL_MASK, base, 0);
+            if (hit) {
                 const unsigned long long slot = base + __popc(hm & lt_mask);
                 if (slot < cap_hits) {
                     imrcd_tri_hit h;

@@ -281,7 +281,7 @@ k_traverse(FrameCtl* ctl, const PairRec* __restrict__ pairrec, const TreeRec* __
 // default was chosen on C3 and C2 (0.68 / 1.63 ms).  A two-phase form of the kernel (face-normal axes for 32 node pairs, survivors parked
 // in shared memory, edge-edge axes for 32 survivors at once) was measured in round 2 and dropped: a warp's wavefront is ~32 node pairs wide
 // (more is donated to starving warps), so the second phase ran half empty exactly like the divergent lanes it was meant to remove, and
-// letting warps hoard 64+ pairs to fill it starved the others (C3: 0.74-0.80 ms against 0.68; profiles/r2_traverse_two_phase.txt).
+// letting warps hoard 64+ pairs to fill it starved the others (C3: 0.74-0.80 ms against 0.68; profiles/r2_traverse_experiments.txt).
 int imr_traverse_prepare(imrcd_ctx* ctx) {
     if (ctx->trav_blocks != 0) return IMRCD_OK;
     int per_sm = 0;

@@ -1,11 +1,10 @@
 #!/bin/bash
-# A/B of the traversal kernels on one GPU: per-rank stage times of a C3 frame at world sizes 1, 2, 4, 8 (scripts/shard_probe.py)
-# usage: scripts/trav_ab.sh "VARIANT PREFETCH KEEP" ...
+# A/B of the traversal's knobs on one GPU: per-rank stage times of a C3 frame at world sizes 1, 2, 4, 8 (scripts/shard_probe.py)
+# usage: scripts/trav_ab.sh "IMRCD_TRAV_X=1 IMRCD_TRAV_Y=2" "..." ...
 mkdir -p gpurun_out
 for cfg in "$@"; do
-  set -- $cfg
-  echo "== IMRCD_TRAV_VARIANT=$1 IMRCD_TRAV_PREFETCH=$2 IMRCD_TRAV_KEEP=$3"
-  IMRCD_TRAV_VARIANT=$1 IMRCD_TRAV_PREFETCH=$2 IMRCD_TRAV_KEEP=$3 python scripts/shard_probe.py 100000 10 2>&1 | python -c "
+  echo "== $cfg"
+  env $cfg python scripts/shard_probe.py 100000 10 2>&1 | python -c "
 import sys, json
 for ln in sys.stdin:
     if ln.startswith('{'):
