@@ -528,7 +528,7 @@ def run_gpu_arm(args):
         "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": desc, "entries": n_entries, "triangles_in_trees": n_tri_total, "bodies": args.bodies,
-                   "parallelism": f"frame sharded by entity over {world} GPUs (flagged entries replicated, the others dealt in blocks of 256; each rank uploads, sorts and sweeps its share only); one end-of-frame ncclAllGather inside the library" if world > 1 else "1 GPU",
+                   "parallelism": f"frame sharded by entity over {world} GPUs (flagged entries replicated, the others dealt in blocks of 256; each rank uploads, sorts and sweeps its share only); end-of-frame merge inside the library: " + ("every rank's last kernel stores its block into every peer's buffer over NVLink and raises a flag (k_p2p_push / k_p2p_wait_compact), no collective call in a frame" if ctx.comm_transport() == 2 else "one ncclAllGather on the frame's stream") if world > 1 else "1 GPU",
                    "l2": "flushed between timed steps (256 MiB write); inputs (~35 MB) would otherwise stay L2-resident",
                    "tree_build": "GPU Morton build (IMRCD_BUILD_MORTON): true PCA boxes, fewer tests for the same answer than the reference's trees (see same_work)" if args.trees == "morton"
                                  else "IMRCD_BUILD_REFERENCE: the reference's own trees bit for bit (OBBtree.cpp:321), so combos, tests and the hit set are the reference's by construction"},

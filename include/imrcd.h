@@ -249,6 +249,10 @@ int imrcd_frame_results_block(imrcd_ctx* ctx, void** d_block, uint64_t* n_pairs,
 int imrcd_comm_unique_id(void* id_out /* IMRCD_COMM_ID_BYTES */);
 int imrcd_comm_init(imrcd_ctx* ctx, const void* id, uint32_t rank, uint32_t n_ranks);
 int imrcd_comm_destroy(imrcd_ctx* ctx);
+/* How the end-of-frame merge of this context travels: 0 = no communicator, 1 = ncclAllGather on the frame's stream, 2 = peer memory
+ * (each rank's last kernel stores its block into every peer's buffer over NVLink and raises a flag; no NCCL call inside a frame).
+ * Decided at the first frame after imrcd_comm_init / imrcd_group_create, collectively; IMRCD_P2P=0 in the environment forces 1. */
+int imrcd_comm_transport(const imrcd_ctx* ctx);
 
 typedef struct imrcd_group imrcd_group;
 int         imrcd_group_create(const int* device_ids, uint32_t n, imrcd_group** out);

@@ -96,6 +96,7 @@ _SIGS = [
     ("imrcd_comm_unique_id", C.c_int, [_P]),
     ("imrcd_comm_init", C.c_int, [_P, _P, C.c_uint32, C.c_uint32]),
     ("imrcd_comm_destroy", C.c_int, [_P]),
+    ("imrcd_comm_transport", C.c_int, [_P]),
     ("imrcd_group_create", C.c_int, [C.POINTER(C.c_int), C.c_uint32, C.POINTER(_P)]),
     ("imrcd_group_destroy", None, [_P]),
     ("imrcd_group_size", C.c_uint32, [_P]),

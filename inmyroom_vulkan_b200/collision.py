@@ -77,6 +77,10 @@ class Context:
     def comm_destroy(self):
         self.check(self.lib.imrcd_comm_destroy(self.h))
 
+    def comm_transport(self) -> int:
+        """0 no communicator, 1 ncclAllGather, 2 peer memory over NVLink (imrcd_comm_transport)."""
+        return int(self.lib.imrcd_comm_transport(self.h))
+
     # ---- unit-level hooks ---------------------------------------------------------------
     def test_sat(self, boxes_a, boxes_b, mats=None):
         a = _c(boxes_a, np.float32).reshape(-1, 12); b = _c(boxes_b, np.float32).reshape(-1, 12)
@@ -456,6 +460,11 @@ class Group:
         if rc != 0:
             msg = self.lib.imrcd_group_last_error(self.h)
             raise ImrcdError(f"{_lib.ERRORS.get(rc, rc)}: {msg.decode() if msg else ''}")
+
+    def comm_transport(self) -> int:
+        """How the group's end-of-frame merge travels (imrcd_comm_transport of its first context): 1 ncclAllGather, 2 peer memory."""
+        self.lib.imrcd_group_ctx.restype = C.c_void_p
+        return int(self.lib.imrcd_comm_transport(C.c_void_p(self.lib.imrcd_group_ctx(self.h, 0))))
 
     def mesh_create(self, positions, normals=None, vertex_ids=None, build_mode: int = IMRCD_BUILD_MORTON) -> int:
         pos = _c(positions, np.float32).reshape(-1, 9)

@@ -1442,7 +1442,7 @@ static uint64_t frame_key(imrcd_ctx* ctx) {
     mix(ctx->n_entries); mix(ctx->n_entries_global); mix(ctx->n_flagged_global <= ctx->few_flagged_max); mix(ctx->n_flagged_global == ctx->n_entries_global);
     mix(ctx->prev_distinct); mix(ctx->shard_rank); mix(ctx->shard_n); mix(ctx->cap_pairs); mix(ctx->cap_queue); mix(ctx->cap_combos); mix(ctx->cap_hits);
     mix(ctx->cap_rays); mix(ctx->cap_lscratch); mix(ctx->pc_large_min); mix(ctx->queue_dirty ? queue_clear_slots(ctx) : 0); mix(imr_frame_spec_rows(ctx));
-    mix(ctx->gcap); mix((uint64_t)ctx->comm); mix(ctx->meshes.size());
+    mix(ctx->gcap); mix((uint64_t)ctx->comm); mix(ctx->meshes.size()); mix((uint64_t)ctx->p2p_buf); mix((uint64_t)(ctx->p2p_state + 1)); mix(ctx->p2p_gcap);
     const DevBuf* bufs[] = { &ctx->d_recs, &ctx->d_tris, &ctx->d_tri_nrm, &ctx->d_tri_vid, &ctx->d_meshes, &ctx->d_cur, &ctx->d_prev, &ctx->d_mesh, &ctx->d_cb, &ctx->d_entity, &ctx->d_gidx,
                              &ctx->d_inv, &ctx->d_ext, &ctx->d_keys, &ctx->d_keys2, &ctx->d_idx, &ctx->d_idx2, &ctx->d_sorted, &ctx->d_sorted_c, &ctx->d_flag, &ctx->d_cpos, &ctx->d_wlen,
                              &ctx->d_chunks, &ctx->d_chunkoff, &ctx->d_cubtmp, &ctx->d_pairs, &ctx->d_pairrec, &ctx->d_pairacc, &ctx->d_queue, &ctx->d_combos, &ctx->d_hits, &ctx->d_epairs,

@@ -221,6 +221,13 @@ struct imrcd_ctx {
     uint32_t comm_rank = 0, comm_n = 1;
     uint64_t gcap = 0;                   // rows per rank in the gathered blocks (after the header row); the same on every rank
     DevBuf d_gather; PinBuf p_gather;    // comm_n x (gcap + 1) x 80 B
+    // the merge over peer memory (imrcd_comm.cu): every rank pushes its block into every peer's buffer over NVLink, no NCCL call in a frame
+    int p2p_state = 0;                   // 0 not tried yet, 1 in use, -1 not available (the NCCL all-gather is used)
+    uint64_t p2p_gcap = 0;               // the capacity the buffers were laid out for
+    void* p2p_buf = nullptr;             // this rank's buffer: [2 parities][comm_n blocks of (gcap + 1) rows] + [2][comm_n] arrival flags
+    void* p2p_ctl = nullptr;             // device: frame sequence number, tickets, the peers' buffer addresses (P2PCtl)
+    std::vector<void*> p2p_opened;       // peers' buffers opened through CUDA IPC (other processes)
+    void* group = nullptr;               // imrcd_group this context belongs to (one process, several GPUs), else null
     uint64_t n_merged = 0; bool merged_valid = false;
     cudaGraphExec_t graph_exec = nullptr; uint64_t graph_key = 0, graph_seen_key = 0, graph_launches = 0, graph_spec_rows = 0; bool capturing = false; int use_graph = -1;      // the frame as a CUDA graph
     uint64_t spec_hint = 0, spec_rows_sent = 0;      // speculative D2H of the result rows (imr_frame_spec_rows)

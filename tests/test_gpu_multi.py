@@ -4,7 +4,9 @@
     the collective retry decision) gives the records the plain context gives, over changing frames;
   * one process, two GPUs (imrcd_group_*) and two processes, one GPU each (imrcd_comm_init, rendezvous over torch.distributed):
     merged records == the single-GPU frame, with entries that change from frame to frame, a frame that outgrows the gather blocks
-    (capacity raised collectively) and a frame with fewer than two entries.  Skipped on a box with one GPU.
+    (capacity raised collectively) and a frame with fewer than two entries.  Skipped on a box with one GPU.  Both transports of the
+    merge are run: peer memory over NVLink (k_p2p_push / k_p2p_wait_compact, the default where the GPUs reach each other) and the
+    ncclAllGather it replaces (IMRCD_P2P=0).
 """
 import os
 import socket
@@ -98,8 +100,15 @@ def _need_two_gpus():
         pytest.skip("needs two GPUs")
 
 
-def test_group_of_two_gpus_in_one_process(gpu_ctx):
+def _peer_access():
+    import torch
+    return torch.cuda.can_device_access_peer(0, 1) and torch.cuda.can_device_access_peer(1, 0)
+
+
+@pytest.mark.parametrize("p2p", [1, 0])
+def test_group_of_two_gpus_in_one_process(gpu_ctx, monkeypatch, p2p):
     _need_two_gpus()
+    monkeypatch.setenv("IMRCD_P2P", str(p2p))
     frames = _frames()
     want = _single_gpu_reference(gpu_ctx, frames)
     g = Group([0, 1])
@@ -109,6 +118,7 @@ def test_group_of_two_gpus_in_one_process(gpu_ctx):
         g.Reset(); g.add_entries(sc.matrices, ids, sc.should_callback, sc.entities, prev); g.ExecuteCollisionDetection()
         ep = g.results()
         _same(w, ep[_key(ep)])
+    assert g.comm_transport() == (2 if (p2p and _peer_access()) else 1)
     sc = frames[0][0]                                                              # one entry: no frame
     g.Reset(); g.add_entries(sc.matrices[:1], np.array([ids_of[sc.mesh_index[0]]], np.uint32), sc.should_callback[:1], sc.entities[:1]); g.ExecuteCollisionDetection()
     assert len(g.results()) == 0
@@ -141,18 +151,24 @@ def _worker(rank, world, port, out_dir):
             assert st["n_entries_local"] < st["n_entries"]                         # this rank kept its share of the entries only
             np.save(os.path.join(out_dir, f"r{rank}_f{k}.npy"), ep)
             np.save(os.path.join(out_dir, f"r{rank}_f{k}_local.npy"), cd.results_local())
+        with open(os.path.join(out_dir, f"r{rank}_transport.txt"), "w") as f:
+            f.write(str(ctx.comm_transport()))
         dist.barrier()
         ctx.comm_destroy()
     finally:
         dist.destroy_process_group()
 
 
-def test_two_processes_one_gpu_each(gpu_ctx, tmp_path):
+@pytest.mark.parametrize("p2p", [1, 0])
+def test_two_processes_one_gpu_each(gpu_ctx, tmp_path, monkeypatch, p2p):
     _need_two_gpus()
+    monkeypatch.setenv("IMRCD_P2P", str(p2p))                                      # the workers are spawned with this environment
     import torch.multiprocessing as mp
     frames = _frames()
     want = _single_gpu_reference(gpu_ctx, frames)
     mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        assert int((tmp_path / f"r{r}_transport.txt").read_text()) == (2 if (p2p and _peer_access()) else 1)
     for k, w in enumerate(want):
         merged = [np.load(tmp_path / f"r{r}_f{k}.npy") for r in range(2)]
         assert np.array_equal(merged[0].view(np.uint8), merged[1].view(np.uint8)), "the ranks disagree on the merged records"
