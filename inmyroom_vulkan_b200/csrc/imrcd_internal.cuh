@@ -70,6 +70,7 @@ struct __align__(128) FrameCtl {
     unsigned long long n_combos;    unsigned long long _p5[15];
     unsigned long long n_hits;      unsigned long long _p6[15];
     unsigned long long n_colliding; unsigned long long _p7[15];
+    unsigned long long tile_cursor; unsigned long long _p8[15];   // narrow phase: next tile of 32 leaf combos to hand out (k_tritri)
     unsigned long long n_class[64];                               // pairs with hits per size class of the contact reduction ([0], [16], [32], [48])
     unsigned long long n_coplanar;
     unsigned long long n_sat;

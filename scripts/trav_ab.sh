@@ -4,7 +4,7 @@
 mkdir -p gpurun_out
 for cfg in "$@"; do
   echo "== $cfg"
-  env $cfg python scripts/shard_probe.py 100000 10 2>&1 | python -c "
+  env $cfg timeout 60 python scripts/shard_probe.py 100000 10 2>&1 | python -c "
 import sys, json
 for ln in sys.stdin:
     if ln.startswith('{'):
