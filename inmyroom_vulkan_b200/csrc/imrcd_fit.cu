@@ -216,11 +216,18 @@ struct FitSmem {
 
 __global__ void __launch_bounds__(FIT_T)
 k_fit_treelets(const FitCounters* __restrict__ cnt, const uint2* __restrict__ troots, const FitSeg* __restrict__ segs, const FitRec* __restrict__ fit,
-               const TriRec* __restrict__ tris, const uint32_t* __restrict__ slot_of, double* __restrict__ mom_out, TreeRec* __restrict__ recs, int write_links) {
+               const TriRec* __restrict__ tris, const uint32_t* __restrict__ slot_of, double* __restrict__ mom_out, TreeRec* __restrict__ recs, int write_links,
+               uint32_t* cursor) {
     extern __shared__ __align__(16) unsigned char fit_smem[];
     FitSmem& sm = *reinterpret_cast<FitSmem*>(fit_smem);
+    __shared__ uint32_t s_next;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    for (uint32_t b = blockIdx.x; b < cnt->n_troot; b += gridDim.x) {
+    for (;;) {                                                           // treelets are handed out through a counter: 1 to 128 triangles each
+        __syncthreads();
+        if (tid == 0) s_next = atomicAdd(cursor, 1u);
+        __syncthreads();
+        const uint32_t b = s_next;
+        if (b >= cnt->n_troot) break;
         const uint2 tr = troots[b];
         const FitSeg sg = segs[tr.y];
         const FitRec root = fit[tr.x];
@@ -435,13 +442,19 @@ __global__ void k_fit_chains(const FitCounters* __restrict__ cnt, const uint2* _
 __global__ void __launch_bounds__(FIT_T)
 k_fit_upper(const FitCounters* __restrict__ cnt, const uint2* __restrict__ troots, const FitRec* __restrict__ fit, const TriRec* __restrict__ tris,
             const uint32_t* __restrict__ slot_of, const uint32_t* __restrict__ chain, const uint32_t* __restrict__ chain_len, const float* __restrict__ frames, uint32_t* ext,
-            const TreeRec* __restrict__ recs) {
+            const TreeRec* __restrict__ recs, uint32_t* cursor) {
     __shared__ uint32_t s_part[FIT_CHAIN][FIT_T / 32][6];
     __shared__ float s_fr[FIT_CHAIN][12];
     __shared__ uint32_t s_slot[FIT_CHAIN];
     __shared__ uint32_t s_need[FIT_CHAIN];
+    __shared__ uint32_t s_next;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    for (uint32_t b = blockIdx.x; b < cnt->n_troot; b += gridDim.x) {
+    for (;;) {                                                           // handed out through a counter: how many ancestors a treelet still moves differs
+        __syncthreads();
+        if (tid == 0) s_next = atomicAdd(cursor, 1u);
+        __syncthreads();
+        const uint32_t b = s_next;
+        if (b >= cnt->n_troot) break;
         const FitRec root = fit[troots[b].x];
         const uint32_t n = root.last - root.first + 1u;
         const uint32_t n_all = chain_len[b], n_anc = n_all < FIT_CHAIN ? n_all : FIT_CHAIN;
@@ -617,7 +630,7 @@ __global__ void k_fit_origin_roots(uint32_t n_seg, FitSeg* segs, const TreeRec* 
 }
 
 struct FitLayout { FitCounters* cnt; FitSeg* segs; uint32_t* prefix; double* mom; uint2* troots; float* frames; uint32_t* ext; uint32_t* uppers; uint32_t* seg_of_upper;
-                   uint32_t* ticket; uint32_t* chain; uint32_t* chain_len; };
+                   uint32_t* ticket; uint32_t* chain; uint32_t* chain_len; uint32_t* cursor; };
 static FitLayout fit_layout(imrcd_ctx* ctx) {
     FitLayout L;
     char* sb = ctx->d_fit_segs.as<char>();
@@ -633,7 +646,8 @@ static FitLayout fit_layout(imrcd_ctx* ctx) {
     L.seg_of_upper = reinterpret_cast<uint32_t*>(b); b += 4 * ctx->fit_max_slots;
     L.ticket = reinterpret_cast<uint32_t*>(b); b += 4 * ctx->fit_max_slots;
     L.chain_len = reinterpret_cast<uint32_t*>(b); b += 4 * ctx->fit_max_troot;
-    L.chain = reinterpret_cast<uint32_t*>(b);
+    L.chain = reinterpret_cast<uint32_t*>(b); b += 4ull * FIT_CHAIN * ctx->fit_max_troot;
+    L.cursor = reinterpret_cast<uint32_t*>(b);                      // [0] k_fit_treelets, [1] k_fit_upper: next treelet to hand out (inside the 256 spare bytes)
     return L;
 }
 FitLists imr_fit_lists(imrcd_ctx* ctx) {
@@ -692,6 +706,7 @@ int imr_fit_launch(imrcd_ctx* ctx, bool write_links, const uint32_t* bounds, boo
     const uint32_t ns = ctx->fit_ns;
     const uint64_t max_troot = ctx->fit_max_troot, max_slots = ctx->fit_max_slots;
     IMR_CUDA(ctx, cudaMemsetAsync(L.ticket, 0, 4 * max_slots, s));
+    IMR_CUDA(ctx, cudaMemsetAsync(L.cursor, 0, 8, s));
     if (bounds) k_fit_origin_bounds<<<1, 1, 0, s>>>(L.segs, bounds);
     else k_fit_origin_roots<<<nb(ns, 128), 128, 0, s>>>(ns, L.segs, ctx->d_recs.as<TreeRec>());
     const FitRec* fit = ctx->d_fit.as<FitRec>();
@@ -705,10 +720,10 @@ int imr_fit_launch(imrcd_ctx* ctx, bool write_links, const uint32_t* bounds, boo
         k_fit_upper_segs<<<nb(max_slots, 256), 256, 0, s>>>(L.cnt, L.uppers, L.segs, ns, L.seg_of_upper);
         k_fit_chains<<<nb(max_troot, 128), 128, 0, s>>>(L.cnt, L.troots, fit, slot_of, L.chain, L.chain_len);
     }
-    k_fit_treelets<<<std::min<unsigned>(g_troot, ctx->fit_blocks), FIT_T, sizeof(FitSmem), s>>>(L.cnt, L.troots, L.segs, fit, tris, slot_of, L.mom, recs, wl);
+    k_fit_treelets<<<std::min<unsigned>(g_troot, ctx->fit_blocks), FIT_T, sizeof(FitSmem), s>>>(L.cnt, L.troots, L.segs, fit, tris, slot_of, L.mom, recs, wl, L.cursor);
     k_fit_climb<<<nb(max_troot, 128), 128, 0, s>>>(L.cnt, L.troots, fit, slot_of, L.mom, L.ticket);
     k_fit_axes<<<nb(max_slots, 128), 128, 0, s>>>(L.cnt, L.uppers, L.segs, L.seg_of_upper, slot_of, L.mom, L.frames, L.ext);
-    k_fit_upper<<<std::min<unsigned>(g_troot, ctx->sm_count * 12), FIT_T, 0, s>>>(L.cnt, L.troots, fit, tris, slot_of, L.chain, L.chain_len, L.frames, L.ext, recs);
+    k_fit_upper<<<std::min<unsigned>(g_troot, ctx->sm_count * 12), FIT_T, 0, s>>>(L.cnt, L.troots, fit, tris, slot_of, L.chain, L.chain_len, L.frames, L.ext, recs, L.cursor + 1);
     k_fit_boxes<<<nb(max_slots, 128), 128, 0, s>>>(L.cnt, L.uppers, L.segs, L.seg_of_upper, fit, slot_of, L.frames, L.ext, recs, wl);
     IMR_CUDA(ctx, cudaGetLastError());
     return IMRCD_OK;

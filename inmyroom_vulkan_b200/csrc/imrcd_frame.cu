@@ -642,7 +642,14 @@ k_pair_contacts_hash(FrameCtl* ctl, const uint32_t* __restrict__ list, int cls, 
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
     if (ctl->overflow & (OVF_PAIRS | OVF_QUEUE | OVF_COMBOS | OVF_HITS)) return;      // the frame is re-run with larger buffers
     const unsigned long long n_list = ctl->n_class[cls * 16];
-    for (unsigned long long b = blockIdx.x; b < n_list; b += gridDim.x) {
+    __shared__ unsigned long long s_next;
+    // pairs are handed out through a counter (the word behind the class's count): a pair of 16 hits and one of 250 do not cost the same
+    for (;;) {
+        __syncthreads();                                             // the last pair's use of the shared tables (and of s_next) is over
+        if (tid == 0) s_next = atomicAdd(&ctl->n_class[cls * 16 + 1], 1ull);
+        __syncthreads();
+        const unsigned long long b = s_next;
+        if (b >= n_list) break;
         const uint32_t p = list[b];
         const uint32_t n = acc[p].n_hits;
         const bool keep_rays = (acc[p].flags & PAIR_MOVED) != 0u;

@@ -216,7 +216,7 @@ struct imrcd_ctx {
     cudaEvent_t ev[10] = {};            // [0..6] frame stages, [6..7] build / refit, [8..9] re-pose
     cudaStream_t stream2 = nullptr, stream3 = nullptr, stream4 = nullptr;      // side streams for independent tail work of a frame
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join3 = nullptr, ev_join4 = nullptr;
-    int trav_blocks = 0, narrow_blocks = 0, trav_variant = 0, shoot_blocks = 0;
+    int trav_blocks = 0, trav_blocks_shard = 0, narrow_blocks = 0, trav_variant = 0, shoot_blocks = 0;
     // end-of-frame merge over NCCL (imrcd_comm.cu): one all-gather of fixed-capacity blocks on the frame's stream
     void* comm = nullptr;                // ncclComm_t
     uint32_t comm_rank = 0, comm_n = 1;

@@ -299,12 +299,17 @@ int imr_traverse_prepare(imrcd_ctx* ctx) {
     }
     IMR_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ctx->trav_fn, TRAV_WARPS * 32, 0));
     if (per_sm < 1) per_sm = 1;
+    if (getenv("IMRCD_TRAV_BLOCKS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(getenv("IMRCD_TRAV_BLOCKS_PER_SM"))));      // probe: a smaller persistent grid
     ctx->trav_blocks = per_sm * ctx->sm_count;
+    // a quarter of a frame or less (4+ ranks): the frontier is too thin for the whole grid, and fewer warps polling for it finish sooner
+    // (4 instead of 5 blocks per SM: 0.195 -> 0.185 ms on an eighth of C3, +3 % on the whole frame; profiles/r2_traverse_experiments.txt)
+    ctx->trav_blocks_shard = std::min(per_sm, 4) * ctx->sm_count;
     return IMRCD_OK;
 }
+static inline int trav_grid(const imrcd_ctx* ctx) { return ctx->shard_n >= 4 ? ctx->trav_blocks_shard : ctx->trav_blocks; }
 
 int imr_traverse_queue_init(imrcd_ctx* ctx, FrameCtl* ctl) {
-    k_queue_init<<<1, 1, 0, ctx->stream>>>(ctl, ctx->cap_pairs, ctx->cap_queue, (uint32_t)(ctx->trav_blocks * TRAV_WARPS));
+    k_queue_init<<<1, 1, 0, ctx->stream>>>(ctl, ctx->cap_pairs, ctx->cap_queue, (uint32_t)(trav_grid(ctx) * TRAV_WARPS));
     return IMRCD_OK;
 }
 
@@ -323,7 +328,7 @@ int imr_traverse_launch(imrcd_ctx* ctx, FrameCtl* ctl) {
         a_trace = ctx->d_trace.as<uint4>();
     }
     void* targs[] = { &ctl, &a_pairrec, &a_recs, &a_queue, &ctx->cap_queue, &a_combos, &ctx->cap_combos, &keep_items, &backoff_max, &a_trace, &trace_cap, &coop };
-    IMR_CUDA(ctx, cudaLaunchKernel(ctx->trav_fn, dim3(ctx->trav_blocks), dim3(TRAV_WARPS * 32), targs, 0, s));
+    IMR_CUDA(ctx, cudaLaunchKernel(ctx->trav_fn, dim3(trav_grid(ctx)), dim3(TRAV_WARPS * 32), targs, 0, s));
     return IMRCD_OK;
 }
 
