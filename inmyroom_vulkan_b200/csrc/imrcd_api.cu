@@ -534,20 +534,24 @@ extern "C" int imrcd_frame_add_entries(imrcd_ctx* ctx, uint64_t n, const float* 
     } else {
         // count what this rank keeps, reserve once, then copy run by run: whole blocks it owns, and the flagged entries of the other blocks
         uint64_t keep = 0;
+        std::vector<uint32_t>& blk_flagged = ctx->shard_blk_flagged;      // flagged entries per block of this call: the copy pass skips foreign blocks without any
+        blk_flagged.clear();
         for (uint64_t i = 0; i < n; ) {
             const uint64_t g = g0 + i, blk_end = std::min<uint64_t>(n, i + (SHARD_BLOCK - g % SHARD_BLOCK));
             uint64_t f = 0;
             if (should_callback) for (uint64_t q = i; q < blk_end; ++q) f += should_callback[q] ? 1 : 0; else f = blk_end - i;
             n_flagged += f;
             keep += shard_owns(ctx, g) ? blk_end - i : f;
+            blk_flagged.push_back((uint32_t)f);
             i = blk_end;
         }
         int rc = entries_reserve(ctx, ctx->n_entries + keep, bulk);
         if (rc) return rc;
-        for (uint64_t i = 0; i < n; ) {
+        size_t bi = 0;
+        for (uint64_t i = 0; i < n; ++bi) {
             const uint64_t g = g0 + i, blk_end = std::min<uint64_t>(n, i + (SHARD_BLOCK - g % SHARD_BLOCK));
             if (shard_owns(ctx, g)) entries_append_run(ctx, i, blk_end - i, g0, current, previous, mesh_ids, should_callback, entities);
-            else for (uint64_t q = i; q < blk_end; ++q) {
+            else if (blk_flagged[bi]) for (uint64_t q = i; q < blk_end; ++q) {
                 if (should_callback && !should_callback[q]) continue;
                 uint64_t r = q + 1;
                 while (r < blk_end && (!should_callback || should_callback[r])) ++r;

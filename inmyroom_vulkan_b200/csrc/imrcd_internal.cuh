@@ -193,6 +193,7 @@ struct imrcd_ctx {
     uint64_t n_entries_global = 0;       // entries added this frame by the caller (every rank of a sharded frame is handed the whole list)
     uint64_t n_flagged_global = 0;       // ... of which shouldCallback
     PinBuf p_gidx; DevBuf d_gidx;        // sharded frames: caller's index of every kept entry (ascending); unsharded: unused (identity)
+    std::vector<uint32_t> shard_blk_flagged;            // scratch of imrcd_frame_add_entries (sharded frames)
     uint32_t shard_rank_next = 0, shard_n_next = 1;     // imrcd_frame_set_shard takes effect at the next frame
     uint64_t n_sent = 0;                 // entries whose H2D copy has been enqueued
     bool prev_distinct = false;          // some entry of this frame carries a previous matrix different from its current one

@@ -1,11 +1,13 @@
 #!/bin/bash
 # every workload of bench.py once on one GPU (+ the reference arm of the default one); lines land in gpurun_out/r2_bench_*.json
 mkdir -p gpurun_out
-for w in c3 c1 c2 c4 c5; do
-  python bench.py --workload $w --steps ${STEPS:-10} --warmup 3 > gpurun_out/r2_bench_$w.json 2> gpurun_out/r2_bench_$w.err || tail -5 gpurun_out/r2_bench_$w.err
+for w in c3 c1 c4 c5; do
+  timeout 300 python bench.py --workload $w --steps ${STEPS:-10} --warmup 3 > gpurun_out/r2_bench_$w.json 2> gpurun_out/r2_bench_$w.err || tail -5 gpurun_out/r2_bench_$w.err
 done
-python bench.py --workload c3 --trees reference --steps ${STEPS:-10} --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench_c3_reftrees.json 2> gpurun_out/r2_bench_c3_reftrees.err || tail -5 gpurun_out/r2_bench_c3_reftrees.err
-python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r2_bench_c3_refarm.json 2> gpurun_out/r2_bench_c3_refarm.err || tail -5 gpurun_out/r2_bench_c3_refarm.err
+# C2's single-thread reference sample takes 80 s of CPU (its sweep is quadratic on 4,096 overlapping tori): skipped here, see profiles/r2_bench_c2.json of the round's first session
+timeout 300 python bench.py --workload c2 --steps ${STEPS:-10} --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench_c2.json 2> gpurun_out/r2_bench_c2.err || tail -5 gpurun_out/r2_bench_c2.err
+timeout 300 python bench.py --workload c3 --trees reference --steps ${STEPS:-10} --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench_c3_reftrees.json 2> gpurun_out/r2_bench_c3_reftrees.err || tail -5 gpurun_out/r2_bench_c3_reftrees.err
+timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r2_bench_c3_refarm.json 2> gpurun_out/r2_bench_c3_refarm.err || tail -5 gpurun_out/r2_bench_c3_refarm.err
 python - <<'PY'
 import json, glob
 for f in sorted(glob.glob("gpurun_out/r2_bench_c*.json")):
