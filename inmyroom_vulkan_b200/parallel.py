@@ -4,8 +4,8 @@ The path shards naturally: trees are replicated, every rank is ha
 (imrcd_frame_set_shard: all entries with shouldCallback + its blocks of the others), so each candidate pair, all of its triangle
 hits, its contact reduction and its response belong to exactly one rank and nothing crosses GPUs before the end of the frame.
 The only collective is the end-of-frame merge of the colliding-pair records (80 B each): ONE all-gather of fixed-capacity blocks
-whose header row carries the rank's record count and overflow bits.  It lives INSIDE libimrcd.so (csrc/imrcd_comm.cu: ncclAllGather
-on the frame's own stream); what is left here is the rendezvous (init_comm: the NCCL unique id travels over torch.distributed) and
+whose header row carries the rank's record count and overflow bits.  It lives INSIDE libimrcd.so (csrc/imrcd_comm.cu: stores into the
+peers' buffers over NVLink + arrival flags where the GPUs reach each other's memory, else ncclAllGather, on the frame's own stream); what is left here is the rendezvous (init_comm: the NCCL unique id travels over torch.distributed) and
 a CPU model of the same block protocol over gloo for the world-size-2 host-logic tests.
 
 The reference has no counterpart (it is a single-threaded host loop, CollisionDetection.cpp:44-129); what is kept is
