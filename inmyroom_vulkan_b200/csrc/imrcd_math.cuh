@@ -271,16 +271,26 @@ IMR_HD void tt_isect2(V3 X0, V3 X1, V3 X2, float VV0, float VV1, float VV2, floa
     diff = mk3(tmp * diff.x, tmp * diff.y, tmp * diff.z);
     ip1 = add3(X0, diff);
 }
-// Triangle.cpp:795-830 ; returns true when coplanar
+// Triangle.cpp:795-830 ; returns true when coplanar.  The reference's five cases call isect2 with one of three orders of the vertices
+// (the vertex alone on its side of the other triangle's plane first); here the order is SELECTED and isect2 runs once: the same
+// operations on the same operands, without five copies of the code that the lanes of a warp would walk through one after the other.
 IMR_HD bool tt_intervals(V3 X0, V3 X1, V3 X2, float VV0, float VV1, float VV2, float D0, float D1, float D2,
                          float D0D1, float D0D2, float& isect0, float& isect1, V3& ip0, V3& ip1) {
-    if (D0D1 > 0.0f)                        tt_isect2(X2, X0, X1, VV2, VV0, VV1, D2, D0, D1, isect0, isect1, ip0, ip1);
-    else if (D0D2 > 0.0f)                   tt_isect2(X1, X0, X2, VV1, VV0, VV2, D1, D0, D2, isect0, isect1, ip0, ip1);
-    else if (D1 * D2 > 0.0f || D0 != 0.0f)  tt_isect2(X0, X1, X2, VV0, VV1, VV2, D0, D1, D2, isect0, isect1, ip0, ip1);
-    else if (D1 != 0.0f)                    tt_isect2(X1, X0, X2, VV1, VV0, VV2, D1, D0, D2, isect0, isect1, ip0, ip1);
-    else if (D2 != 0.0f)                    tt_isect2(X2, X0, X1, VV2, VV0, VV1, D2, D0, D1, isect0, isect1, ip0, ip1);
-    else return true;
-    return false;
+    int first;                                  // which vertex goes first: 0 -> (0,1,2), 1 -> (1,0,2), 2 -> (2,0,1)
+    bool coplanar = false;
+    if (D0D1 > 0.0f)                        first = 2;
+    else if (D0D2 > 0.0f)                   first = 1;
+    else if (D1 * D2 > 0.0f || D0 != 0.0f)  first = 0;
+    else if (D1 != 0.0f)                    first = 1;
+    else if (D2 != 0.0f)                    first = 2;
+    else { first = 0; coplanar = true; }
+    const V3 A = first == 0 ? X0 : (first == 1 ? X1 : X2), B = first == 0 ? X1 : X0, C = first == 2 ? X1 : X2;
+    const float VA = first == 0 ? VV0 : (first == 1 ? VV1 : VV2), VB = first == 0 ? VV1 : VV0, VC = first == 2 ? VV1 : VV2;
+    const float DA = first == 0 ? D0 : (first == 1 ? D1 : D2), DB = first == 0 ? D1 : D0, DC = first == 2 ? D1 : D2;
+    float t0, t1; V3 p0, p1;
+    tt_isect2(A, B, C, VA, VB, VC, DA, DB, DC, t0, t1, p0, p1);
+    if (!coplanar) { isect0 = t0; isect1 = t1; ip0 = p0; ip1 = p1; }           // coplanar: the outputs stay as the caller left them (:830)
+    return coplanar;
 }
 IMR_HD float tt_pick(V3 a, int index) { return index == 0 ? a.x : (index == 1 ? a.y : a.z); }
 
