@@ -402,7 +402,9 @@ extern "C" int imrcd_frame_reset(imrcd_ctx* ctx) {
 }
 
 #define ENTRY_CHUNK 16384u     // entries per H2D chunk of the pipelined upload (1 MiB of matrices)
-#define SHARD_BLOCK 256u       // sharded frames: entries without shouldCallback are dealt to the ranks in blocks of this many caller indices
+// sharded frames: entries without shouldCallback are dealt to the ranks in blocks of this many caller indices (every rank must use the same
+// value; IMRCD_SHARD_BLOCK in the environment overrides it for experiments)
+static const uint64_t SHARD_BLOCK = []() -> uint64_t { const char* ev = getenv("IMRCD_SHARD_BLOCK"); const long v = ev ? atol(ev) : 0; return v > 0 ? (uint64_t)v : 256ull; }();
 
 // Sharded frames (imrcd_frame_set_shard, SURVEY 8e "sharded by entity").  A pair needs shouldCallback on one side at least
 // (SweepAndPrune.cpp:60), so entries WITH the flag go to every rank and entries WITHOUT it to exactly one: a pair with an unflagged entity is
