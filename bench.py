@@ -380,6 +380,7 @@ def run_gpu_arm(args):
     cd.Reset(); cd.add_entries(scene.matrices, mesh_ids, scene.should_callback, scene.entities); cd.upload()
 
     align = torch.zeros(1, device="cuda") if multi else None
+    SPIN_CYCLES = 2_000_000
 
     def device_step():
         with torch.cuda.stream(stream):
@@ -387,6 +388,8 @@ def run_gpu_arm(args):
             if multi:
                 dist.all_reduce(align)              # not part of the frame: the ranks leave their L2 flushes at different times, and a step timed
                                                     # from an early rank's start would count its wait for the latest one inside the frame's collective
+            torch.cuda._sleep(SPIN_CYCLES)          # ~1 ms of GPU spin in front of the timed region: the host gets the frame's graph enqueued while it
+                                                    # runs, so that the events time the DEVICE and not how fast a (shared, busy) host gets a launch out
             e0.record(stream)
             cd.run_async()                          # the frame's kernels and, with N ranks, the end-of-frame all-gather right behind them
             e1.record(stream)                       # (both enqueued by the library on this stream); the host does not wait here
@@ -530,6 +533,7 @@ def run_gpu_arm(args):
         "config": {"workload": desc, "entries": n_entries, "triangles_in_trees": n_tri_total, "bodies": args.bodies,
                    "parallelism": f"frame sharded by entity over {world} GPUs (flagged entries replicated, the others dealt in blocks of 256; each rank uploads, sorts and sweeps its share only); end-of-frame merge inside the library: " + ("every rank's last kernel stores its block into every peer's buffer over NVLink and raises a flag (k_p2p_push / k_p2p_wait_compact), no collective call in a frame" if ctx.comm_transport() == 2 else "one ncclAllGather on the frame's stream") if world > 1 else "1 GPU",
                    "l2": "flushed between timed steps (256 MiB write); inputs (~35 MB) would otherwise stay L2-resident",
+                   "timing": "CUDA events on the frame's stream around every step, max over ranks; a 1-ms GPU spin is enqueued in front of the first event so that the frame's graph is already queued when the timed region starts (device time, not host launch latency)",
                    "tree_build": "GPU Morton build (IMRCD_BUILD_MORTON): true PCA boxes, fewer tests for the same answer than the reference's trees (see same_work)" if args.trees == "morton"
                                  else "IMRCD_BUILD_REFERENCE: the reference's own trees bit for bit (OBBtree.cpp:321), so combos, tests and the hit set are the reference's by construction"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

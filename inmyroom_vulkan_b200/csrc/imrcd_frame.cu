@@ -10,6 +10,7 @@
 #include <cub/device/device_scan.cuh>
 #include <algorithm>
 #include <cstring>
+#include <cstdio>
 #include <cstdlib>
 
 // ------------------------------------------------------------------------------------------
@@ -345,7 +346,13 @@ int imr_frame_complete(imrcd_ctx* ctx, bool* retry) {
     IMR_CUDA(ctx, cudaGetLastError());
     ctx->ctl_host = *ctx->p_ctl.as<FrameCtl>();
     const FrameCtl& c = ctx->ctl_host;
-    ctx->queue_dirty = std::min<uint64_t>(std::max(c.q_tail, c.q_head), ctx->cap_queue);
+    // High-water mark, with headroom: how many slots the next frame clears is part of what a captured frame is made of (frame_key), and
+    // q_head depends on how many tickets idle warps happened to take - a per-frame value made the key flip between two powers of two
+    // from frame to frame (N = 4 on C3: 200-300 k slots around 262,144), and a frame whose key changes is not replayed but re-captured.
+    {
+        const uint64_t used = std::min<uint64_t>(std::max(c.q_tail, c.q_head), ctx->cap_queue);
+        ctx->queue_dirty = std::max<uint64_t>(ctx->queue_dirty, std::min<uint64_t>(used + used / 2, ctx->cap_queue));
+    }
     bool fatal = (c.overflow & OVF_RAYSTACK) != 0;
     if (ctx->comm) { const int rc = imr_comm_decide(ctx, ctx->spec_rows_sent, retry, &fatal); if (rc) return rc; }
     else *retry = c.overflow != 0;
@@ -375,6 +382,11 @@ int imr_frame_complete(imrcd_ctx* ctx, bool* retry) {
     cudaEventElapsedTime(&st.ms_narrow, ctx->ev[3], ctx->ev[4]);
     cudaEventElapsedTime(&st.ms_reduce, ctx->ev[4], ctx->ev[5]);
     cudaEventElapsedTime(&st.ms_response, ctx->ev[6], ctx->ev[5]);
+    if (ctx->comm && ctx->ev_merge[0] && getenv("IMRCD_MERGE_DEBUG")) {
+        float a = 0.f, b = 0.f, t = 0.f;
+        cudaEventElapsedTime(&a, ctx->ev[5], ctx->ev_merge[0]); cudaEventElapsedTime(&b, ctx->ev_merge[0], ctx->ev_merge[2]); cudaEventElapsedTime(&t, ctx->ev[0], ctx->ev_merge[2]);
+        fprintf(stderr, "[imrcd rank %u] frame %.3f ms | header -> push done %.3f | wait + compact + D2H %.3f | whole %.3f\n", ctx->comm_rank, st.ms_total, a, b, t);
+    }
     st.n_rays_shot = c.n_rays_kept; st.n_responses = c.n_responses;
     st.n_merged = ctx->comm ? ctx->n_merged : c.n_colliding;
     return IMRCD_OK;
@@ -588,9 +600,13 @@ static int frame_enqueue_body(imrcd_ctx* ctx) {
     int rc = imr_frame_enqueue(ctx);
     if (rc) return rc;
     if (ctx->comm) {
+        static const bool dbg = getenv("IMRCD_MERGE_DEBUG") != nullptr;      // stage times of the merge, printed by imr_frame_complete
+        if (dbg && !ctx->ev_merge[0]) for (auto& e : ctx->ev_merge) IMR_CUDA(ctx, cudaEventCreate(&e));
         rc = imr_comm_allgather(ctx); if (rc) return rc;
+        if (dbg) IMR_CUDA(ctx, frame_event(ctx, ctx->ev_merge[0], ctx->stream));
         ctx->spec_rows_sent = imr_frame_spec_rows(ctx);
         rc = imr_comm_after_gather(ctx, ctx->spec_rows_sent); if (rc) return rc;
+        if (dbg) IMR_CUDA(ctx, frame_event(ctx, ctx->ev_merge[2], ctx->stream));
     }
     return IMRCD_OK;
 }

@@ -214,6 +214,7 @@ struct imrcd_ctx {
     FrameCtl ctl_host;
     imrcd_frame_stats stats;
     bool hits_fetched = false;
+    cudaEvent_t ev_merge[3] = {};       // diagnostic (IMRCD_MERGE_DEBUG): after the push / all-gather, after the compaction, after the merged records' D2H
     cudaEvent_t ev[10] = {};            // [0..6] frame stages, [6..7] build / refit, [8..9] re-pose
     cudaStream_t stream2 = nullptr, stream3 = nullptr, stream4 = nullptr;      // side streams for independent tail work of a frame
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join3 = nullptr, ev_join4 = nullptr;
