@@ -69,3 +69,16 @@ def test_product_never_imports_the_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".h", "Makefile")):
                 txt = open(os.path.join(dp, fn)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "liboracle" not in txt and "libimr_ref" not in txt, fn
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/imrcd.h is the drop-in boundary: it has to compile as C99 (plain pointers and sizes, no C++), warnings on."""
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("gcc not available")
+    src = tmp_path / "t.c"
+    src.write_text('#include "imrcd.h"\nint main(void) { imrcd_ctx* c = 0; (void)c; return (int)sizeof(imrcd_entity_pair) - 80; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), "-c", str(src), "-o", str(tmp_path / "t.o")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
